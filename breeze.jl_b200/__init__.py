@@ -1,0 +1,12 @@
+"""breeze.jl_b200 — B200-native drop-in for Breeze.jl's anelastic SSP-RK3 tendency + pressure-correction path.
+
+Import as `breeze_b200` (repo-root shim; a directory name containing a dot cannot be imported directly).
+Everything numerical runs in csrc/libbreeze_b200.so (hand-written sm_100a CUDA behind the C ABI of
+include/breeze_b200.h). There is no CPU fallback: constructing a model without the built library raises.
+"""
+from .abi import BreezeError, Context, Library, bz_config, load_cuda_library, cuda_library_path, FIELD_IDS
+from .model import (B200, AnelasticDynamics, AtmosphereModel, Bounded, Flat, Periodic, RectilinearGrid, ReferenceState,
+                    SaturationAdjustment, Simulation, ThermodynamicConstants, TimeStepWizard, WENO,
+                    conjure_time_step_wizard_, many_time_steps_, run_, set_, time_step_)
+
+__all__ = [n for n in dir() if not n.startswith("_")]

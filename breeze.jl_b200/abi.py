@@ -1,0 +1,261 @@
+"""ctypes binding of the C ABI declared in include/breeze_b200.h.
+
+`Library(path, prefix)` binds one shared object exporting that ABI. The product uses exactly one:
+`load_cuda_library()` → breeze.jl_b200/csrc/libbreeze_b200.so (prefix ``bz_``). It raises if the CUDA
+library is missing or does not load: there is no CPU fallback in this package. (The CPU oracle under
+oracle/ exports the same ABI with prefix ``orc_``; only tests, smoke() and bench.py's CPU-baseline legs
+bind it, through oracle/oracle_lib.py.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+BZ_ABI_VERSION = 1
+BZ_PERIODIC, BZ_FLAT = 0, 1
+BZ_MICROPHYSICS_NONE, BZ_MICROPHYSICS_WARM_SATURATION_ADJUSTMENT = 0, 1
+
+FIELD_IDS = {
+    "ρu": 0, "ρv": 1, "ρw": 2, "ρθ": 3, "ρqᵛ": 4, "ρqᵉ": 4, "ρq": 4,
+    "u": 5, "v": 6, "w": 7, "θ": 8, "qᵛ": 9, "T": 10, "φ": 11, "qˡ": 12,
+    # ASCII aliases
+    "rho_u": 0, "rho_v": 1, "rho_w": 2, "rho_theta": 3, "rho_q": 4,
+    "theta": 8, "qv": 9, "phi": 11, "ql": 12,
+}
+PROGNOSTIC = ("ρu", "ρv", "ρw", "ρθ", "ρq")
+Z_FACE_FIELDS = {2, 7}
+
+
+class bz_config(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32),
+        ("Nx", C.c_int32), ("Ny", C.c_int32), ("Nz", C.c_int32),
+        ("topology_x", C.c_int32), ("topology_y", C.c_int32),
+        ("x0", C.c_double), ("x1", C.c_double), ("y0", C.c_double), ("y1", C.c_double),
+        ("z0", C.c_double), ("z1", C.c_double),
+        ("surface_pressure", C.c_double), ("potential_temperature", C.c_double),
+        ("standard_pressure", C.c_double),
+        ("molar_gas_constant", C.c_double), ("gravitational_acceleration", C.c_double),
+        ("energy_reference_temperature", C.c_double), ("triple_point_temperature", C.c_double),
+        ("triple_point_pressure", C.c_double), ("dry_air_molar_mass", C.c_double),
+        ("dry_air_heat_capacity", C.c_double), ("vapor_molar_mass", C.c_double),
+        ("vapor_heat_capacity", C.c_double), ("liquid_reference_latent_heat", C.c_double),
+        ("liquid_heat_capacity", C.c_double), ("ice_reference_latent_heat", C.c_double),
+        ("ice_heat_capacity", C.c_double),
+        ("advection_order", C.c_int32), ("microphysics", C.c_int32),
+        ("n_ranks", C.c_int32), ("rank", C.c_int32), ("device", C.c_int32), ("reserved0", C.c_int32),
+        ("nccl_unique_id", C.c_uint8 * 128),
+        ("use_tma", C.c_int32), ("z_chunks", C.c_int32), ("reserved", C.c_int32 * 6),
+    ]
+
+
+class BreezeError(RuntimeError):
+    pass
+
+
+_dp = C.POINTER(C.c_double)
+_vp = C.c_void_p
+
+# name -> (restype, argtypes); every symbol include/breeze_b200.h declares
+ABI_SYMBOLS = {
+    "default_config": (None, [C.POINTER(bz_config)]),
+    "abi_version": (C.c_int, []),
+    "create": (C.c_int, [C.POINTER(bz_config), C.POINTER(_vp)]),
+    "destroy": (None, [_vp]),
+    "last_error": (C.c_char_p, [_vp]),
+    "get_reference_state": (C.c_int, [_vp, _dp, _dp, _dp]),
+    "set_reference_state": (C.c_int, [_vp, _dp, _dp, _dp]),
+    "set_state": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _dp, C.c_int]),
+    "time_step": (C.c_int, [_vp, C.c_double]),
+    "time_steps": (C.c_int, [_vp, C.c_double, C.c_int]),
+    "compute_tendencies": (C.c_int, [_vp]),
+    "get_tendency": (C.c_int, [_vp, C.c_int, _dp]),
+    "pressure_correct": (C.c_int, [_vp, C.c_double]),
+    "get_field": (C.c_int, [_vp, C.c_int, _dp]),
+    "get_state": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _dp]),
+    "get_clock": (C.c_int, [_vp, _dp, C.POINTER(C.c_int64)]),
+    "cell_advection_timescale": (C.c_int, [_vp, _dp]),
+    "max_abs_divergence": (C.c_int, [_vp, _dp]),
+    "synchronize": (C.c_int, [_vp]),
+}
+# CUDA-library-only symbols (instrumentation); the oracle does not export them
+CUDA_ONLY_SYMBOLS = {
+    "profile_enable": (C.c_int, [_vp, C.c_int]),
+    "profile_read": (C.c_int, [_vp, _dp, C.POINTER(C.c_int64)]),
+    "kernel_launch_count": (C.c_int64, [_vp]),
+    "stream": (_vp, [_vp]),
+    "device_bytes": (C.c_int64, [_vp]),
+}
+
+
+def _as_dp(a):
+    if a is None:
+        return None
+    assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(_dp)
+
+
+class Library:
+    """One loaded shared object exporting the ABI with a given prefix."""
+
+    def __init__(self, path: str, prefix: str, cuda: bool):
+        if not os.path.exists(path):
+            raise BreezeError(f"{path} is missing — build it first (python -c 'import __graft_entry__ as g; g.build()')")
+        self.path, self.prefix, self.cuda = path, prefix, cuda
+        self.dll = C.CDLL(path, mode=C.RTLD_GLOBAL if not cuda else C.RTLD_LOCAL)
+        table = dict(ABI_SYMBOLS)
+        if cuda:
+            table.update(CUDA_ONLY_SYMBOLS)
+        for name, (res, args) in table.items():
+            fn = getattr(self.dll, prefix + name)      # AttributeError if the symbol is not exported
+            fn.restype, fn.argtypes = res, args
+            setattr(self, name, fn)
+
+    def default_config_struct(self) -> bz_config:
+        cfg = bz_config()
+        self.default_config(C.byref(cfg))
+        return cfg
+
+
+class Context:
+    """Owns one bz_ctx / orc_ctx. Array arguments and results are numpy float64, shaped (Nz[+1], Ny, Nx)
+    in C order — i.e. x fastest, the memory order of Julia's `interior(field)`."""
+
+    def __init__(self, lib: Library, cfg: bz_config):
+        self.lib = lib
+        self.cfg = cfg
+        self.handle = _vp()
+        rc = lib.create(C.byref(cfg), C.byref(self.handle))
+        if rc != 0:
+            msg = lib.last_error(None)
+            raise BreezeError(f"{lib.prefix}create failed ({rc}): {msg.decode() if msg else ''}")
+        self.Nx_local = cfg.Nx // max(1, cfg.n_ranks)
+        self.Ny, self.Nz = cfg.Ny, cfg.Nz
+
+    def _check(self, rc, what):
+        if rc != 0:
+            msg = self.lib.last_error(self.handle)
+            raise BreezeError(f"{self.lib.prefix}{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+    def close(self):
+        if self.handle:
+            self.lib.destroy(self.handle)
+            self.handle = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def shape(self, field_id: int):
+        nz = self.Nz + 1 if field_id in Z_FACE_FIELDS else self.Nz
+        return (nz, self.Ny, self.Nx_local)
+
+    # --- reference state -------------------------------------------------------------------------
+    def reference_state(self):
+        rho, p, T = (np.empty(self.Nz) for _ in range(3))
+        self._check(self.lib.get_reference_state(self.handle, _as_dp(rho), _as_dp(p), _as_dp(T)), "get_reference_state")
+        return rho, p, T
+
+    def set_reference_state(self, density=None, pressure=None, temperature=None):
+        arrs = [None if a is None else np.ascontiguousarray(a, dtype=np.float64) for a in (density, pressure, temperature)]
+        self._check(self.lib.set_reference_state(self.handle, *[_as_dp(a) for a in arrs]), "set_reference_state")
+
+    # --- state -----------------------------------------------------------------------------------
+    def set_state(self, rho_u=None, rho_v=None, rho_w=None, rho_theta=None, rho_q=None, enforce_mass_conservation=True):
+        arrs = []
+        for fid, a in enumerate((rho_u, rho_v, rho_w, rho_theta, rho_q)):
+            if a is None:
+                arrs.append(None)
+                continue
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            if a.shape != self.shape(fid):
+                raise BreezeError(f"field {fid}: expected shape {self.shape(fid)}, got {a.shape}")
+            arrs.append(a)
+        self._check(self.lib.set_state(self.handle, *[_as_dp(a) for a in arrs], int(enforce_mass_conservation)), "set_state")
+
+    def get_field(self, name_or_id):
+        fid = FIELD_IDS[name_or_id] if isinstance(name_or_id, str) else int(name_or_id)
+        out = np.empty(self.shape(fid))
+        self._check(self.lib.get_field(self.handle, fid, _as_dp(out)), "get_field")
+        return out
+
+    def get_state(self, out=None):
+        if out is None:
+            out = [np.empty(self.shape(f)) for f in range(5)]
+        self._check(self.lib.get_state(self.handle, *[_as_dp(a) for a in out]), "get_state")
+        return out
+
+    def get_tendency(self, name_or_id):
+        fid = FIELD_IDS[name_or_id] if isinstance(name_or_id, str) else int(name_or_id)
+        out = np.empty(self.shape(fid))
+        self._check(self.lib.get_tendency(self.handle, fid, _as_dp(out)), "get_tendency")
+        return out
+
+    # --- stepping --------------------------------------------------------------------------------
+    def time_step(self, dt):
+        self._check(self.lib.time_step(self.handle, float(dt)), "time_step")
+
+    def time_steps(self, dt, n):
+        self._check(self.lib.time_steps(self.handle, float(dt), int(n)), "time_steps")
+
+    def compute_tendencies(self):
+        self._check(self.lib.compute_tendencies(self.handle), "compute_tendencies")
+
+    def pressure_correct(self, dt):
+        self._check(self.lib.pressure_correct(self.handle, float(dt)), "pressure_correct")
+
+    def synchronize(self):
+        self._check(self.lib.synchronize(self.handle), "synchronize")
+
+    def clock(self):
+        t, it = C.c_double(), C.c_int64()
+        self._check(self.lib.get_clock(self.handle, C.byref(t), C.byref(it)), "get_clock")
+        return t.value, it.value
+
+    def cell_advection_timescale(self):
+        tau = C.c_double()
+        self._check(self.lib.cell_advection_timescale(self.handle, C.byref(tau)), "cell_advection_timescale")
+        return tau.value
+
+    def max_abs_divergence(self):
+        d = C.c_double()
+        self._check(self.lib.max_abs_divergence(self.handle, C.byref(d)), "max_abs_divergence")
+        return d.value
+
+    # --- instrumentation (CUDA library only) -----------------------------------------------------
+    def profile_enable(self, on=True):
+        self._check(self.lib.profile_enable(self.handle, int(on)), "profile_enable")
+
+    def profile_read(self):
+        ms = np.zeros(8)
+        n = np.zeros(8, dtype=np.int64)
+        self._check(self.lib.profile_read(self.handle, _as_dp(ms), n.ctypes.data_as(C.POINTER(C.c_int64))), "profile_read")
+        return ms, n
+
+    def kernel_launch_count(self):
+        return int(self.lib.kernel_launch_count(self.handle))
+
+    def stream(self):
+        return self.lib.stream(self.handle)
+
+    def device_bytes(self):
+        return int(self.lib.device_bytes(self.handle))
+
+
+_CUDA_LIB = None
+
+
+def cuda_library_path() -> str:
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libbreeze_b200.so")
+
+
+def load_cuda_library() -> Library:
+    """The product's only compute backend. Fails loudly when the CUDA extension is missing."""
+    global _CUDA_LIB
+    if _CUDA_LIB is None:
+        _CUDA_LIB = Library(cuda_library_path(), "bz_", cuda=True)
+    return _CUDA_LIB
