@@ -1,0 +1,734 @@
+// api.cu — the C ABI of include/breeze_b200.h: context, orchestration of one SSP-RK3 step, marshalling.
+//
+// Per stage (reference: src/TimeSteppers/ssp_runge_kutta_3.jl:225-270):
+//   stage_kernel      tendencies of the projected state + RK update          cur -> nxt   (1 launch)
+//   halo_fill         ρu, ρv ghosts for the divergence
+//   poisson_*         source term + FFT(y) → FFT(x) → Thomas(z) → FFT⁻¹(x) → FFT⁻¹(y) → φ
+//   halo_fill φ, project_momentum (in place), halo_fill of the five prognostics
+// U⁰ is never copied: three buffer sets rotate (the step's input set IS U⁰ while stages ping-pong on the other two).
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#include "common.cuh"
+#include "stage_kernel.cuh"
+#include "poisson.cuh"
+#include "aux_kernels.cuh"
+#include "comm.cuh"
+
+struct bz_ctx {
+    bz_config cfg;
+    Layout L;
+    Thermo th;
+    Columns col;                         // device pointers
+    std::vector<double> h_rho, h_p, h_T; // host copies (Nz)
+    double* col_store = nullptr;         // one allocation behind `col`
+    double* set[3][NPROG] = {};          // three rotating sets of prognostic fields (padded)
+    CUtensorMap tmap[3][NPROG];
+    int cur = 0;                         // index of the set holding the current state
+    double* phi = nullptr;
+    double* G[NPROG] = {};               // tendencies, allocated on first bz_compute_tendencies
+    double* dense = nullptr;             // nx*Ny*(Nz+1) staging buffer for host transfers
+    double* scalar = nullptr;            // device scalar for reductions
+    // Poisson solver
+    PoissonGeom PG;
+    double2* W = nullptr;
+    double2* W2 = nullptr;               // transposed layout (multi-GPU only)
+    double2 *tw_x = nullptr, *tw_y = nullptr;
+    double *lam_x = nullptr, *lam_y = nullptr, *inv_beta = nullptr, *tfac = nullptr;
+    int lines_x = 1, lines_y = 1;
+    cudaStream_t stream = nullptr;
+    Comm comm;
+    int use_tma = 0, z_chunks = 1;
+    double time = 0.0;
+    int64_t iteration = 0;
+    int64_t launches = 0;
+    int64_t bytes = 0;
+    // profiling
+    int prof_on = 0;
+    std::vector<cudaEvent_t> prof_ev;    // pairs
+    std::vector<int> prof_fam;
+    double prof_ms[NFAM] = {};
+    int64_t prof_n[NFAM] = {};
+    char err[512] = {};
+};
+
+static char g_err[512];
+
+void bz_set_error(bz_ctx* ctx, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(ctx ? ctx->err : g_err, 512, fmt, ap);
+    va_end(ap);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+static int dev_alloc(bz_ctx* c, T** p, size_t count) {
+    CUDA_TRY(c, cudaMalloc((void**)p, count * sizeof(T)));
+    CUDA_TRY(c, cudaMemsetAsync(*p, 0, count * sizeof(T), c->stream));
+    c->bytes += (int64_t)(count * sizeof(T));
+    return BZ_OK;
+}
+
+struct ProfScope {
+    bz_ctx* c; int fam; cudaEvent_t a = nullptr, b = nullptr;
+    ProfScope(bz_ctx* c_, int fam_) : c(c_), fam(fam_) {
+        if (!c->prof_on) return;
+        cudaEventCreate(&a); cudaEventCreate(&b);
+        cudaEventRecord(a, c->stream);
+    }
+    ~ProfScope() {
+        if (!c->prof_on) return;
+        cudaEventRecord(b, c->stream);
+        c->prof_ev.push_back(a); c->prof_ev.push_back(b); c->prof_fam.push_back(fam);
+    }
+};
+
+static int is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_tensor_maps(bz_ctx* c, int box_w, int box_h) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CUDA_TRY(c, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) { bz_set_error(c, "cuTensorMapEncodeTiled unavailable"); return BZ_ERR_CUDA; }
+    PFN_encodeTiled encode = (PFN_encodeTiled)fn;
+    const Layout& L = c->L;
+    cuuint64_t dims[3] = {(cuuint64_t)L.PX, (cuuint64_t)L.PY, (cuuint64_t)L.Nz};
+    cuuint64_t strides[2] = {(cuuint64_t)L.PX * 8, (cuuint64_t)L.plane * 8};
+    cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    for (int s = 0; s < 3; ++s)
+        for (int f = 0; f < NPROG; ++f) {
+            CUresult r = encode(&c->tmap[s][f], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, c->set[s][f], dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { bz_set_error(c, "cuTensorMapEncodeTiled failed (%d)", (int)r); return BZ_ERR_CUDA; }
+        }
+    return BZ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// reference state columns (src/Thermodynamics/reference_states.jl:88-123, 326-330)
+// ---------------------------------------------------------------------------------------------------------------
+static int upload_columns(bz_ctx* c) {
+    const int Nz = c->L.Nz;
+    const bz_config& g = c->cfg;
+    std::vector<double> h((size_t)8 * (Nz + 1), 0.0);
+    double* rho = &h[0]; double* rho_inv = rho + (Nz + 1); double* rho_f = rho_inv + (Nz + 1); double* rho_f_inv = rho_f + (Nz + 1);
+    double* p = rho_f_inv + (Nz + 1); double* T = p + (Nz + 1); double* ex = T + (Nz + 1); double* lg = ex + (Nz + 1);
+    for (int k = 0; k < Nz; ++k) {
+        rho[k] = c->h_rho[k]; rho_inv[k] = 1.0 / rho[k];
+        p[k] = c->h_p[k]; T[k] = c->h_T[k];
+        ex[k] = pow(p[k] / g.standard_pressure, c->th.Rd / c->th.cpd);
+        lg[k] = log(p[k] / g.standard_pressure);
+    }
+    for (int k = 1; k < Nz; ++k) rho_f[k] = 0.5 * (rho[k] + rho[k - 1]);
+    rho_f[0] = rho[0]; rho_f[Nz] = rho[Nz - 1];          // wall faces: only ever multiply w = 0
+    for (int k = 0; k <= Nz; ++k) rho_f_inv[k] = 1.0 / rho_f[k];
+    CUDA_TRY(c, cudaMemcpyAsync(c->col_store, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    double* d = c->col_store;
+    c->col.rho = d; c->col.rho_inv = d + (Nz + 1); c->col.rho_f = d + 2 * (Nz + 1); c->col.rho_f_inv = d + 3 * (Nz + 1);
+    c->col.p = d + 4 * (Nz + 1); c->col.T = d + 5 * (Nz + 1); c->col.exner_dry = d + 6 * (Nz + 1); c->col.log_p_pst = d + 7 * (Nz + 1);
+    return BZ_OK;
+}
+
+static void default_reference_state(bz_ctx* c) {
+    const bz_config& g = c->cfg;
+    const int Nz = g.Nz;
+    const double Rd = c->th.Rd, cpd = c->th.cpd, grav = c->th.g;
+    const double p0 = g.surface_pressure, th0 = g.potential_temperature, pst = g.standard_pressure;
+    const double T0 = th0 * pow(p0 / pst, Rd / cpd);
+    const double rho0 = p0 / (Rd * (pow(p0 / pst, Rd / cpd) * th0));
+    c->h_rho.resize(Nz); c->h_p.resize(Nz); c->h_T.resize(Nz);
+    const double dz = (g.z1 - g.z0) / Nz;
+    for (int k = 0; k < Nz; ++k) {
+        double z = g.z0 + (k + 0.5) * dz;
+        double pr = p0 * pow(1 - grav * z / (cpd * T0), cpd / Rd);
+        c->h_p[k] = pr;
+        c->h_rho[k] = rho0 * pow(pr / p0, 1 - Rd / cpd);
+        c->h_T[k] = th0 * pow(pr / pst, Rd / cpd);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Poisson solver setup / solve
+// ---------------------------------------------------------------------------------------------------------------
+static int setup_thomas(bz_ctx* c) {
+    const PoissonGeom& G = c->PG;
+    dim3 grid((G.Nx + 127) / 128, G.nky_loc);
+    thomas_setup<<<grid, 128, 0, c->stream>>>(G, c->col.rho, c->col.rho_f, c->L.dz, c->lam_x, c->lam_y, c->inv_beta, c->tfac);
+    c->launches++;
+    CUDA_TRY(c, cudaGetLastError());
+    return BZ_OK;
+}
+
+static int setup_poisson(bz_ctx* c) {
+    const Layout& L = c->L;
+    const bz_config& g = c->cfg;
+    PoissonGeom& G = c->PG;
+    G.Nx = g.Nx; G.Ny = g.Ny; G.Nz = g.Nz;
+    G.nky = L.flat_y ? 1 : g.Ny / 2 + 1;
+    comm_split_ky(c->comm, G.nky, &G.ky0, &G.nky_loc);
+    // twiddles and eigenvalues (Oceananigans poisson_eigenvalues: λ = (2 sin(π i / N) / Δ)², Flat: 0)
+    std::vector<double2> twx(g.Nx), twy(g.Ny);
+    std::vector<double> lx(g.Nx), ly(G.nky);
+    for (int i = 0; i < g.Nx; ++i) {
+        long double a = -2.0L * M_PIl * i / g.Nx;
+        twx[i] = make_double2((double)cosl(a), (double)sinl(a));
+        double s = 2 * sin(M_PI * i / g.Nx) / L.dx;
+        lx[i] = L.flat_x ? 0.0 : s * s;
+    }
+    for (int j = 0; j < g.Ny; ++j) {
+        long double a = -2.0L * M_PIl * j / g.Ny;
+        twy[j] = make_double2((double)cosl(a), (double)sinl(a));
+    }
+    for (int j = 0; j < G.nky; ++j) {
+        double s = 2 * sin(M_PI * j / g.Ny) / L.dy;
+        ly[j] = L.flat_y ? 0.0 : s * s;
+    }
+    int rc;
+    if ((rc = dev_alloc(c, &c->tw_x, g.Nx))) return rc;
+    if ((rc = dev_alloc(c, &c->tw_y, g.Ny))) return rc;
+    if ((rc = dev_alloc(c, &c->lam_x, g.Nx))) return rc;
+    if ((rc = dev_alloc(c, &c->lam_y, G.nky))) return rc;
+    CUDA_TRY(c, cudaMemcpyAsync(c->tw_x, twx.data(), sizeof(double2) * g.Nx, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(c->tw_y, twy.data(), sizeof(double2) * g.Ny, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(c->lam_x, lx.data(), sizeof(double) * g.Nx, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(c->lam_y, ly.data(), sizeof(double) * G.nky, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    size_t nW = (size_t)L.nx * G.nky * G.Nz;                  // x-slab layout
+    size_t nW2 = (size_t)G.Nx * G.nky_loc * G.Nz;             // transposed layout
+    if ((rc = dev_alloc(c, &c->W, nW))) return rc;
+    if (c->comm.n_ranks > 1) { if ((rc = dev_alloc(c, &c->W2, nW2 > 0 ? nW2 : 1))) return rc; }
+    else c->W2 = c->W;
+    if ((rc = dev_alloc(c, &c->inv_beta, nW2 > 0 ? nW2 : 1))) return rc;
+    if ((rc = dev_alloc(c, &c->tfac, nW2 > 0 ? nW2 : 1))) return rc;
+    // launch shapes: each thread owns 8 points of a line
+    if (!L.flat_y) {
+        int lines = 4096 / g.Ny; if (lines < 1) lines = 1;
+        int half = (L.nx + 1) / 2; if (lines > half) lines = half;
+        c->lines_y = lines;
+        size_t sm = (size_t)2 * lines * (g.Ny + 1) * sizeof(double);
+        CUDA_TRY(c, cudaFuncSetAttribute(poisson_forward_y, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        CUDA_TRY(c, cudaFuncSetAttribute(poisson_inverse_y, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    }
+    if (!L.flat_x) {
+        int lines = 4096 / g.Nx; if (lines < 1) lines = 1;
+        long long nl = (long long)G.Nz * G.nky_loc; if (nl < 1) nl = 1;
+        if (lines > nl) lines = (int)nl;
+        c->lines_x = lines;
+        size_t sm = (size_t)2 * lines * (g.Nx + 1) * sizeof(double);
+        CUDA_TRY(c, cudaFuncSetAttribute(fft_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    }
+    return setup_thomas(c);
+}
+
+// compute_pressure_correction! (anelastic_time_stepping.jl:26-39): momentum ghosts must be valid on entry.
+static int poisson_solve(bz_ctx* c, double dt) {
+    const Layout& L = c->L;
+    const PoissonGeom& G = c->PG;
+    double** U = c->set[c->cur];
+    const double dz_over_dt = L.dz / dt;
+    {
+        ProfScope ps(c, 1);
+        if (!L.flat_y) {
+            int lines = c->lines_y;
+            dim3 grid((L.nx + 2 * lines - 1) / (2 * lines), L.Nz);
+            size_t sm = (size_t)2 * lines * (G.Ny + 1) * sizeof(double);
+            poisson_forward_y<<<grid, lines * G.Ny / 8, sm, c->stream>>>(L, G, U[0], U[1], U[2], dz_over_dt, c->W, c->tw_y, lines);
+        } else {
+            dim3 grid((L.nx + 127) / 128, L.Nz);
+            poisson_pack_flat_y<<<grid, 128, 0, c->stream>>>(L, U[0], U[1], U[2], dz_over_dt, c->W);
+        }
+        c->launches++;
+    }
+    if (c->comm.n_ranks > 1) {
+        ProfScope ps(c, 5);
+        int rc = comm_transpose_forward(c->comm, c->W, c->W2, L.nx, G, c->stream, &c->launches);
+        if (rc) { bz_set_error(c, "transpose: %s", c->comm.err); return rc; }
+    }
+    const long long n_lines = (long long)G.Nz * G.nky_loc;
+    if (!L.flat_x && n_lines > 0) {
+        ProfScope ps(c, 1);
+        int lines = c->lines_x;
+        size_t sm = (size_t)2 * lines * (G.Nx + 1) * sizeof(double);
+        fft_x_kernel<<<(unsigned)((n_lines + lines - 1) / lines), lines * G.Nx / 8, sm, c->stream>>>(c->W2, G.Nx, n_lines, c->tw_x, lines, 0);
+        c->launches++;
+    }
+    if (G.nky_loc > 0) {
+        ProfScope ps(c, 2);
+        dim3 grid((G.Nx + 127) / 128, G.nky_loc);
+        thomas_z<<<grid, 128, 0, c->stream>>>(G, c->W2, c->col.rho_f, L.dz, c->inv_beta, c->tfac);
+        c->launches++;
+        if (G.ky0 == 0) { remove_mean_mode<<<1, 256, 0, c->stream>>>(G, c->W2); c->launches++; }
+    }
+    if (!L.flat_x && n_lines > 0) {
+        ProfScope ps(c, 3);
+        int lines = c->lines_x;
+        size_t sm = (size_t)2 * lines * (G.Nx + 1) * sizeof(double);
+        fft_x_kernel<<<(unsigned)((n_lines + lines - 1) / lines), lines * G.Nx / 8, sm, c->stream>>>(c->W2, G.Nx, n_lines, c->tw_x, lines, 1);
+        c->launches++;
+    }
+    if (c->comm.n_ranks > 1) {
+        ProfScope ps(c, 5);
+        int rc = comm_transpose_backward(c->comm, c->W2, c->W, L.nx, G, c->stream, &c->launches);
+        if (rc) { bz_set_error(c, "transpose: %s", c->comm.err); return rc; }
+    }
+    {
+        ProfScope ps(c, 3);
+        double scale = 1.0 / ((L.flat_x ? 1.0 : (double)G.Nx) * (L.flat_y ? 1.0 : (double)G.Ny));
+        if (!L.flat_y) {
+            int lines = c->lines_y;
+            dim3 grid((L.nx + 2 * lines - 1) / (2 * lines), L.Nz);
+            size_t sm = (size_t)2 * lines * (G.Ny + 1) * sizeof(double);
+            poisson_inverse_y<<<grid, lines * G.Ny / 8, sm, c->stream>>>(L, G, c->W, c->phi, c->tw_y, lines, scale);
+        } else {
+            dim3 grid((L.nx + 127) / 128, L.Nz);
+            poisson_unpack_flat_y<<<grid, 128, 0, c->stream>>>(L, c->W, c->phi, scale);
+        }
+        c->launches++;
+    }
+    CUDA_TRY(c, cudaGetLastError());
+    return BZ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// halo fills
+// ---------------------------------------------------------------------------------------------------------------
+static int fill_halos(bz_ctx* c, double* const* fields, int nf, int fam) {
+    const Layout& L = c->L;
+    if (L.HX == 0 && L.HY == 0) return BZ_OK;
+    ProfScope ps(c, fam);
+    FieldSet F; F.n = nf;
+    for (int f = 0; f < nf; ++f) F.f[f] = fields[f];
+    int mode = 3;
+    if (c->comm.n_ranks > 1) {
+        int rc = comm_exchange_x_halos(c->comm, L, F, c->stream, &c->launches);
+        if (rc) { bz_set_error(c, "halo exchange: %s", c->comm.err); return rc; }
+        mode = 2;
+    }
+    if (mode == 2 && L.HY == 0) return BZ_OK;
+    long long per_level = (long long)((mode & 2) ? 2 * L.HY * L.PX : 0) + (long long)((mode & 1) ? 2 * L.HX * L.Ny : 0);
+    long long total = per_level * L.Nz;
+    if (total == 0) return BZ_OK;
+    int blocks = (int)((total + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
+    halo_fill_periodic<<<blocks, 256, 0, c->stream>>>(L, F, mode);
+    c->launches++;
+    CUDA_TRY(c, cudaGetLastError());
+    return BZ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// stage kernel launch
+// ---------------------------------------------------------------------------------------------------------------
+template <int TX, int TY, bool HAS_Y, int MICRO>
+static int launch_stage_t(bz_ctx* c, const StageParams& P, int nz_chunks) {
+    using SM = StageShared<TX, TY, HAS_Y>;
+    static bool configured = false;
+    auto kern = stage_kernel<TX, TY, HAS_Y, MICRO>;
+    if (!configured) {
+        CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SM)));
+        configured = true;
+    }
+    dim3 grid((P.nx_u + TX - 2) / (TX - 1), (c->L.Ny + TY - 1) / TY, nz_chunks);
+    kern<<<grid, TX * TY, sizeof(SM), c->stream>>>(P);
+    c->launches++;
+    CUDA_TRY(c, cudaGetLastError());
+    return BZ_OK;
+}
+
+// mode 0: out = RK update of set[in]; mode 1: out = tendencies
+static int launch_stage(bz_ctx* c, int in, double* const* out, int u0, double dt, double alpha, int mode) {
+    ProfScope ps(c, 0);
+    StageParams P;
+    memset(&P, 0, sizeof(P));
+    for (int f = 0; f < NPROG; ++f) {
+        P.tmap[f] = c->tmap[in][f];
+        P.U[f] = c->set[in][f]; P.U0[f] = c->set[u0][f]; P.out[f] = out[f];
+    }
+    P.L = c->L; P.col = c->col; P.th = c->th;
+    P.dt = dt; P.alpha = alpha; P.mode = mode;
+    P.nx_u = c->L.nx + ((c->comm.n_ranks > 1 && mode == 0) ? 1 : 0);
+    P.use_tma = c->use_tma;
+    int chunks = c->z_chunks;
+    P.k_chunk = (c->L.Nz + chunks - 1) / chunks;
+    const bool moist = c->cfg.microphysics != BZ_MICROPHYSICS_NONE;
+    if (!c->L.flat_y) {
+        return moist ? launch_stage_t<32, 8, true, 1>(c, P, chunks) : launch_stage_t<32, 8, true, 0>(c, P, chunks);
+    }
+    return moist ? launch_stage_t<128, 1, false, 1>(c, P, chunks) : launch_stage_t<128, 1, false, 0>(c, P, chunks);
+}
+
+// compute_pressure_correction! + make_pressure_correction! on set[cur], then refresh all ghosts
+static int pressure_correct(bz_ctx* c, double dt) {
+    int rc;
+    double** U = c->set[c->cur];
+    if (c->comm.n_ranks == 1) { if ((rc = fill_halos(c, U, 2, 4))) return rc; }       // ρu, ρv ghosts for the divergence
+    else { double* uv[1] = {U[1]}; if ((rc = fill_halos(c, uv, 1, 4))) return rc; }      // ρu[nx] was produced by the stage kernel
+    if ((rc = poisson_solve(c, dt))) return rc;
+    double* ph[1] = {c->phi};
+    if ((rc = fill_halos(c, ph, 1, 4))) return rc;
+    {
+        ProfScope ps(c, 4);
+        const Layout& L = c->L;
+        dim3 grid((L.nx + 127) / 128, L.Ny, L.Nz);
+        project_momentum<<<grid, 128, 0, c->stream>>>(L, c->col, U[0], U[1], U[2], c->phi, dt);
+        c->launches++;
+        CUDA_TRY(c, cudaGetLastError());
+    }
+    return fill_halos(c, U, NPROG, 4);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// ABI
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+void bz_default_config(bz_config* c) {
+    memset(c, 0, sizeof(*c));
+    c->abi_version = BZ_ABI_VERSION;
+    c->Nx = c->Ny = c->Nz = 8;
+    c->topology_x = c->topology_y = BZ_PERIODIC;
+    c->x1 = c->y1 = c->z1 = 1.0;
+    c->surface_pressure = 101325.0; c->potential_temperature = 288.0; c->standard_pressure = 1e5;
+    c->molar_gas_constant = 8.314462618; c->gravitational_acceleration = 9.81;
+    c->energy_reference_temperature = 273.15; c->triple_point_temperature = 273.16; c->triple_point_pressure = 611.657;
+    c->dry_air_molar_mass = 0.02897; c->dry_air_heat_capacity = 1005.0;
+    c->vapor_molar_mass = 0.018015; c->vapor_heat_capacity = 1850.0;
+    c->liquid_reference_latent_heat = 2500800.0; c->liquid_heat_capacity = 4181.0;
+    c->ice_reference_latent_heat = 2834000.0; c->ice_heat_capacity = 2108.0;
+    c->advection_order = 5; c->microphysics = BZ_MICROPHYSICS_NONE;
+    c->n_ranks = 1; c->rank = 0; c->device = 0;
+}
+
+int bz_abi_version(void) { return BZ_ABI_VERSION; }
+
+const char* bz_last_error(const bz_ctx* c) { return c ? c->err : g_err; }
+
+void bz_destroy(bz_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->cfg.device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    comm_destroy(c->comm);
+    for (int s = 0; s < 3; ++s) for (int f = 0; f < NPROG; ++f) cudaFree(c->set[s][f]);
+    for (int f = 0; f < NPROG; ++f) cudaFree(c->G[f]);
+    cudaFree(c->phi); cudaFree(c->dense); cudaFree(c->scalar); cudaFree(c->col_store);
+    if (c->W2 != c->W) cudaFree(c->W2);
+    cudaFree(c->W); cudaFree(c->tw_x); cudaFree(c->tw_y); cudaFree(c->lam_x); cudaFree(c->lam_y);
+    cudaFree(c->inv_beta); cudaFree(c->tfac);
+    for (auto e : c->prof_ev) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int bz_create(const bz_config* cfg, bz_ctx** out) {
+    if (!cfg || !out) return BZ_ERR_INVALID;
+    *out = nullptr;
+#define FAIL(code, ...) do { bz_set_error(nullptr, __VA_ARGS__); return (code); } while (0)
+    if (cfg->abi_version != BZ_ABI_VERSION) FAIL(BZ_ERR_INVALID, "abi_version %d != %d", cfg->abi_version, BZ_ABI_VERSION);
+    if (cfg->Nx < 1 || cfg->Ny < 1 || cfg->Nz < 2) FAIL(BZ_ERR_INVALID, "grid size must be positive (Nz >= 2)");
+    if (cfg->advection_order != 5) FAIL(BZ_ERR_UNSUPPORTED, "only WENO(order=5) is on the path");
+    const int fx = cfg->topology_x == BZ_FLAT, fy = cfg->topology_y == BZ_FLAT;
+    if ((fx && cfg->Nx != 1) || (fy && cfg->Ny != 1)) FAIL(BZ_ERR_INVALID, "a Flat dimension must have size 1");
+    if (fx && !fy) FAIL(BZ_ERR_UNSUPPORTED, "(Flat, Periodic, Bounded) is not supported; use (Periodic, Flat, Bounded)");
+    if (!fx && (!is_pow2(cfg->Nx) || cfg->Nx < 8 || cfg->Nx > 4096)) FAIL(BZ_ERR_UNSUPPORTED, "Nx must be a power of two in [8, 4096] (in-house FFT)");
+    if (!fy && (!is_pow2(cfg->Ny) || cfg->Ny < 8 || cfg->Ny > 4096)) FAIL(BZ_ERR_UNSUPPORTED, "Ny must be a power of two in [8, 4096] (in-house FFT)");
+    const int P = cfg->n_ranks < 1 ? 1 : cfg->n_ranks;
+    if (P > 1 && (fx || cfg->Nx % P != 0 || (cfg->Nx / P) < 8)) FAIL(BZ_ERR_INVALID, "x-slabs: Nx must be divisible by n_ranks with at least 8 columns per rank");
+    if (cfg->rank < 0 || cfg->rank >= P) FAIL(BZ_ERR_INVALID, "rank out of range");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) FAIL(BZ_ERR_CUDA, "no CUDA device: libbreeze_b200 has no CPU fallback");
+    if (cfg->device < 0 || cfg->device >= ndev) FAIL(BZ_ERR_INVALID, "device ordinal %d out of range (%d devices)", cfg->device, ndev);
+    if (cudaSetDevice(cfg->device) != cudaSuccess) FAIL(BZ_ERR_CUDA, "cudaSetDevice failed");
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, cfg->device);
+    if (prop.major < 10) FAIL(BZ_ERR_UNSUPPORTED, "compute capability %d.%d: this library is built for sm_100a (B200) only", prop.major, prop.minor);
+#undef FAIL
+
+    bz_ctx* c = new bz_ctx();
+    c->cfg = *cfg;
+    c->cfg.n_ranks = P;
+    Layout& L = c->L;
+    L.nx = cfg->Nx / P; L.Ny = cfg->Ny; L.Nz = cfg->Nz;
+    L.flat_x = fx; L.flat_y = fy;
+    L.HX = fx ? 0 : BZ_HALO; L.HY = fy ? 0 : BZ_HALO;
+    L.PX = L.nx + 2 * L.HX; L.PY = L.Ny + 2 * L.HY;
+    L.plane = (long long)L.PX * L.PY; L.n = L.plane * L.Nz;
+    L.dx = fx ? 1.0 : (cfg->x1 - cfg->x0) / cfg->Nx;
+    L.dy = fy ? 1.0 : (cfg->y1 - cfg->y0) / cfg->Ny;
+    L.dz = (cfg->z1 - cfg->z0) / cfg->Nz;
+    L.rdx = fx ? 0.0 : 1.0 / L.dx; L.rdy = fy ? 0.0 : 1.0 / L.dy; L.rdz = 1.0 / L.dz;
+    Thermo& th = c->th;
+    th.Rd = cfg->molar_gas_constant / cfg->dry_air_molar_mass; th.Rv = cfg->molar_gas_constant / cfg->vapor_molar_mass;
+    th.cpd = cfg->dry_air_heat_capacity; th.cpv = cfg->vapor_heat_capacity;
+    th.cl = cfg->liquid_heat_capacity; th.ci = cfg->ice_heat_capacity; th.g = cfg->gravitational_acceleration;
+    th.Ll = cfg->liquid_reference_latent_heat; th.Li = cfg->ice_reference_latent_heat; th.pst = cfg->standard_pressure;
+    th.Tr_energy = cfg->energy_reference_temperature; th.Ttr = cfg->triple_point_temperature; th.ptr = cfg->triple_point_pressure;
+    th.microphysics = cfg->microphysics;
+
+    int rc = BZ_OK;
+#define TRY(x) do { rc = (x); if (rc) { strncpy(g_err, c->err, 511); bz_destroy(c); return rc; } } while (0)
+#define TRYCUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { bz_set_error(nullptr, "%s: %s", #x, cudaGetErrorString(e_)); bz_destroy(c); return BZ_ERR_CUDA; } } while (0)
+    TRYCUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    rc = comm_init(c->comm, cfg, c->stream);
+    if (rc) { bz_set_error(nullptr, "comm_init: %s", c->comm.err); bz_destroy(c); return rc; }
+    for (int s = 0; s < 3; ++s) for (int f = 0; f < NPROG; ++f) TRY(dev_alloc(c, &c->set[s][f], (size_t)L.n));
+    TRY(dev_alloc(c, &c->phi, (size_t)L.n));
+    TRY(dev_alloc(c, &c->dense, (size_t)L.nx * L.Ny * (L.Nz + 1)));
+    TRY(dev_alloc(c, &c->scalar, 8));
+    TRY(dev_alloc(c, &c->col_store, (size_t)8 * (L.Nz + 1)));
+    default_reference_state(c);
+    TRY(upload_columns(c));
+    TRY(setup_poisson(c));
+    TRY(comm_alloc_buffers(c->comm, L, c->PG, &c->bytes));
+    // staging of the stage kernel's operands
+    const bool tma_possible = !fx && (L.PX % 2 == 0);
+    c->use_tma = (cfg->use_tma == 2) ? 0 : (tma_possible ? 1 : 0);
+    if (cfg->use_tma == 1 && !tma_possible) { bz_set_error(nullptr, "TMA staging needs an even padded row length"); bz_destroy(c); return BZ_ERR_UNSUPPORTED; }
+    if (c->use_tma) {
+        if (!fy) TRY(make_tensor_maps(c, StageShared<32, 8, true>::SW, StageShared<32, 8, true>::SH));
+        else TRY(make_tensor_maps(c, StageShared<128, 1, false>::SW, 1));
+    }
+    {
+        int gx = fy ? (L.nx + 126) / 127 : (L.nx + 30) / 31, gy = fy ? 1 : (L.Ny + 7) / 8;
+        int want = (4 * 148 + gx * gy - 1) / (gx * gy);
+        int maxc = L.Nz / 32 > 1 ? L.Nz / 32 : 1;
+        c->z_chunks = cfg->z_chunks > 0 ? cfg->z_chunks : (want < 1 ? 1 : (want > maxc ? maxc : want));
+        if (c->z_chunks > L.Nz) c->z_chunks = L.Nz;
+    }
+    // initialize_model_thermodynamics!: θ = θ₀ (anelastic_time_stepping.jl:15-19)
+    {
+        std::vector<double> h((size_t)L.nx * L.Ny * L.Nz);
+        for (int k = 0; k < L.Nz; ++k)
+            for (size_t a = 0; a < (size_t)L.nx * L.Ny; ++a) h[(size_t)k * L.nx * L.Ny + a] = c->h_rho[k] * cfg->potential_temperature;
+        TRYCUDA(cudaMemcpyAsync(c->dense, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        dim3 grid((L.nx + 127) / 128, L.Ny, L.Nz);
+        scatter_interior<<<grid, 128, 0, c->stream>>>(L, c->dense, c->set[0][BZ_RHO_THETA], 0);
+        c->launches++;
+        TRYCUDA(cudaStreamSynchronize(c->stream));
+        TRY(fill_halos(c, c->set[0], NPROG, 4));
+    }
+    TRYCUDA(cudaStreamSynchronize(c->stream));
+#undef TRY
+#undef TRYCUDA
+    *out = c;
+    return BZ_OK;
+}
+
+int bz_get_reference_state(bz_ctx* c, double* rho, double* p, double* T) {
+    if (!c) return BZ_ERR_INVALID;
+    for (int k = 0; k < c->L.Nz; ++k) {
+        if (rho) rho[k] = c->h_rho[k];
+        if (p) p[k] = c->h_p[k];
+        if (T) T[k] = c->h_T[k];
+    }
+    return BZ_OK;
+}
+
+int bz_set_reference_state(bz_ctx* c, const double* rho, const double* p, const double* T) {
+    if (!c) return BZ_ERR_INVALID;
+    cudaSetDevice(c->cfg.device);
+    for (int k = 0; k < c->L.Nz; ++k) {
+        if (rho) c->h_rho[k] = rho[k];
+        if (p) c->h_p[k] = p[k];
+        if (T) c->h_T[k] = T[k];
+    }
+    int rc = upload_columns(c);
+    if (rc) return rc;
+    return setup_thomas(c);
+}
+
+static int upload_field(bz_ctx* c, const double* host, double* dst, int zero_level0) {
+    const Layout& L = c->L;
+    size_t n = (size_t)L.nx * L.Ny * L.Nz;             // a z-face field's top wall level is ignored (always 0)
+    CUDA_TRY(c, cudaMemcpyAsync(c->dense, host, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    dim3 grid((L.nx + 127) / 128, L.Ny, L.Nz);
+    scatter_interior<<<grid, 128, 0, c->stream>>>(L, c->dense, dst, zero_level0);
+    c->launches++;
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));    // the caller's buffer and `dense` are free again
+    return BZ_OK;
+}
+
+int bz_set_state(bz_ctx* c, const double* ru, const double* rv, const double* rw, const double* rth, const double* rq, int enforce) {
+    if (!c) return BZ_ERR_INVALID;
+    cudaSetDevice(c->cfg.device);
+    const double* src[NPROG] = {ru, rv, rw, rth, rq};
+    int rc;
+    for (int f = 0; f < NPROG; ++f)
+        if (src[f] && (rc = upload_field(c, src[f], c->set[c->cur][f], f == BZ_RHO_W))) return rc;
+    if ((rc = fill_halos(c, c->set[c->cur], NPROG, 4))) return rc;
+    if (enforce && (rc = pressure_correct(c, 1.0))) return rc;
+    return BZ_OK;
+}
+
+int bz_time_step(bz_ctx* c, double dt) {
+    if (!c) return BZ_ERR_INVALID;
+    cudaSetDevice(c->cfg.device);
+    const double alpha[3] = {1.0, 1.0 / 4.0, 2.0 / 3.0};
+    const int u0 = c->cur;                             // store_initial_state! without a copy
+    int rc;
+    for (int s = 0; s < 3; ++s) {
+        int in = c->cur;
+        int nxt = 0;
+        while (nxt == in || nxt == u0) ++nxt;          // the free set
+        if ((rc = launch_stage(c, in, c->set[nxt], u0, dt, alpha[s], 0))) return rc;
+        c->cur = nxt;
+        if ((rc = pressure_correct(c, alpha[s] * dt))) return rc;
+    }
+    c->time += dt;
+    c->iteration += 1;
+    return BZ_OK;
+}
+
+int bz_time_steps(bz_ctx* c, double dt, int n) {
+    for (int s = 0; s < n; ++s) { int rc = bz_time_step(c, dt); if (rc) return rc; }
+    return BZ_OK;
+}
+
+int bz_compute_tendencies(bz_ctx* c) {
+    if (!c) return BZ_ERR_INVALID;
+    cudaSetDevice(c->cfg.device);
+    int rc;
+    for (int f = 0; f < NPROG; ++f) if (!c->G[f] && (rc = dev_alloc(c, &c->G[f], (size_t)c->L.n))) return rc;
+    return launch_stage(c, c->cur, c->G, c->cur, 0.0, 1.0, 1);
+}
+
+static int download_dense(bz_ctx* c, double* host, int nz_out) {
+    size_t n = (size_t)c->L.nx * c->L.Ny * nz_out;
+    CUDA_TRY(c, cudaMemcpyAsync(host, c->dense, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return BZ_OK;
+}
+
+int bz_get_tendency(bz_ctx* c, int f, double* out) {
+    if (!c || f < 0 || f >= NPROG || !out) return BZ_ERR_INVALID;
+    if (!c->G[f]) { bz_set_error(c, "call bz_compute_tendencies first"); return BZ_ERR_STATE; }
+    cudaSetDevice(c->cfg.device);
+    const Layout& L = c->L;
+    int nz_out = (f == BZ_RHO_W) ? L.Nz + 1 : L.Nz;
+    dim3 grid((L.nx + 127) / 128, L.Ny, nz_out);
+    extract_interior<<<grid, 128, 0, c->stream>>>(L, c->G[f], c->dense, nz_out);
+    c->launches++;
+    CUDA_TRY(c, cudaGetLastError());
+    return download_dense(c, out, nz_out);
+}
+
+int bz_pressure_correct(bz_ctx* c, double dt) {
+    if (!c) return BZ_ERR_INVALID;
+    cudaSetDevice(c->cfg.device);
+    int rc;
+    if ((rc = fill_halos(c, c->set[c->cur], NPROG, 4))) return rc;
+    return pressure_correct(c, dt);
+}
+
+int bz_get_field(bz_ctx* c, int f, double* out) {
+    if (!c || !out) return BZ_ERR_INVALID;
+    cudaSetDevice(c->cfg.device);
+    const Layout& L = c->L;
+    int nz_out = (f == BZ_RHO_W || f == BZ_W) ? L.Nz + 1 : L.Nz;
+    dim3 grid((L.nx + 127) / 128, L.Ny, nz_out);
+    if (f >= 0 && f < NPROG) extract_interior<<<grid, 128, 0, c->stream>>>(L, c->set[c->cur][f], c->dense, nz_out);
+    else if (f == BZ_PHI) extract_interior<<<grid, 128, 0, c->stream>>>(L, c->phi, c->dense, nz_out);
+    else if (f >= BZ_U && f <= BZ_QL) {
+        FieldSet U; U.n = NPROG;
+        for (int a = 0; a < NPROG; ++a) U.f[a] = c->set[c->cur][a];
+        if (c->cfg.microphysics == BZ_MICROPHYSICS_NONE) diagnose_field<0><<<grid, 128, 0, c->stream>>>(L, c->col, c->th, U, f, c->dense, nz_out);
+        else diagnose_field<1><<<grid, 128, 0, c->stream>>>(L, c->col, c->th, U, f, c->dense, nz_out);
+    } else return BZ_ERR_INVALID;
+    c->launches++;
+    CUDA_TRY(c, cudaGetLastError());
+    return download_dense(c, out, nz_out);
+}
+
+int bz_get_state(bz_ctx* c, double* ru, double* rv, double* rw, double* rth, double* rq) {
+    double* dst[NPROG] = {ru, rv, rw, rth, rq};
+    for (int f = 0; f < NPROG; ++f)
+        if (dst[f]) { int rc = bz_get_field(c, f, dst[f]); if (rc) return rc; }
+    return BZ_OK;
+}
+
+int bz_get_clock(bz_ctx* c, double* time, int64_t* iteration) {
+    if (!c) return BZ_ERR_INVALID;
+    if (time) *time = c->time;
+    if (iteration) *iteration = c->iteration;
+    return BZ_OK;
+}
+
+static int reduce_max(bz_ctx* c, int which, double* out) {
+    cudaSetDevice(c->cfg.device);
+    const Layout& L = c->L;
+    double** U = c->set[c->cur];
+    CUDA_TRY(c, cudaMemsetAsync(c->scalar, 0, sizeof(double), c->stream));
+    long long total = (long long)L.nx * L.Ny * L.Nz;
+    int blocks = (int)((total + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
+    reduce_max_kernel<<<blocks, 256, 0, c->stream>>>(L, c->col, U[0], U[1], U[2], which, c->scalar);
+    c->launches++;
+    CUDA_TRY(c, cudaGetLastError());
+    double v = 0.0;
+    CUDA_TRY(c, cudaMemcpyAsync(&v, c->scalar, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (c->comm.n_ranks > 1) { int rc = comm_allreduce_max(c->comm, &v, c->scalar, c->stream); if (rc) { bz_set_error(c, "allreduce: %s", c->comm.err); return rc; } }
+    *out = v;
+    return BZ_OK;
+}
+
+int bz_cell_advection_timescale(bz_ctx* c, double* tau) {
+    if (!c || !tau) return BZ_ERR_INVALID;
+    double m; int rc = reduce_max(c, 1, &m);
+    if (rc) return rc;
+    *tau = 1.0 / m;
+    return BZ_OK;
+}
+
+int bz_max_abs_divergence(bz_ctx* c, double* out) {
+    if (!c || !out) return BZ_ERR_INVALID;
+    return reduce_max(c, 0, out);
+}
+
+int bz_synchronize(bz_ctx* c) {
+    if (!c) return BZ_ERR_INVALID;
+    cudaSetDevice(c->cfg.device);
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return BZ_OK;
+}
+
+int bz_profile_enable(bz_ctx* c, int on) {
+    if (!c) return BZ_ERR_INVALID;
+    c->prof_on = on;
+    return BZ_OK;
+}
+
+int bz_profile_read(bz_ctx* c, double* ms, int64_t* n) {
+    if (!c) return BZ_ERR_INVALID;
+    cudaSetDevice(c->cfg.device);
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    for (size_t e = 0; e < c->prof_fam.size(); ++e) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, c->prof_ev[2 * e], c->prof_ev[2 * e + 1]);
+        c->prof_ms[c->prof_fam[e]] += t; c->prof_n[c->prof_fam[e]] += 1;
+        cudaEventDestroy(c->prof_ev[2 * e]); cudaEventDestroy(c->prof_ev[2 * e + 1]);
+    }
+    c->prof_ev.clear(); c->prof_fam.clear();
+    for (int f = 0; f < NFAM; ++f) { if (ms) ms[f] = c->prof_ms[f]; if (n) n[f] = c->prof_n[f]; c->prof_ms[f] = 0; c->prof_n[f] = 0; }
+    return BZ_OK;
+}
+
+int64_t bz_kernel_launch_count(const bz_ctx* c) { return c ? c->launches : 0; }
+void* bz_stream(bz_ctx* c) { return c ? (void*)c->stream : nullptr; }
+int64_t bz_device_bytes(const bz_ctx* c) { return c ? c->bytes : 0; }
+
+}  // extern "C"

@@ -1,0 +1,138 @@
+// aux_kernels.cuh — halo fills, momentum projection, host <-> device marshalling, diagnostics and reductions.
+#pragma once
+#include "common.cuh"
+#include "stage_kernel.cuh"   // thermodynamic helpers shared with the diagnostics
+
+struct FieldSet { double* f[NPROG + 1]; int n; };
+
+// fill_halo_regions! for Periodic x / y on one GPU: every ghost point copies its periodic image from the interior
+// (one launch for up to six fields; corners included). mode bit 0: x ghosts, bit 1: y ghosts (full padded width,
+// used after an x-face exchange across GPUs so that the corners pick up the neighbour's data).
+__global__ void halo_fill_periodic(Layout L, FieldSet F, int mode) {
+    const int ny_rows = (mode & 2) ? 2 * L.HY : 0;                 // ghost rows, full width PX
+    const int nx_cols = (mode & 1) ? 2 * L.HX : 0;                 // ghost columns of the interior rows
+    const int per_level = ny_rows * L.PX + nx_cols * L.Ny;
+    const long long total = (long long)per_level * L.Nz;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        int k = (int)(e / per_level), r = (int)(e % per_level);
+        int px, py;
+        if (r < ny_rows * L.PX) {
+            int row = r / L.PX; px = r % L.PX;
+            py = row < L.HY ? row : L.Ny + row;                    // rows 0..HY-1 and Ny+HY..Ny+2HY-1
+        } else {
+            r -= ny_rows * L.PX;
+            int col = r % nx_cols; py = L.HY + r / nx_cols;
+            px = col < L.HX ? col : L.nx + col;
+        }
+        int si = px - L.HX, sj = py - L.HY;
+        if (mode & 1) { if (si < 0) si += L.nx; else if (si >= L.nx) si -= L.nx; }
+        if (sj < 0) sj += L.Ny; else if (sj >= L.Ny) sj -= L.Ny;
+        long long dst = ((long long)k * L.PY + py) * L.PX + px;
+        long long src = ((long long)k * L.PY + (sj + L.HY)) * L.PX + (si + L.HX);
+        for (int f = 0; f < F.n; ++f) F.f[f][dst] = F.f[f][src];
+    }
+}
+
+// _pressure_correct_momentum! (src/AnelasticEquations/anelastic_time_stepping.jl:45-54), in place.
+__global__ void project_momentum(Layout L, Columns col, double* __restrict__ ru, double* __restrict__ rv, double* __restrict__ rw,
+                                 const double* __restrict__ phi, double dt) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, k = blockIdx.z;
+    if (i >= L.nx) return;
+    long long n = lidx(L, i, j, k);
+    double p = phi[n];
+    double rc = col.rho[k];
+    if (!L.flat_x) ru[n] -= rc * dt * ((p - phi[n - 1]) * L.rdx);
+    if (!L.flat_y) rv[n] -= rc * dt * ((p - phi[n - L.PX]) * L.rdy);
+    if (k >= 1) rw[n] -= col.rho_f[k] * dt * ((p - phi[n - L.plane]) * L.rdz);
+}
+
+// dense interior (x fastest, nz_out levels) <- padded field; levels >= Nz are the top wall (0)
+__global__ void extract_interior(Layout L, const double* __restrict__ src, double* __restrict__ dst, int nz_out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, k = blockIdx.z;
+    if (i >= L.nx) return;
+    dst[((size_t)k * L.Ny + j) * L.nx + i] = (k < L.Nz) ? src[lidx(L, i, j, k)] : 0.0;
+}
+__global__ void scatter_interior(Layout L, const double* __restrict__ src, double* __restrict__ dst, int zero_level0) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, k = blockIdx.z;
+    if (i >= L.nx) return;
+    double v = src[((size_t)k * L.Ny + j) * L.nx + i];
+    if (zero_level0 && k == 0) v = 0.0;
+    dst[lidx(L, i, j, k)] = v;
+}
+
+// Diagnostic fields on demand (the stage kernel never materialises them):
+// _compute_velocities! / _compute_auxiliary_thermodynamic_variables! (update_atmosphere_model_state.jl:248-292)
+template <int MICRO>
+__global__ void diagnose_field(Layout L, Columns col, Thermo th, FieldSet U, int which, double* __restrict__ dst, int nz_out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, k = blockIdx.z;
+    if (i >= L.nx) return;
+    double v = 0.0;
+    if (k < L.Nz) {
+        long long n = lidx(L, i, j, k);
+        switch (which) {
+            case BZ_U: v = U.f[0][n] / col.rho[k]; break;
+            case BZ_V: v = U.f[1][n] / col.rho[k]; break;
+            case BZ_W: v = U.f[2][n] / col.rho_f[k]; break;
+            case BZ_THETA: v = U.f[3][n] / col.rho[k]; break;
+            default: {
+                double theta = U.f[3][n] / col.rho[k], q = U.f[4][n] / col.rho[k];
+                double qv = q, ql = 0.0, T;
+                if (MICRO == BZ_MICROPHYSICS_NONE) T = (q == 0.0) ? col.exner_dry[k] * theta : lipt_temperature(th, theta, col.log_p_pst[k], q, 0.0);
+                else T = saturation_adjust(th, theta, col.p[k], col.log_p_pst[k], q, qv, ql);
+                v = which == BZ_T ? T : (which == BZ_QV ? qv : ql);
+            }
+        }
+    }
+    dst[((size_t)k * L.Ny + j) * L.nx + i] = v;
+}
+
+__device__ __forceinline__ void atomic_max_nonneg(double* addr, double v) {
+    atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
+}
+
+// which = 0: max |div(ρu)|; which = 1: max (|u|/Δx + |v|/Δy + |w|/Δz)  (cell_advection_timescale.jl:46-65)
+__global__ void reduce_max_kernel(Layout L, Columns col, const double* __restrict__ ru, const double* __restrict__ rv,
+                                  const double* __restrict__ rw, int which, double* __restrict__ out) {
+    double m = 0.0;
+    const long long total = (long long)L.nx * L.Ny * L.Nz;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        int i = (int)(e % L.nx), j = (int)((e / L.nx) % L.Ny), k = (int)(e / ((long long)L.nx * L.Ny));
+        long long n = lidx(L, i, j, k);
+        double v;
+        if (which == 0) {
+            double d = 0.0;
+            if (!L.flat_x) d += (ru[n + 1] - ru[n]) * L.rdx;
+            if (!L.flat_y) d += (rv[n + L.PX] - rv[n]) * L.rdy;
+            double wt = (k + 1 < L.Nz) ? rw[n + L.plane] : 0.0;
+            d += (wt - rw[n]) * L.rdz;
+            v = fabs(d);
+        } else {
+            v = fabs(rw[n] / col.rho_f[k]) * L.rdz;
+            if (!L.flat_x) v += fabs(ru[n] / col.rho[k]) * L.rdx;
+            if (!L.flat_y) v += fabs(rv[n] / col.rho[k]) * L.rdy;
+        }
+        m = fmax(m, v);
+    }
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomic_max_nonneg(out, m);
+}
+
+// x-face packing for the slab halo exchange: `w` columns starting at interior index i_src of nf fields -> contiguous buffer
+__global__ void pack_x_faces(Layout L, FieldSet F, int i_src, int w, double* __restrict__ buf) {
+    const long long per_field = (long long)w * L.Ny * L.Nz;
+    const long long total = per_field * F.n;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        int f = (int)(e / per_field); long long r = e % per_field;
+        int c = (int)(r % w), j = (int)((r / w) % L.Ny), k = (int)(r / ((long long)w * L.Ny));
+        buf[e] = F.f[f][lidx(L, i_src + c, j, k)];
+    }
+}
+__global__ void unpack_x_faces(Layout L, FieldSet F, int i_dst, int w, const double* __restrict__ buf) {
+    const long long per_field = (long long)w * L.Ny * L.Nz;
+    const long long total = per_field * F.n;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        int f = (int)(e / per_field); long long r = e % per_field;
+        int c = (int)(r % w), j = (int)((r / w) % L.Ny), k = (int)(r / ((long long)w * L.Ny));
+        F.f[f][lidx(L, i_dst + c, j, k)] = buf[e];
+    }
+}

@@ -1,0 +1,210 @@
+// comm.cuh — x-slab decomposition across the GPUs of one box: NCCL (NVLink 5 / NVSwitch) point-to-point groups.
+//
+// The reference has no multi-GPU path at all; this is the B200-side design:
+//   * WENO ghost cells: the BZ_HALO-wide x-faces of the prognostics travel to the two periodic neighbours in ONE
+//     ncclGroup (send left + send right + 2 recv) between a pack and an unpack kernel;
+//   * distributed FFT: after the local y transform the spectrum W[k][ky][i_local] is re-partitioned to
+//     W2[k][ky_local][kx_global] by a grouped all-to-all (ncclSend/ncclRecv per peer), so that the x transform and
+//     the z Thomas solve are local; the inverse runs the same exchange backwards.
+// libnccl is dlopen'ed on first multi-rank use (torch's bundled libnccl.so.2 if already loaded, else the system
+// one), so a single-GPU context has no NCCL dependency. One process per GPU; rank r's periodic neighbours are r±1.
+#pragma once
+#include <dlfcn.h>
+#include <string.h>
+#include "common.cuh"
+#include "poisson.cuh"
+#include "aux_kernels.cuh"
+
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId_t;
+enum { NCCL_FLOAT64 = 8, NCCL_MAX = 2 };      // ncclDataType_t / ncclRedOp_t values (nccl.h)
+
+struct NcclApi {
+    void* lib = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId_t, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+
+struct Comm {
+    int n_ranks = 1, rank = 0;
+    NcclApi api;
+    ncclComm_t comm = nullptr;
+    double* halo_send = nullptr;    // [2][nf][HX][Ny][Nz]
+    double* halo_recv = nullptr;
+    double2* tr_send = nullptr;     // transpose staging
+    double2* tr_recv = nullptr;
+    size_t halo_cap = 0, tr_cap = 0;
+    char err[256] = {};
+};
+
+#define NCCL_TRY(cm, call)                                                                                  \
+    do {                                                                                                    \
+        int r_ = (call);                                                                                    \
+        if (r_ != 0) {                                                                                      \
+            snprintf((cm).err, 256, "%s: %s", #call, (cm).api.GetErrorString ? (cm).api.GetErrorString(r_) : "nccl error"); \
+            return BZ_ERR_NCCL;                                                                             \
+        }                                                                                                   \
+    } while (0)
+
+static inline void comm_split_range(int n, int P, int r, int* start, int* count) {
+    int base = n / P, rem = n % P;
+    *count = base + (r < rem ? 1 : 0);
+    *start = r * base + (r < rem ? r : rem);
+}
+static inline void comm_split_ky(const Comm& cm, int nky, int* ky0, int* nky_loc) { comm_split_range(nky, cm.n_ranks, cm.rank, ky0, nky_loc); }
+
+static int comm_init(Comm& cm, const bz_config* cfg, cudaStream_t) {
+    cm.n_ranks = cfg->n_ranks < 1 ? 1 : cfg->n_ranks;
+    cm.rank = cfg->rank;
+    if (cm.n_ranks == 1) return BZ_OK;
+    const char* names[] = {"libnccl.so.2", "libnccl.so", nullptr};
+    for (int n = 0; names[n] && !cm.api.lib; ++n) cm.api.lib = dlopen(names[n], RTLD_NOW | RTLD_GLOBAL);
+    if (!cm.api.lib) { snprintf(cm.err, 256, "cannot dlopen libnccl.so.2: %s", dlerror()); return BZ_ERR_NCCL; }
+#define SYM(field, name) *(void**)(&cm.api.field) = dlsym(cm.api.lib, name); if (!cm.api.field) { snprintf(cm.err, 256, "missing symbol %s", name); return BZ_ERR_NCCL; }
+    SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy") SYM(Send, "ncclSend") SYM(Recv, "ncclRecv")
+    SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd") SYM(AllReduce, "ncclAllReduce") SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+    ncclUniqueId_t id;
+    memcpy(id.internal, cfg->nccl_unique_id, 128);
+    NCCL_TRY(cm, cm.api.CommInitRank(&cm.comm, cm.n_ranks, id, cm.rank));
+    return BZ_OK;
+}
+
+static void comm_destroy(Comm& cm) {
+    if (cm.comm && cm.api.CommDestroy) cm.api.CommDestroy(cm.comm);
+    cm.comm = nullptr;
+    cudaFree(cm.halo_send); cudaFree(cm.halo_recv); cudaFree(cm.tr_send); cudaFree(cm.tr_recv);
+    cm.halo_send = cm.halo_recv = nullptr; cm.tr_send = cm.tr_recv = nullptr;
+}
+
+static int comm_alloc_buffers(Comm& cm, const Layout& L, const PoissonGeom& G, int64_t* bytes) {
+    if (cm.n_ranks == 1) return BZ_OK;
+    cm.halo_cap = (size_t)2 * (NPROG + 1) * L.HX * L.Ny * L.Nz;
+    size_t a = (size_t)L.nx * G.nky * G.Nz, b = (size_t)G.Nx * G.nky_loc * G.Nz;
+    cm.tr_cap = a > b ? a : b;
+    if (cudaMalloc(&cm.halo_send, cm.halo_cap * 8) || cudaMalloc(&cm.halo_recv, cm.halo_cap * 8) ||
+        cudaMalloc(&cm.tr_send, cm.tr_cap * 16) || cudaMalloc(&cm.tr_recv, cm.tr_cap * 16)) {
+        snprintf(cm.err, 256, "cudaMalloc of communication buffers failed"); return BZ_ERR_NOMEM;
+    }
+    *bytes += (int64_t)(2 * cm.halo_cap * 8 + 2 * cm.tr_cap * 16);
+    return BZ_OK;
+}
+
+// Periodic x-halo exchange of F.n fields: my right-most HX columns go to the right neighbour's left ghosts and vice versa.
+static int comm_exchange_x_halos(Comm& cm, const Layout& L, const FieldSet& F, cudaStream_t s, int64_t* launches) {
+    const int P = cm.n_ranks, left = (cm.rank + P - 1) % P, right = (cm.rank + 1) % P;
+    const size_t face = (size_t)F.n * L.HX * L.Ny * L.Nz;
+    const int blocks = (int)((face + 255) / 256) > 148 * 8 ? 148 * 8 : (int)((face + 255) / 256);
+    pack_x_faces<<<blocks, 256, 0, s>>>(L, F, 0, L.HX, cm.halo_send);                       // my left-most interior columns → left neighbour
+    pack_x_faces<<<blocks, 256, 0, s>>>(L, F, L.nx - L.HX, L.HX, cm.halo_send + face);      // my right-most interior columns → right neighbour
+    NCCL_TRY(cm, cm.api.GroupStart());
+    NCCL_TRY(cm, cm.api.Send(cm.halo_send, face, NCCL_FLOAT64, left, cm.comm, s));
+    NCCL_TRY(cm, cm.api.Send(cm.halo_send + face, face, NCCL_FLOAT64, right, cm.comm, s));
+    NCCL_TRY(cm, cm.api.Recv(cm.halo_recv, face, NCCL_FLOAT64, right, cm.comm, s));         // right neighbour's left-most columns → my right ghosts
+    NCCL_TRY(cm, cm.api.Recv(cm.halo_recv + face, face, NCCL_FLOAT64, left, cm.comm, s));   // left neighbour's right-most columns → my left ghosts
+    NCCL_TRY(cm, cm.api.GroupEnd());
+    unpack_x_faces<<<blocks, 256, 0, s>>>(L, F, L.nx, L.HX, cm.halo_recv);
+    unpack_x_faces<<<blocks, 256, 0, s>>>(L, F, -L.HX, L.HX, cm.halo_recv + face);
+    *launches += 4;
+    return BZ_OK;
+}
+
+// pack W[k][ky][i] (x-slab) into per-peer contiguous blocks [peer][k][ky in peer's range][i]
+__global__ void transpose_pack_fwd(const double2* __restrict__ W, double2* __restrict__ buf, int nx, int nky, int Nz, int P) {
+    const long long total = (long long)nx * nky * Nz;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        int i = (int)(e % nx), ky = (int)((e / nx) % nky), k = (int)(e / ((long long)nx * nky));
+        // owner of ky and its offset
+        int base = nky / P, rem = nky % P;
+        int p = (ky < rem * (base + 1)) ? ky / (base + 1) : rem + (ky - rem * (base + 1)) / (base > 0 ? base : 1);
+        int start = p * base + (p < rem ? p : rem), cnt = base + (p < rem ? 1 : 0);
+        long long off = (long long)start * nx * Nz;                 // blocks are laid out in peer order
+        buf[off + ((long long)k * cnt + (ky - start)) * nx + i] = W[e];
+    }
+}
+// unpack received blocks [peer][k][ky_loc][i_peer] into W2[k][ky_loc][kx = peer*nx + i]
+__global__ void transpose_unpack_fwd(const double2* __restrict__ buf, double2* __restrict__ W2, int nx, int nky_loc, int Nz, int P) {
+    const long long total = (long long)nx * P * nky_loc * Nz;
+    const int Nx = nx * P;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        int kx = (int)(e % Nx), ky = (int)((e / Nx) % nky_loc), k = (int)(e / ((long long)Nx * nky_loc));
+        int p = kx / nx, i = kx % nx;
+        W2[e] = buf[(long long)p * nx * nky_loc * Nz + ((long long)k * nky_loc + ky) * nx + i];
+    }
+}
+__global__ void transpose_pack_bwd(const double2* __restrict__ W2, double2* __restrict__ buf, int nx, int nky_loc, int Nz, int P) {
+    const long long total = (long long)nx * P * nky_loc * Nz;
+    const int Nx = nx * P;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        int kx = (int)(e % Nx), ky = (int)((e / Nx) % nky_loc), k = (int)(e / ((long long)Nx * nky_loc));
+        int p = kx / nx, i = kx % nx;
+        buf[(long long)p * nx * nky_loc * Nz + ((long long)k * nky_loc + ky) * nx + i] = W2[e];
+    }
+}
+__global__ void transpose_unpack_bwd(const double2* __restrict__ buf, double2* __restrict__ W, int nx, int nky, int Nz, int P) {
+    const long long total = (long long)nx * nky * Nz;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        int i = (int)(e % nx), ky = (int)((e / nx) % nky), k = (int)(e / ((long long)nx * nky));
+        int base = nky / P, rem = nky % P;
+        int p = (ky < rem * (base + 1)) ? ky / (base + 1) : rem + (ky - rem * (base + 1)) / (base > 0 ? base : 1);
+        int start = p * base + (p < rem ? p : rem), cnt = base + (p < rem ? 1 : 0);
+        long long off = (long long)start * nx * Nz;
+        W[e] = buf[off + ((long long)k * cnt + (ky - start)) * nx + i];
+    }
+}
+
+static int comm_alltoall(Comm& cm, const double2* send, double2* recv, int nx, const PoissonGeom& G, bool forward, cudaStream_t s) {
+    const int P = cm.n_ranks;
+    NCCL_TRY(cm, cm.api.GroupStart());
+    for (int p = 0; p < P; ++p) {
+        int st, cnt;
+        comm_split_range(G.nky, P, p, &st, &cnt);
+        // x-slab side: block for peer p holds p's ky range of my columns; transposed side: block from peer p holds my ky range of p's columns
+        size_t slab_off = (size_t)st * nx * G.Nz, slab_n = (size_t)cnt * nx * G.Nz;
+        size_t tr_off = (size_t)p * nx * G.nky_loc * G.Nz, tr_n = (size_t)nx * G.nky_loc * G.Nz;
+        if (forward) {
+            if (slab_n) NCCL_TRY(cm, cm.api.Send(send + slab_off, slab_n * 2, NCCL_FLOAT64, p, cm.comm, s));
+            if (tr_n) NCCL_TRY(cm, cm.api.Recv(recv + tr_off, tr_n * 2, NCCL_FLOAT64, p, cm.comm, s));
+        } else {
+            if (tr_n) NCCL_TRY(cm, cm.api.Send(send + tr_off, tr_n * 2, NCCL_FLOAT64, p, cm.comm, s));
+            if (slab_n) NCCL_TRY(cm, cm.api.Recv(recv + slab_off, slab_n * 2, NCCL_FLOAT64, p, cm.comm, s));
+        }
+    }
+    NCCL_TRY(cm, cm.api.GroupEnd());
+    return BZ_OK;
+}
+
+static inline int grid_for(long long total) { long long b = (total + 255) / 256; return (int)(b > 148 * 16 ? 148 * 16 : (b < 1 ? 1 : b)); }
+
+static int comm_transpose_forward(Comm& cm, const double2* W, double2* W2, int nx, const PoissonGeom& G, cudaStream_t s, int64_t* launches) {
+    const int P = cm.n_ranks;
+    transpose_pack_fwd<<<grid_for((long long)nx * G.nky * G.Nz), 256, 0, s>>>(W, cm.tr_send, nx, G.nky, G.Nz, P);
+    int rc = comm_alltoall(cm, cm.tr_send, cm.tr_recv, nx, G, true, s);
+    if (rc) return rc;
+    if (G.nky_loc > 0) transpose_unpack_fwd<<<grid_for((long long)G.Nx * G.nky_loc * G.Nz), 256, 0, s>>>(cm.tr_recv, W2, nx, G.nky_loc, G.Nz, P);
+    *launches += 2;
+    return BZ_OK;
+}
+static int comm_transpose_backward(Comm& cm, const double2* W2, double2* W, int nx, const PoissonGeom& G, cudaStream_t s, int64_t* launches) {
+    const int P = cm.n_ranks;
+    if (G.nky_loc > 0) transpose_pack_bwd<<<grid_for((long long)G.Nx * G.nky_loc * G.Nz), 256, 0, s>>>(W2, cm.tr_send, nx, G.nky_loc, G.Nz, P);
+    int rc = comm_alltoall(cm, cm.tr_send, cm.tr_recv, nx, G, false, s);
+    if (rc) return rc;
+    transpose_unpack_bwd<<<grid_for((long long)nx * G.nky * G.Nz), 256, 0, s>>>(cm.tr_recv, W, nx, G.nky, G.Nz, P);
+    *launches += 2;
+    return BZ_OK;
+}
+
+static int comm_allreduce_max(Comm& cm, double* host_value, double* dev_scalar, cudaStream_t s) {
+    if (cudaMemcpyAsync(dev_scalar, host_value, 8, cudaMemcpyHostToDevice, s)) return BZ_ERR_CUDA;
+    NCCL_TRY(cm, cm.api.AllReduce(dev_scalar, dev_scalar, 1, NCCL_FLOAT64, NCCL_MAX, cm.comm, s));
+    if (cudaMemcpyAsync(host_value, dev_scalar, 8, cudaMemcpyDeviceToHost, s)) return BZ_ERR_CUDA;
+    if (cudaStreamSynchronize(s)) return BZ_ERR_CUDA;
+    return BZ_OK;
+}

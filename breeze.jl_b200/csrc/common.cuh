@@ -1,0 +1,65 @@
+// common.cuh — context, layout and small device helpers shared by the kernels of libbreeze_b200.so.
+//
+// Device layout of a 3-D field (one x-slab per GPU):
+//   padded in x and y by HX / HY = 4 ghost cells (0 in a Flat dimension), NOT padded in z:
+//     index(i, j, k) = (k * PY + (j + HY)) * PX + (i + HX),   PX = nx + 2 HX, PY = Ny + 2 HY
+//   x fastest (the reference's memory order), so a warp reads 256 contiguous bytes and a z-plane
+//   tile (x-range × y-range) is one TMA box. Ghost cells are kept valid by halo_fill (periodic copy on one
+//   GPU, NCCL exchange of x-faces across GPUs); Bounded z needs no ghosts because the reconstructions
+//   drop their order next to the walls (weno.cuh).
+//   rho_w lives on z-faces: level k is the BOTTOM face of cell k, k = 0..Nz-1; face 0 is the bottom wall
+//   (stored, always 0) and face Nz is the top wall (not stored, always 0).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/breeze_b200.h"
+
+#define BZ_HALO 4
+#define NPROG 5
+#define NFAM 8
+
+struct Layout {
+    int nx, Ny, Nz;          // local interior size
+    int HX, HY;              // ghost widths
+    int PX, PY;              // padded row / plane sizes
+    long long plane;         // PX * PY
+    long long n;             // PX * PY * Nz
+    int flat_x, flat_y;
+    double dx, dy, dz;
+    double rdx, rdy, rdz;    // reciprocals (0 in a Flat dimension: the derivative vanishes)
+};
+
+__host__ __device__ __forceinline__ long long lidx(const Layout& L, int i, int j, int k) {
+    return ((long long)k * L.PY + (j + L.HY)) * L.PX + (i + L.HX);
+}
+
+// per-level column data of the reference state, all length Nz (+1 where noted), device pointers
+struct Columns {
+    const double* rho;       // ρᵣ at centres
+    const double* rho_inv;   // 1/ρᵣ
+    const double* rho_f;     // ℑz ρᵣ at z-faces k = 0..Nz (wall faces hold the one-sided value; only ever × 0)
+    const double* rho_f_inv; // 1/rho_f
+    const double* p;         // pᵣ
+    const double* T;         // Tᵣ
+    const double* exner_dry; // (pᵣ/pˢᵗ)^(Rᵈ/cᵖᵈ)
+    const double* log_p_pst; // log(pᵣ/pˢᵗ)
+};
+
+struct Thermo {
+    double Rd, Rv, cpd, cpv, cl, ci, g, Ll, Li, pst;
+    double Tr_energy, Ttr, ptr;
+    int microphysics;
+};
+
+#define CUDA_TRY(ctx, call)                                                                       \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess) {                                                                  \
+            bz_set_error((ctx), "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            return BZ_ERR_CUDA;                                                                   \
+        }                                                                                         \
+    } while (0)
+
+void bz_set_error(bz_ctx* ctx, const char* fmt, ...);

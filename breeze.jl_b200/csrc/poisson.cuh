@@ -1,0 +1,315 @@
+// poisson.cuh — in-house anelastic pressure solver: slab FFT (y real-to-complex, x complex) + batched Thomas in z.
+//
+// Replaces compute_anelastic_source_term! + Oceananigans' solve!(::FourierTridiagonalPoissonSolver)
+// (src/AnelasticEquations/anelastic_pressure_solver.jl:84-105; oracle: compute_pressure_correction).
+// No cuFFT: the transforms are Stockham radix-8/4/2 passes on lines held in shared memory, FP64, with a
+// precomputed twiddle table, so that the source term (Δz·div(ρu)/Δt) is formed while the first pass loads its
+// lines and the inverse's last pass writes φ straight into the padded field.
+//
+//   pass 1  poisson_forward_y : rhs on the fly → real-to-complex FFT along y (two real x-columns per complex line)
+//                               → W[k][ky][i], ky = 0..Ny/2                                   (x-slab layout)
+//   (multi-GPU: all-to-all so that x becomes local and ky distributed → W[k][ky_local][kx_global])
+//   pass 2  fft_x (forward)   : complex FFT along x, in place
+//   pass 3  thomas_z          : tridiagonal solve in z per (kx, ky); 1/β and the elimination factors are
+//                               precomputed once (they depend on the grid and ρᵣ only); the singular (0,0) mode is
+//                               pinned and its vertical mean removed (= the reference's φ .-= mean(φ))
+//   pass 4  fft_x (inverse), (transpose back), pass 5 poisson_inverse_y : complex-to-real along y → φ
+#pragma once
+#include "common.cuh"
+
+struct PoissonGeom {
+    int Nx;        // GLOBAL x size (length of the x transforms)
+    int Ny;        // y size (length of the y transforms), 1 if Flat
+    int Nz;
+    int nky;       // number of ky modes held after the y transform: Ny/2 + 1 (1 if Flat y)
+    int nky_loc;   // ky modes on this rank in the transposed layout
+    int ky0;       // first global ky of this rank in the transposed layout
+};
+
+// ---- register butterflies (forward: e^{-2πi/R}) ----------------------------------------------------------------
+struct cpx { double x, y; };
+__device__ __forceinline__ cpx operator+(cpx a, cpx b) { return {a.x + b.x, a.y + b.y}; }
+__device__ __forceinline__ cpx operator-(cpx a, cpx b) { return {a.x - b.x, a.y - b.y}; }
+__device__ __forceinline__ cpx cmul(cpx a, cpx b) { return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
+__device__ __forceinline__ cpx mul_mi(cpx a) { return {a.y, -a.x}; }    // × (-i)
+
+__device__ __forceinline__ void dft2(cpx& a, cpx& b) { cpx t = a - b; a = a + b; b = t; }
+__device__ __forceinline__ void dft4(cpx& x0, cpx& x1, cpx& x2, cpx& x3) {
+    cpx s02 = x0 + x2, d02 = x0 - x2, s13 = x1 + x3, d13 = mul_mi(x1 - x3);
+    x0 = s02 + s13; x2 = s02 - s13; x1 = d02 + d13; x3 = d02 - d13;
+}
+__device__ __forceinline__ void dft8(cpx* v) {
+    const double h = 0.70710678118654752440;
+    cpx a0 = v[0] + v[4], a4 = v[0] - v[4];
+    cpx a1 = v[1] + v[5], a5 = v[1] - v[5];
+    cpx a2 = v[2] + v[6], a6 = v[2] - v[6];
+    cpx a3 = v[3] + v[7], a7 = v[3] - v[7];
+    a5 = {h * (a5.x + a5.y), h * (a5.y - a5.x)};          // × W8   = (1 - i)/√2
+    a6 = mul_mi(a6);                                       // × W8²  = -i
+    a7 = {h * (a7.y - a7.x), -h * (a7.x + a7.y)};          // × W8³  = (-1 - i)/√2
+    dft4(a0, a1, a2, a3);
+    dft4(a4, a5, a6, a7);
+    v[0] = a0; v[2] = a1; v[4] = a2; v[6] = a3;
+    v[1] = a4; v[3] = a5; v[5] = a6; v[7] = a7;
+}
+
+// One Stockham pass of radix R over `lines` lines of length N held as re[l*LP + n], im[l*LP + n].
+// Each thread owns 8/R butterflies (8 complex values in registers): blockDim.x == lines * N / 8.
+template <int R>
+__device__ __forceinline__ void stockham_pass(double* re, double* im, int LP, int N, int Ns, const double2* __restrict__ tw) {
+    constexpr int ITEMS = 8 / R;
+    const int per_line = N / 8;                    // threads per line
+    const int l = threadIdx.x / per_line, t = threadIdx.x % per_line;
+    double* lre = re + (size_t)l * LP;
+    double* lim = im + (size_t)l * LP;
+    const int NR = N / R;
+    cpx v[ITEMS][R];
+    int jj[ITEMS];
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it) {
+        int j = t + it * per_line;                 // butterfly index in [0, N/R)
+        jj[it] = j;
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[it][r] = {lre[j + r * NR], lim[j + r * NR]};
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it) {
+        int j = jj[it];
+        int k = j & (Ns - 1);
+        if (Ns > 1) {
+            int step = N / (Ns * R);
+#pragma unroll
+            for (int r = 1; r < R; ++r) {
+                double2 w = __ldg(&tw[r * k * step]);
+                v[it][r] = cmul(v[it][r], cpx{w.x, w.y});
+            }
+        }
+        if (R == 8) dft8(v[it]);
+        else if (R == 4) dft4(v[it][0], v[it][1], v[it][2], v[it][3]);
+        else dft2(v[it][0], v[it][1]);
+        int j0 = (j - k) * R + k;
+#pragma unroll
+        for (int r = 0; r < R; ++r) { lre[j0 + r * Ns] = v[it][r].x; lim[j0 + r * Ns] = v[it][r].y; }
+    }
+    __syncthreads();
+}
+
+// Forward DFT (e^{-2πi nk/N}) of every line in shared memory; N = 2^m >= 8. Callers conjugate for the inverse.
+__device__ __forceinline__ void fft_lines_smem(double* re, double* im, int LP, int N, const double2* __restrict__ tw) {
+    int m = 31 - __clz(N);
+    int Ns = 1;
+    for (int p = 0; p < m / 3; ++p) { stockham_pass<8>(re, im, LP, N, Ns, tw); Ns *= 8; }
+    if (m % 3 == 2) stockham_pass<4>(re, im, LP, N, Ns, tw);
+    else if (m % 3 == 1) stockham_pass<2>(re, im, LP, N, Ns, tw);
+}
+
+// ---- source term ------------------------------------------------------------------------------------------------
+// _compute_anelastic_source_term!: rhs = Δzᶜ · divᶜᶜᶜ(ρu, ρv, ρw) / Δt  (anelastic_pressure_solver.jl:99-105)
+__device__ __forceinline__ double source_term(const Layout& L, const double* __restrict__ ru, const double* __restrict__ rv,
+                                              const double* __restrict__ rw, int i, int j, int k, double dz_over_dt) {
+    long long n = lidx(L, i, j, k);
+    double d = 0.0;
+    if (!L.flat_x) d += (ru[n + 1] - ru[n]) * L.rdx;
+    if (!L.flat_y) d += (rv[n + L.PX] - rv[n]) * L.rdy;
+    double wt = (k + 1 < L.Nz) ? rw[n + L.plane] : 0.0;
+    d += (wt - rw[n]) * L.rdz;
+    return d * dz_over_dt;
+}
+
+// ---- pass 1: source term + real-to-complex FFT along y ----------------------------------------------------------
+// grid (ceil(nx / (2*lines)), Nz); block lines*Ny/8 threads; smem 2*lines*(Ny+1) doubles.
+__global__ void poisson_forward_y(Layout L, PoissonGeom G, const double* __restrict__ ru, const double* __restrict__ rv,
+                                  const double* __restrict__ rw, double dz_over_dt, double2* __restrict__ W,
+                                  const double2* __restrict__ tw_y, int lines) {
+    extern __shared__ double sm[];
+    const int N = G.Ny, LP = N + 1;
+    double* re = sm;
+    double* im = sm + (size_t)lines * LP;
+    const int k = blockIdx.y;
+    const int XB = 2 * lines;
+    const int ib = blockIdx.x * XB;
+    for (int e = threadIdx.x; e < N * XB; e += blockDim.x) {
+        int c = e % XB, y = e / XB;
+        int i = ib + c;
+        double v = (i < L.nx) ? source_term(L, ru, rv, rw, i, y, k, dz_over_dt) : 0.0;
+        ((c & 1) ? im : re)[(size_t)(c >> 1) * LP + y] = v;
+    }
+    __syncthreads();
+    fft_lines_smem(re, im, LP, N, tw_y);
+    // untangle the two real transforms: A = (Z[ky] + conj Z[N-ky])/2, B = (Z[ky] - conj Z[N-ky])/(2i)
+    for (int e = threadIdx.x; e < G.nky * XB; e += blockDim.x) {
+        int c = e % XB, ky = e / XB;
+        int i = ib + c;
+        if (i >= L.nx) continue;
+        int l = c >> 1, km = (N - ky) & (N - 1);
+        double zr = re[(size_t)l * LP + ky], zi = im[(size_t)l * LP + ky];
+        double yr = re[(size_t)l * LP + km], yi = im[(size_t)l * LP + km];
+        double2 o = (c & 1) ? make_double2(0.5 * (zi + yi), -0.5 * (zr - yr)) : make_double2(0.5 * (zr + yr), 0.5 * (zi - yi));
+        W[((size_t)k * G.nky + ky) * L.nx + i] = o;
+    }
+}
+
+// Flat y: no y transform; W[k][0][i] = rhs + 0i.
+__global__ void poisson_pack_flat_y(Layout L, const double* __restrict__ ru, const double* __restrict__ rv,
+                                    const double* __restrict__ rw, double dz_over_dt, double2* __restrict__ W) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
+    if (i < L.nx) W[(size_t)k * L.nx + i] = make_double2(source_term(L, ru, rv, rw, i, 0, k, dz_over_dt), 0.0);
+}
+
+// ---- pass 5: complex-to-real inverse FFT along y → φ (padded field interior) -------------------------------------
+__global__ void poisson_inverse_y(Layout L, PoissonGeom G, const double2* __restrict__ W, double* __restrict__ phi,
+                                  const double2* __restrict__ tw_y, int lines, double scale) {
+    extern __shared__ double sm[];
+    const int N = G.Ny, LP = N + 1;
+    double* re = sm;
+    double* im = sm + (size_t)lines * LP;
+    const int k = blockIdx.y;
+    const int XB = 2 * lines;
+    const int ib = blockIdx.x * XB;
+    // rebuild the packed spectrum Z = A + iB (Hermitian halves), conjugated for the inverse-by-forward trick
+    for (int e = threadIdx.x; e < G.nky * lines; e += blockDim.x) {
+        int l = e % lines, ky = e / lines;
+        int i = ib + 2 * l;
+        double2 A = make_double2(0.0, 0.0), B = make_double2(0.0, 0.0);
+        if (i < L.nx) A = W[((size_t)k * G.nky + ky) * L.nx + i];
+        if (i + 1 < L.nx) B = W[((size_t)k * G.nky + ky) * L.nx + i + 1];
+        // Z[ky] = A + iB, Z[N-ky] = conj(A) + i conj(B); store conj(Z)
+        re[(size_t)l * LP + ky] = A.x - B.y;
+        im[(size_t)l * LP + ky] = -(A.y + B.x);
+        if (ky > 0 && ky < N / 2) {
+            re[(size_t)l * LP + N - ky] = A.x + B.y;
+            im[(size_t)l * LP + N - ky] = -(B.x - A.y);
+        }
+    }
+    __syncthreads();
+    fft_lines_smem(re, im, LP, N, tw_y);
+    for (int e = threadIdx.x; e < N * XB; e += blockDim.x) {
+        int c = e % XB, y = e / XB;
+        int i = ib + c;
+        if (i >= L.nx) continue;
+        int l = c >> 1;
+        double v = (c & 1) ? -im[(size_t)l * LP + y] : re[(size_t)l * LP + y];
+        phi[lidx(L, i, y, k)] = v * scale;
+    }
+}
+
+__global__ void poisson_unpack_flat_y(Layout L, const double2* __restrict__ W, double* __restrict__ phi, double scale) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
+    if (i < L.nx) phi[lidx(L, i, 0, k)] = W[(size_t)k * L.nx + i].x * scale;
+}
+
+// ---- passes 2 / 4: complex FFT along x, in place; one line = Nx contiguous complex numbers ----------------------
+// grid ceil(n_lines / lines); block lines*Nx/8 threads; smem 2*lines*(Nx+1) doubles.
+__global__ void fft_x_kernel(double2* __restrict__ W, int Nx, long long n_lines, const double2* __restrict__ tw_x, int lines, int inverse) {
+    extern __shared__ double sm[];
+    const int N = Nx, LP = N + 1;
+    double* re = sm;
+    double* im = sm + (size_t)lines * LP;
+    const long long l0 = (long long)blockIdx.x * lines;
+    const double sgn = inverse ? -1.0 : 1.0;
+    for (int e = threadIdx.x; e < N * lines; e += blockDim.x) {
+        int x = e % N, l = e / N;
+        double2 v = make_double2(0.0, 0.0);
+        if (l0 + l < n_lines) v = W[(l0 + l) * N + x];
+        re[(size_t)l * LP + x] = v.x;
+        im[(size_t)l * LP + x] = sgn * v.y;
+    }
+    __syncthreads();
+    fft_lines_smem(re, im, LP, N, tw_x);
+    for (int e = threadIdx.x; e < N * lines; e += blockDim.x) {
+        int x = e % N, l = e / N;
+        if (l0 + l < n_lines) W[(l0 + l) * N + x] = make_double2(re[(size_t)l * LP + x], sgn * im[(size_t)l * LP + x]);
+    }
+}
+
+// ---- pass 3: batched Thomas in z -----------------------------------------------------------------------------------
+// Setup (once per grid / ρᵣ): the forward-elimination pivots depend on (kx, ky, k) only.
+//   D_k = -(ρ̄ᶠ_{k+1}/Δz + ρ̄ᶠ_k/Δz) - ρ_k Δz (λx + λy)   (one-sided at k = 0, Nz-1; anelastic_pressure_solver.jl:39-62)
+//   a_k = ρ̄ᶠ_{k+1}/Δz                                      (:72-78)
+//   t_k = a_{k-1}/β_{k-1},  β_k = D_k - a_{k-1} t_k,  and 1/β_k := 0 where |β_k| <= 10 eps (the reference's elision
+//   of the update for the singular (0,0) mode; it then keeps a stale value, here 0 — any constant is removed with the mean).
+__global__ void thomas_setup(PoissonGeom G, const double* __restrict__ rho, const double* __restrict__ rho_f, double dz,
+                             const double* __restrict__ lam_x, const double* __restrict__ lam_y,
+                             double* __restrict__ inv_beta, double* __restrict__ tfac) {
+    int kx = blockIdx.x * blockDim.x + threadIdx.x, ky = blockIdx.y;
+    if (kx >= G.Nx || ky >= G.nky_loc) return;
+    const double lam = lam_x[kx] + lam_y[G.ky0 + ky];
+    const size_t stride = (size_t)G.nky_loc * G.Nx;
+    size_t n = (size_t)ky * G.Nx + kx;
+    const int Nz = G.Nz;
+    double beta = 0.0;
+    for (int k = 0; k < Nz; ++k, n += stride) {
+        double up = (k + 1 < Nz) ? rho_f[k + 1] / dz : 0.0;
+        double lo = (k > 0) ? rho_f[k] / dz : 0.0;
+        double D = -(up + lo) - rho[k] * dz * lam;
+        double t = 0.0;
+        if (k > 0) { t = lo / beta; beta = D - lo * t; } else beta = D;
+        tfac[n] = t;
+        inv_beta[n] = (fabs(beta) > 10.0 * 2.220446049250313e-16) ? 1.0 / beta : 0.0;
+    }
+}
+
+// grid (ceil(Nx/128), nky_loc), block 128: thread = one (kx, ky) column, coalesced over kx. Levels are processed in
+// batches of TB whose loads are all issued before the dependent recurrence, so each thread keeps TB loads in flight.
+#define TB 8
+__global__ void thomas_z(PoissonGeom G, double2* __restrict__ W, const double* __restrict__ rho_f, double dz,
+                         const double* __restrict__ inv_beta, const double* __restrict__ tfac) {
+    int kx = blockIdx.x * blockDim.x + threadIdx.x, ky = blockIdx.y;
+    if (kx >= G.Nx) return;
+    const size_t stride = (size_t)G.nky_loc * G.Nx;
+    const size_t n0 = (size_t)ky * G.Nx + kx;
+    const int Nz = G.Nz;
+    const double rdz = 1.0 / dz;
+    double2 prev = make_double2(0.0, 0.0);
+    for (int kb = 0; kb < Nz; kb += TB) {
+        double2 f[TB]; double ib[TB];
+#pragma unroll
+        for (int b = 0; b < TB; ++b) {
+            int k = kb + b;
+            if (k < Nz) { f[b] = W[n0 + k * stride]; ib[b] = inv_beta[n0 + k * stride]; }
+        }
+#pragma unroll
+        for (int b = 0; b < TB; ++b) {
+            int k = kb + b;
+            if (k < Nz) {
+                double a = (k > 0) ? rho_f[k] * rdz : 0.0;
+                prev = make_double2((f[b].x - a * prev.x) * ib[b], (f[b].y - a * prev.y) * ib[b]);
+                W[n0 + k * stride] = prev;
+            }
+        }
+    }
+    // back substitution: φ_k -= t_{k+1} φ_{k+1}; prev holds φ_{Nz-1}
+    for (int kt = Nz - 2; kt >= 0; kt -= TB) {
+        double2 v[TB]; double t[TB];
+#pragma unroll
+        for (int b = 0; b < TB; ++b) {
+            int k = kt - b;
+            if (k >= 0) { v[b] = W[n0 + k * stride]; t[b] = tfac[n0 + (k + 1) * stride]; }
+        }
+#pragma unroll
+        for (int b = 0; b < TB; ++b) {
+            int k = kt - b;
+            if (k >= 0) {
+                prev = make_double2(v[b].x - t[b] * prev.x, v[b].y - t[b] * prev.y);
+                W[n0 + k * stride] = prev;
+            }
+        }
+    }
+}
+
+// φ .-= mean(φ): only the (kx, ky) = (0, 0) column carries the mean. One block.
+__global__ void remove_mean_mode(PoissonGeom G, double2* __restrict__ W) {
+    __shared__ double sr[256], si[256];
+    const size_t stride = (size_t)G.nky_loc * G.Nx;
+    double ar = 0.0, ai = 0.0;
+    for (int k = threadIdx.x; k < G.Nz; k += blockDim.x) { double2 v = W[k * stride]; ar += v.x; ai += v.y; }
+    sr[threadIdx.x] = ar; si[threadIdx.x] = ai;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) { sr[threadIdx.x] += sr[threadIdx.x + s]; si[threadIdx.x] += si[threadIdx.x + s]; }
+        __syncthreads();
+    }
+    double mr = sr[0] / G.Nz, mi = si[0] / G.Nz;
+    for (int k = threadIdx.x; k < G.Nz; k += blockDim.x) { double2 v = W[k * stride]; W[k * stride] = make_double2(v.x - mr, v.y - mi); }
+}

@@ -1,0 +1,89 @@
+// weno.cuh — WENO5-Z / WENO3-Z / upwind biased reconstructions and Centered(4) interpolation, FP64.
+//
+// Same scheme the reference obtains from Oceananigans' WENO(order = 5) (oracle:
+// oracle/breeze_oracle.c weno5_biased / weno3_biased / symmetric_interp / red_face / red_center), written for the
+// FP64 pipe of sm_100a, which — not HBM — bounds the fused stage kernel:
+//   * smoothness indicators in difference form  β = 13/4 (δ²ψ)² + 3/4 (δ̃ψ)²  (= 3 × Jiang–Shu, the reference's
+//     scaling, so ε = 1e-8 means the same thing). Algebraically identical to the reference's quadratic forms but
+//     21 instead of 30 FP64 instructions and free of their cancellation error;
+//   * the three weight divisions and the normalising division collapse into ONE reciprocal:
+//       Σ α_r q_r / Σ α_r,  α_r = C_r (1 + τ²/b_r²),  b_r = β_r + ε
+//       = Σ C_r (b_r² + τ²) Π_{s≠r} b_s² q_r / Σ C_r (b_r² + τ²) Π_{s≠r} b_s²
+//   * that reciprocal is MUFU.RCP64H + two Newton steps (≤ 2 ulp) instead of the IEEE division sequence.
+// Results differ from the oracle's by FP64 round-off only (tests/test_gpu_parity.py states the tolerance).
+#pragma once
+
+#define WENO_EPS 1e-8
+
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+
+// Left-biased value at the face between c and d from the five cells a b c | d e (a = ψ[i-3] … e = ψ[i+1]).
+__device__ __forceinline__ double weno5z(double a, double b, double c, double d, double e) {
+    // second differences and the one-sided / centred first differences of the three candidate stencils
+    double s0 = (c - 2.0 * d) + e, t0 = (3.0 * c - 4.0 * d) + e;   // stencil (c, d, e)
+    double s1 = (b - 2.0 * c) + d, t1 = b - d;                     // stencil (b, c, d)
+    double s2 = (a - 2.0 * b) + c, t2 = (a - 4.0 * b) + 3.0 * c;   // stencil (a, b, c)
+    double b0 = 3.25 * s0 * s0 + 0.75 * t0 * t0;
+    double b1 = 3.25 * s1 * s1 + 0.75 * t1 * t1;
+    double b2 = 3.25 * s2 * s2 + 0.75 * t2 * t2;
+    double tau = fabs(b0 - b2);
+    double tt = tau * tau;
+    b0 += WENO_EPS; b1 += WENO_EPS; b2 += WENO_EPS;
+    double q0 = b0 * b0, q1 = b1 * b1, q2 = b2 * b2;
+    // un-normalised weights × Π b_s² (the common factor cancels in the ratio); C = (3, 6, 1)/10
+    double w0 = 3.0 * ((q0 + tt) * (q1 * q2));
+    double w1 = 6.0 * ((q1 + tt) * (q0 * q2));
+    double w2 = (q2 + tt) * (q0 * q1);
+    // candidate polynomials × 6
+    double p0 = (2.0 * c + 5.0 * d) - e;
+    double p1 = (5.0 * c - b) + 2.0 * d;
+    double p2 = (2.0 * a - 7.0 * b) + 11.0 * c;
+    double num = w0 * p0 + w1 * p1 + w2 * p2;
+    double den = 6.0 * (w0 + w1 + w2);
+    return num * fast_rcp(den);
+}
+
+// WENO3-Z: left-biased value at the face between b and c from a b | c.
+__device__ __forceinline__ double weno3z(double a, double b, double c) {
+    double d0 = c - b, d1 = b - a;
+    double b0 = d0 * d0, b1 = d1 * d1;
+    double tau = fabs(b0 - b1);
+    double tt = tau * tau;
+    b0 += WENO_EPS; b1 += WENO_EPS;
+    double q0 = b0 * b0, q1 = b1 * b1;
+    double w0 = 2.0 * ((q0 + tt) * q1);      // C = (2, 1)/3
+    double w1 = (q1 + tt) * q0;
+    double p0 = b + c;                       // × 2
+    double p1 = 3.0 * b - a;
+    return (w0 * p0 + w1 * p1) * fast_rcp(2.0 * (w0 + w1));
+}
+
+// Six consecutive values v0..v5 = ψ[i-3..i+2] around the "face" between v2 and v3; R = buffer (3, 2 or 1).
+__device__ __forceinline__ double biased6(double v0, double v1, double v2, double v3, double v4, double v5, int R, bool left) {
+    if (R >= 3) {
+        double a = left ? v0 : v5, b = left ? v1 : v4, c = left ? v2 : v3, d = left ? v3 : v2, e = left ? v4 : v1;
+        return weno5z(a, b, c, d, e);
+    } else if (R == 2) {
+        double a = left ? v1 : v4, b = left ? v2 : v3, c = left ? v3 : v2;
+        return weno3z(a, b, c);
+    }
+    return left ? v2 : v3;
+}
+
+// Centered(order = 4) interpolation to the face between v1 and v2 from v0 v1 | v2 v3; R = 2 (4th) or 1 (2nd order).
+__device__ __forceinline__ double sym4(double v0, double v1, double v2, double v3, int R) {
+    if (R >= 2) return ((7.0 / 12.0) * (v1 + v2)) - ((1.0 / 12.0) * (v0 + v3));
+    return 0.5 * (v1 + v2);
+}
+
+// Order reduction next to the Bounded z walls: z-face k (0..Nz) from centres, and centre k (0..Nz-1) from z-faces.
+__device__ __forceinline__ int red_face(int k, int Nz, int B) { return max(1, min(B, min(k, Nz - k))); }
+__device__ __forceinline__ int red_center(int k, int Nz, int B) { return max(1, min(B, min(k + 1, Nz - k))); }

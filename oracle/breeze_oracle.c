@@ -259,6 +259,13 @@ static void fill_halos(const orc_ctx* c, double* f, int loc) {
 /* ------------------------------------------------------------------------------------------------ */
 #define WENO_EPS 1e-8
 
+/* Option 0 (default): smoothness indicators as the reference evaluates them (quadratic forms in the stencil values).
+ * Option 1: the algebraically identical difference form β = 13/4 (δ²ψ)² + 3/4 (δ̃ψ)², free of the quadratic forms'
+ * cancellation error (|ψ|² · eps instead of |δψ|² · eps). Used by the tests to separate "different arithmetic for the
+ * same scheme" from genuine disagreement: the CUDA kernels use the difference form. */
+static int g_beta_form = 0;
+void orc_set_beta_form(int form) { g_beta_form = form; }
+
 /* Left-biased reconstruction at the face whose upwind cell is s[2] and downwind cell is s[3]:
  * s[0..4] = psi[i-3], psi[i-2], psi[i-1], psi[i], psi[i+1] for face i. Right bias = mirrored arguments. */
 static inline double weno5_biased(double m3, double m2, double m1, double p0, double p1) {
@@ -267,9 +274,19 @@ static inline double weno5_biased(double m3, double m2, double m1, double p0, do
     double q1 = (-m2 + 5 * m1 + 2 * p0) / 6;
     double q2 = (2 * m3 - 7 * m2 + 11 * m1) / 6;
     /* smoothness indicators as quadratic forms, stencils (m1,p0,p1), (m2,m1,p0), (m3,m2,m1) */
-    double b0 = m1 * (10 * m1 - 31 * p0 + 11 * p1) + p0 * (25 * p0 - 19 * p1) + 4 * p1 * p1;
-    double b1 = m2 * (4 * m2 - 13 * m1 + 5 * p0) + m1 * (13 * m1 - 13 * p0) + 4 * p0 * p0;
-    double b2 = m3 * (4 * m3 - 19 * m2 + 11 * m1) + m2 * (25 * m2 - 31 * m1) + 10 * m1 * m1;
+    double b0, b1, b2;
+    if (g_beta_form == 0) {
+        b0 = m1 * (10 * m1 - 31 * p0 + 11 * p1) + p0 * (25 * p0 - 19 * p1) + 4 * p1 * p1;
+        b1 = m2 * (4 * m2 - 13 * m1 + 5 * p0) + m1 * (13 * m1 - 13 * p0) + 4 * p0 * p0;
+        b2 = m3 * (4 * m3 - 19 * m2 + 11 * m1) + m2 * (25 * m2 - 31 * m1) + 10 * m1 * m1;
+    } else {
+        double s0 = (m1 - 2 * p0) + p1, t0 = (3 * m1 - 4 * p0) + p1;
+        double s1 = (m2 - 2 * m1) + p0, t1 = m2 - p0;
+        double s2 = (m3 - 2 * m2) + m1, t2 = (m3 - 4 * m2) + 3 * m1;
+        b0 = 3.25 * s0 * s0 + 0.75 * t0 * t0;
+        b1 = 3.25 * s1 * s1 + 0.75 * t1 * t1;
+        b2 = 3.25 * s2 * s2 + 0.75 * t2 * t2;
+    }
     /* WENO-Z weights */
     double tau = fabs(b0 - b2);
     double r0 = tau / (b0 + WENO_EPS), r1 = tau / (b1 + WENO_EPS), r2 = tau / (b2 + WENO_EPS);
@@ -493,6 +510,9 @@ static inline double div_rhoUc(const orc_ctx* c, const double* cfield, int i, in
 #define SX 1
 #define SY ((ptrdiff_t)c->Px)
 #define SZ ((ptrdiff_t)c->Px * c->Py)
+/* interpolation along a Flat dimension is the identity (Oceananigans Flat topology) */
+#define SYM_X(a, R) ((c->cfg.topology_x == BZ_FLAT) ? (a)[0] : symmetric_interp((a), SX, (R)))
+#define SYM_Y(a, R) ((c->cfg.topology_y == BZ_FLAT) ? (a)[0] : symmetric_interp((a), SY, (R)))
 
 static inline double flux_Uu(const orc_ctx* c, int i, int j, int k) {        /* at centre i */
     size_t n1 = IDX(c, i + 1, j, k);
@@ -501,18 +521,18 @@ static inline double flux_Uu(const orc_ctx* c, int i, int j, int k) {        /* 
 }
 static inline double flux_Vu(const orc_ctx* c, int i, int j, int k) {        /* at (face i, face j) */
     size_t n = IDX(c, i, j, k);
-    double vt = c->dx * c->dz * symmetric_interp(c->U[BZ_RHO_V] + n, SX, 2);
+    double vt = c->dx * c->dz * SYM_X(c->U[BZ_RHO_V] + n, 2);
     return vt * biased_interp(c->u + n, SY, 3, vt > 0);
 }
 static inline double flux_Wu(const orc_ctx* c, int i, int j, int k) {        /* at (face i, z-face k) */
     if (k == 0 || k == c->Nz) return 0.0;
     size_t n = IDX(c, i, j, k);
-    double wt = c->dx * c->dy * symmetric_interp(c->U[BZ_RHO_W] + n, SX, 2);
+    double wt = c->dx * c->dy * SYM_X(c->U[BZ_RHO_W] + n, 2);
     return wt * biased_interp(c->u + n, SZ, red_face(k, c->Nz, 3), wt > 0);
 }
 static inline double flux_Uv(const orc_ctx* c, int i, int j, int k) {        /* at (face i, face j) */
     size_t n = IDX(c, i, j, k);
-    double ut = c->dy * c->dz * symmetric_interp(c->U[BZ_RHO_U] + n, SY, 2);
+    double ut = c->dy * c->dz * SYM_Y(c->U[BZ_RHO_U] + n, 2);
     return ut * biased_interp(c->v + n, SX, 3, ut > 0);
 }
 static inline double flux_Vv(const orc_ctx* c, int i, int j, int k) {        /* at centre j */
@@ -523,7 +543,7 @@ static inline double flux_Vv(const orc_ctx* c, int i, int j, int k) {        /* 
 static inline double flux_Wv(const orc_ctx* c, int i, int j, int k) {        /* at (face j, z-face k) */
     if (k == 0 || k == c->Nz) return 0.0;
     size_t n = IDX(c, i, j, k);
-    double wt = c->dx * c->dy * symmetric_interp(c->U[BZ_RHO_W] + n, SY, 2);
+    double wt = c->dx * c->dy * SYM_Y(c->U[BZ_RHO_W] + n, 2);
     return wt * biased_interp(c->v + n, SZ, red_face(k, c->Nz, 3), wt > 0);
 }
 static inline double flux_Uw(const orc_ctx* c, int i, int j, int k) {        /* at (face i, z-face k), 1 <= k <= Nz-1 */

@@ -46,6 +46,7 @@ def load_oracle_library() -> abi.Library:
         d.orc_weno3_biased.restype = C.c_double
         d.orc_weno3_biased.argtypes = [C.POINTER(C.c_double)]
         d.orc_num_threads.restype = C.c_int
+        d.orc_set_beta_form.argtypes = [C.c_int]
         d.orc_set_num_threads.argtypes = [C.c_int]
     return _LIB
 
@@ -56,3 +57,8 @@ class CPUOracle:
 
     def library(self):
         return load_oracle_library()
+
+
+def set_beta_form(form: int):
+    """0: the reference's quadratic-form smoothness indicators (default); 1: difference form (what the CUDA kernels use)."""
+    load_oracle_library().dll.orc_set_beta_form(int(form))
