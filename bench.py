@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the hot path: Mcell-updates/s of one anelastic SSP-RK3 time step (WENO5) on a dry
+thermal bubble, the reference's `grid_points_per_second` (benchmarking/src/utils.jl:138-141; protocol :119-136).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--size 512] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One JSON line on stdout (rank 0). A "step" is one full time step (3 RK stages, 3 pressure solves) of the whole grid.
+  value    device-timed (CUDA events on the context's stream, max over ranks), state resident in HBM
+  e2e      same metric through the C ABI with HOST buffers: per step bz_set_state (pinned host → device) +
+           bz_time_step + bz_get_state (device → pinned host), all inside the timed region
+  roofline the fused stage kernel: algorithmic bytes (88 B/cell stage 1, 128 B/cell stages 2-3) ÷ its
+           average duration, measured live with CUDA events around every launch, ÷ measured HBM peak
+  cpu_baseline   the CPU oracle (restatement of the reference algorithm, C + OpenMP) timed on this box's host cores
+--impl reference times that same CPU restatement as the reference arm (Julia is not installed anywhere in this project, so
+Breeze's own CPU() run cannot execute).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+STAGE_BYTES_PER_CELL = (88.0 + 128.0 + 128.0) / 3.0      # average over the three stage-kernel launches of a step
+METRIC = "Mcell-updates/s"
+
+
+def bubble(x, y, z):
+    r = np.sqrt(x ** 2 + y ** 2 + (z - 2000.0) ** 2)
+    return 300.0 + 2.0 * np.cos(np.pi / 2 * np.minimum(1.0, r / 2000.0)) ** 2
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.proc, self.lines = device, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [a.strip() for a in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_oracle(size, steps, warmup, dt):
+    """Time the CPU oracle on `size`^3 cells of the same bubble, all host threads. Returns (Mcell/s, cores, seconds/step)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import breeze_b200 as bz
+    import oracle_lib
+    lib = oracle_lib.load_oracle_library()
+    cores = lib.dll.orc_num_threads()
+    grid = bz.RectilinearGrid(oracle_lib.CPUOracle(), size=(size, size, size), x=(-10e3, 10e3), y=(-10e3, 10e3), z=(0, 10e3))
+    m = bz.AtmosphereModel(grid, dynamics=bz.AnelasticDynamics(bz.ReferenceState(grid, potential_temperature=300)), advection=bz.WENO(order=5))
+    m.set(θ=bubble)
+    for _ in range(warmup):
+        m.time_step(dt)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        m.time_step(dt)
+    el = time.perf_counter() - t0
+    return size ** 3 * steps / el / 1e6, cores, el / steps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--size", type=int, default=512, help="global grid is size^3 (strong scaling: fixed as N grows)")
+    ap.add_argument("--dt", type=float, default=0.5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-size", type=int, default=96)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--use-tma", type=int, default=0)
+    ap.add_argument("--z-chunks", type=int, default=0)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = f"3-D dry thermal bubble {args.size}^3, anelastic, WENO5, SSP-RK3, FP64, dt={args.dt}"
+
+    # ---------------------------------------------------------------- reference arm: the CPU restatement, rank 0 only
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cs = min(args.cpu_size, args.size)
+        steps, warm = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
+        v, cores, sps = run_oracle(cs, steps, warm, args.dt)
+        sample = f"{cs}^3 cells of the same bubble ({steps} steps after {warm} warm-up), all host threads"
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": v, "unit": "Mcell-updates/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+            "ms_per_step": sps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": workload, "note": "CPU restatement of the reference algorithm (oracle/); Breeze CPU() needs Julia, not installed"},
+            "cpu_baseline": {"value": v, "unit": "Mcell-updates/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "Mcell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    # ---------------------------------------------------------------- our arm
+    import torch
+    import torch.distributed as dist
+    import breeze_b200 as bz
+    from breeze_b200 import abi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libbreeze_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    uid = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            buf.copy_(torch.tensor(list(abi.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(buf, 0)
+        uid = bytes(buf.cpu().tolist())
+    if args.gpus != world:
+        if rank == 0:
+            sys.stderr.write(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}\n")
+        args.gpus = world
+
+    arch = bz.B200(device=local_rank, rank=rank, n_ranks=world, nccl_unique_id=uid, use_tma=args.use_tma, z_chunks=args.z_chunks)
+    N = args.size
+    grid = bz.RectilinearGrid(arch, size=(N, N, N), x=(-10e3, 10e3), y=(-10e3, 10e3), z=(0, 10e3))
+    model = bz.AtmosphereModel(grid, dynamics=bz.AnelasticDynamics(bz.ReferenceState(grid, potential_temperature=300)), advection=bz.WENO(order=5))
+    model.set(θ=bubble)
+    ctx = model.context
+    cells = N ** 3
+    cells_local = cells // world
+
+    def barrier():
+        ctx.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ext_stream = torch.cuda.ExternalStream(ctx.stream())
+
+    # warm-up
+    for _ in range(max(args.warmup, 3)):
+        ctx.time_step(args.dt)
+    barrier()
+
+    # timed region: K steps, CUDA events on the launching stream, per-kernel-family events for the roofline
+    ctx.profile_enable(True)
+    ctx.profile_read()                                     # reset
+    launches0 = ctx.kernel_launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(ext_stream)
+    for _ in range(args.steps):
+        ctx.time_step(args.dt)
+    e1.record(ext_stream)
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ctx.kernel_launch_count() - launches0
+    fam_ms, fam_n = ctx.profile_read()
+    ctx.profile_enable(False)
+    ms_per_step = ms / args.steps
+    value = cells / (ms_per_step * 1e-3) / 1e6
+
+    # roofline of the dominant kernel (fused stage kernel = family 0), this rank's slab
+    peak, peak_src = measured_peak()
+    stage_ms = fam_ms[0] / max(1, fam_n[0])
+    achieved = STAGE_BYTES_PER_CELL * cells_local / (stage_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "stage_kernel_traffic.json")
+    if os.path.exists(tp):
+        try:
+            t = json.load(open(tp))
+            if t.get("size") == N and t.get("n_gpus") == world:
+                traffic = t.get("dram_bytes_per_launch")
+        except Exception:
+            pass
+    families = ["stage_tendency_rk", "poisson_forward", "thomas", "poisson_inverse", "projection_halo", "exchange"]
+    breakdown = {families[f]: round(fam_ms[f] / args.steps, 4) for f in range(len(families))}
+
+    # e2e: HOST buffers in, HOST buffers out, every step, through the C ABI
+    e2e_steps = max(1, args.e2e_steps)
+    shapes = [ctx.shape(f) for f in range(5)]
+    pinned_in = [torch.empty(s, dtype=torch.float64).pin_memory() for s in shapes]
+    pinned_out = [torch.empty(s, dtype=torch.float64).pin_memory() for s in shapes]
+    state = ctx.get_state([t.numpy() for t in pinned_in])
+    h2d = sum(int(np.prod(s)) * 8 for s in shapes)
+    d2h = h2d
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ctx.set_state(*[t.numpy() for t in pinned_in], enforce_mass_conservation=False)
+        ctx.time_step(args.dt)
+        ctx.get_state([t.numpy() for t in pinned_out])
+        pinned_in, pinned_out = pinned_out, pinned_in
+    barrier()
+    e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+    e2e_value = cells / e2e_s / 1e6
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cs = min(args.cpu_size, N)
+        v, cores, sps = run_oracle(cs, 2, 1, args.dt)
+        cpu = {"value": v, "unit": "Mcell-updates/s", "cores": cores, "kind": "port",
+               "sample": f"{cs}^3 cells of the same bubble, 2 steps after 1 warm-up, {sps:.2f} s/step (CPU restatement of the reference algorithm)"}
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": "Mcell-updates/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload, "grid": [N, N, N], "parallelism": f"x-slabs x{world}", "l2": "inputs larger than L2 (5 fields x %.2f GB per rank)" % (cells_local * 8 / 1e9),
+                       "staging": "tma" if args.use_tma != 2 else "plain", "device_bytes": ctx.device_bytes()},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "kernel": "stage_kernel (fused WENO5 tendencies + RK update)", "kernel_ms": stage_ms, "peak_source": peak_src,
+                         "bytes_per_cell": STAGE_BYTES_PER_CELL},
+            "breakdown_ms_per_step": breakdown,
+            "e2e": {"value": e2e_value, "unit": "Mcell-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if cpu:
+            out["cpu_baseline"] = cpu
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

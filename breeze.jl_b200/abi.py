@@ -87,6 +87,7 @@ CUDA_ONLY_SYMBOLS = {
     "kernel_launch_count": (C.c_int64, [_vp]),
     "stream": (_vp, [_vp]),
     "device_bytes": (C.c_int64, [_vp]),
+    "nccl_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
 }
 
 
@@ -251,6 +252,16 @@ _CUDA_LIB = None
 
 def cuda_library_path() -> str:
     return os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libbreeze_b200.so")
+
+
+def nccl_unique_id() -> bytes:
+    """Rank 0: a fresh ncclUniqueId to broadcast to the other ranks."""
+    lib = load_cuda_library()
+    buf = (C.c_uint8 * 128)()
+    rc = lib.nccl_unique_id(buf)
+    if rc != 0:
+        raise BreezeError(f"bz_nccl_unique_id failed ({rc}): {lib.last_error(None).decode()}")
+    return bytes(buf)
 
 
 def load_cuda_library() -> Library:

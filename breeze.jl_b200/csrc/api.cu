@@ -727,6 +727,11 @@ int bz_profile_read(bz_ctx* c, double* ms, int64_t* n) {
     return BZ_OK;
 }
 
+int bz_nccl_unique_id(uint8_t* out128) {
+    if (!out128) return BZ_ERR_INVALID;
+    return comm_unique_id(out128, g_err);
+}
+
 int64_t bz_kernel_launch_count(const bz_ctx* c) { return c ? c->launches : 0; }
 void* bz_stream(bz_ctx* c) { return c ? (void*)c->stream : nullptr; }
 int64_t bz_device_bytes(const bz_ctx* c) { return c ? c->bytes : 0; }

@@ -59,12 +59,30 @@ static inline void comm_split_range(int n, int P, int r, int* start, int* count)
 }
 static inline void comm_split_ky(const Comm& cm, int nky, int* ky0, int* nky_loc) { comm_split_range(nky, cm.n_ranks, cm.rank, ky0, nky_loc); }
 
+static void* comm_dlopen_nccl() {
+    const char* names[] = {"libnccl.so.2", "libnccl.so", nullptr};
+    void* lib = nullptr;
+    for (int n = 0; names[n] && !lib; ++n) lib = dlopen(names[n], RTLD_NOW | RTLD_GLOBAL);
+    return lib;
+}
+
+// ncclGetUniqueId for rank 0; the caller broadcasts the 128 bytes to the other ranks (any transport).
+static int comm_unique_id(uint8_t* out, char* err) {
+    void* lib = comm_dlopen_nccl();
+    if (!lib) { snprintf(err, 256, "cannot dlopen libnccl.so.2: %s", dlerror()); return BZ_ERR_NCCL; }
+    int (*get)(ncclUniqueId_t*) = nullptr;
+    *(void**)(&get) = dlsym(lib, "ncclGetUniqueId");
+    ncclUniqueId_t id;
+    if (!get || get(&id) != 0) { snprintf(err, 256, "ncclGetUniqueId failed"); return BZ_ERR_NCCL; }
+    memcpy(out, id.internal, 128);
+    return BZ_OK;
+}
+
 static int comm_init(Comm& cm, const bz_config* cfg, cudaStream_t) {
     cm.n_ranks = cfg->n_ranks < 1 ? 1 : cfg->n_ranks;
     cm.rank = cfg->rank;
     if (cm.n_ranks == 1) return BZ_OK;
-    const char* names[] = {"libnccl.so.2", "libnccl.so", nullptr};
-    for (int n = 0; names[n] && !cm.api.lib; ++n) cm.api.lib = dlopen(names[n], RTLD_NOW | RTLD_GLOBAL);
+    cm.api.lib = comm_dlopen_nccl();
     if (!cm.api.lib) { snprintf(cm.err, 256, "cannot dlopen libnccl.so.2: %s", dlerror()); return BZ_ERR_NCCL; }
 #define SYM(field, name) *(void**)(&cm.api.field) = dlsym(cm.api.lib, name); if (!cm.api.field) { snprintf(cm.err, 256, "missing symbol %s", name); return BZ_ERR_NCCL; }
     SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy") SYM(Send, "ncclSend") SYM(Recv, "ncclRecv")

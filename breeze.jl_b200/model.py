@@ -153,20 +153,17 @@ class SaturationAdjustment:
 def _evaluate(value, grid: RectilinearGrid, xs, ys, zs, shape):
     """set!(field, value): a number, an array of the interior shape, or a function of the non-Flat coordinates."""
     if callable(value):
-        Z, Y, X = np.meshgrid(zs, ys, xs, indexing="ij")
+        Z, Y, X = np.meshgrid(zs, ys, xs, indexing="ij", sparse=True)      # broadcastable 1-D axes
         args = [a for a, t in zip((X, Y, Z), grid.topology) if t is not Flat]
-        out = np.vectorize(value, otypes=[float])(*args) if not _is_vectorised(value, args) else value(*args)
-        return np.ascontiguousarray(np.broadcast_to(out, shape), dtype=np.float64)
+        try:
+            out = np.asarray(value(*args), dtype=np.float64)                # numpy-vectorised callable
+            out = np.broadcast_to(out, shape)
+        except Exception:
+            full = [np.broadcast_to(a, shape) for a in args]
+            out = np.vectorize(value, otypes=[float])(*full)                # scalar callable
+        return np.ascontiguousarray(out, dtype=np.float64)
     arr = np.asarray(value, dtype=np.float64)
     return np.ascontiguousarray(np.broadcast_to(arr, shape)).copy()
-
-
-def _is_vectorised(f, args):
-    try:
-        out = f(*args)
-        return np.shape(out) == np.shape(args[0]) or np.ndim(out) == 0
-    except Exception:
-        return False
 
 
 class AtmosphereModel:

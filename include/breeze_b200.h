@@ -152,6 +152,10 @@ int bz_max_abs_divergence(bz_ctx* ctx, double* out);
 
 int bz_synchronize(bz_ctx* ctx);
 
+/* Multi-GPU bootstrap: rank 0 obtains an ncclUniqueId (128 bytes) and hands it to the other ranks by any means
+ * (torch.distributed broadcast in bench.py); every rank then puts it in bz_config.nccl_unique_id. */
+int bz_nccl_unique_id(uint8_t* out128);
+
 /* Instrumentation for bench.py: CUDA-event time (ms) accumulated per kernel family since the last reset, and the
  * number of kernels this library launched. Families: 0 stage(tendency+RK), 1 Poisson forward (div+FFT), 2 Thomas,
  * 3 Poisson inverse, 4 projection(+halo), 5 halo exchange / transposes. Profiling adds event records only when enabled. */
