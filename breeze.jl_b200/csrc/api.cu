@@ -344,7 +344,7 @@ static int launch_stage_t(bz_ctx* c, const StageParams& P, int nz_chunks) {
         configured = true;
     }
     dim3 grid((P.nx_u + TX - 2) / (TX - 1), (c->L.Ny + TY - 1) / TY, nz_chunks);
-    kern<<<grid, TX * TY, sizeof(SM), c->stream>>>(P);
+    kern<<<grid, 2 * TX * TY, sizeof(SM), c->stream>>>(P);
     c->launches++;
     CUDA_TRY(c, cudaGetLastError());
     return BZ_OK;

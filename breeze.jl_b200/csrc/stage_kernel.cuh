@@ -146,15 +146,19 @@ struct StageShared {
 };
 
 template <int TX, int TY, bool HAS_Y, int MICRO>
-__global__ void __launch_bounds__(TX * TY, 1) stage_kernel(const __grid_constant__ StageParams P) {
+__global__ void __launch_bounds__(2 * TX * TY, 1) stage_kernel(const __grid_constant__ StageParams P) {
     using SM = StageShared<TX, TY, HAS_Y>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     SM& S = *reinterpret_cast<SM*>(smem_raw);
-    constexpr int SW = SM::SW, SH = SM::SH, YO = SM::YO, NT = TX * TY;
+    constexpr int SW = SM::SW, SH = SM::SH, YO = SM::YO, NCELL = TX * TY, NT = 2 * NCELL;
 
+    // Two threads per cell column ("roles", warp-uniform): the FP64 pipe needs ~4 warps per scheduler to stay busy and the
+    // plane ring leaves room for one CTA per SM, so the 15 flux kinds of a cell are split between two warps sets that share
+    // the ring:   role 0: ρu, ρv (all directions) + the x/y fluxes of θ;   role 1: ρw, the z flux of θ, ρq, buoyancy.
     const Layout& L = P.L;
     const int tid = threadIdx.x;
-    const int tx = tid % TX, ty = tid / TX;
+    const int role = tid / NCELL, ctid = tid % NCELL;
+    const int tx = ctid % TX, ty = ctid / TX;
     const int i0 = blockIdx.x * (TX - 1), j0 = blockIdx.y * TY;
     const int i = i0 + tx, j = j0 + ty;
     const int Nz = L.Nz;
@@ -231,11 +235,13 @@ __global__ void __launch_bounds__(TX * TY, 1) stage_kernel(const __grid_constant
         for (int kk = kstart - 2; kk <= kstart + 2; ++kk) load_plane_direct(kk);
     }
 
-    // carried from the level below: z-type fluxes through the bottom face, buoyancy of the cell below
-    double zb_u = 0.0, zb_v = 0.0, zb_w = 0.0, zb_t = 0.0, zb_q = 0.0, b_below = 0.0;
+    // carried from the level below: z-type fluxes through the bottom face (role 0: ρu, ρv; role 1: ρw, θ, q), buoyancy below
+    double zb0 = 0.0, zb1 = 0.0, zb2 = 0.0, b_below = 0.0;
 
     const double rdx = L.rdx, rdy = L.rdy, rdz = L.rdz;
     const bool own_cell = (tx < TX - 1) && (j < L.Ny);
+    const bool in_x = i < L.nx;
+    const int f_first = role == 0 ? 0 : 2, f_count = role == 0 ? 2 : 3;   // fields this thread assembles and stores
 
     for (int k = kstart; k < ke; ++k) {
         // ---- stage plane k+3 ------------------------------------------------------------------------------------
@@ -249,6 +255,21 @@ __global__ void __launch_bounds__(TX * TY, 1) stage_kernel(const __grid_constant
             __syncthreads();
         }
 
+        // own-point values for the RK update: issued now, consumed after the flux phase
+        const long long n = lidx(L, i, j, k);
+        const bool do_store = (k >= kb) && own_cell;
+        double Uc[3] = {0.0, 0.0, 0.0}, U0c[3] = {0.0, 0.0, 0.0};
+        if (do_store && P.mode == 0) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                int f = f_first + a;
+                if (a < f_count && (in_x || (f == 0 && i < P.nx_u))) {
+                    Uc[a] = P.U[f][n];
+                    if (P.alpha != 1.0) U0c[a] = P.U0[f][n];
+                }
+            }
+        }
+
         const double rho_k = P.col.rho[k];
         const int kf = k + 1;                                          // top face of this cell
         const double rho_ft = P.col.rho_f[kf];                         // ℑz ρ at the top face (kf <= Nz)
@@ -256,43 +277,42 @@ __global__ void __launch_bounds__(TX * TY, 1) stage_kernel(const __grid_constant
         const int Rf_k2 = red_face(k, Nz, 2);                          // symmetric z interpolation to the face k
         const int Rc3 = red_center(k, Nz, 3), Rc2 = red_center(k, Nz, 2);
 
-        // ---- X-type fluxes: through x-face i (or at centre i-1 for ρu) -------------------------------------------
-        if (!flat_x) {
+        // ---- X-type fluxes: through x-face i (or at centre i-1 for ρu); kinds 0 ρu, 1 ρv, 2 ρw, 3 θ, 4 q ---------------
+        auto x_flux = [&](int kind) -> double {
             const double u_i = ld(0, k, sx, sy);
-            {   // FUu at centre i-1
-                double ut = rho_k * sym4(ld(0, k, sx - 2, sy), ld(0, k, sx - 1, sy), u_i, ld(0, k, sx + 1, sy), 2);
-                double uh = biased6(ld(0, k, sx - 3, sy), ld(0, k, sx - 2, sy), ld(0, k, sx - 1, sy), u_i, ld(0, k, sx + 1, sy), ld(0, k, sx + 2, sy), 3, ut > 0.0);
-                S.fx[0][ty][tx] = ut * uh;
-            }
-            {   // FUv at (face i, face j)
-                double ut;
-                if (HAS_Y) ut = rho_k * sym4(ld(0, k, sx, sy - 2), ld(0, k, sx, sy - 1), u_i, ld(0, k, sx, sy + 1), 2);
-                else ut = rho_k * u_i;
-                double vh = biased6(ld(1, k, sx - 3, sy), ld(1, k, sx - 2, sy), ld(1, k, sx - 1, sy), ld(1, k, sx, sy), ld(1, k, sx + 1, sy), ld(1, k, sx + 2, sy), 3, ut > 0.0);
-                S.fx[1][ty][tx] = ut * vh;
-            }
-            {   // FUw at (face i, z-face k); the wall face k = 0 carries no w tendency
-                double fl = 0.0;
-                if (k >= 1) {
+            switch (kind) {
+                case 0: {   // FUu at centre i-1
+                    double ut = rho_k * sym4(ld(0, k, sx - 2, sy), ld(0, k, sx - 1, sy), u_i, ld(0, k, sx + 1, sy), 2);
+                    double uh = biased6(ld(0, k, sx - 3, sy), ld(0, k, sx - 2, sy), ld(0, k, sx - 1, sy), u_i, ld(0, k, sx + 1, sy), ld(0, k, sx + 2, sy), 3, ut > 0.0);
+                    return ut * uh;
+                }
+                case 1: {   // FUv at (face i, face j)
+                    double ut;
+                    if (HAS_Y) ut = rho_k * sym4(ld(0, k, sx, sy - 2), ld(0, k, sx, sy - 1), u_i, ld(0, k, sx, sy + 1), 2);
+                    else ut = rho_k * u_i;
+                    double vh = biased6(ld(1, k, sx - 3, sy), ld(1, k, sx - 2, sy), ld(1, k, sx - 1, sy), ld(1, k, sx, sy), ld(1, k, sx + 1, sy), ld(1, k, sx + 2, sy), 3, ut > 0.0);
+                    return ut * vh;
+                }
+                case 2: {   // FUw at (face i, z-face k); the wall face k = 0 carries no w tendency
+                    if (k < 1) return 0.0;
                     double a0 = (k >= 2) ? P.col.rho[k - 2] * ld(0, k - 2, sx, sy) : 0.0;
                     double a1 = P.col.rho[k - 1] * ld(0, k - 1, sx, sy);
                     double a2 = rho_k * u_i;
                     double a3 = (k + 1 < Nz) ? P.col.rho[k + 1] * ld(0, k + 1, sx, sy) : 0.0;
                     double ut = sym4(a0, a1, a2, a3, Rf_k2);
                     double wh = biased6(ld(2, k, sx - 3, sy), ld(2, k, sx - 2, sy), ld(2, k, sx - 1, sy), ld(2, k, sx, sy), ld(2, k, sx + 1, sy), ld(2, k, sx + 2, sy), 3, ut > 0.0);
-                    fl = ut * wh;
+                    return ut * wh;
                 }
-                S.fx[2][ty][tx] = fl;
+                case 3: {   // tracer mass flux ρ u θ̂
+                    double th = biased6(ld(3, k, sx - 3, sy), ld(3, k, sx - 2, sy), ld(3, k, sx - 1, sy), ld(3, k, sx, sy), ld(3, k, sx + 1, sy), ld(3, k, sx + 2, sy), 3, u_i > 0.0);
+                    return rho_k * u_i * th;
+                }
+                default: {
+                    double qh = biased6(ld(4, k, sx - 3, sy), ld(4, k, sx - 2, sy), ld(4, k, sx - 1, sy), ld(4, k, sx, sy), ld(4, k, sx + 1, sy), ld(4, k, sx + 2, sy), 3, u_i > 0.0);
+                    return rho_k * u_i * qh;
+                }
             }
-            {   // tracer mass fluxes ρ u ĉ
-                double ru = rho_k * u_i;
-                bool left = u_i > 0.0;
-                double th = biased6(ld(3, k, sx - 3, sy), ld(3, k, sx - 2, sy), ld(3, k, sx - 1, sy), ld(3, k, sx, sy), ld(3, k, sx + 1, sy), ld(3, k, sx + 2, sy), 3, left);
-                double qh = biased6(ld(4, k, sx - 3, sy), ld(4, k, sx - 2, sy), ld(4, k, sx - 1, sy), ld(4, k, sx, sy), ld(4, k, sx + 1, sy), ld(4, k, sx + 2, sy), 3, left);
-                S.fx[3][ty][tx] = ru * th;
-                S.fx[4][ty][tx] = ru * qh;
-            }
-        }
+        };
 
         // ---- Y-type fluxes: through y-face j (or at centre j-1 for ρv); row `yy` of the plane --------------------
         auto y_flux = [&](int kind, int yy) -> double {
@@ -328,80 +348,89 @@ __global__ void __launch_bounds__(TX * TY, 1) stage_kernel(const __grid_constant
                 }
             }
         };
-        if (HAS_Y) {
-#pragma unroll
-            for (int kind = 0; kind < NPROG; ++kind) S.fy[kind][ty][tx] = y_flux(kind, sy);
-            if (ty < NPROG) S.fy[ty][TY][tx] = y_flux(ty, TY + YO);   // the extra row of y-faces, one kind per warp
-        }
 
         // ---- Z-type fluxes through the top face kf (or at centre k for ρw) ---------------------------------------
-        double zt_u, zt_v, zt_w, zt_t, zt_q;
-        {
+        auto z_flux = [&](int kind) -> double {
             const double w_top = ld(2, kf, sx, sy);                    // 0 on the top wall (zero plane)
-            {   // FWu at (face i, z-face kf)
-                double wt = flat_x ? rho_ft * w_top : rho_ft * sym4(ld(2, kf, sx - 2, sy), ld(2, kf, sx - 1, sy), w_top, ld(2, kf, sx + 1, sy), 2);
-                double uh = biased6(ld(0, kf - 3, sx, sy), ld(0, kf - 2, sx, sy), ld(0, kf - 1, sx, sy), ld(0, kf, sx, sy), ld(0, kf + 1, sx, sy), ld(0, kf + 2, sx, sy), Rf_top, wt > 0.0);
-                zt_u = wt * uh;
+            switch (kind) {
+                case 0: {   // FWu at (face i, z-face kf)
+                    double wt = flat_x ? rho_ft * w_top : rho_ft * sym4(ld(2, kf, sx - 2, sy), ld(2, kf, sx - 1, sy), w_top, ld(2, kf, sx + 1, sy), 2);
+                    double uh = biased6(ld(0, kf - 3, sx, sy), ld(0, kf - 2, sx, sy), ld(0, kf - 1, sx, sy), ld(0, kf, sx, sy), ld(0, kf + 1, sx, sy), ld(0, kf + 2, sx, sy), Rf_top, wt > 0.0);
+                    return wt * uh;
+                }
+                case 1: {   // FWv at (face j, z-face kf)
+                    double wt = HAS_Y ? rho_ft * sym4(ld(2, kf, sx, sy - 2), ld(2, kf, sx, sy - 1), w_top, ld(2, kf, sx, sy + 1), 2) : rho_ft * w_top;
+                    double vh = biased6(ld(1, kf - 3, sx, sy), ld(1, kf - 2, sx, sy), ld(1, kf - 1, sx, sy), ld(1, kf, sx, sy), ld(1, kf + 1, sx, sy), ld(1, kf + 2, sx, sy), Rf_top, wt > 0.0);
+                    return wt * vh;
+                }
+                case 2: {   // FWw at centre k: faces k-1 .. k+2 (advecting), k-2 .. k+3 (advected)
+                    double a0 = (k >= 1) ? P.col.rho_f[k - 1] * ld(2, k - 1, sx, sy) : 0.0;
+                    double a1 = P.col.rho_f[k] * ld(2, k, sx, sy);
+                    double a2 = rho_ft * w_top;
+                    double a3 = (k + 2 <= Nz) ? P.col.rho_f[k + 2] * ld(2, k + 2, sx, sy) : 0.0;
+                    double wt = sym4(a0, a1, a2, a3, Rc2);
+                    double wh = biased6(ld(2, k - 2, sx, sy), ld(2, k - 1, sx, sy), ld(2, k, sx, sy), w_top, ld(2, k + 2, sx, sy), ld(2, k + 3, sx, sy), Rc3, wt > 0.0);
+                    return wt * wh;
+                }
+                case 3: {   // tracer mass flux ℑz(ρ) w θ̂
+                    double th = biased6(ld(3, kf - 3, sx, sy), ld(3, kf - 2, sx, sy), ld(3, kf - 1, sx, sy), ld(3, kf, sx, sy), ld(3, kf + 1, sx, sy), ld(3, kf + 2, sx, sy), Rf_top, w_top > 0.0);
+                    return rho_ft * w_top * th;
+                }
+                default: {
+                    double qh = biased6(ld(4, kf - 3, sx, sy), ld(4, kf - 2, sx, sy), ld(4, kf - 1, sx, sy), ld(4, kf, sx, sy), ld(4, kf + 1, sx, sy), ld(4, kf + 2, sx, sy), Rf_top, w_top > 0.0);
+                    return rho_ft * w_top * qh;
+                }
             }
-            {   // FWv at (face j, z-face kf)
-                double wt = HAS_Y ? rho_ft * sym4(ld(2, kf, sx, sy - 2), ld(2, kf, sx, sy - 1), w_top, ld(2, kf, sx, sy + 1), 2) : rho_ft * w_top;
-                double vh = biased6(ld(1, kf - 3, sx, sy), ld(1, kf - 2, sx, sy), ld(1, kf - 1, sx, sy), ld(1, kf, sx, sy), ld(1, kf + 1, sx, sy), ld(1, kf + 2, sx, sy), Rf_top, wt > 0.0);
-                zt_v = wt * vh;
+        };
+
+        double zt0, zt1, zt2 = 0.0, b_here = 0.0;
+        if (role == 0) {
+            if (!flat_x) { S.fx[0][ty][tx] = x_flux(0); S.fx[1][ty][tx] = x_flux(1); S.fx[3][ty][tx] = x_flux(3); }
+            if (HAS_Y) {
+                S.fy[0][ty][tx] = y_flux(0, sy); S.fy[1][ty][tx] = y_flux(1, sy); S.fy[3][ty][tx] = y_flux(3, sy);
+                // the extra row of y-faces above the tile: one flux kind per warp (rows 0..2 of this role)
+                if (ty == 0) S.fy[0][TY][tx] = y_flux(0, TY + YO);
+                else if (ty == 1) S.fy[1][TY][tx] = y_flux(1, TY + YO);
+                else if (ty == 2) S.fy[3][TY][tx] = y_flux(3, TY + YO);
             }
-            {   // FWw at centre k: faces k-1 .. k+2 (advecting), k-2 .. k+3 (advected)
-                double a0 = (k >= 1) ? P.col.rho_f[k - 1] * ld(2, k - 1, sx, sy) : 0.0;
-                double a1 = P.col.rho_f[k] * ld(2, k, sx, sy);
-                double a2 = rho_ft * w_top;
-                double a3 = (k + 2 <= Nz) ? P.col.rho_f[k + 2] * ld(2, k + 2, sx, sy) : 0.0;
-                double wt = sym4(a0, a1, a2, a3, Rc2);
-                double wh = biased6(ld(2, k - 2, sx, sy), ld(2, k - 1, sx, sy), ld(2, k, sx, sy), w_top, ld(2, k + 2, sx, sy), ld(2, k + 3, sx, sy), Rc3, wt > 0.0);
-                zt_w = wt * wh;
+            zt0 = z_flux(0); zt1 = z_flux(1);
+        } else {
+            if (!flat_x) { S.fx[2][ty][tx] = x_flux(2); S.fx[4][ty][tx] = x_flux(4); }
+            if (HAS_Y) {
+                S.fy[2][ty][tx] = y_flux(2, sy); S.fy[4][ty][tx] = y_flux(4, sy);
+                if (ty == 0) S.fy[2][TY][tx] = y_flux(2, TY + YO);
+                else if (ty == 1) S.fy[4][TY][tx] = y_flux(4, TY + YO);
             }
-            {   // tracer mass fluxes ℑz(ρ) w ĉ
-                double rw = rho_ft * w_top;
-                bool left = w_top > 0.0;
-                double th = biased6(ld(3, kf - 3, sx, sy), ld(3, kf - 2, sx, sy), ld(3, kf - 1, sx, sy), ld(3, kf, sx, sy), ld(3, kf + 1, sx, sy), ld(3, kf + 2, sx, sy), Rf_top, left);
-                double qh = biased6(ld(4, kf - 3, sx, sy), ld(4, kf - 2, sx, sy), ld(4, kf - 1, sx, sy), ld(4, kf, sx, sy), ld(4, kf + 1, sx, sy), ld(4, kf + 2, sx, sy), Rf_top, left);
-                zt_t = rw * th;
-                zt_q = rw * qh;
-            }
+            zt0 = z_flux(2); zt1 = z_flux(3); zt2 = z_flux(4);
+            b_here = buoyancy_center<MICRO>(P.th, P.col, k, ld(3, k, sx, sy), ld(4, k, sx, sy));
         }
-        const double b_here = buoyancy_center<MICRO>(P.th, P.col, k, ld(3, k, sx, sy), ld(4, k, sx, sy));
 
         __syncthreads();                                               // fx / fy complete
 
         // ---- tendencies, RK update, store -----------------------------------------------------------------------
-        if (k >= kb && own_cell) {
-            double G[NPROG];
+        if (do_store) {
+            double zt[3] = {zt0, zt1, zt2}, zb[3] = {zb0, zb1, zb2};
 #pragma unroll
-            for (int f = 0; f < NPROG; ++f) {
+            for (int a = 0; a < 3; ++a) {
+                const int f = f_first + a;
+                if (a >= f_count) break;
+                if (!(in_x || (f == 0 && i < P.nx_u))) continue;
                 double g = 0.0;
                 if (!flat_x) g += (S.fx[f][ty][tx + 1] - S.fx[f][ty][tx]) * rdx;
                 if (HAS_Y) g += (S.fy[f][ty + 1][tx] - S.fy[f][ty][tx]) * rdy;
-                G[f] = g;
-            }
-            G[0] = -(G[0] + (zt_u - zb_u) * rdz);
-            G[1] = -(G[1] + (zt_v - zb_v) * rdz);
-            G[2] = (k >= 1) ? -(G[2] + (zt_w - zb_w) * rdz) + 0.5 * (b_here + b_below) : 0.0;
-            G[3] = -(G[3] + (zt_t - zb_t) * rdz);
-            G[4] = -(G[4] + (zt_q - zb_q) * rdz);
-
-            const long long n = lidx(L, i, j, k);
-            const bool in_x = i < L.nx;
-#pragma unroll
-            for (int f = 0; f < NPROG; ++f) {
-                if (!(in_x || (f == 0 && i < P.nx_u))) continue;
+                g = -(g + (zt[a] - zb[a]) * rdz);
+                if (f == 2) g = (k >= 1) ? g + 0.5 * (b_here + b_below) : 0.0;
                 double r;
-                if (P.mode == 1) r = G[f];
+                if (P.mode == 1) r = g;
                 else {
-                    double un = P.U[f][n] + P.dt * G[f];
-                    r = (P.alpha == 1.0) ? un : (1.0 - P.alpha) * P.U0[f][n] + P.alpha * un;
+                    double un = Uc[a] + P.dt * g;
+                    r = (P.alpha == 1.0) ? un : (1.0 - P.alpha) * U0c[a] + P.alpha * un;
                     if (f == 2 && k == 0) r = 0.0;                     // impenetrable bottom wall
                 }
                 P.out[f][n] = r;
             }
         }
-        zb_u = zt_u; zb_v = zt_v; zb_w = zt_w; zb_t = zt_t; zb_q = zt_q; b_below = b_here;
+        zb0 = zt0; zb1 = zt1; zb2 = zt2; b_below = b_here;
         // the next level's staging barrier also protects fx / fy
     }
 }
