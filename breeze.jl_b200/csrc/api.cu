@@ -218,19 +218,19 @@ static int setup_poisson(bz_ctx* c) {
     if ((rc = dev_alloc(c, &c->tfac, nW2 > 0 ? nW2 : 1))) return rc;
     // launch shapes: each thread owns 8 points of a line
     if (!L.flat_y) {
-        int lines = 4096 / g.Ny; if (lines < 1) lines = 1;
+        int lines = 2048 / g.Ny; if (lines < 1) lines = 1;
         int half = (L.nx + 1) / 2; if (lines > half) lines = half;
         c->lines_y = lines;
-        size_t sm = (size_t)2 * lines * (g.Ny + 1) * sizeof(double);
+        size_t sm = (size_t)2 * lines * line_pitch(g.Ny) * sizeof(double);
         CUDA_TRY(c, cudaFuncSetAttribute(poisson_forward_y, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
         CUDA_TRY(c, cudaFuncSetAttribute(poisson_inverse_y, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     }
     if (!L.flat_x) {
-        int lines = 4096 / g.Nx; if (lines < 1) lines = 1;
+        int lines = 2048 / g.Nx; if (lines < 1) lines = 1;
         long long nl = (long long)G.Nz * G.nky_loc; if (nl < 1) nl = 1;
         if (lines > nl) lines = (int)nl;
         c->lines_x = lines;
-        size_t sm = (size_t)2 * lines * (g.Nx + 1) * sizeof(double);
+        size_t sm = (size_t)2 * lines * line_pitch(g.Nx) * sizeof(double);
         CUDA_TRY(c, cudaFuncSetAttribute(fft_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     }
     return setup_thomas(c);
@@ -247,7 +247,7 @@ static int poisson_solve(bz_ctx* c, double dt) {
         if (!L.flat_y) {
             int lines = c->lines_y;
             dim3 grid((L.nx + 2 * lines - 1) / (2 * lines), L.Nz);
-            size_t sm = (size_t)2 * lines * (G.Ny + 1) * sizeof(double);
+            size_t sm = (size_t)2 * lines * line_pitch(G.Ny) * sizeof(double);
             poisson_forward_y<<<grid, lines * G.Ny / 8, sm, c->stream>>>(L, G, U[0], U[1], U[2], dz_over_dt, c->W, c->tw_y, lines);
         } else {
             dim3 grid((L.nx + 127) / 128, L.Nz);
@@ -264,7 +264,7 @@ static int poisson_solve(bz_ctx* c, double dt) {
     if (!L.flat_x && n_lines > 0) {
         ProfScope ps(c, 1);
         int lines = c->lines_x;
-        size_t sm = (size_t)2 * lines * (G.Nx + 1) * sizeof(double);
+        size_t sm = (size_t)2 * lines * line_pitch(G.Nx) * sizeof(double);
         fft_x_kernel<<<(unsigned)((n_lines + lines - 1) / lines), lines * G.Nx / 8, sm, c->stream>>>(c->W2, G.Nx, n_lines, c->tw_x, lines, 0);
         c->launches++;
     }
@@ -278,7 +278,7 @@ static int poisson_solve(bz_ctx* c, double dt) {
     if (!L.flat_x && n_lines > 0) {
         ProfScope ps(c, 3);
         int lines = c->lines_x;
-        size_t sm = (size_t)2 * lines * (G.Nx + 1) * sizeof(double);
+        size_t sm = (size_t)2 * lines * line_pitch(G.Nx) * sizeof(double);
         fft_x_kernel<<<(unsigned)((n_lines + lines - 1) / lines), lines * G.Nx / 8, sm, c->stream>>>(c->W2, G.Nx, n_lines, c->tw_x, lines, 1);
         c->launches++;
     }
@@ -293,7 +293,7 @@ static int poisson_solve(bz_ctx* c, double dt) {
         if (!L.flat_y) {
             int lines = c->lines_y;
             dim3 grid((L.nx + 2 * lines - 1) / (2 * lines), L.Nz);
-            size_t sm = (size_t)2 * lines * (G.Ny + 1) * sizeof(double);
+            size_t sm = (size_t)2 * lines * line_pitch(G.Ny) * sizeof(double);
             poisson_inverse_y<<<grid, lines * G.Ny / 8, sm, c->stream>>>(L, G, c->W, c->phi, c->tw_y, lines, scale);
         } else {
             dim3 grid((L.nx + 127) / 128, L.Nz);
@@ -444,8 +444,8 @@ int bz_create(const bz_config* cfg, bz_ctx** out) {
     const int fx = cfg->topology_x == BZ_FLAT, fy = cfg->topology_y == BZ_FLAT;
     if ((fx && cfg->Nx != 1) || (fy && cfg->Ny != 1)) FAIL(BZ_ERR_INVALID, "a Flat dimension must have size 1");
     if (fx && !fy) FAIL(BZ_ERR_UNSUPPORTED, "(Flat, Periodic, Bounded) is not supported; use (Periodic, Flat, Bounded)");
-    if (!fx && (!is_pow2(cfg->Nx) || cfg->Nx < 8 || cfg->Nx > 4096)) FAIL(BZ_ERR_UNSUPPORTED, "Nx must be a power of two in [8, 4096] (in-house FFT)");
-    if (!fy && (!is_pow2(cfg->Ny) || cfg->Ny < 8 || cfg->Ny > 4096)) FAIL(BZ_ERR_UNSUPPORTED, "Ny must be a power of two in [8, 4096] (in-house FFT)");
+    if (!fx && (!is_pow2(cfg->Nx) || cfg->Nx < 8 || cfg->Nx > 2048)) FAIL(BZ_ERR_UNSUPPORTED, "Nx must be a power of two in [8, 2048] (in-house FFT)");
+    if (!fy && (!is_pow2(cfg->Ny) || cfg->Ny < 8 || cfg->Ny > 2048)) FAIL(BZ_ERR_UNSUPPORTED, "Ny must be a power of two in [8, 2048] (in-house FFT)");
     const int P = cfg->n_ranks < 1 ? 1 : cfg->n_ranks;
     if (P > 1 && (fx || cfg->Nx % P != 0 || (cfg->Nx / P) < 8)) FAIL(BZ_ERR_INVALID, "x-slabs: Nx must be divisible by n_ranks with at least 8 columns per rank");
     if (cfg->rank < 0 || cfg->rank >= P) FAIL(BZ_ERR_INVALID, "rank out of range");

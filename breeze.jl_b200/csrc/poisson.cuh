@@ -53,7 +53,12 @@ __device__ __forceinline__ void dft8(cpx* v) {
     v[1] = a4; v[3] = a5; v[5] = a6; v[7] = a7;
 }
 
-// One Stockham pass of radix R over `lines` lines of length N held as re[l*LP + n], im[l*LP + n].
+// Shared-memory index of element n of a line: one pad double every 8 keeps the stride-8 / stride-64 scatter of the
+// radix-8 passes (and the line-to-line stride) free of bank conflicts.
+__device__ __forceinline__ int pidx(int n) { return n + (n >> 3); }
+__host__ __device__ __forceinline__ int line_pitch(int N) { return N + (N >> 3) + 1; }
+
+// One Stockham pass of radix R over `lines` lines of length N held as re[l*LP + pidx(n)], im[l*LP + pidx(n)].
 // Each thread owns 8/R butterflies (8 complex values in registers): blockDim.x == lines * N / 8.
 template <int R>
 __device__ __forceinline__ void stockham_pass(double* re, double* im, int LP, int N, int Ns, const double2* __restrict__ tw) {
@@ -70,7 +75,7 @@ __device__ __forceinline__ void stockham_pass(double* re, double* im, int LP, in
         int j = t + it * per_line;                 // butterfly index in [0, N/R)
         jj[it] = j;
 #pragma unroll
-        for (int r = 0; r < R; ++r) v[it][r] = {lre[j + r * NR], lim[j + r * NR]};
+        for (int r = 0; r < R; ++r) v[it][r] = {lre[pidx(j + r * NR)], lim[pidx(j + r * NR)]};
     }
     __syncthreads();
 #pragma unroll
@@ -90,7 +95,7 @@ __device__ __forceinline__ void stockham_pass(double* re, double* im, int LP, in
         else dft2(v[it][0], v[it][1]);
         int j0 = (j - k) * R + k;
 #pragma unroll
-        for (int r = 0; r < R; ++r) { lre[j0 + r * Ns] = v[it][r].x; lim[j0 + r * Ns] = v[it][r].y; }
+        for (int r = 0; r < R; ++r) { lre[pidx(j0 + r * Ns)] = v[it][r].x; lim[pidx(j0 + r * Ns)] = v[it][r].y; }
     }
     __syncthreads();
 }
@@ -118,12 +123,12 @@ __device__ __forceinline__ double source_term(const Layout& L, const double* __r
 }
 
 // ---- pass 1: source term + real-to-complex FFT along y ----------------------------------------------------------
-// grid (ceil(nx / (2*lines)), Nz); block lines*Ny/8 threads; smem 2*lines*(Ny+1) doubles.
-__global__ void poisson_forward_y(Layout L, PoissonGeom G, const double* __restrict__ ru, const double* __restrict__ rv,
+// grid (ceil(nx / (2*lines)), Nz); block lines*Ny/8 <= 256 threads; smem 2*lines*line_pitch(Ny) doubles.
+__global__ void __launch_bounds__(256, 3) poisson_forward_y(Layout L, PoissonGeom G, const double* __restrict__ ru, const double* __restrict__ rv,
                                   const double* __restrict__ rw, double dz_over_dt, double2* __restrict__ W,
                                   const double2* __restrict__ tw_y, int lines) {
     extern __shared__ double sm[];
-    const int N = G.Ny, LP = N + 1;
+    const int N = G.Ny, LP = line_pitch(N);
     double* re = sm;
     double* im = sm + (size_t)lines * LP;
     const int k = blockIdx.y;
@@ -133,7 +138,7 @@ __global__ void poisson_forward_y(Layout L, PoissonGeom G, const double* __restr
         int c = e % XB, y = e / XB;
         int i = ib + c;
         double v = (i < L.nx) ? source_term(L, ru, rv, rw, i, y, k, dz_over_dt) : 0.0;
-        ((c & 1) ? im : re)[(size_t)(c >> 1) * LP + y] = v;
+        ((c & 1) ? im : re)[(size_t)(c >> 1) * LP + pidx(y)] = v;
     }
     __syncthreads();
     fft_lines_smem(re, im, LP, N, tw_y);
@@ -143,8 +148,8 @@ __global__ void poisson_forward_y(Layout L, PoissonGeom G, const double* __restr
         int i = ib + c;
         if (i >= L.nx) continue;
         int l = c >> 1, km = (N - ky) & (N - 1);
-        double zr = re[(size_t)l * LP + ky], zi = im[(size_t)l * LP + ky];
-        double yr = re[(size_t)l * LP + km], yi = im[(size_t)l * LP + km];
+        double zr = re[(size_t)l * LP + pidx(ky)], zi = im[(size_t)l * LP + pidx(ky)];
+        double yr = re[(size_t)l * LP + pidx(km)], yi = im[(size_t)l * LP + pidx(km)];
         double2 o = (c & 1) ? make_double2(0.5 * (zi + yi), -0.5 * (zr - yr)) : make_double2(0.5 * (zr + yr), 0.5 * (zi - yi));
         W[((size_t)k * G.nky + ky) * L.nx + i] = o;
     }
@@ -158,10 +163,10 @@ __global__ void poisson_pack_flat_y(Layout L, const double* __restrict__ ru, con
 }
 
 // ---- pass 5: complex-to-real inverse FFT along y → φ (padded field interior) -------------------------------------
-__global__ void poisson_inverse_y(Layout L, PoissonGeom G, const double2* __restrict__ W, double* __restrict__ phi,
+__global__ void __launch_bounds__(256, 3) poisson_inverse_y(Layout L, PoissonGeom G, const double2* __restrict__ W, double* __restrict__ phi,
                                   const double2* __restrict__ tw_y, int lines, double scale) {
     extern __shared__ double sm[];
-    const int N = G.Ny, LP = N + 1;
+    const int N = G.Ny, LP = line_pitch(N);
     double* re = sm;
     double* im = sm + (size_t)lines * LP;
     const int k = blockIdx.y;
@@ -175,11 +180,11 @@ __global__ void poisson_inverse_y(Layout L, PoissonGeom G, const double2* __rest
         if (i < L.nx) A = W[((size_t)k * G.nky + ky) * L.nx + i];
         if (i + 1 < L.nx) B = W[((size_t)k * G.nky + ky) * L.nx + i + 1];
         // Z[ky] = A + iB, Z[N-ky] = conj(A) + i conj(B); store conj(Z)
-        re[(size_t)l * LP + ky] = A.x - B.y;
-        im[(size_t)l * LP + ky] = -(A.y + B.x);
+        re[(size_t)l * LP + pidx(ky)] = A.x - B.y;
+        im[(size_t)l * LP + pidx(ky)] = -(A.y + B.x);
         if (ky > 0 && ky < N / 2) {
-            re[(size_t)l * LP + N - ky] = A.x + B.y;
-            im[(size_t)l * LP + N - ky] = -(B.x - A.y);
+            re[(size_t)l * LP + pidx(N - ky)] = A.x + B.y;
+            im[(size_t)l * LP + pidx(N - ky)] = -(B.x - A.y);
         }
     }
     __syncthreads();
@@ -189,7 +194,7 @@ __global__ void poisson_inverse_y(Layout L, PoissonGeom G, const double2* __rest
         int i = ib + c;
         if (i >= L.nx) continue;
         int l = c >> 1;
-        double v = (c & 1) ? -im[(size_t)l * LP + y] : re[(size_t)l * LP + y];
+        double v = (c & 1) ? -im[(size_t)l * LP + pidx(y)] : re[(size_t)l * LP + pidx(y)];
         phi[lidx(L, i, y, k)] = v * scale;
     }
 }
@@ -200,10 +205,10 @@ __global__ void poisson_unpack_flat_y(Layout L, const double2* __restrict__ W, d
 }
 
 // ---- passes 2 / 4: complex FFT along x, in place; one line = Nx contiguous complex numbers ----------------------
-// grid ceil(n_lines / lines); block lines*Nx/8 threads; smem 2*lines*(Nx+1) doubles.
-__global__ void fft_x_kernel(double2* __restrict__ W, int Nx, long long n_lines, const double2* __restrict__ tw_x, int lines, int inverse) {
+// grid ceil(n_lines / lines); block lines*Nx/8 <= 256 threads; smem 2*lines*line_pitch(Nx) doubles.
+__global__ void __launch_bounds__(256, 3) fft_x_kernel(double2* __restrict__ W, int Nx, long long n_lines, const double2* __restrict__ tw_x, int lines, int inverse) {
     extern __shared__ double sm[];
-    const int N = Nx, LP = N + 1;
+    const int N = Nx, LP = line_pitch(N);
     double* re = sm;
     double* im = sm + (size_t)lines * LP;
     const long long l0 = (long long)blockIdx.x * lines;
@@ -212,14 +217,14 @@ __global__ void fft_x_kernel(double2* __restrict__ W, int Nx, long long n_lines,
         int x = e % N, l = e / N;
         double2 v = make_double2(0.0, 0.0);
         if (l0 + l < n_lines) v = W[(l0 + l) * N + x];
-        re[(size_t)l * LP + x] = v.x;
-        im[(size_t)l * LP + x] = sgn * v.y;
+        re[(size_t)l * LP + pidx(x)] = v.x;
+        im[(size_t)l * LP + pidx(x)] = sgn * v.y;
     }
     __syncthreads();
     fft_lines_smem(re, im, LP, N, tw_x);
     for (int e = threadIdx.x; e < N * lines; e += blockDim.x) {
         int x = e % N, l = e / N;
-        if (l0 + l < n_lines) W[(l0 + l) * N + x] = make_double2(re[(size_t)l * LP + x], sgn * im[(size_t)l * LP + x]);
+        if (l0 + l < n_lines) W[(l0 + l) * N + x] = make_double2(re[(size_t)l * LP + pidx(x)], sgn * im[(size_t)l * LP + pidx(x)]);
     }
 }
 

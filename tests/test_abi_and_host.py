@@ -1,0 +1,102 @@
+"""CPU-only checks of the boundary: the CUDA library loads, exports every symbol include/breeze_b200.h declares, refuses to
+run without a GPU (no CPU fallback), and the host mirror validates its arguments like the reference does."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import breeze_b200 as bz
+from breeze_b200 import abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "breeze_b200.h")).read()
+    return sorted(set(re.findall(r"\b(bz_[a-z_0-9]+)\s*\(", text)) - {"bz_ctx", "bz_config"})
+
+
+def test_cuda_library_exports_every_declared_symbol():
+    lib = abi.load_cuda_library()
+    for name in _declared_symbols():
+        assert hasattr(lib.dll, name), name
+    assert lib.abi_version() == abi.BZ_ABI_VERSION
+
+
+def test_oracle_exports_the_same_abi(oracle_arch):
+    lib = oracle_arch.library()
+    for name in abi.ABI_SYMBOLS:
+        assert hasattr(lib.dll, "orc_" + name), name
+
+
+def test_config_struct_layout_matches_c():
+    # sizeof(bz_config) seen by ctypes must equal the C compiler's (the library fills it in bz_default_config)
+    lib = abi.load_cuda_library()
+    cfg = lib.default_config_struct()
+    assert cfg.abi_version == 1 and cfg.advection_order == 5 and cfg.n_ranks == 1
+    assert cfg.surface_pressure == 101325.0 and cfg.ice_heat_capacity == 2108.0
+    assert C.sizeof(abi.bz_config) == 4 * 6 + 8 * 22 + 4 * 6 + 128 + 4 * 8
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = abi.load_cuda_library()
+    cfg = lib.default_config_struct()
+    h = C.c_void_p()
+    assert lib.create(C.byref(cfg), C.byref(h)) != 0
+    assert b"no CPU fallback" in lib.last_error(None)
+    with pytest.raises(bz.BreezeError):
+        grid = bz.RectilinearGrid(size=(8, 8, 8), x=(0, 1), y=(0, 1), z=(0, 1))
+        bz.AtmosphereModel(grid)
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "breeze.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert not re.search(r"^\s*(import|from)\s+oracle", text, re.M), f
+                assert "liboracle" not in text, f
+
+
+def test_grid_and_model_argument_validation(oracle_arch):
+    with pytest.raises(ValueError):
+        bz.RectilinearGrid(oracle_arch, size=(8, 8, 8), x=(0, 1), y=(0, 1), z=(0, 1), topology=(bz.Periodic, bz.Periodic, bz.Periodic))
+    with pytest.raises(ValueError):
+        bz.RectilinearGrid(oracle_arch, size=(8, 8), x=(0, 1), y=(0, 1), z=(0, 1))
+    grid = bz.RectilinearGrid(oracle_arch, size=(8, 8, 8), x=(0, 1), y=(0, 1), z=(0, 1))
+    with pytest.raises(NotImplementedError):
+        bz.AtmosphereModel(grid, advection=bz.WENO(order=9))
+    model = bz.AtmosphereModel(grid)
+    with pytest.raises(ValueError):
+        model.set(banana=1.0)
+    with pytest.raises(bz.BreezeError):
+        model.context.set_state(rho_u=np.zeros((3, 3, 3)))
+    # model construction leaves θ = θ₀ (initialize_model_thermodynamics!)
+    assert np.allclose(model.field("θ"), 288.0)
+    assert model.field("ρw").shape == (9, 8, 8) and model.field("ρu").shape == (8, 8, 8)
+
+
+def test_set_velocity_uses_face_density(oracle_arch):
+    grid = bz.RectilinearGrid(oracle_arch, size=(8, 8, 8), x=(0, 1), y=(0, 1), z=(0, 4000.0))
+    model = bz.AtmosphereModel(grid)
+    model.set(u=2.0, enforce_mass_conservation=False)
+    rho = model.reference_profiles()[0]
+    assert np.allclose(model.field("ρu"), 2.0 * rho[:, None, None])
+    assert np.allclose(model.field("u"), 2.0)
+
+
+def test_time_step_wizard(oracle_arch):
+    grid = bz.RectilinearGrid(oracle_arch, size=(8, 8, 8), x=(0, 800.0), y=(0, 800.0), z=(0, 800.0))
+    model = bz.AtmosphereModel(grid)
+    model.set(u=10.0)
+    assert model.context.cell_advection_timescale() == pytest.approx(100.0 / 10.0, rel=1e-12)
+    sim = bz.Simulation(model, Δt=1.0, stop_iteration=1)
+    bz.conjure_time_step_wizard_(sim, cfl=0.5, interval=1)
+    bz.run_(sim)
+    assert sim.Δt == pytest.approx(1.1)                              # max_change limits the growth towards cfl·τ = 5
