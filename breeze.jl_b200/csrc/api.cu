@@ -334,11 +334,11 @@ static int fill_halos(bz_ctx* c, double* const* fields, int nf, int fam) {
 // ---------------------------------------------------------------------------------------------------------------
 // stage kernel launch
 // ---------------------------------------------------------------------------------------------------------------
-template <int TX, int TY, bool HAS_Y, int MICRO>
+template <int TX, int TY, bool HAS_Y, bool FLAT_X, int MICRO>
 static int launch_stage_t(bz_ctx* c, const StageParams& P, int nz_chunks) {
     using SM = StageShared<TX, TY, HAS_Y>;
     static bool configured = false;
-    auto kern = stage_kernel<TX, TY, HAS_Y, MICRO>;
+    auto kern = stage_kernel<TX, TY, HAS_Y, FLAT_X, MICRO>;
     if (!configured) {
         CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SM)));
         configured = true;
@@ -367,9 +367,10 @@ static int launch_stage(bz_ctx* c, int in, double* const* out, int u0, double dt
     P.k_chunk = (c->L.Nz + chunks - 1) / chunks;
     const bool moist = c->cfg.microphysics != BZ_MICROPHYSICS_NONE;
     if (!c->L.flat_y) {
-        return moist ? launch_stage_t<32, 8, true, 1>(c, P, chunks) : launch_stage_t<32, 8, true, 0>(c, P, chunks);
+        return moist ? launch_stage_t<32, 8, true, false, 1>(c, P, chunks) : launch_stage_t<32, 8, true, false, 0>(c, P, chunks);
     }
-    return moist ? launch_stage_t<128, 1, false, 1>(c, P, chunks) : launch_stage_t<128, 1, false, 0>(c, P, chunks);
+    if (c->L.flat_x) return moist ? launch_stage_t<32, 1, false, true, 1>(c, P, chunks) : launch_stage_t<32, 1, false, true, 0>(c, P, chunks);
+    return moist ? launch_stage_t<128, 1, false, false, 1>(c, P, chunks) : launch_stage_t<128, 1, false, false, 0>(c, P, chunks);
 }
 
 // compute_pressure_correction! + make_pressure_correction! on set[cur], then refresh all ghosts

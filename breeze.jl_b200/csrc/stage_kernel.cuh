@@ -22,6 +22,7 @@
 #pragma once
 #include "common.cuh"
 #include "weno.cuh"
+#include <type_traits>
 
 #define RING 8
 
@@ -145,15 +146,30 @@ struct StageShared {
     uint64_t bar[RING];
 };
 
-template <int TX, int TY, bool HAS_Y, int MICRO>
+// Biased reconstruction from six consecutive values with the buffer R known at compile time on the fast path.
+template <int R>
+__device__ __forceinline__ double biased6c(double v0, double v1, double v2, double v3, double v4, double v5, bool left) {
+    if (R >= 3) {
+        double a = left ? v0 : v5, b = left ? v1 : v4, c = left ? v2 : v3, d = left ? v3 : v2, e = left ? v4 : v1;
+        return weno5z(a, b, c, d, e);
+    } else if (R == 2) {
+        double a = left ? v1 : v4, b = left ? v2 : v3, c = left ? v3 : v2;
+        return weno3z(a, b, c);
+    }
+    return left ? v2 : v3;
+}
+
+template <int TX, int TY, bool HAS_Y, bool FLAT_X, int MICRO>
 __global__ void __launch_bounds__(2 * TX * TY, 1) stage_kernel(const __grid_constant__ StageParams P) {
     using SM = StageShared<TX, TY, HAS_Y>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     SM& S = *reinterpret_cast<SM*>(smem_raw);
     constexpr int SW = SM::SW, SH = SM::SH, YO = SM::YO, NCELL = TX * TY, NT = 2 * NCELL;
+    constexpr int PL = SM::PLANE;                 // doubles per field slice
+    constexpr int SLOT = NPROG * PL;              // doubles per ring slot
 
     // Two threads per cell column ("roles", warp-uniform): the FP64 pipe needs ~4 warps per scheduler to stay busy and the
-    // plane ring leaves room for one CTA per SM, so the 15 flux kinds of a cell are split between two warps sets that share
+    // plane ring leaves room for one CTA per SM, so the 15 flux kinds of a cell are split between two warp sets that share
     // the ring:   role 0: ρu, ρv (all directions) + the x/y fluxes of θ;   role 1: ρw, the z flux of θ, ρq, buoyancy.
     const Layout& L = P.L;
     const int tid = threadIdx.x;
@@ -169,9 +185,8 @@ __global__ void __launch_bounds__(2 * TX * TY, 1) stage_kernel(const __grid_cons
     // column further left (SW has the slack) and shift their threads by one column inside the plane.
     const int xs = i0 & 1;
     const int sx = tx + 4 + xs, sy = ty + YO;         // this thread's cell inside a plane
-    const bool flat_x = L.flat_x;
-
-    auto ld = [&](int f, int kk, int x, int y) -> double { return S.ring[kk & (RING - 1)][f][y * SW + x]; };
+    double* const ring = &S.ring[0][0][0];
+    const int toff = sy * SW + sx;                    // this thread's element inside a field slice
 
     // -- plane staging --------------------------------------------------------------------------------------------
     auto scale_of = [&](int f, int kk) -> double {
@@ -189,8 +204,8 @@ __global__ void __launch_bounds__(2 * TX * TY, 1) stage_kernel(const __grid_cons
                 int gx = i0 - xs + x;                      // padded x index (i0 - xs - 4 + x + HX)
                 int gy = HAS_Y ? (j0 + y + L.HY - 3) : 0;  // padded y index
                 double v = 0.0;
-                if (inside && gx < L.PX && gy < L.PY && (flat_x ? (x == 4) : true)) {
-                    int px = flat_x ? 0 : gx;
+                if (inside && gx < L.PX && gy < L.PY && (FLAT_X ? (x == 4) : true)) {
+                    int px = FLAT_X ? 0 : gx;
                     v = src[(long long)gy * L.PX + px] * sc;
                 }
                 dst[e] = v;
@@ -243,6 +258,13 @@ __global__ void __launch_bounds__(2 * TX * TY, 1) stage_kernel(const __grid_cons
     const bool in_x = i < L.nx;
     const int f_first = role == 0 ? 0 : 2, f_count = role == 0 ? 2 : 3;   // fields this thread assembles and stores
 
+    // reference density at centres k-2..k+1 and z-faces k-1..k+2, rolled along the march (0 outside the column: those
+    // entries only ever multiply zero planes or are ignored by the reduced-order interpolation)
+    auto rho_c = [&](int kk) -> double { return (kk >= 0 && kk < Nz) ? P.col.rho[kk] : 0.0; };
+    auto rho_fc = [&](int kk) -> double { return (kk >= 0 && kk <= Nz) ? P.col.rho_f[kk] : 0.0; };
+    double r_m2 = rho_c(kstart - 3), r_m1 = rho_c(kstart - 2), r_0 = rho_c(kstart - 1), r_p1 = rho_c(kstart);
+    double f_m1 = rho_fc(kstart - 2), f_0 = rho_fc(kstart - 1), f_p1 = rho_fc(kstart), f_p2 = rho_fc(kstart + 1);
+
     for (int k = kstart; k < ke; ++k) {
         // ---- stage plane k+3 ------------------------------------------------------------------------------------
         if (P.use_tma) {
@@ -254,6 +276,9 @@ __global__ void __launch_bounds__(2 * TX * TY, 1) stage_kernel(const __grid_cons
             load_plane_direct(k + 3);
             __syncthreads();
         }
+        r_m2 = r_m1; r_m1 = r_0; r_0 = r_p1; r_p1 = rho_c(k + 1);
+        f_m1 = f_0; f_0 = f_p1; f_p1 = f_p2; f_p2 = rho_fc(k + 2);
+        const double rho_k = r_0, rho_ft = f_p1;                       // ρ at this centre, ℑz ρ at the top face k+1
 
         // own-point values for the RK update: issued now, consumed after the flux phase
         const long long n = lidx(L, i, j, k);
@@ -270,140 +295,112 @@ __global__ void __launch_bounds__(2 * TX * TY, 1) stage_kernel(const __grid_cons
             }
         }
 
-        const double rho_k = P.col.rho[k];
-        const int kf = k + 1;                                          // top face of this cell
-        const double rho_ft = P.col.rho_f[kf];                         // ℑz ρ at the top face (kf <= Nz)
-        const int Rf_top = red_face(kf, Nz, 3);                        // biased z reconstruction at the top face
-        const int Rf_k2 = red_face(k, Nz, 2);                          // symmetric z interpolation to the face k
-        const int Rc3 = red_center(k, Nz, 3), Rc2 = red_center(k, Nz, 2);
+        // this thread's element in the planes k-2 .. k+3 (index m+2)
+        const double* Lp[6];
+#pragma unroll
+        for (int m = 0; m < 6; ++m) Lp[m] = ring + ((k + m - 2) & (RING - 1)) * SLOT + toff;
+        const double* const Lk = Lp[2];
+        const double* const Lt = Lp[3];                                // level of the top face / of cell k+1
 
-        // ---- X-type fluxes: through x-face i (or at centre i-1 for ρu); kinds 0 ρu, 1 ρv, 2 ρw, 3 θ, 4 q ---------------
-        auto x_flux = [&](int kind) -> double {
-            const double u_i = ld(0, k, sx, sy);
-            switch (kind) {
-                case 0: {   // FUu at centre i-1
-                    double ut = rho_k * sym4(ld(0, k, sx - 2, sy), ld(0, k, sx - 1, sy), u_i, ld(0, k, sx + 1, sy), 2);
-                    double uh = biased6(ld(0, k, sx - 3, sy), ld(0, k, sx - 2, sy), ld(0, k, sx - 1, sy), u_i, ld(0, k, sx + 1, sy), ld(0, k, sx + 2, sy), 3, ut > 0.0);
-                    return ut * uh;
+        double zt0 = 0.0, zt1 = 0.0, zt2 = 0.0, b_here = 0.0;
+
+        // One level of flux work. FULL: every z stencil is at full order (2 <= k <= Nz-4): all orders are compile-time.
+        auto level = [&](auto full_tag) {
+            constexpr bool FULL = decltype(full_tag)::value;
+            const int kf = k + 1;
+            const int Rf_top = FULL ? 3 : red_face(kf, Nz, 3);
+            const int Rf_k2 = FULL ? 2 : red_face(k, Nz, 2);
+            const int Rc3 = FULL ? 3 : red_center(k, Nz, 3), Rc2 = FULL ? 2 : red_center(k, Nz, 2);
+            auto bz = [&](double v0, double v1, double v2, double v3, double v4, double v5, int R, bool left) -> double {
+                return FULL ? biased6c<3>(v0, v1, v2, v3, v4, v5, left) : biased6(v0, v1, v2, v3, v4, v5, R, left);
+            };
+            auto sz = [&](double v0, double v1, double v2, double v3, int R) -> double { return FULL ? sym4(v0, v1, v2, v3, 2) : sym4(v0, v1, v2, v3, R); };
+#define XS(f, dx) Lk[(f) * PL + (dx)]
+#define YS(f, dy) row[(f) * PL + (dy) * SW]
+#define ZS(f, m) Lp[(m) + 2][(f) * PL]
+            // X-type fluxes: through x-face i (or at centre i-1 for ρu); kinds 0 ρu, 1 ρv, 2 ρw, 3 θ, 4 q
+            auto x_flux = [&](auto kind_tag) -> double {
+                constexpr int kind = decltype(kind_tag)::value;
+                const double u_i = XS(0, 0);
+                if (kind == 0) {          // FUu at centre i-1
+                    double ut = rho_k * sym4(XS(0, -2), XS(0, -1), u_i, XS(0, 1), 2);
+                    return ut * biased6c<3>(XS(0, -3), XS(0, -2), XS(0, -1), u_i, XS(0, 1), XS(0, 2), ut > 0.0);
+                } else if (kind == 1) {   // FUv at (face i, face j)
+                    double ut = HAS_Y ? rho_k * sym4(Lk[-2 * SW], Lk[-SW], u_i, Lk[SW], 2) : rho_k * u_i;
+                    return ut * biased6c<3>(XS(1, -3), XS(1, -2), XS(1, -1), XS(1, 0), XS(1, 1), XS(1, 2), ut > 0.0);
+                } else if (kind == 2) {   // FUw at (face i, z-face k); the wall face k = 0 carries no w tendency
+                    if (!FULL && k < 1) return 0.0;
+                    double ut = sz(r_m2 * ZS(0, -2), r_m1 * ZS(0, -1), rho_k * u_i, r_p1 * ZS(0, 1), Rf_k2);
+                    return ut * biased6c<3>(XS(2, -3), XS(2, -2), XS(2, -1), XS(2, 0), XS(2, 1), XS(2, 2), ut > 0.0);
+                } else {                  // tracer mass flux ρ u ĉ
+                    return rho_k * u_i * biased6c<3>(XS(kind, -3), XS(kind, -2), XS(kind, -1), XS(kind, 0), XS(kind, 1), XS(kind, 2), u_i > 0.0);
                 }
-                case 1: {   // FUv at (face i, face j)
-                    double ut;
-                    if (HAS_Y) ut = rho_k * sym4(ld(0, k, sx, sy - 2), ld(0, k, sx, sy - 1), u_i, ld(0, k, sx, sy + 1), 2);
-                    else ut = rho_k * u_i;
-                    double vh = biased6(ld(1, k, sx - 3, sy), ld(1, k, sx - 2, sy), ld(1, k, sx - 1, sy), ld(1, k, sx, sy), ld(1, k, sx + 1, sy), ld(1, k, sx + 2, sy), 3, ut > 0.0);
-                    return ut * vh;
+            };
+            // Y-type fluxes: through y-face j (or at centre j-1 for ρv) of the cell whose plane element is `row`
+            auto y_flux = [&](auto kind_tag, const double* row, int zoff) -> double {
+                constexpr int kind = decltype(kind_tag)::value;
+                const double v_j = YS(1, 0);
+                if (kind == 0) {          // FVu at (face i, face j)
+                    double vt = FLAT_X ? rho_k * v_j : rho_k * sym4(row[PL - 2], row[PL - 1], v_j, row[PL + 1], 2);
+                    return vt * biased6c<3>(YS(0, -3), YS(0, -2), YS(0, -1), YS(0, 0), YS(0, 1), YS(0, 2), vt > 0.0);
+                } else if (kind == 1) {   // FVv at centre j-1
+                    double vt = rho_k * sym4(YS(1, -2), YS(1, -1), v_j, YS(1, 1), 2);
+                    return vt * biased6c<3>(YS(1, -3), YS(1, -2), YS(1, -1), v_j, YS(1, 1), YS(1, 2), vt > 0.0);
+                } else if (kind == 2) {   // FVw at (face j, z-face k)
+                    if (!FULL && k < 1) return 0.0;
+                    double vt = sz(r_m2 * Lp[0][PL + zoff], r_m1 * Lp[1][PL + zoff], rho_k * v_j, r_p1 * Lp[3][PL + zoff], Rf_k2);
+                    return vt * biased6c<3>(YS(2, -3), YS(2, -2), YS(2, -1), YS(2, 0), YS(2, 1), YS(2, 2), vt > 0.0);
+                } else {
+                    return rho_k * v_j * biased6c<3>(YS(kind, -3), YS(kind, -2), YS(kind, -1), YS(kind, 0), YS(kind, 1), YS(kind, 2), v_j > 0.0);
                 }
-                case 2: {   // FUw at (face i, z-face k); the wall face k = 0 carries no w tendency
-                    if (k < 1) return 0.0;
-                    double a0 = (k >= 2) ? P.col.rho[k - 2] * ld(0, k - 2, sx, sy) : 0.0;
-                    double a1 = P.col.rho[k - 1] * ld(0, k - 1, sx, sy);
-                    double a2 = rho_k * u_i;
-                    double a3 = (k + 1 < Nz) ? P.col.rho[k + 1] * ld(0, k + 1, sx, sy) : 0.0;
-                    double ut = sym4(a0, a1, a2, a3, Rf_k2);
-                    double wh = biased6(ld(2, k, sx - 3, sy), ld(2, k, sx - 2, sy), ld(2, k, sx - 1, sy), ld(2, k, sx, sy), ld(2, k, sx + 1, sy), ld(2, k, sx + 2, sy), 3, ut > 0.0);
-                    return ut * wh;
+            };
+            // Z-type fluxes through the top face k+1 (or at centre k for ρw)
+            auto z_flux = [&](auto kind_tag) -> double {
+                constexpr int kind = decltype(kind_tag)::value;
+                const double w_top = Lt[2 * PL];                           // 0 on the top wall (zero plane)
+                if (kind == 0) {          // FWu at (face i, z-face k+1)
+                    double wt = FLAT_X ? rho_ft * w_top : rho_ft * sym4(Lt[2 * PL - 2], Lt[2 * PL - 1], w_top, Lt[2 * PL + 1], 2);
+                    return wt * bz(ZS(0, -2), ZS(0, -1), ZS(0, 0), ZS(0, 1), ZS(0, 2), ZS(0, 3), Rf_top, wt > 0.0);
+                } else if (kind == 1) {   // FWv at (face j, z-face k+1)
+                    double wt = HAS_Y ? rho_ft * sym4(Lt[2 * PL - 2 * SW], Lt[2 * PL - SW], w_top, Lt[2 * PL + SW], 2) : rho_ft * w_top;
+                    return wt * bz(ZS(1, -2), ZS(1, -1), ZS(1, 0), ZS(1, 1), ZS(1, 2), ZS(1, 3), Rf_top, wt > 0.0);
+                } else if (kind == 2) {   // FWw at centre k: faces k-1 .. k+2 (advecting), k-2 .. k+3 (advected)
+                    double wt = sz(f_m1 * ZS(2, -1), f_0 * ZS(2, 0), rho_ft * w_top, f_p2 * ZS(2, 2), Rc2);
+                    return wt * bz(ZS(2, -2), ZS(2, -1), ZS(2, 0), w_top, ZS(2, 2), ZS(2, 3), Rc3, wt > 0.0);
+                } else {                  // tracer mass flux ℑz(ρ) w ĉ
+                    return rho_ft * w_top * bz(ZS(kind, -2), ZS(kind, -1), ZS(kind, 0), ZS(kind, 1), ZS(kind, 2), ZS(kind, 3), Rf_top, w_top > 0.0);
                 }
-                case 3: {   // tracer mass flux ρ u θ̂
-                    double th = biased6(ld(3, k, sx - 3, sy), ld(3, k, sx - 2, sy), ld(3, k, sx - 1, sy), ld(3, k, sx, sy), ld(3, k, sx + 1, sy), ld(3, k, sx + 2, sy), 3, u_i > 0.0);
-                    return rho_k * u_i * th;
+            };
+            using K0 = std::integral_constant<int, 0>; using K1 = std::integral_constant<int, 1>; using K2 = std::integral_constant<int, 2>;
+            using K3 = std::integral_constant<int, 3>; using K4 = std::integral_constant<int, 4>;
+            const double* const edge = Lk + (TY - ty) * SW;               // the row of y-faces just above the tile
+            const int ezoff = (TY - ty) * SW;
+            if (role == 0) {
+                if (!FLAT_X) { S.fx[0][ty][tx] = x_flux(K0{}); S.fx[1][ty][tx] = x_flux(K1{}); S.fx[3][ty][tx] = x_flux(K3{}); }
+                if (HAS_Y) {
+                    S.fy[0][ty][tx] = y_flux(K0{}, Lk, 0); S.fy[1][ty][tx] = y_flux(K1{}, Lk, 0); S.fy[3][ty][tx] = y_flux(K3{}, Lk, 0);
+                    // the extra row of y-faces above the tile: one flux kind per warp (rows 0..2 of this role)
+                    if (ty == 0) S.fy[0][TY][tx] = y_flux(K0{}, edge, ezoff);
+                    else if (ty == 1) S.fy[1][TY][tx] = y_flux(K1{}, edge, ezoff);
+                    else if (ty == 2) S.fy[3][TY][tx] = y_flux(K3{}, edge, ezoff);
                 }
-                default: {
-                    double qh = biased6(ld(4, k, sx - 3, sy), ld(4, k, sx - 2, sy), ld(4, k, sx - 1, sy), ld(4, k, sx, sy), ld(4, k, sx + 1, sy), ld(4, k, sx + 2, sy), 3, u_i > 0.0);
-                    return rho_k * u_i * qh;
+                zt0 = z_flux(K0{}); zt1 = z_flux(K1{});
+            } else {
+                if (!FLAT_X) { S.fx[2][ty][tx] = x_flux(K2{}); S.fx[4][ty][tx] = x_flux(K4{}); }
+                if (HAS_Y) {
+                    S.fy[2][ty][tx] = y_flux(K2{}, Lk, 0); S.fy[4][ty][tx] = y_flux(K4{}, Lk, 0);
+                    if (ty == 0) S.fy[2][TY][tx] = y_flux(K2{}, edge, ezoff);
+                    else if (ty == 1) S.fy[4][TY][tx] = y_flux(K4{}, edge, ezoff);
                 }
+                zt0 = z_flux(K2{}); zt1 = z_flux(K3{}); zt2 = z_flux(K4{});
+                b_here = buoyancy_center<MICRO>(P.th, P.col, k, Lk[3 * PL], Lk[4 * PL]);
             }
+#undef XS
+#undef YS
+#undef ZS
         };
-
-        // ---- Y-type fluxes: through y-face j (or at centre j-1 for ρv); row `yy` of the plane --------------------
-        auto y_flux = [&](int kind, int yy) -> double {
-            const double v_j = ld(1, k, sx, yy);
-            switch (kind) {
-                case 0: {   // FVu at (face i, face j)
-                    double vt = flat_x ? rho_k * v_j : rho_k * sym4(ld(1, k, sx - 2, yy), ld(1, k, sx - 1, yy), v_j, ld(1, k, sx + 1, yy), 2);
-                    double uh = biased6(ld(0, k, sx, yy - 3), ld(0, k, sx, yy - 2), ld(0, k, sx, yy - 1), ld(0, k, sx, yy), ld(0, k, sx, yy + 1), ld(0, k, sx, yy + 2), 3, vt > 0.0);
-                    return vt * uh;
-                }
-                case 1: {   // FVv at centre j-1
-                    double vt = rho_k * sym4(ld(1, k, sx, yy - 2), ld(1, k, sx, yy - 1), v_j, ld(1, k, sx, yy + 1), 2);
-                    double vh = biased6(ld(1, k, sx, yy - 3), ld(1, k, sx, yy - 2), ld(1, k, sx, yy - 1), v_j, ld(1, k, sx, yy + 1), ld(1, k, sx, yy + 2), 3, vt > 0.0);
-                    return vt * vh;
-                }
-                case 2: {   // FVw at (face j, z-face k)
-                    if (k < 1) return 0.0;
-                    double a0 = (k >= 2) ? P.col.rho[k - 2] * ld(1, k - 2, sx, yy) : 0.0;
-                    double a1 = P.col.rho[k - 1] * ld(1, k - 1, sx, yy);
-                    double a2 = rho_k * v_j;
-                    double a3 = (k + 1 < Nz) ? P.col.rho[k + 1] * ld(1, k + 1, sx, yy) : 0.0;
-                    double vt = sym4(a0, a1, a2, a3, Rf_k2);
-                    double wh = biased6(ld(2, k, sx, yy - 3), ld(2, k, sx, yy - 2), ld(2, k, sx, yy - 1), ld(2, k, sx, yy), ld(2, k, sx, yy + 1), ld(2, k, sx, yy + 2), 3, vt > 0.0);
-                    return vt * wh;
-                }
-                case 3: {
-                    double th = biased6(ld(3, k, sx, yy - 3), ld(3, k, sx, yy - 2), ld(3, k, sx, yy - 1), ld(3, k, sx, yy), ld(3, k, sx, yy + 1), ld(3, k, sx, yy + 2), 3, v_j > 0.0);
-                    return rho_k * v_j * th;
-                }
-                default: {
-                    double qh = biased6(ld(4, k, sx, yy - 3), ld(4, k, sx, yy - 2), ld(4, k, sx, yy - 1), ld(4, k, sx, yy), ld(4, k, sx, yy + 1), ld(4, k, sx, yy + 2), 3, v_j > 0.0);
-                    return rho_k * v_j * qh;
-                }
-            }
-        };
-
-        // ---- Z-type fluxes through the top face kf (or at centre k for ρw) ---------------------------------------
-        auto z_flux = [&](int kind) -> double {
-            const double w_top = ld(2, kf, sx, sy);                    // 0 on the top wall (zero plane)
-            switch (kind) {
-                case 0: {   // FWu at (face i, z-face kf)
-                    double wt = flat_x ? rho_ft * w_top : rho_ft * sym4(ld(2, kf, sx - 2, sy), ld(2, kf, sx - 1, sy), w_top, ld(2, kf, sx + 1, sy), 2);
-                    double uh = biased6(ld(0, kf - 3, sx, sy), ld(0, kf - 2, sx, sy), ld(0, kf - 1, sx, sy), ld(0, kf, sx, sy), ld(0, kf + 1, sx, sy), ld(0, kf + 2, sx, sy), Rf_top, wt > 0.0);
-                    return wt * uh;
-                }
-                case 1: {   // FWv at (face j, z-face kf)
-                    double wt = HAS_Y ? rho_ft * sym4(ld(2, kf, sx, sy - 2), ld(2, kf, sx, sy - 1), w_top, ld(2, kf, sx, sy + 1), 2) : rho_ft * w_top;
-                    double vh = biased6(ld(1, kf - 3, sx, sy), ld(1, kf - 2, sx, sy), ld(1, kf - 1, sx, sy), ld(1, kf, sx, sy), ld(1, kf + 1, sx, sy), ld(1, kf + 2, sx, sy), Rf_top, wt > 0.0);
-                    return wt * vh;
-                }
-                case 2: {   // FWw at centre k: faces k-1 .. k+2 (advecting), k-2 .. k+3 (advected)
-                    double a0 = (k >= 1) ? P.col.rho_f[k - 1] * ld(2, k - 1, sx, sy) : 0.0;
-                    double a1 = P.col.rho_f[k] * ld(2, k, sx, sy);
-                    double a2 = rho_ft * w_top;
-                    double a3 = (k + 2 <= Nz) ? P.col.rho_f[k + 2] * ld(2, k + 2, sx, sy) : 0.0;
-                    double wt = sym4(a0, a1, a2, a3, Rc2);
-                    double wh = biased6(ld(2, k - 2, sx, sy), ld(2, k - 1, sx, sy), ld(2, k, sx, sy), w_top, ld(2, k + 2, sx, sy), ld(2, k + 3, sx, sy), Rc3, wt > 0.0);
-                    return wt * wh;
-                }
-                case 3: {   // tracer mass flux ℑz(ρ) w θ̂
-                    double th = biased6(ld(3, kf - 3, sx, sy), ld(3, kf - 2, sx, sy), ld(3, kf - 1, sx, sy), ld(3, kf, sx, sy), ld(3, kf + 1, sx, sy), ld(3, kf + 2, sx, sy), Rf_top, w_top > 0.0);
-                    return rho_ft * w_top * th;
-                }
-                default: {
-                    double qh = biased6(ld(4, kf - 3, sx, sy), ld(4, kf - 2, sx, sy), ld(4, kf - 1, sx, sy), ld(4, kf, sx, sy), ld(4, kf + 1, sx, sy), ld(4, kf + 2, sx, sy), Rf_top, w_top > 0.0);
-                    return rho_ft * w_top * qh;
-                }
-            }
-        };
-
-        double zt0, zt1, zt2 = 0.0, b_here = 0.0;
-        if (role == 0) {
-            if (!flat_x) { S.fx[0][ty][tx] = x_flux(0); S.fx[1][ty][tx] = x_flux(1); S.fx[3][ty][tx] = x_flux(3); }
-            if (HAS_Y) {
-                S.fy[0][ty][tx] = y_flux(0, sy); S.fy[1][ty][tx] = y_flux(1, sy); S.fy[3][ty][tx] = y_flux(3, sy);
-                // the extra row of y-faces above the tile: one flux kind per warp (rows 0..2 of this role)
-                if (ty == 0) S.fy[0][TY][tx] = y_flux(0, TY + YO);
-                else if (ty == 1) S.fy[1][TY][tx] = y_flux(1, TY + YO);
-                else if (ty == 2) S.fy[3][TY][tx] = y_flux(3, TY + YO);
-            }
-            zt0 = z_flux(0); zt1 = z_flux(1);
-        } else {
-            if (!flat_x) { S.fx[2][ty][tx] = x_flux(2); S.fx[4][ty][tx] = x_flux(4); }
-            if (HAS_Y) {
-                S.fy[2][ty][tx] = y_flux(2, sy); S.fy[4][ty][tx] = y_flux(4, sy);
-                if (ty == 0) S.fy[2][TY][tx] = y_flux(2, TY + YO);
-                else if (ty == 1) S.fy[4][TY][tx] = y_flux(4, TY + YO);
-            }
-            zt0 = z_flux(2); zt1 = z_flux(3); zt2 = z_flux(4);
-            b_here = buoyancy_center<MICRO>(P.th, P.col, k, ld(3, k, sx, sy), ld(4, k, sx, sy));
-        }
+        if (k >= 2 && k <= Nz - 4) level(std::true_type{});
+        else level(std::false_type{});
 
         __syncthreads();                                               // fx / fy complete
 
@@ -416,7 +413,7 @@ __global__ void __launch_bounds__(2 * TX * TY, 1) stage_kernel(const __grid_cons
                 if (a >= f_count) break;
                 if (!(in_x || (f == 0 && i < P.nx_u))) continue;
                 double g = 0.0;
-                if (!flat_x) g += (S.fx[f][ty][tx + 1] - S.fx[f][ty][tx]) * rdx;
+                if (!FLAT_X) g += (S.fx[f][ty][tx + 1] - S.fx[f][ty][tx]) * rdx;
                 if (HAS_Y) g += (S.fy[f][ty + 1][tx] - S.fy[f][ty][tx]) * rdy;
                 g = -(g + (zt[a] - zb[a]) * rdz);
                 if (f == 2) g = (k >= 1) ? g + 0.5 * (b_here + b_below) : 0.0;

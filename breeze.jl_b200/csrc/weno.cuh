@@ -26,28 +26,31 @@ __device__ __forceinline__ double fast_rcp(double x) {
 }
 
 // Left-biased value at the face between c and d from the five cells a b c | d e (a = ψ[i-3] … e = ψ[i+1]).
+// Written with explicit fma() so that ptxas emits the minimal 52 FP64 instructions + one reciprocal:
+// β' = β / 0.75 = (13/3) s² + t² (ε scaled alike: the weights only see the ratios τ/(β+ε)); the optimal weights
+// (3, 6, 1)/10 and the 1/6 of the candidate polynomials are folded into the polynomial coefficients and the final sums.
 __device__ __forceinline__ double weno5z(double a, double b, double c, double d, double e) {
-    // second differences and the one-sided / centred first differences of the three candidate stencils
-    double s0 = (c - 2.0 * d) + e, t0 = (3.0 * c - 4.0 * d) + e;   // stencil (c, d, e)
-    double s1 = (b - 2.0 * c) + d, t1 = b - d;                     // stencil (b, c, d)
-    double s2 = (a - 2.0 * b) + c, t2 = (a - 4.0 * b) + 3.0 * c;   // stencil (a, b, c)
-    double b0 = 3.25 * s0 * s0 + 0.75 * t0 * t0;
-    double b1 = 3.25 * s1 * s1 + 0.75 * t1 * t1;
-    double b2 = 3.25 * s2 * s2 + 0.75 * t2 * t2;
+    const double K = 13.0 / 3.0, EPSP = WENO_EPS / 0.75;
+    double s0 = fma(-2.0, d, c) + e, t0 = fma(3.0, c, fma(-4.0, d, e));   // stencil (c, d, e)
+    double s1 = fma(-2.0, c, b) + d, t1 = b - d;                          // stencil (b, c, d)
+    double s2 = fma(-2.0, b, a) + c, t2 = fma(3.0, c, fma(-4.0, b, a));   // stencil (a, b, c)
+    double b0 = fma(s0 * K, s0, t0 * t0);
+    double b1 = fma(s1 * K, s1, t1 * t1);
+    double b2 = fma(s2 * K, s2, t2 * t2);
     double tau = fabs(b0 - b2);
     double tt = tau * tau;
-    b0 += WENO_EPS; b1 += WENO_EPS; b2 += WENO_EPS;
+    b0 += EPSP; b1 += EPSP; b2 += EPSP;
     double q0 = b0 * b0, q1 = b1 * b1, q2 = b2 * b2;
-    // un-normalised weights × Π b_s² (the common factor cancels in the ratio); C = (3, 6, 1)/10
-    double w0 = 3.0 * ((q0 + tt) * (q1 * q2));
-    double w1 = 6.0 * ((q1 + tt) * (q0 * q2));
+    // un-normalised weights × Π b_s² (the common factor cancels in the ratio)
+    double w0 = (q0 + tt) * (q1 * q2);
+    double w1 = (q1 + tt) * (q0 * q2);
     double w2 = (q2 + tt) * (q0 * q1);
-    // candidate polynomials × 6
-    double p0 = (2.0 * c + 5.0 * d) - e;
-    double p1 = (5.0 * c - b) + 2.0 * d;
-    double p2 = (2.0 * a - 7.0 * b) + 11.0 * c;
-    double num = w0 * p0 + w1 * p1 + w2 * p2;
-    double den = 6.0 * (w0 + w1 + w2);
+    // C_r × 10 × (candidate polynomial × 6)
+    double p0 = fma(6.0, c, fma(15.0, d, -3.0 * e));
+    double p1 = fma(-6.0, b, fma(30.0, c, 12.0 * d));
+    double p2 = fma(2.0, a, fma(-7.0, b, 11.0 * c));
+    double num = fma(w0, p0, fma(w1, p1, w2 * p2));
+    double den = fma(18.0, w0, fma(36.0, w1, 6.0 * w2));
     return num * fast_rcp(den);
 }
 
