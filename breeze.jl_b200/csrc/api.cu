@@ -226,7 +226,7 @@ static int setup_poisson(bz_ctx* c) {
         CUDA_TRY(c, cudaFuncSetAttribute(poisson_inverse_y, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     }
     if (!L.flat_x) {
-        int lines = 2048 / g.Nx; if (lines < 1) lines = 1;
+        int lines = 1024 / g.Nx; if (lines < 1) lines = 1;
         long long nl = (long long)G.Nz * G.nky_loc; if (nl < 1) nl = 1;
         if (lines > nl) lines = (int)nl;
         c->lines_x = lines;
@@ -505,8 +505,8 @@ int bz_create(const bz_config* cfg, bz_ctx** out) {
     }
     {
         int gx = fy ? (L.nx + 126) / 127 : (L.nx + 30) / 31, gy = fy ? 1 : (L.Ny + 7) / 8;
-        int want = (4 * 148 + gx * gy - 1) / (gx * gy);
-        int maxc = L.Nz / 32 > 1 ? L.Nz / 32 : 1;
+        int want = (20 * 148 + gx * gy - 1) / (gx * gy);   // ~20 waves of CTAs keep the tail of the last wave small
+        int maxc = L.Nz / 64 > 1 ? L.Nz / 64 : 1;
         c->z_chunks = cfg->z_chunks > 0 ? cfg->z_chunks : (want < 1 ? 1 : (want > maxc ? maxc : want));
         if (c->z_chunks > L.Nz) c->z_chunks = L.Nz;
     }

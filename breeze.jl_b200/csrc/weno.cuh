@@ -26,9 +26,10 @@ __device__ __forceinline__ double fast_rcp(double x) {
 }
 
 // Left-biased value at the face between c and d from the five cells a b c | d e (a = ψ[i-3] … e = ψ[i+1]).
-// Written with explicit fma() so that ptxas emits the minimal 52 FP64 instructions + one reciprocal:
-// β' = β / 0.75 = (13/3) s² + t² (ε scaled alike: the weights only see the ratios τ/(β+ε)); the optimal weights
-// (3, 6, 1)/10 and the 1/6 of the candidate polynomials are folded into the polynomial coefficients and the final sums.
+// Written with explicit fma() for the minimal FP64 instruction count (46 + one reciprocal):
+//   β' = β / 0.75 = (13/3) s² + t²  (ε scaled alike: the weights only see the ratios τ/(β+ε));
+//   Σ ω_r q_r = q₁ + ω₀ (q₀ - q₁) + ω₂ (q₂ - q₁)  with  q₀ - q₁ = (s₁ - s₀)/6,  q₂ - q₁ = (s₂ - s₁)/3
+// (s_r are the second differences already formed for β), so only the central candidate polynomial is evaluated.
 __device__ __forceinline__ double weno5z(double a, double b, double c, double d, double e) {
     const double K = 13.0 / 3.0, EPSP = WENO_EPS / 0.75;
     double s0 = fma(-2.0, d, c) + e, t0 = fma(3.0, c, fma(-4.0, d, e));   // stencil (c, d, e)
@@ -41,17 +42,14 @@ __device__ __forceinline__ double weno5z(double a, double b, double c, double d,
     double tt = tau * tau;
     b0 += EPSP; b1 += EPSP; b2 += EPSP;
     double q0 = b0 * b0, q1 = b1 * b1, q2 = b2 * b2;
-    // un-normalised weights × Π b_s² (the common factor cancels in the ratio)
+    // un-normalised weights × Π b_s² (the common factor cancels in the ratio); optimal weights (3, 6, 1)/10 applied below
     double w0 = (q0 + tt) * (q1 * q2);
     double w1 = (q1 + tt) * (q0 * q2);
     double w2 = (q2 + tt) * (q0 * q1);
-    // C_r × 10 × (candidate polynomial × 6)
-    double p0 = fma(6.0, c, fma(15.0, d, -3.0 * e));
-    double p1 = fma(-6.0, b, fma(30.0, c, 12.0 * d));
-    double p2 = fma(2.0, a, fma(-7.0, b, 11.0 * c));
-    double num = fma(w0, p0, fma(w1, p1, w2 * p2));
-    double den = fma(18.0, w0, fma(36.0, w1, 6.0 * w2));
-    return num * fast_rcp(den);
+    double qc = fma(-1.0 / 6.0, b, fma(5.0 / 6.0, c, (1.0 / 3.0) * d));   // central candidate (stencil b, c, d)
+    double num = fma(0.5 * w0, s1 - s0, ((1.0 / 3.0) * w2) * (s2 - s1));  // 3 w0 (q0 - qc) + w2 (q2 - qc)
+    double den = fma(3.0, w0, fma(6.0, w1, w2));
+    return fma(num, fast_rcp(den), qc);
 }
 
 // WENO3-Z: left-biased value at the face between b and c from a b | c.
