@@ -93,17 +93,18 @@ __device__ double saturation_adjust(const Thermo& th, double theta, double pr, d
 
 // buoyancy_forceᶜᶜᶜ: -g ρᵣ (Rᵐᵣ Tᵣ / (Rᵐ T) - 1), reference moisture = 0 (anelastic_buoyancy.jl:36-72)
 template <int MICRO>
-__device__ __forceinline__ double buoyancy_center(const Thermo& th, const Columns& col, int k, double theta, double q) {
+__device__ __forceinline__ double buoyancy_center(const Thermo& th, const Columns& col, int k, double rho_k, double exner_dry_k, double Tr_k,
+                                                  double theta, double q) {
     double T, Rm;
     if (MICRO == BZ_MICROPHYSICS_NONE) {
-        if (q == 0.0) { T = col.exner_dry[k] * theta; Rm = th.Rd; }
+        if (q == 0.0) { T = exner_dry_k * theta; Rm = th.Rd; }
         else { T = lipt_temperature(th, theta, col.log_p_pst[k], q, 0.0); Rm = (1.0 - q) * th.Rd + q * th.Rv; }
     } else {
         double qv, ql;
         T = saturation_adjust(th, theta, col.p[k], col.log_p_pst[k], q, qv, ql);
         Rm = (1.0 - (qv + ql)) * th.Rd + qv * th.Rv;
     }
-    double rho_p = col.rho[k] * (th.Rd * col.T[k] / (Rm * T) - 1.0);
+    double rho_p = rho_k * (th.Rd * Tr_k / (Rm * T) - 1.0);
     return -th.g * rho_p;
 }
 
@@ -218,12 +219,9 @@ __global__ void __launch_bounds__(2 * TX * TY, 1) stage_kernel(const __grid_cons
         for (int f = 0; f < NPROG; ++f)
             tma_load_3d(S.ring[kk & (RING - 1)][f], &P.tmap[f], bar, i0 - xs, HAS_Y ? (j0 + L.HY - 3) : 0, kk);
     };
-    auto convert_plane = [&](int kk) {           // raw prognostics → velocities / specific values, in place
-        for (int f = 0; f < NPROG; ++f) {
-            const double sc = scale_of(f, kk);
-            double* dst = S.ring[kk & (RING - 1)][f];
-            for (int e = tid; e < SW * SH; e += NT) dst[e] *= sc;
-        }
+    auto convert_plane = [&](int kk, double sc_c, double sc_f) {   // raw prognostics → velocities / specific values, in place
+        double* dst = S.ring[kk & (RING - 1)][0];                      // the five (padded) field slices of a slot are contiguous
+        for (int e = tid; e < NPROG * PL; e += NT) dst[e] *= (e >= 2 * PL && e < 3 * PL) ? sc_f : sc_c;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes before a later TMA refill of the slot
     };
 
@@ -245,7 +243,7 @@ __global__ void __launch_bounds__(2 * TX * TY, 1) stage_kernel(const __grid_cons
     // prologue: planes kstart-2 .. kstart+2 (the loop brings in kstart+3)
     if (P.use_tma) {
         if (tid == 0) for (int kk = kstart - 2; kk <= kstart + 3; ++kk) issue_plane_tma(kk);
-        for (int kk = kstart - 2; kk <= kstart + 2; ++kk) { wait_plane_tma(kk); convert_plane(kk); }
+        for (int kk = kstart - 2; kk <= kstart + 2; ++kk) { wait_plane_tma(kk); convert_plane(kk, scale_of(0, kk), scale_of(2, kk)); }
     } else {
         for (int kk = kstart - 2; kk <= kstart + 2; ++kk) load_plane_direct(kk);
     }
@@ -264,21 +262,29 @@ __global__ void __launch_bounds__(2 * TX * TY, 1) stage_kernel(const __grid_cons
     auto rho_fc = [&](int kk) -> double { return (kk >= 0 && kk <= Nz) ? P.col.rho_f[kk] : 0.0; };
     double r_m2 = rho_c(kstart - 3), r_m1 = rho_c(kstart - 2), r_0 = rho_c(kstart - 1), r_p1 = rho_c(kstart);
     double f_m1 = rho_fc(kstart - 2), f_0 = rho_fc(kstart - 1), f_p1 = rho_fc(kstart), f_p2 = rho_fc(kstart + 1);
+    // per-level column values are fetched one level ahead of their use so that their (L2) latency never stalls a level
+    double nx_rc = rho_c(kstart + 1), nx_rf = rho_fc(kstart + 2);                       // become r_p1 / f_p2 of level kstart
+    double nx_sc = scale_of(0, kstart + 3), nx_sf = scale_of(2, kstart + 3);            // conversion scales of plane kstart+3
+    double nx_ex = P.col.exner_dry[kstart], nx_Tr = P.col.T[kstart];                    // buoyancy inputs of level kstart
 
     for (int k = kstart; k < ke; ++k) {
         // ---- stage plane k+3 ------------------------------------------------------------------------------------
         if (P.use_tma) {
             wait_plane_tma(k + 3);
-            convert_plane(k + 3);
+            convert_plane(k + 3, nx_sc, nx_sf);
             __syncthreads();                                           // plane k+3 converted; slot of k-4 (== k+4) is free
-            if (tid == 0 && k + 1 < ke) issue_plane_tma(k + 4);        // prefetch for the next level
+            if (tid == NT - 32 && k + 1 < ke) issue_plane_tma(k + 4);  // prefetch for the next level (the least loaded warp issues)
         } else {
             load_plane_direct(k + 3);
             __syncthreads();
         }
-        r_m2 = r_m1; r_m1 = r_0; r_0 = r_p1; r_p1 = rho_c(k + 1);
-        f_m1 = f_0; f_0 = f_p1; f_p1 = f_p2; f_p2 = rho_fc(k + 2);
+        r_m2 = r_m1; r_m1 = r_0; r_0 = r_p1; r_p1 = nx_rc;
+        f_m1 = f_0; f_0 = f_p1; f_p1 = f_p2; f_p2 = nx_rf;
         const double rho_k = r_0, rho_ft = f_p1;                       // ρ at this centre, ℑz ρ at the top face k+1
+        const double ex_k = nx_ex, Tr_k = nx_Tr;
+        nx_rc = rho_c(k + 2); nx_rf = rho_fc(k + 3);
+        nx_sc = scale_of(0, k + 4); nx_sf = scale_of(2, k + 4);
+        { int kn = min(k + 1, Nz - 1); nx_ex = P.col.exner_dry[kn]; nx_Tr = P.col.T[kn]; }
 
         // own-point values for the RK update: issued now, consumed after the flux phase
         const long long n = lidx(L, i, j, k);
@@ -393,7 +399,7 @@ __global__ void __launch_bounds__(2 * TX * TY, 1) stage_kernel(const __grid_cons
                     else if (ty == 1) S.fy[4][TY][tx] = y_flux(K4{}, edge, ezoff);
                 }
                 zt0 = z_flux(K2{}); zt1 = z_flux(K3{}); zt2 = z_flux(K4{});
-                b_here = buoyancy_center<MICRO>(P.th, P.col, k, Lk[3 * PL], Lk[4 * PL]);
+                b_here = buoyancy_center<MICRO>(P.th, P.col, k, rho_k, ex_k, Tr_k, Lk[3 * PL], Lk[4 * PL]);
             }
 #undef XS
 #undef YS
