@@ -142,8 +142,8 @@ struct StageShared {
     static constexpr int PLANE = (SW * SH + 15) & ~15;   // every field slice stays 128-byte aligned (TMA destination)
     static_assert(!HAS_Y || (TY >= NPROG && TX == 32), "the extra y-face row is spread one flux kind per warp");
     double ring[RING][NPROG][PLANE];
-    double fx[NPROG][TY][TX];
-    double fy[NPROG][HAS_Y ? TY + 1 : 1][TX];
+    double fx[2][NPROG][TY][TX];                      // double-buffered by level parity: one CTA barrier per level
+    double fy[2][NPROG][HAS_Y ? TY + 1 : 1][TX];
     uint64_t bar[RING];
 };
 
@@ -247,6 +247,7 @@ __global__ void __launch_bounds__(2 * TX * TY, 1) stage_kernel(const __grid_cons
     } else {
         for (int kk = kstart - 2; kk <= kstart + 2; ++kk) load_plane_direct(kk);
     }
+    __syncthreads();                             // prologue planes are converted and visible
 
     // carried from the level below: z-type fluxes through the bottom face (role 0: ρu, ρv; role 1: ρw, θ, q), buoyancy below
     double zb0 = 0.0, zb1 = 0.0, zb2 = 0.0, b_below = 0.0;
@@ -268,20 +269,10 @@ __global__ void __launch_bounds__(2 * TX * TY, 1) stage_kernel(const __grid_cons
     double nx_ex = P.col.exner_dry[kstart], nx_Tr = P.col.T[kstart];                    // buoyancy inputs of level kstart
 
     for (int k = kstart; k < ke; ++k) {
-        // ---- stage plane k+3 ------------------------------------------------------------------------------------
-        if (P.use_tma) {
-            wait_plane_tma(k + 3);
-            convert_plane(k + 3, nx_sc, nx_sf);
-            __syncthreads();                                           // plane k+3 converted; slot of k-4 (== k+4) is free
-            if (tid == NT - 32 && k + 1 < ke) issue_plane_tma(k + 4);  // prefetch for the next level (the least loaded warp issues)
-        } else {
-            load_plane_direct(k + 3);
-            __syncthreads();
-        }
         r_m2 = r_m1; r_m1 = r_0; r_0 = r_p1; r_p1 = nx_rc;
         f_m1 = f_0; f_0 = f_p1; f_p1 = f_p2; f_p2 = nx_rf;
         const double rho_k = r_0, rho_ft = f_p1;                       // ρ at this centre, ℑz ρ at the top face k+1
-        const double ex_k = nx_ex, Tr_k = nx_Tr;
+        const double ex_k = nx_ex, Tr_k = nx_Tr, sc_now = nx_sc, sf_now = nx_sf;
         nx_rc = rho_c(k + 2); nx_rf = rho_fc(k + 3);
         nx_sc = scale_of(0, k + 4); nx_sf = scale_of(2, k + 4);
         { int kn = min(k + 1, Nz - 1); nx_ex = P.col.exner_dry[kn]; nx_Tr = P.col.T[kn]; }
@@ -311,8 +302,9 @@ __global__ void __launch_bounds__(2 * TX * TY, 1) stage_kernel(const __grid_cons
         double zt0 = 0.0, zt1 = 0.0, zt2 = 0.0, b_here = 0.0;
 
         // One level of flux work. FULL: every z stencil is at full order (2 <= k <= Nz-4): all orders are compile-time.
-        auto level = [&](auto full_tag) {
+        auto level = [&](auto full_tag, auto phase_tag) {
             constexpr bool FULL = decltype(full_tag)::value;
+            constexpr int PHASE = decltype(phase_tag)::value;          // 0: x/y fluxes → shared memory; 1: z fluxes, buoyancy
             const int kf = k + 1;
             const int Rf_top = FULL ? 3 : red_face(kf, Nz, 3);
             const int Rf_k2 = FULL ? 2 : red_face(k, Nz, 2);
@@ -381,34 +373,47 @@ __global__ void __launch_bounds__(2 * TX * TY, 1) stage_kernel(const __grid_cons
             using K3 = std::integral_constant<int, 3>; using K4 = std::integral_constant<int, 4>;
             const double* const edge = Lk + (TY - ty) * SW;               // the row of y-faces just above the tile
             const int ezoff = (TY - ty) * SW;
-            if (role == 0) {
-                if (!FLAT_X) { S.fx[0][ty][tx] = x_flux(K0{}); S.fx[1][ty][tx] = x_flux(K1{}); S.fx[3][ty][tx] = x_flux(K3{}); }
-                if (HAS_Y) {
-                    S.fy[0][ty][tx] = y_flux(K0{}, Lk, 0); S.fy[1][ty][tx] = y_flux(K1{}, Lk, 0); S.fy[3][ty][tx] = y_flux(K3{}, Lk, 0);
-                    // the extra row of y-faces above the tile: one flux kind per warp (rows 0..2 of this role)
-                    if (ty == 0) S.fy[0][TY][tx] = y_flux(K0{}, edge, ezoff);
-                    else if (ty == 1) S.fy[1][TY][tx] = y_flux(K1{}, edge, ezoff);
-                    else if (ty == 2) S.fy[3][TY][tx] = y_flux(K3{}, edge, ezoff);
+            auto& FX = S.fx[k & 1];
+            auto& FY = S.fy[k & 1];
+            if (PHASE == 0) {
+                if (role == 0) {
+                    if (!FLAT_X) { FX[0][ty][tx] = x_flux(K0{}); FX[1][ty][tx] = x_flux(K1{}); FX[3][ty][tx] = x_flux(K3{}); }
+                    if (HAS_Y) {
+                        FY[0][ty][tx] = y_flux(K0{}, Lk, 0); FY[1][ty][tx] = y_flux(K1{}, Lk, 0); FY[3][ty][tx] = y_flux(K3{}, Lk, 0);
+                        // the extra row of y-faces above the tile: one flux kind per warp (rows 0..2 of this role)
+                        if (ty == 0) FY[0][TY][tx] = y_flux(K0{}, edge, ezoff);
+                        else if (ty == 1) FY[1][TY][tx] = y_flux(K1{}, edge, ezoff);
+                        else if (ty == 2) FY[3][TY][tx] = y_flux(K3{}, edge, ezoff);
+                    }
+                } else {
+                    if (!FLAT_X) { FX[2][ty][tx] = x_flux(K2{}); FX[4][ty][tx] = x_flux(K4{}); }
+                    if (HAS_Y) {
+                        FY[2][ty][tx] = y_flux(K2{}, Lk, 0); FY[4][ty][tx] = y_flux(K4{}, Lk, 0);
+                        if (ty == 0) FY[2][TY][tx] = y_flux(K2{}, edge, ezoff);
+                        else if (ty == 1) FY[4][TY][tx] = y_flux(K4{}, edge, ezoff);
+                    }
                 }
-                zt0 = z_flux(K0{}); zt1 = z_flux(K1{});
             } else {
-                if (!FLAT_X) { S.fx[2][ty][tx] = x_flux(K2{}); S.fx[4][ty][tx] = x_flux(K4{}); }
-                if (HAS_Y) {
-                    S.fy[2][ty][tx] = y_flux(K2{}, Lk, 0); S.fy[4][ty][tx] = y_flux(K4{}, Lk, 0);
-                    if (ty == 0) S.fy[2][TY][tx] = y_flux(K2{}, edge, ezoff);
-                    else if (ty == 1) S.fy[4][TY][tx] = y_flux(K4{}, edge, ezoff);
+                if (role == 0) { zt0 = z_flux(K0{}); zt1 = z_flux(K1{}); }
+                else {
+                    zt0 = z_flux(K2{}); zt1 = z_flux(K3{}); zt2 = z_flux(K4{});
+                    b_here = buoyancy_center<MICRO>(P.th, P.col, k, rho_k, ex_k, Tr_k, Lk[3 * PL], Lk[4 * PL]);
                 }
-                zt0 = z_flux(K2{}); zt1 = z_flux(K3{}); zt2 = z_flux(K4{});
-                b_here = buoyancy_center<MICRO>(P.th, P.col, k, rho_k, ex_k, Tr_k, Lk[3 * PL], Lk[4 * PL]);
             }
 #undef XS
 #undef YS
 #undef ZS
         };
-        if (k >= 2 && k <= Nz - 4) level(std::true_type{});
-        else level(std::false_type{});
-
-        __syncthreads();                                               // fx / fy complete
+        const bool full = (k >= 2 && k <= Nz - 4);
+        using PH0 = std::integral_constant<int, 0>; using PH1 = std::integral_constant<int, 1>;
+        // x/y fluxes of level k need the planes k-2 .. k+1 only …
+        if (full) level(std::true_type{}, PH0{}); else level(std::false_type{}, PH0{});
+        // … so plane k+3 (needed by the z stencils) is staged behind them: its TMA had a whole level to land
+        if (P.use_tma) { wait_plane_tma(k + 3); convert_plane(k + 3, sc_now, sf_now); }
+        else load_plane_direct(k + 3);
+        __syncthreads();                                               // the level's only CTA barrier: plane k+3 and fx / fy are complete
+        if (P.use_tma && tid == NT - 32 && k + 1 < ke) issue_plane_tma(k + 4);   // slot of plane k-4; the least loaded warp issues
+        if (full) level(std::true_type{}, PH1{}); else level(std::false_type{}, PH1{});
 
         // ---- tendencies, RK update, store -----------------------------------------------------------------------
         if (do_store) {
@@ -419,8 +424,8 @@ __global__ void __launch_bounds__(2 * TX * TY, 1) stage_kernel(const __grid_cons
                 if (a >= f_count) break;
                 if (!(in_x || (f == 0 && i < P.nx_u))) continue;
                 double g = 0.0;
-                if (!FLAT_X) g += (S.fx[f][ty][tx + 1] - S.fx[f][ty][tx]) * rdx;
-                if (HAS_Y) g += (S.fy[f][ty + 1][tx] - S.fy[f][ty][tx]) * rdy;
+                if (!FLAT_X) g += (S.fx[k & 1][f][ty][tx + 1] - S.fx[k & 1][f][ty][tx]) * rdx;
+                if (HAS_Y) g += (S.fy[k & 1][f][ty + 1][tx] - S.fy[k & 1][f][ty][tx]) * rdy;
                 g = -(g + (zt[a] - zb[a]) * rdz);
                 if (f == 2) g = (k >= 1) ? g + 0.5 * (b_here + b_below) : 0.0;
                 double r;
@@ -434,6 +439,7 @@ __global__ void __launch_bounds__(2 * TX * TY, 1) stage_kernel(const __grid_cons
             }
         }
         zb0 = zt0; zb1 = zt1; zb2 = zt2; b_below = b_here;
-        // the next level's staging barrier also protects fx / fy
+        // fx / fy are double-buffered by level parity: the next level writes the other buffer, and the barrier after that
+        // orders it against this level's readers
     }
 }
