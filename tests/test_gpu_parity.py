@@ -140,3 +140,44 @@ def test_projection_is_divergence_free_rho_one(oracle_arch):
     model = bz.AtmosphereModel(grid, dynamics=bz.AnelasticDynamics(bz.ReferenceState(grid, density=np.ones(N))))
     model.set(ρu=rng.random((N, N, N)), ρv=rng.random((N, N, N)), ρw=rng.random((N + 1, N, N)))
     assert model.context.max_abs_divergence() < N ** 3 * 2.220446049250313e-16
+
+
+def _moist_pair(oracle_arch, size):
+    import breeze_b200 as bz
+    rng = np.random.default_rng(11)
+    models = [make_bubble_model(a, size, microphysics=bz.SaturationAdjustment()) for a in (bz.B200(), oracle_arch)]
+    g = models[0].grid
+    shp = (g.Nz, g.Ny, g.Nx)
+    z = g.znodes()[:, None, None]
+    qt = 0.016 * np.exp(-z / 2500.0) * (1 + 0.5 * rng.random(shp))      # super-saturated in places → cloud
+    u, w = rng.standard_normal(shp), 0.5 * rng.standard_normal((g.Nz + 1, g.Ny, g.Nx))
+    for m in models:
+        m.set(θ=bubble_theta(theta0=300.0, dtheta=3.0), qᵗ=qt, u=u, w=w)
+    return models
+
+
+def test_saturation_adjustment_diagnostics_and_tendencies(oracle_arch):
+    """BASELINE config 3's thermodynamics: warm-phase SaturationAdjustment inside the stage kernel (buoyancy) and diagnostics."""
+    import oracle_lib
+    gpu, cpu = _moist_pair(oracle_arch, (32, 16, 24))
+    ql = cpu.field("qˡ")
+    assert (ql > 0).mean() > 0.02, "the test state must contain cloud"
+    for name in ("T", "qᵛ", "qˡ", "θ"):
+        assert rel_err(gpu.field(name), cpu.field(name)) < 1e-11, name
+    gpu.context.compute_tendencies()
+    oracle_lib.set_beta_form(1)
+    try:
+        cpu.context.compute_tendencies()
+    finally:
+        oracle_lib.set_beta_form(0)
+    for name in PROGNOSTIC:
+        assert rel_err(gpu.context.get_tendency(name), cpu.context.get_tendency(name)) < TOL_SAME_FORM, name
+
+
+def test_saturation_adjustment_steps(oracle_arch):
+    gpu, cpu = _moist_pair(oracle_arch, (32, 16, 24))
+    for _ in range(5):
+        gpu.time_step(1.0)
+        cpu.time_step(1.0)
+    for name in PROGNOSTIC + ["T", "qˡ"]:
+        assert rel_err(gpu.field(name), cpu.field(name)) < TOL_STEPS, name

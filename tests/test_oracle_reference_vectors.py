@@ -244,3 +244,39 @@ def test_readme_quickstart_2d_runs(oracle_arch):
     w = model.field("w")
     assert np.isfinite(w).all() and w.max() > 0.05                # the bubble starts rising
     assert model.context.max_abs_divergence() < 1e-12
+
+
+def test_warm_phase_saturation_adjustment_constructive(oracle_arch):
+    """test/saturation_adjustment.jl:31-97 with the θ formulation: build a saturated state at a known T₂, recover T, qᵛ, qˡ."""
+    grid = bz.RectilinearGrid(oracle_arch, size=4, z=(0, 4.0), topology=(bz.Flat, bz.Flat, bz.Bounded))
+    ref = bz.ReferenceState(grid, surface_pressure=101325, potential_temperature=288)
+    model = bz.AtmosphereModel(grid, dynamics=bz.AnelasticDynamics(ref), microphysics=bz.SaturationAdjustment())
+    rho, p, _ = model.reference_profiles()
+    c = bz.ThermodynamicConstants()
+    Rd, Rv = c.molar_gas_constant / c.dry_air_molar_mass, c.molar_gas_constant / c.vapor_molar_mass
+    dcl = c.vapor_heat_capacity - c.liquid_heat_capacity
+    L0 = c.liquid_reference_latent_heat - dcl * c.energy_reference_temperature
+
+    def pvs(T):
+        return c.triple_point_pressure * (T / c.triple_point_temperature) ** (dcl / Rv) * np.exp((1 / c.triple_point_temperature - 1 / T) * L0 / Rv)
+
+    checked = 0
+    for T2 in (280.0, 300.0, 320.0):
+        for qt in (1e-2, 3e-2, 5e-2):
+            qvs = Rd / Rv * (1 - qt) * pvs(T2) / (p[0] - pvs(T2))        # adjustment_saturation_specific_humidity
+            if qt <= qvs:
+                continue
+            ql = qt - qvs
+            Rm = (1 - qt) * Rd + qvs * Rv
+            cpm = (1 - qt) * c.dry_air_heat_capacity + qvs * c.vapor_heat_capacity + ql * c.liquid_heat_capacity
+            Pi = (p[0] / 1e5) ** (Rm / cpm)
+            theta = (T2 - c.liquid_reference_latent_heat * ql / cpm) / Pi   # with_temperature (dynamic_states.jl:129-141)
+            model.set(θ=theta, qᵗ=qt)
+            assert model.field("T")[0, 0, 0] == pytest.approx(T2, abs=1e-2)
+            assert model.field("qᵛ")[0, 0, 0] == pytest.approx(qvs, abs=1e-2 * 1e-2)
+            assert model.field("qˡ")[0, 0, 0] == pytest.approx(ql, abs=1e-2 * 1e-2)
+            checked += 1
+    assert checked >= 5
+    # unsaturated air is left alone
+    model.set(θ=300.0, qᵗ=1e-3)
+    assert np.all(model.field("qˡ") == 0.0) and np.allclose(model.field("qᵛ"), 1e-3)
