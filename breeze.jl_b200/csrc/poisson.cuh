@@ -134,11 +134,23 @@ __global__ void __launch_bounds__(256, 3) poisson_forward_y(Layout L, PoissonGeo
     const int k = blockIdx.y;
     const int XB = 2 * lines;
     const int ib = blockIdx.x * XB;
-    for (int e = threadIdx.x; e < N * XB; e += blockDim.x) {
-        int c = e % XB, y = e / XB;
-        int i = ib + c;
-        double v = (i < L.nx) ? source_term(L, ru, rv, rw, i, y, k, dz_over_dt) : 0.0;
-        ((c & 1) ? im : re)[(size_t)(c >> 1) * LP + pidx(y)] = v;
+    // blockDim.x == lines * N / 8 and XB == 2 * lines: every thread evaluates 16 source-term values, 8 at a time so that
+    // their loads are in flight together
+    for (int half = 0; half < 2; ++half) {
+        double v[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            int e = threadIdx.x + (half * 8 + it) * blockDim.x;
+            int c = e % XB, y = e / XB;
+            int i = ib + c;
+            v[it] = (i < L.nx) ? source_term(L, ru, rv, rw, i, y, k, dz_over_dt) : 0.0;
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            int e = threadIdx.x + (half * 8 + it) * blockDim.x;
+            int c = e % XB, y = e / XB;
+            ((c & 1) ? im : re)[(size_t)(c >> 1) * LP + pidx(y)] = v[it];
+        }
     }
     __syncthreads();
     fft_lines_smem(re, im, LP, N, tw_y);
@@ -173,18 +185,34 @@ __global__ void __launch_bounds__(256, 3) poisson_inverse_y(Layout L, PoissonGeo
     const int XB = 2 * lines;
     const int ib = blockIdx.x * XB;
     // rebuild the packed spectrum Z = A + iB (Hermitian halves), conjugated for the inverse-by-forward trick
-    for (int e = threadIdx.x; e < G.nky * lines; e += blockDim.x) {
-        int l = e % lines, ky = e / lines;
-        int i = ib + 2 * l;
-        double2 A = make_double2(0.0, 0.0), B = make_double2(0.0, 0.0);
-        if (i < L.nx) A = W[((size_t)k * G.nky + ky) * L.nx + i];
-        if (i + 1 < L.nx) B = W[((size_t)k * G.nky + ky) * L.nx + i + 1];
-        // Z[ky] = A + iB, Z[N-ky] = conj(A) + i conj(B); store conj(Z)
-        re[(size_t)l * LP + pidx(ky)] = A.x - B.y;
-        im[(size_t)l * LP + pidx(ky)] = -(A.y + B.x);
-        if (ky > 0 && ky < N / 2) {
-            re[(size_t)l * LP + pidx(N - ky)] = A.x + B.y;
-            im[(size_t)l * LP + pidx(N - ky)] = -(B.x - A.y);
+    // (N/2 + 1) * lines <= 5 * blockDim.x elements; loads are batched ahead of their use
+    {
+        const int total = G.nky * lines;
+        double2 A[5], B[5];
+#pragma unroll
+        for (int it = 0; it < 5; ++it) {
+            int e = threadIdx.x + it * blockDim.x;
+            A[it] = make_double2(0.0, 0.0); B[it] = make_double2(0.0, 0.0);
+            if (e < total) {
+                int l = e % lines, ky = e / lines;
+                int i = ib + 2 * l;
+                if (i < L.nx) A[it] = W[((size_t)k * G.nky + ky) * L.nx + i];
+                if (i + 1 < L.nx) B[it] = W[((size_t)k * G.nky + ky) * L.nx + i + 1];
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < 5; ++it) {
+            int e = threadIdx.x + it * blockDim.x;
+            if (e < total) {
+                int l = e % lines, ky = e / lines;
+                // Z[ky] = A + iB, Z[N-ky] = conj(A) + i conj(B); store conj(Z)
+                re[(size_t)l * LP + pidx(ky)] = A[it].x - B[it].y;
+                im[(size_t)l * LP + pidx(ky)] = -(A[it].y + B[it].x);
+                if (ky > 0 && ky < N / 2) {
+                    re[(size_t)l * LP + pidx(N - ky)] = A[it].x + B[it].y;
+                    im[(size_t)l * LP + pidx(N - ky)] = -(B[it].x - A[it].y);
+                }
+            }
         }
     }
     __syncthreads();
@@ -213,12 +241,22 @@ __global__ void __launch_bounds__(256, 3) fft_x_kernel(double2* __restrict__ W, 
     double* im = sm + (size_t)lines * LP;
     const long long l0 = (long long)blockIdx.x * lines;
     const double sgn = inverse ? -1.0 : 1.0;
-    for (int e = threadIdx.x; e < N * lines; e += blockDim.x) {
-        int x = e % N, l = e / N;
-        double2 v = make_double2(0.0, 0.0);
-        if (l0 + l < n_lines) v = W[(l0 + l) * N + x];
-        re[(size_t)l * LP + pidx(x)] = v.x;
-        im[(size_t)l * LP + pidx(x)] = sgn * v.y;
+    // blockDim.x == lines * N / 8: every thread moves exactly 8 elements; all 8 loads are issued before the first use
+    {
+        double2 v[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            int e = threadIdx.x + it * blockDim.x;
+            int l = e / N;
+            v[it] = (l0 + l < n_lines) ? W[l0 * N + e] : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            int e = threadIdx.x + it * blockDim.x;
+            int x = e % N, l = e / N;
+            re[(size_t)l * LP + pidx(x)] = v[it].x;
+            im[(size_t)l * LP + pidx(x)] = sgn * v[it].y;
+        }
     }
     __syncthreads();
     fft_lines_smem(re, im, LP, N, tw_x);
