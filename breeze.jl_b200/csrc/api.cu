@@ -221,7 +221,7 @@ static int setup_poisson(bz_ctx* c) {
         int lines = 2048 / g.Ny; if (lines < 1) lines = 1;
         int half = (L.nx + 1) / 2; if (lines > half) lines = half;
         c->lines_y = lines;
-        size_t sm = (size_t)2 * lines * line_pitch(g.Ny) * sizeof(double);
+        size_t sm = fft_smem_bytes(g.Ny, lines);
         CUDA_TRY(c, cudaFuncSetAttribute(poisson_forward_y, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
         CUDA_TRY(c, cudaFuncSetAttribute(poisson_inverse_y, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     }
@@ -230,7 +230,7 @@ static int setup_poisson(bz_ctx* c) {
         long long nl = (long long)G.Nz * G.nky_loc; if (nl < 1) nl = 1;
         if (lines > nl) lines = (int)nl;
         c->lines_x = lines;
-        size_t sm = (size_t)2 * lines * line_pitch(g.Nx) * sizeof(double);
+        size_t sm = fft_smem_bytes(g.Nx, lines);
         CUDA_TRY(c, cudaFuncSetAttribute(fft_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     }
     return setup_thomas(c);
@@ -247,7 +247,7 @@ static int poisson_solve(bz_ctx* c, double dt) {
         if (!L.flat_y) {
             int lines = c->lines_y;
             dim3 grid((L.nx + 2 * lines - 1) / (2 * lines), L.Nz);
-            size_t sm = (size_t)2 * lines * line_pitch(G.Ny) * sizeof(double);
+            size_t sm = fft_smem_bytes(G.Ny, lines);
             poisson_forward_y<<<grid, lines * G.Ny / 8, sm, c->stream>>>(L, G, U[0], U[1], U[2], dz_over_dt, c->W, c->tw_y, lines);
         } else {
             dim3 grid((L.nx + 127) / 128, L.Nz);
@@ -264,7 +264,7 @@ static int poisson_solve(bz_ctx* c, double dt) {
     if (!L.flat_x && n_lines > 0) {
         ProfScope ps(c, 1);
         int lines = c->lines_x;
-        size_t sm = (size_t)2 * lines * line_pitch(G.Nx) * sizeof(double);
+        size_t sm = fft_smem_bytes(G.Nx, lines);
         fft_x_kernel<<<(unsigned)((n_lines + lines - 1) / lines), lines * G.Nx / 8, sm, c->stream>>>(c->W2, G.Nx, n_lines, c->tw_x, lines, 0);
         c->launches++;
     }
@@ -278,7 +278,7 @@ static int poisson_solve(bz_ctx* c, double dt) {
     if (!L.flat_x && n_lines > 0) {
         ProfScope ps(c, 3);
         int lines = c->lines_x;
-        size_t sm = (size_t)2 * lines * line_pitch(G.Nx) * sizeof(double);
+        size_t sm = fft_smem_bytes(G.Nx, lines);
         fft_x_kernel<<<(unsigned)((n_lines + lines - 1) / lines), lines * G.Nx / 8, sm, c->stream>>>(c->W2, G.Nx, n_lines, c->tw_x, lines, 1);
         c->launches++;
     }
@@ -293,7 +293,7 @@ static int poisson_solve(bz_ctx* c, double dt) {
         if (!L.flat_y) {
             int lines = c->lines_y;
             dim3 grid((L.nx + 2 * lines - 1) / (2 * lines), L.Nz);
-            size_t sm = (size_t)2 * lines * line_pitch(G.Ny) * sizeof(double);
+            size_t sm = fft_smem_bytes(G.Ny, lines);
             poisson_inverse_y<<<grid, lines * G.Ny / 8, sm, c->stream>>>(L, G, c->W, c->phi, c->tw_y, lines, scale);
         } else {
             dim3 grid((L.nx + 127) / 128, L.Nz);

@@ -53,10 +53,15 @@ __device__ __forceinline__ void dft8(cpx* v) {
     v[1] = a4; v[3] = a5; v[5] = a6; v[7] = a7;
 }
 
-// Shared-memory index of element n of a line: one pad double every 8 keeps the stride-8 / stride-64 scatter of the
-// radix-8 passes (and the line-to-line stride) free of bank conflicts.
-__device__ __forceinline__ int pidx(int n) { return n + (n >> 3); }
-__host__ __device__ __forceinline__ int line_pitch(int N) { return N + (N >> 3) + 1; }
+// Shared-memory layout of the FFT lines (doubles; 16 bank pairs of 8 bytes):
+//   element n of a line sits at pidx(n) = n + n/16  → unit-stride and stride-8 accesses of a half-warp are conflict-free
+//   (the 8-contiguous/stride-64 scatter of the second radix-8 pass is 2-way);
+//   line pitch LP ≡ 4 (mod 16) and the imaginary array starts ≡ 2 (mod 16) after the real one → the transposing accesses of
+//   the y kernels (lanes spanning 4 lines × 2..4 consecutive elements × re/im) are conflict-free as well.
+__host__ __device__ __forceinline__ int pidx(int n) { return n + (n >> 4); }
+__host__ __device__ __forceinline__ int line_pitch(int N) { return ((N + (N >> 4) + 15) & ~15) + 4; }
+__host__ __device__ __forceinline__ int imag_offset(int N, int lines) { int o = lines * line_pitch(N); return o + ((2 - o) & 15); }
+__host__ __device__ __forceinline__ size_t fft_smem_bytes(int N, int lines) { return (size_t)(imag_offset(N, lines) + lines * line_pitch(N)) * sizeof(double); }
 
 // One Stockham pass of radix R over `lines` lines of length N held as re[l*LP + pidx(n)], im[l*LP + pidx(n)].
 // Each thread owns 8/R butterflies (8 complex values in registers): blockDim.x == lines * N / 8.
@@ -130,7 +135,7 @@ __global__ void __launch_bounds__(256, 3) poisson_forward_y(Layout L, PoissonGeo
     extern __shared__ double sm[];
     const int N = G.Ny, LP = line_pitch(N);
     double* re = sm;
-    double* im = sm + (size_t)lines * LP;
+    double* im = sm + imag_offset(N, lines);
     const int k = blockIdx.y;
     const int XB = 2 * lines;
     const int ib = blockIdx.x * XB;
@@ -180,7 +185,7 @@ __global__ void __launch_bounds__(256, 3) poisson_inverse_y(Layout L, PoissonGeo
     extern __shared__ double sm[];
     const int N = G.Ny, LP = line_pitch(N);
     double* re = sm;
-    double* im = sm + (size_t)lines * LP;
+    double* im = sm + imag_offset(N, lines);
     const int k = blockIdx.y;
     const int XB = 2 * lines;
     const int ib = blockIdx.x * XB;
@@ -238,7 +243,7 @@ __global__ void __launch_bounds__(256, 3) fft_x_kernel(double2* __restrict__ W, 
     extern __shared__ double sm[];
     const int N = Nx, LP = line_pitch(N);
     double* re = sm;
-    double* im = sm + (size_t)lines * LP;
+    double* im = sm + imag_offset(N, lines);
     const long long l0 = (long long)blockIdx.x * lines;
     const double sgn = inverse ? -1.0 : 1.0;
     // blockDim.x == lines * N / 8: every thread moves exactly 8 elements; all 8 loads are issued before the first use
