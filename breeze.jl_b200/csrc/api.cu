@@ -41,6 +41,8 @@ struct bz_ctx {
     double2* W2 = nullptr;               // transposed layout (multi-GPU only)
     double2 *tw_x = nullptr, *tw_y = nullptr;
     double *lam_x = nullptr, *lam_y = nullptr, *inv_beta = nullptr, *tfac = nullptr;
+    long long* ky_base = nullptr;
+    int* ky_kstride = nullptr;
     int lines_x = 1, lines_y = 1;
     cudaStream_t stream = nullptr;
     Comm comm;
@@ -182,6 +184,9 @@ static int setup_poisson(bz_ctx* c) {
     G.Nx = g.Nx; G.Ny = g.Ny; G.Nz = g.Nz;
     G.nky = L.flat_y ? 1 : g.Ny / 2 + 1;
     comm_split_ky(c->comm, G.nky, &G.ky0, &G.nky_loc);
+    G.P = c->comm.n_ranks;
+    G.nx_shift = 0;
+    while ((1 << G.nx_shift) < L.nx) ++G.nx_shift;
     // twiddles and eigenvalues (Oceananigans poisson_eigenvalues: λ = (2 sin(π i / N) / Δ)², Flat: 0)
     std::vector<double2> twx(g.Nx), twy(g.Ny);
     std::vector<double> lx(g.Nx), ly(G.nky);
@@ -204,6 +209,19 @@ static int setup_poisson(bz_ctx* c) {
     if ((rc = dev_alloc(c, &c->tw_y, g.Ny))) return rc;
     if ((rc = dev_alloc(c, &c->lam_x, g.Nx))) return rc;
     if ((rc = dev_alloc(c, &c->lam_y, G.nky))) return rc;
+    if ((rc = dev_alloc(c, &c->ky_base, G.nky))) return rc;
+    if ((rc = dev_alloc(c, &c->ky_kstride, G.nky))) return rc;
+    {
+        std::vector<long long> kb(G.nky); std::vector<int> ks(G.nky);
+        for (int p = 0; p < G.P; ++p) {
+            int st, cnt; ky_block(G.nky, G.P, p, &st, &cnt);
+            for (int ky = st; ky < st + cnt; ++ky) { kb[ky] = (long long)st * L.nx * G.Nz + (long long)(ky - st) * L.nx; ks[ky] = cnt * L.nx; }
+        }
+        CUDA_TRY(c, cudaMemcpyAsync(c->ky_base, kb.data(), sizeof(long long) * G.nky, cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(c, cudaMemcpyAsync(c->ky_kstride, ks.data(), sizeof(int) * G.nky, cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        G.ky_base = c->ky_base; G.ky_kstride = c->ky_kstride;
+    }
     CUDA_TRY(c, cudaMemcpyAsync(c->tw_x, twx.data(), sizeof(double2) * g.Nx, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(c, cudaMemcpyAsync(c->tw_y, twy.data(), sizeof(double2) * g.Ny, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(c, cudaMemcpyAsync(c->lam_x, lx.data(), sizeof(double) * g.Nx, cudaMemcpyHostToDevice, c->stream));
@@ -251,7 +269,7 @@ static int poisson_solve(bz_ctx* c, double dt) {
             poisson_forward_y<<<grid, lines * G.Ny / 8, sm, c->stream>>>(L, G, U[0], U[1], U[2], dz_over_dt, c->W, c->tw_y, lines);
         } else {
             dim3 grid((L.nx + 127) / 128, L.Nz);
-            poisson_pack_flat_y<<<grid, 128, 0, c->stream>>>(L, U[0], U[1], U[2], dz_over_dt, c->W);
+            poisson_pack_flat_y<<<grid, 128, 0, c->stream>>>(L, G, U[0], U[1], U[2], dz_over_dt, c->W);
         }
         c->launches++;
     }
@@ -265,7 +283,7 @@ static int poisson_solve(bz_ctx* c, double dt) {
         ProfScope ps(c, 1);
         int lines = c->lines_x;
         size_t sm = fft_smem_bytes(G.Nx, lines);
-        fft_x_kernel<<<(unsigned)((n_lines + lines - 1) / lines), lines * G.Nx / 8, sm, c->stream>>>(c->W2, G.Nx, n_lines, c->tw_x, lines, 0);
+        fft_x_kernel<<<(unsigned)((n_lines + lines - 1) / lines), lines * G.Nx / 8, sm, c->stream>>>(G, c->W2, n_lines, c->tw_x, lines, 0);
         c->launches++;
     }
     if (G.nky_loc > 0) {
@@ -279,7 +297,7 @@ static int poisson_solve(bz_ctx* c, double dt) {
         ProfScope ps(c, 3);
         int lines = c->lines_x;
         size_t sm = fft_smem_bytes(G.Nx, lines);
-        fft_x_kernel<<<(unsigned)((n_lines + lines - 1) / lines), lines * G.Nx / 8, sm, c->stream>>>(c->W2, G.Nx, n_lines, c->tw_x, lines, 1);
+        fft_x_kernel<<<(unsigned)((n_lines + lines - 1) / lines), lines * G.Nx / 8, sm, c->stream>>>(G, c->W2, n_lines, c->tw_x, lines, 1);
         c->launches++;
     }
     if (c->comm.n_ranks > 1) {
@@ -297,7 +315,7 @@ static int poisson_solve(bz_ctx* c, double dt) {
             poisson_inverse_y<<<grid, lines * G.Ny / 8, sm, c->stream>>>(L, G, c->W, c->phi, c->tw_y, lines, scale);
         } else {
             dim3 grid((L.nx + 127) / 128, L.Nz);
-            poisson_unpack_flat_y<<<grid, 128, 0, c->stream>>>(L, c->W, c->phi, scale);
+            poisson_unpack_flat_y<<<grid, 128, 0, c->stream>>>(L, G, c->W, c->phi, scale);
         }
         c->launches++;
     }
@@ -308,7 +326,7 @@ static int poisson_solve(bz_ctx* c, double dt) {
 // ---------------------------------------------------------------------------------------------------------------
 // halo fills
 // ---------------------------------------------------------------------------------------------------------------
-static int fill_halos(bz_ctx* c, double* const* fields, int nf, int fam) {
+static int fill_halos(bz_ctx* c, double* const* fields, int nf, int fam, bool exchange_x = true) {
     const Layout& L = c->L;
     if (L.HX == 0 && L.HY == 0) return BZ_OK;
     ProfScope ps(c, fam);
@@ -316,8 +334,10 @@ static int fill_halos(bz_ctx* c, double* const* fields, int nf, int fam) {
     for (int f = 0; f < nf; ++f) F.f[f] = fields[f];
     int mode = 3;
     if (c->comm.n_ranks > 1) {
-        int rc = comm_exchange_x_halos(c->comm, L, F, c->stream, &c->launches);
-        if (rc) { bz_set_error(c, "halo exchange: %s", c->comm.err); return rc; }
+        if (exchange_x) {
+            int rc = comm_exchange_x_halos(c->comm, L, F, c->stream, &c->launches);
+            if (rc) { bz_set_error(c, "halo exchange: %s", c->comm.err); return rc; }
+        }
         mode = 2;
     }
     if (mode == 2 && L.HY == 0) return BZ_OK;
@@ -378,7 +398,7 @@ static int pressure_correct(bz_ctx* c, double dt) {
     int rc;
     double** U = c->set[c->cur];
     if (c->comm.n_ranks == 1) { if ((rc = fill_halos(c, U, 2, 4))) return rc; }       // ρu, ρv ghosts for the divergence
-    else { double* uv[1] = {U[1]}; if ((rc = fill_halos(c, uv, 1, 4))) return rc; }      // ρu[nx] was produced by the stage kernel
+    else { double* uv[1] = {U[1]}; if ((rc = fill_halos(c, uv, 1, 4, false))) return rc; }   // y ghosts of ρv only: ρu[nx] came from the stage kernel / the last exchange
     if ((rc = poisson_solve(c, dt))) return rc;
     double* ph[1] = {c->phi};
     if ((rc = fill_halos(c, ph, 1, 4))) return rc;
@@ -429,7 +449,7 @@ void bz_destroy(bz_ctx* c) {
     cudaFree(c->phi); cudaFree(c->dense); cudaFree(c->scalar); cudaFree(c->col_store);
     if (c->W2 != c->W) cudaFree(c->W2);
     cudaFree(c->W); cudaFree(c->tw_x); cudaFree(c->tw_y); cudaFree(c->lam_x); cudaFree(c->lam_y);
-    cudaFree(c->inv_beta); cudaFree(c->tfac);
+    cudaFree(c->inv_beta); cudaFree(c->tfac); cudaFree(c->ky_base); cudaFree(c->ky_kstride);
     for (auto e : c->prof_ev) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;

@@ -37,9 +37,7 @@ struct Comm {
     ncclComm_t comm = nullptr;
     double* halo_send = nullptr;    // [2][nf][HX][Ny][Nz]
     double* halo_recv = nullptr;
-    double2* tr_send = nullptr;     // transpose staging
-    double2* tr_recv = nullptr;
-    size_t halo_cap = 0, tr_cap = 0;
+    size_t halo_cap = 0;
     char err[256] = {};
 };
 
@@ -97,20 +95,17 @@ static int comm_init(Comm& cm, const bz_config* cfg, cudaStream_t) {
 static void comm_destroy(Comm& cm) {
     if (cm.comm && cm.api.CommDestroy) cm.api.CommDestroy(cm.comm);
     cm.comm = nullptr;
-    cudaFree(cm.halo_send); cudaFree(cm.halo_recv); cudaFree(cm.tr_send); cudaFree(cm.tr_recv);
-    cm.halo_send = cm.halo_recv = nullptr; cm.tr_send = cm.tr_recv = nullptr;
+    cudaFree(cm.halo_send); cudaFree(cm.halo_recv);
+    cm.halo_send = cm.halo_recv = nullptr;
 }
 
-static int comm_alloc_buffers(Comm& cm, const Layout& L, const PoissonGeom& G, int64_t* bytes) {
+static int comm_alloc_buffers(Comm& cm, const Layout& L, const PoissonGeom&, int64_t* bytes) {
     if (cm.n_ranks == 1) return BZ_OK;
     cm.halo_cap = (size_t)2 * (NPROG + 1) * L.HX * L.Ny * L.Nz;
-    size_t a = (size_t)L.nx * G.nky * G.Nz, b = (size_t)G.Nx * G.nky_loc * G.Nz;
-    cm.tr_cap = a > b ? a : b;
-    if (cudaMalloc(&cm.halo_send, cm.halo_cap * 8) || cudaMalloc(&cm.halo_recv, cm.halo_cap * 8) ||
-        cudaMalloc(&cm.tr_send, cm.tr_cap * 16) || cudaMalloc(&cm.tr_recv, cm.tr_cap * 16)) {
+    if (cudaMalloc(&cm.halo_send, cm.halo_cap * 8) || cudaMalloc(&cm.halo_recv, cm.halo_cap * 8)) {
         snprintf(cm.err, 256, "cudaMalloc of communication buffers failed"); return BZ_ERR_NOMEM;
     }
-    *bytes += (int64_t)(2 * cm.halo_cap * 8 + 2 * cm.tr_cap * 16);
+    *bytes += (int64_t)(2 * cm.halo_cap * 8);
     return BZ_OK;
 }
 
@@ -133,57 +128,15 @@ static int comm_exchange_x_halos(Comm& cm, const Layout& L, const FieldSet& F, c
     return BZ_OK;
 }
 
-// pack W[k][ky][i] (x-slab) into per-peer contiguous blocks [peer][k][ky in peer's range][i]
-__global__ void transpose_pack_fwd(const double2* __restrict__ W, double2* __restrict__ buf, int nx, int nky, int Nz, int P) {
-    const long long total = (long long)nx * nky * Nz;
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-        int i = (int)(e % nx), ky = (int)((e / nx) % nky), k = (int)(e / ((long long)nx * nky));
-        // owner of ky and its offset
-        int base = nky / P, rem = nky % P;
-        int p = (ky < rem * (base + 1)) ? ky / (base + 1) : rem + (ky - rem * (base + 1)) / (base > 0 ? base : 1);
-        int start = p * base + (p < rem ? p : rem), cnt = base + (p < rem ? 1 : 0);
-        long long off = (long long)start * nx * Nz;                 // blocks are laid out in peer order
-        buf[off + ((long long)k * cnt + (ky - start)) * nx + i] = W[e];
-    }
-}
-// unpack received blocks [peer][k][ky_loc][i_peer] into W2[k][ky_loc][kx = peer*nx + i]
-__global__ void transpose_unpack_fwd(const double2* __restrict__ buf, double2* __restrict__ W2, int nx, int nky_loc, int Nz, int P) {
-    const long long total = (long long)nx * P * nky_loc * Nz;
-    const int Nx = nx * P;
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-        int kx = (int)(e % Nx), ky = (int)((e / Nx) % nky_loc), k = (int)(e / ((long long)Nx * nky_loc));
-        int p = kx / nx, i = kx % nx;
-        W2[e] = buf[(long long)p * nx * nky_loc * Nz + ((long long)k * nky_loc + ky) * nx + i];
-    }
-}
-__global__ void transpose_pack_bwd(const double2* __restrict__ W2, double2* __restrict__ buf, int nx, int nky_loc, int Nz, int P) {
-    const long long total = (long long)nx * P * nky_loc * Nz;
-    const int Nx = nx * P;
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-        int kx = (int)(e % Nx), ky = (int)((e / Nx) % nky_loc), k = (int)(e / ((long long)Nx * nky_loc));
-        int p = kx / nx, i = kx % nx;
-        buf[(long long)p * nx * nky_loc * Nz + ((long long)k * nky_loc + ky) * nx + i] = W2[e];
-    }
-}
-__global__ void transpose_unpack_bwd(const double2* __restrict__ buf, double2* __restrict__ W, int nx, int nky, int Nz, int P) {
-    const long long total = (long long)nx * nky * Nz;
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-        int i = (int)(e % nx), ky = (int)((e / nx) % nky), k = (int)(e / ((long long)nx * nky));
-        int base = nky / P, rem = nky % P;
-        int p = (ky < rem * (base + 1)) ? ky / (base + 1) : rem + (ky - rem * (base + 1)) / (base > 0 ? base : 1);
-        int start = p * base + (p < rem ? p : rem), cnt = base + (p < rem ? 1 : 0);
-        long long off = (long long)start * nx * Nz;
-        W[e] = buf[off + ((long long)k * cnt + (ky - start)) * nx + i];
-    }
-}
-
+// All-to-all of the distributed FFT. Both spectral arrays are kept in peer-blocked layouts (poisson.cuh), so every
+// ncclSend / ncclRecv moves one contiguous block and no pack / unpack kernel is needed.
 static int comm_alltoall(Comm& cm, const double2* send, double2* recv, int nx, const PoissonGeom& G, bool forward, cudaStream_t s) {
     const int P = cm.n_ranks;
     NCCL_TRY(cm, cm.api.GroupStart());
     for (int p = 0; p < P; ++p) {
         int st, cnt;
         comm_split_range(G.nky, P, p, &st, &cnt);
-        // x-slab side: block for peer p holds p's ky range of my columns; transposed side: block from peer p holds my ky range of p's columns
+        // x-slab side: block p = peer p's ky range of my columns; transposed side: block p = my ky range of peer p's columns
         size_t slab_off = (size_t)st * nx * G.Nz, slab_n = (size_t)cnt * nx * G.Nz;
         size_t tr_off = (size_t)p * nx * G.nky_loc * G.Nz, tr_n = (size_t)nx * G.nky_loc * G.Nz;
         if (forward) {
@@ -198,25 +151,11 @@ static int comm_alltoall(Comm& cm, const double2* send, double2* recv, int nx, c
     return BZ_OK;
 }
 
-static inline int grid_for(long long total) { long long b = (total + 255) / 256; return (int)(b > 148 * 16 ? 148 * 16 : (b < 1 ? 1 : b)); }
-
-static int comm_transpose_forward(Comm& cm, const double2* W, double2* W2, int nx, const PoissonGeom& G, cudaStream_t s, int64_t* launches) {
-    const int P = cm.n_ranks;
-    transpose_pack_fwd<<<grid_for((long long)nx * G.nky * G.Nz), 256, 0, s>>>(W, cm.tr_send, nx, G.nky, G.Nz, P);
-    int rc = comm_alltoall(cm, cm.tr_send, cm.tr_recv, nx, G, true, s);
-    if (rc) return rc;
-    if (G.nky_loc > 0) transpose_unpack_fwd<<<grid_for((long long)G.Nx * G.nky_loc * G.Nz), 256, 0, s>>>(cm.tr_recv, W2, nx, G.nky_loc, G.Nz, P);
-    *launches += 2;
-    return BZ_OK;
+static int comm_transpose_forward(Comm& cm, const double2* W, double2* W2, int nx, const PoissonGeom& G, cudaStream_t s, int64_t*) {
+    return comm_alltoall(cm, W, W2, nx, G, true, s);
 }
-static int comm_transpose_backward(Comm& cm, const double2* W2, double2* W, int nx, const PoissonGeom& G, cudaStream_t s, int64_t* launches) {
-    const int P = cm.n_ranks;
-    if (G.nky_loc > 0) transpose_pack_bwd<<<grid_for((long long)G.Nx * G.nky_loc * G.Nz), 256, 0, s>>>(W2, cm.tr_send, nx, G.nky_loc, G.Nz, P);
-    int rc = comm_alltoall(cm, cm.tr_send, cm.tr_recv, nx, G, false, s);
-    if (rc) return rc;
-    transpose_unpack_bwd<<<grid_for((long long)nx * G.nky * G.Nz), 256, 0, s>>>(cm.tr_recv, W, nx, G.nky, G.Nz, P);
-    *launches += 2;
-    return BZ_OK;
+static int comm_transpose_backward(Comm& cm, const double2* W2, double2* W, int nx, const PoissonGeom& G, cudaStream_t s, int64_t*) {
+    return comm_alltoall(cm, W2, W, nx, G, false, s);
 }
 
 static int comm_allreduce_max(Comm& cm, double* host_value, double* dev_scalar, cudaStream_t s) {

@@ -24,7 +24,29 @@ struct PoissonGeom {
     int nky;       // number of ky modes held after the y transform: Ny/2 + 1 (1 if Flat y)
     int nky_loc;   // ky modes on this rank in the transposed layout
     int ky0;       // first global ky of this rank in the transposed layout
+    int P;         // ranks (x-slabs); nx = Nx / P is a power of two
+    int nx_shift;  // log2(nx)
+    const long long* ky_base;   // per ky: offset of (k = 0, ky, i = 0) in the peer-blocked W   (device, nky entries)
+    const int* ky_kstride;      // per ky: level stride of its block = count_p * nx              (device, nky entries)
 };
+
+// Peer-blocked layouts of the two spectral arrays. The all-to-all of the distributed FFT then moves CONTIGUOUS blocks
+// straight between them (no pack / unpack passes); with one rank both reduce to the plain [k][ky][x] order.
+//   W  (x-slab side,   nx × nky × Nz):      block p = the ky range owned by rank p  → [p][k][ky - start_p][i]
+//   W2 (transposed,    Nx × nky_loc × Nz):  block p = the x columns of rank p       → [p][k][ky_loc][i_p]
+__host__ __device__ __forceinline__ void ky_block(int nky, int P, int p, int* start, int* count) {
+    int base = nky / P, rem = nky % P;
+    *count = base + (p < rem ? 1 : 0);
+    *start = p * base + (p < rem ? p : rem);
+}
+__device__ __forceinline__ size_t w_index(const PoissonGeom& G, int k, int ky, int i) {
+    if (G.P == 1) return (((size_t)k * G.nky + ky) << G.nx_shift) + i;
+    return (size_t)__ldg(&G.ky_base[ky]) + (size_t)k * __ldg(&G.ky_kstride[ky]) + i;
+}
+__device__ __forceinline__ size_t w2_index(const PoissonGeom& G, int k, int kyl, int kx) {
+    const int p = kx >> G.nx_shift, i = kx & ((1 << G.nx_shift) - 1);
+    return (((size_t)p * G.Nz + k) * G.nky_loc + kyl << G.nx_shift) + i;
+}
 
 // ---- register butterflies (forward: e^{-2πi/R}) ----------------------------------------------------------------
 struct cpx { double x, y; };
@@ -168,15 +190,15 @@ __global__ void __launch_bounds__(256, 3) poisson_forward_y(Layout L, PoissonGeo
         double zr = re[(size_t)l * LP + pidx(ky)], zi = im[(size_t)l * LP + pidx(ky)];
         double yr = re[(size_t)l * LP + pidx(km)], yi = im[(size_t)l * LP + pidx(km)];
         double2 o = (c & 1) ? make_double2(0.5 * (zi + yi), -0.5 * (zr - yr)) : make_double2(0.5 * (zr + yr), 0.5 * (zi - yi));
-        W[((size_t)k * G.nky + ky) * L.nx + i] = o;
+        W[w_index(G, k, ky, i)] = o;
     }
 }
 
 // Flat y: no y transform; W[k][0][i] = rhs + 0i.
-__global__ void poisson_pack_flat_y(Layout L, const double* __restrict__ ru, const double* __restrict__ rv,
+__global__ void poisson_pack_flat_y(Layout L, PoissonGeom G, const double* __restrict__ ru, const double* __restrict__ rv,
                                     const double* __restrict__ rw, double dz_over_dt, double2* __restrict__ W) {
     int i = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
-    if (i < L.nx) W[(size_t)k * L.nx + i] = make_double2(source_term(L, ru, rv, rw, i, 0, k, dz_over_dt), 0.0);
+    if (i < L.nx) W[w_index(G, k, 0, i)] = make_double2(source_term(L, ru, rv, rw, i, 0, k, dz_over_dt), 0.0);
 }
 
 // ---- pass 5: complex-to-real inverse FFT along y → φ (padded field interior) -------------------------------------
@@ -201,8 +223,8 @@ __global__ void __launch_bounds__(256, 3) poisson_inverse_y(Layout L, PoissonGeo
             if (e < total) {
                 int l = e % lines, ky = e / lines;
                 int i = ib + 2 * l;
-                if (i < L.nx) A[it] = W[((size_t)k * G.nky + ky) * L.nx + i];
-                if (i + 1 < L.nx) B[it] = W[((size_t)k * G.nky + ky) * L.nx + i + 1];
+                if (i < L.nx) A[it] = W[w_index(G, k, ky, i)];
+                if (i + 1 < L.nx) B[it] = W[w_index(G, k, ky, i + 1)];
             }
         }
 #pragma unroll
@@ -232,14 +254,15 @@ __global__ void __launch_bounds__(256, 3) poisson_inverse_y(Layout L, PoissonGeo
     }
 }
 
-__global__ void poisson_unpack_flat_y(Layout L, const double2* __restrict__ W, double* __restrict__ phi, double scale) {
+__global__ void poisson_unpack_flat_y(Layout L, PoissonGeom G, const double2* __restrict__ W, double* __restrict__ phi, double scale) {
     int i = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
-    if (i < L.nx) phi[lidx(L, i, 0, k)] = W[(size_t)k * L.nx + i].x * scale;
+    if (i < L.nx) phi[lidx(L, i, 0, k)] = W[w_index(G, k, 0, i)].x * scale;
 }
 
 // ---- passes 2 / 4: complex FFT along x, in place; one line = Nx contiguous complex numbers ----------------------
 // grid ceil(n_lines / lines); block lines*Nx/8 <= 256 threads; smem 2*lines*line_pitch(Nx) doubles.
-__global__ void __launch_bounds__(256, 3) fft_x_kernel(double2* __restrict__ W, int Nx, long long n_lines, const double2* __restrict__ tw_x, int lines, int inverse) {
+__global__ void __launch_bounds__(256, 3) fft_x_kernel(PoissonGeom G, double2* __restrict__ W, long long n_lines, const double2* __restrict__ tw_x, int lines, int inverse) {
+    const int Nx = G.Nx;
     extern __shared__ double sm[];
     const int N = Nx, LP = line_pitch(N);
     double* re = sm;
@@ -253,7 +276,8 @@ __global__ void __launch_bounds__(256, 3) fft_x_kernel(double2* __restrict__ W, 
         for (int it = 0; it < 8; ++it) {
             int e = threadIdx.x + it * blockDim.x;
             int l = e / N;
-            v[it] = (l0 + l < n_lines) ? W[l0 * N + e] : make_double2(0.0, 0.0);
+            long long line = l0 + l;                                   // line = k * nky_loc + ky_loc
+            v[it] = (line < n_lines) ? W[w2_index(G, (int)(line / G.nky_loc), (int)(line % G.nky_loc), e - l * N)] : make_double2(0.0, 0.0);
         }
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
@@ -267,7 +291,8 @@ __global__ void __launch_bounds__(256, 3) fft_x_kernel(double2* __restrict__ W, 
     fft_lines_smem(re, im, LP, N, tw_x);
     for (int e = threadIdx.x; e < N * lines; e += blockDim.x) {
         int x = e % N, l = e / N;
-        if (l0 + l < n_lines) W[(l0 + l) * N + x] = make_double2(re[(size_t)l * LP + pidx(x)], sgn * im[(size_t)l * LP + pidx(x)]);
+        long long line = l0 + l;
+        if (line < n_lines) W[w2_index(G, (int)(line / G.nky_loc), (int)(line % G.nky_loc), x)] = make_double2(re[(size_t)l * LP + pidx(x)], sgn * im[(size_t)l * LP + pidx(x)]);
     }
 }
 
@@ -305,8 +330,10 @@ __global__ void thomas_z(PoissonGeom G, double2* __restrict__ W, const double* _
                          const double* __restrict__ inv_beta, const double* __restrict__ tfac) {
     int kx = blockIdx.x * blockDim.x + threadIdx.x, ky = blockIdx.y;
     if (kx >= G.Nx) return;
-    const size_t stride = (size_t)G.nky_loc * G.Nx;
+    const size_t stride = (size_t)G.nky_loc * G.Nx;                    // level stride of the factor arrays (plain layout)
     const size_t n0 = (size_t)ky * G.Nx + kx;
+    const size_t wstride = (size_t)G.nky_loc << G.nx_shift;            // level stride of W2 inside its peer block
+    const size_t w0 = w2_index(G, 0, ky, kx);
     const int Nz = G.Nz;
     const double rdz = 1.0 / dz;
     double2 prev = make_double2(0.0, 0.0);
@@ -315,7 +342,7 @@ __global__ void thomas_z(PoissonGeom G, double2* __restrict__ W, const double* _
 #pragma unroll
         for (int b = 0; b < TB; ++b) {
             int k = kb + b;
-            if (k < Nz) { f[b] = W[n0 + k * stride]; ib[b] = inv_beta[n0 + k * stride]; }
+            if (k < Nz) { f[b] = W[w0 + k * wstride]; ib[b] = inv_beta[n0 + k * stride]; }
         }
 #pragma unroll
         for (int b = 0; b < TB; ++b) {
@@ -323,7 +350,7 @@ __global__ void thomas_z(PoissonGeom G, double2* __restrict__ W, const double* _
             if (k < Nz) {
                 double a = (k > 0) ? rho_f[k] * rdz : 0.0;
                 prev = make_double2((f[b].x - a * prev.x) * ib[b], (f[b].y - a * prev.y) * ib[b]);
-                W[n0 + k * stride] = prev;
+                W[w0 + k * wstride] = prev;
             }
         }
     }
@@ -333,14 +360,14 @@ __global__ void thomas_z(PoissonGeom G, double2* __restrict__ W, const double* _
 #pragma unroll
         for (int b = 0; b < TB; ++b) {
             int k = kt - b;
-            if (k >= 0) { v[b] = W[n0 + k * stride]; t[b] = tfac[n0 + (k + 1) * stride]; }
+            if (k >= 0) { v[b] = W[w0 + k * wstride]; t[b] = tfac[n0 + (k + 1) * stride]; }
         }
 #pragma unroll
         for (int b = 0; b < TB; ++b) {
             int k = kt - b;
             if (k >= 0) {
                 prev = make_double2(v[b].x - t[b] * prev.x, v[b].y - t[b] * prev.y);
-                W[n0 + k * stride] = prev;
+                W[w0 + k * wstride] = prev;
             }
         }
     }
@@ -349,7 +376,7 @@ __global__ void thomas_z(PoissonGeom G, double2* __restrict__ W, const double* _
 // φ .-= mean(φ): only the (kx, ky) = (0, 0) column carries the mean. One block.
 __global__ void remove_mean_mode(PoissonGeom G, double2* __restrict__ W) {
     __shared__ double sr[256], si[256];
-    const size_t stride = (size_t)G.nky_loc * G.Nx;
+    const size_t stride = (size_t)G.nky_loc << G.nx_shift;             // (kx, ky) = (0, 0) lives in peer block 0
     double ar = 0.0, ai = 0.0;
     for (int k = threadIdx.x; k < G.Nz; k += blockDim.x) { double2 v = W[k * stride]; ar += v.x; ai += v.y; }
     sr[threadIdx.x] = ar; si[threadIdx.x] = ai;
