@@ -363,7 +363,7 @@ static int launch_stage_t(bz_ctx* c, const StageParams& P, int nz_chunks) {
         CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SM)));
         configured = true;
     }
-    dim3 grid((P.nx_u + TX - 2) / (TX - 1), (c->L.Ny + TY - 1) / TY, nz_chunks);
+    dim3 grid((P.nx_u + TX - 1) / TX, (c->L.Ny + TY - 1) / TY, nz_chunks);
     kern<<<grid, 2 * TX * TY, sizeof(SM), c->stream>>>(P);
     c->launches++;
     CUDA_TRY(c, cudaGetLastError());
@@ -381,7 +381,7 @@ static int launch_stage(bz_ctx* c, int in, double* const* out, int u0, double dt
     }
     P.L = c->L; P.col = c->col; P.th = c->th;
     P.dt = dt; P.alpha = alpha; P.mode = mode;
-    P.nx_u = c->L.nx + ((c->comm.n_ranks > 1 && mode == 0) ? 1 : 0);
+    P.nx_u = c->L.nx;
     P.use_tma = c->use_tma;
     int chunks = c->z_chunks;
     P.k_chunk = (c->L.Nz + chunks - 1) / chunks;
@@ -398,7 +398,12 @@ static int pressure_correct(bz_ctx* c, double dt) {
     int rc;
     double** U = c->set[c->cur];
     if (c->comm.n_ranks == 1) { if ((rc = fill_halos(c, U, 2, 4))) return rc; }       // ρu, ρv ghosts for the divergence
-    else { double* uv[1] = {U[1]}; if ((rc = fill_halos(c, uv, 1, 4, false))) return rc; }   // y ghosts of ρv only: ρu[nx] came from the stage kernel / the last exchange
+    else {                                                                               // slabs: y ghosts of ρv are local; ρu at the first ghost face
+        double* uv[1] = {U[1]};                                                          // comes from the right neighbour's first column
+        if ((rc = fill_halos(c, uv, 1, 4, false))) return rc;
+        ProfScope ps(c, 5);
+        if ((rc = comm_exchange_u_face(c->comm, c->L, U[0], c->stream, &c->launches))) { bz_set_error(c, "face exchange: %s", c->comm.err); return rc; }
+    }
     if ((rc = poisson_solve(c, dt))) return rc;
     double* ph[1] = {c->phi};
     if ((rc = fill_halos(c, ph, 1, 4))) return rc;
@@ -524,7 +529,7 @@ int bz_create(const bz_config* cfg, bz_ctx** out) {
         else TRY(make_tensor_maps(c, StageShared<128, 1, false>::SW, 1));
     }
     {
-        int gx = fy ? (L.nx + 126) / 127 : (L.nx + 30) / 31, gy = fy ? 1 : (L.Ny + 7) / 8;
+        int gx = fy ? (L.nx + 127) / 128 : (L.nx + 31) / 32, gy = fy ? 1 : (L.Ny + 7) / 8;
         int want = (20 * 148 + gx * gy - 1) / (gx * gy);   // ~20 waves of CTAs keep the tail of the last wave small
         int maxc = L.Nz / 64 > 1 ? L.Nz / 64 : 1;
         c->z_chunks = cfg->z_chunks > 0 ? cfg->z_chunks : (want < 1 ? 1 : (want > maxc ? maxc : want));

@@ -128,6 +128,22 @@ static int comm_exchange_x_halos(Comm& cm, const Layout& L, const FieldSet& F, c
     return BZ_OK;
 }
 
+// ρu at the first ghost face (i = nx) = the right neighbour's first column: one column, one direction.
+static int comm_exchange_u_face(Comm& cm, const Layout& L, double* ru, cudaStream_t s, int64_t* launches) {
+    const int P = cm.n_ranks, left = (cm.rank + P - 1) % P, right = (cm.rank + 1) % P;
+    FieldSet F; F.n = 1; F.f[0] = ru;
+    const size_t face = (size_t)L.Ny * L.Nz;
+    const int blocks = (int)((face + 255) / 256) > 148 * 8 ? 148 * 8 : (int)((face + 255) / 256);
+    pack_x_faces<<<blocks, 256, 0, s>>>(L, F, 0, 1, cm.halo_send);
+    NCCL_TRY(cm, cm.api.GroupStart());
+    NCCL_TRY(cm, cm.api.Send(cm.halo_send, face, NCCL_FLOAT64, left, cm.comm, s));
+    NCCL_TRY(cm, cm.api.Recv(cm.halo_recv, face, NCCL_FLOAT64, right, cm.comm, s));
+    NCCL_TRY(cm, cm.api.GroupEnd());
+    unpack_x_faces<<<blocks, 256, 0, s>>>(L, F, L.nx, 1, cm.halo_recv);
+    *launches += 2;
+    return BZ_OK;
+}
+
 // All-to-all of the distributed FFT. Both spectral arrays are kept in peer-blocked layouts (poisson.cuh), so every
 // ncclSend / ncclRecv moves one contiguous block and no pack / unpack kernel is needed.
 static int comm_alltoall(Comm& cm, const double2* send, double2* recv, int nx, const PoissonGeom& G, bool forward, cudaStream_t s) {

@@ -276,8 +276,9 @@ __global__ void __launch_bounds__(256, 3) fft_x_kernel(PoissonGeom G, double2* _
         for (int it = 0; it < 8; ++it) {
             int e = threadIdx.x + it * blockDim.x;
             int l = e / N;
-            long long line = l0 + l;                                   // line = k * nky_loc + ky_loc
-            v[it] = (line < n_lines) ? W[w2_index(G, (int)(line / G.nky_loc), (int)(line % G.nky_loc), e - l * N)] : make_double2(0.0, 0.0);
+            int line = (int)l0 + l;                                    // line = k * nky_loc + ky_loc (fits an int)
+            int kk = line / G.nky_loc;
+            v[it] = (line < n_lines) ? W[w2_index(G, kk, line - kk * G.nky_loc, e - l * N)] : make_double2(0.0, 0.0);
         }
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
@@ -291,8 +292,9 @@ __global__ void __launch_bounds__(256, 3) fft_x_kernel(PoissonGeom G, double2* _
     fft_lines_smem(re, im, LP, N, tw_x);
     for (int e = threadIdx.x; e < N * lines; e += blockDim.x) {
         int x = e % N, l = e / N;
-        long long line = l0 + l;
-        if (line < n_lines) W[w2_index(G, (int)(line / G.nky_loc), (int)(line % G.nky_loc), x)] = make_double2(re[(size_t)l * LP + pidx(x)], sgn * im[(size_t)l * LP + pidx(x)]);
+        int line = (int)l0 + l;
+        int kk = line / G.nky_loc;
+        if (line < n_lines) W[w2_index(G, kk, line - kk * G.nky_loc, x)] = make_double2(re[(size_t)l * LP + pidx(x)], sgn * im[(size_t)l * LP + pidx(x)]);
     }
 }
 

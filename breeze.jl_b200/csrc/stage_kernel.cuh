@@ -10,13 +10,13 @@
 // It reads the five projected prognostics (+ U⁰ in stages 2, 3) once and writes the five predictor fields once:
 // 88 / 128 algorithmic bytes per cell.
 //
-// Decomposition: a CTA owns a column of (TX-1) × TY cells and marches up z. An 8-slot ring of z-planes
+// Decomposition: a CTA owns a column of TX × TY cells and marches up z. An 8-slot ring of z-planes
 // (TX+8) × (TY+6) of the five fields lives in shared memory as VELOCITIES / SPECIFIC values (u, v, w, θ, q —
 // converted once per loaded element); every x-, y- and z-stencil of the 15 WENO5 reconstructions per cell is
 // read from it. Each thread computes only the fluxes through the LOW x/y faces and the TOP z face of its cell;
-// the high-side x/y fluxes come from the neighbouring thread through shared memory (the CTA's last x-column only
-// produces fluxes: tiles overlap by one cell in x; the extra y-row of fluxes is spread over five warps), the
-// bottom z flux is carried in registers from the previous level. So every face flux is evaluated once.
+// the high-side x/y fluxes come from the neighbouring thread through shared memory (the extra column of x-faces and
+// the extra row of y-faces at the tile's high edges are spread one flux kind per warp), the bottom z flux is carried
+// in registers from the previous level. So every face flux is evaluated once.
 // Planes are staged either by TMA (cp.async.bulk.tensor, one 3-D box per field and level, mbarrier
 // completion, prefetched one level ahead) or by plain coalesced loads (selected at run time; bit-identical).
 #pragma once
@@ -142,7 +142,7 @@ struct StageShared {
     static constexpr int PLANE = (SW * SH + 15) & ~15;   // every field slice stays 128-byte aligned (TMA destination)
     static_assert(!HAS_Y || (TY >= NPROG && TX == 32), "the extra y-face row is spread one flux kind per warp");
     double ring[RING][NPROG][PLANE];
-    double fx[2][NPROG][TY][TX];                      // double-buffered by level parity: one CTA barrier per level
+    double fx[2][NPROG][TY][TX + 1];                  // double-buffered by level parity: one CTA barrier per level
     double fy[2][NPROG][HAS_Y ? TY + 1 : 1][TX];
     uint64_t bar[RING];
 };
@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(2 * TX * TY, 1) stage_kernel(const __grid_cons
     const int tid = threadIdx.x;
     const int role = tid / NCELL, ctid = tid % NCELL;
     const int tx = ctid % TX, ty = ctid / TX;
-    const int i0 = blockIdx.x * (TX - 1), j0 = blockIdx.y * TY;
+    const int i0 = blockIdx.x * TX, j0 = blockIdx.y * TY;
     const int i = i0 + tx, j = j0 + ty;
     const int Nz = L.Nz;
     const int kb = blockIdx.z * P.k_chunk;
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(2 * TX * TY, 1) stage_kernel(const __grid_cons
     double zb0 = 0.0, zb1 = 0.0, zb2 = 0.0, b_below = 0.0;
 
     const double rdx = L.rdx, rdy = L.rdy, rdz = L.rdz;
-    const bool own_cell = (tx < TX - 1) && (j < L.Ny);
+    const bool own_cell = (j < L.Ny);
     const bool in_x = i < L.nx;
     const int f_first = role == 0 ? 0 : 2, f_count = role == 0 ? 2 : 3;   // fields this thread assembles and stores
 
@@ -313,22 +313,23 @@ __global__ void __launch_bounds__(2 * TX * TY, 1) stage_kernel(const __grid_cons
                 return FULL ? biased6c<3>(v0, v1, v2, v3, v4, v5, left) : biased6(v0, v1, v2, v3, v4, v5, R, left);
             };
             auto sz = [&](double v0, double v1, double v2, double v3, int R) -> double { return FULL ? sym4(v0, v1, v2, v3, 2) : sym4(v0, v1, v2, v3, R); };
-#define XS(f, dx) Lk[(f) * PL + (dx)]
+#define XS(f, dx) cell[(f) * PL + (dx)]
 #define YS(f, dy) row[(f) * PL + (dy) * SW]
 #define ZS(f, m) Lp[(m) + 2][(f) * PL]
             // X-type fluxes: through x-face i (or at centre i-1 for ρu); kinds 0 ρu, 1 ρv, 2 ρw, 3 θ, 4 q
-            auto x_flux = [&](auto kind_tag) -> double {
+            // `cell` is the plane element of the cell whose low x-face is meant (own cell, or the column just right of the tile)
+            auto x_flux = [&](auto kind_tag, const double* cell, int zoff) -> double {
                 constexpr int kind = decltype(kind_tag)::value;
                 const double u_i = XS(0, 0);
                 if (kind == 0) {          // FUu at centre i-1
                     double ut = rho_k * sym4(XS(0, -2), XS(0, -1), u_i, XS(0, 1), 2);
                     return ut * biased6c<3>(XS(0, -3), XS(0, -2), XS(0, -1), u_i, XS(0, 1), XS(0, 2), ut > 0.0);
                 } else if (kind == 1) {   // FUv at (face i, face j)
-                    double ut = HAS_Y ? rho_k * sym4(Lk[-2 * SW], Lk[-SW], u_i, Lk[SW], 2) : rho_k * u_i;
+                    double ut = HAS_Y ? rho_k * sym4(cell[-2 * SW], cell[-SW], u_i, cell[SW], 2) : rho_k * u_i;
                     return ut * biased6c<3>(XS(1, -3), XS(1, -2), XS(1, -1), XS(1, 0), XS(1, 1), XS(1, 2), ut > 0.0);
                 } else if (kind == 2) {   // FUw at (face i, z-face k); the wall face k = 0 carries no w tendency
                     if (!FULL && k < 1) return 0.0;
-                    double ut = sz(r_m2 * ZS(0, -2), r_m1 * ZS(0, -1), rho_k * u_i, r_p1 * ZS(0, 1), Rf_k2);
+                    double ut = sz(r_m2 * Lp[0][zoff], r_m1 * Lp[1][zoff], rho_k * u_i, r_p1 * Lp[3][zoff], Rf_k2);
                     return ut * biased6c<3>(XS(2, -3), XS(2, -2), XS(2, -1), XS(2, 0), XS(2, 1), XS(2, 2), ut > 0.0);
                 } else {                  // tracer mass flux ρ u ĉ
                     return rho_k * u_i * biased6c<3>(XS(kind, -3), XS(kind, -2), XS(kind, -1), XS(kind, 0), XS(kind, 1), XS(kind, 2), u_i > 0.0);
@@ -375,9 +376,21 @@ __global__ void __launch_bounds__(2 * TX * TY, 1) stage_kernel(const __grid_cons
             const int ezoff = (TY - ty) * SW;
             auto& FX = S.fx[k & 1];
             auto& FY = S.fy[k & 1];
+            // the column of x-faces just right of the tile: one flux kind per warp, one lane per row
+            const int wrp = ctid >> 5, lane = ctid & 31;
+            const int xoff = ((lane + YO) * SW + (TX + 4 + xs)) - toff;
+            const double* const xedge = Lk + xoff;
+            constexpr int XE0 = HAS_Y ? 3 : 1, XE1 = HAS_Y ? 2 : 1;
             if (PHASE == 0) {
                 if (role == 0) {
-                    if (!FLAT_X) { FX[0][ty][tx] = x_flux(K0{}); FX[1][ty][tx] = x_flux(K1{}); FX[3][ty][tx] = x_flux(K3{}); }
+                    if (!FLAT_X) {
+                        FX[0][ty][tx] = x_flux(K0{}, Lk, 0); FX[1][ty][tx] = x_flux(K1{}, Lk, 0); FX[3][ty][tx] = x_flux(K3{}, Lk, 0);
+                        if (lane < TY) {
+                            if (wrp == XE0) FX[0][lane][TX] = x_flux(K0{}, xedge, xoff);
+                            else if (wrp == XE0 + 1) FX[1][lane][TX] = x_flux(K1{}, xedge, xoff);
+                            else if (wrp == XE0 + 2) FX[3][lane][TX] = x_flux(K3{}, xedge, xoff);
+                        }
+                    }
                     if (HAS_Y) {
                         FY[0][ty][tx] = y_flux(K0{}, Lk, 0); FY[1][ty][tx] = y_flux(K1{}, Lk, 0); FY[3][ty][tx] = y_flux(K3{}, Lk, 0);
                         // the extra row of y-faces above the tile: one flux kind per warp (rows 0..2 of this role)
@@ -386,7 +399,13 @@ __global__ void __launch_bounds__(2 * TX * TY, 1) stage_kernel(const __grid_cons
                         else if (ty == 2) FY[3][TY][tx] = y_flux(K3{}, edge, ezoff);
                     }
                 } else {
-                    if (!FLAT_X) { FX[2][ty][tx] = x_flux(K2{}); FX[4][ty][tx] = x_flux(K4{}); }
+                    if (!FLAT_X) {
+                        FX[2][ty][tx] = x_flux(K2{}, Lk, 0); FX[4][ty][tx] = x_flux(K4{}, Lk, 0);
+                        if (lane < TY) {
+                            if (wrp == XE1) FX[2][lane][TX] = x_flux(K2{}, xedge, xoff);
+                            else if (wrp == XE1 + 1) FX[4][lane][TX] = x_flux(K4{}, xedge, xoff);
+                        }
+                    }
                     if (HAS_Y) {
                         FY[2][ty][tx] = y_flux(K2{}, Lk, 0); FY[4][ty][tx] = y_flux(K4{}, Lk, 0);
                         if (ty == 0) FY[2][TY][tx] = y_flux(K2{}, edge, ezoff);
