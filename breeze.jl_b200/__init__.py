@@ -4,8 +4,10 @@ Import as `breeze_b200` (repo-root shim; a directory name containing a dot canno
 Everything numerical runs in csrc/libbreeze_b200.so (hand-written sm_100a CUDA behind the C ABI of
 include/breeze_b200.h). There is no CPU fallback: constructing a model without the built library raises.
 """
-from .abi import BreezeError, Context, Library, bz_config, load_cuda_library, cuda_library_path, FIELD_IDS
-from .model import (B200, AnelasticDynamics, AtmosphereModel, Bounded, Flat, Periodic, RectilinearGrid, ReferenceState,
+from . import cases
+from .abi import BreezeError, Context, Library, bz_config, bz_forcing, load_cuda_library, cuda_library_path, FIELD_IDS
+from .model import (B200, DragFluxBoundaryCondition, FluxBoundaryCondition, Forcing, FPlane, GeostrophicForcing, SubsidenceForcing,
+                    geostrophic_forcings, AnelasticDynamics, AtmosphereModel, Bounded, Flat, Periodic, RectilinearGrid, ReferenceState,
                     SaturationAdjustment, Simulation, ThermodynamicConstants, TimeStepWizard, WENO,
                     conjure_time_step_wizard_, many_time_steps_, run_, set_, time_step_)
 

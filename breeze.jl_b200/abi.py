@@ -51,6 +51,16 @@ class bz_config(C.Structure):
     ]
 
 
+class bz_forcing(C.Structure):
+    _fields_ = [
+        ("coriolis_f", C.c_double),
+        ("subsidence_w", C.POINTER(C.c_double)), ("subsidence_mask", C.c_int32), ("reserved0", C.c_int32),
+        ("geostrophic_u", C.POINTER(C.c_double)), ("geostrophic_v", C.POINTER(C.c_double)),
+        ("q_tendency", C.POINTER(C.c_double)), ("e_tendency", C.POINTER(C.c_double)),
+        ("theta_flux", C.c_double), ("q_flux", C.c_double), ("drag_rho_ustar2", C.c_double),
+    ]
+
+
 class BreezeError(RuntimeError):
     pass
 
@@ -68,6 +78,7 @@ ABI_SYMBOLS = {
     "get_reference_state": (C.c_int, [_vp, _dp, _dp, _dp]),
     "set_reference_state": (C.c_int, [_vp, _dp, _dp, _dp]),
     "set_state": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _dp, C.c_int]),
+    "set_forcing": (C.c_int, [_vp, C.POINTER(bz_forcing)]),
     "time_step": (C.c_int, [_vp, C.c_double]),
     "time_steps": (C.c_int, [_vp, C.c_double, C.c_int]),
     "compute_tendencies": (C.c_int, [_vp]),
@@ -177,6 +188,32 @@ class Context:
                 raise BreezeError(f"field {fid}: expected shape {self.shape(fid)}, got {a.shape}")
             arrs.append(a)
         self._check(self.lib.set_state(self.handle, *[_as_dp(a) for a in arrs], int(enforce_mass_conservation)), "set_state")
+
+    def set_forcing(self, coriolis_f=0.0, subsidence_w=None, subsidence_on=("u", "v", "θ", "q"), geostrophic_u=None,
+                    geostrophic_v=None, q_tendency=None, e_tendency=None, theta_flux=0.0, q_flux=0.0, drag_rho_ustar2=0.0):
+        """Install the forcing / Coriolis / bottom-flux terms (bz_forcing). Profiles are arrays over the z levels."""
+        F = bz_forcing()
+        keep = []
+
+        def ptr(a, n):
+            if a is None:
+                return None
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            if a.shape != (n,):
+                raise BreezeError(f"forcing profile: expected {n} values, got {a.shape}")
+            keep.append(a)
+            return a.ctypes.data_as(_dp)
+
+        F.coriolis_f = float(coriolis_f)
+        F.subsidence_w = ptr(subsidence_w, self.Nz + 1)
+        F.subsidence_mask = sum(1 << {"u": 0, "v": 1, "θ": 2, "q": 3}[n] for n in subsidence_on) if subsidence_w is not None else 0
+        F.geostrophic_u, F.geostrophic_v = ptr(geostrophic_u, self.Nz), ptr(geostrophic_v, self.Nz)
+        F.q_tendency, F.e_tendency = ptr(q_tendency, self.Nz), ptr(e_tendency, self.Nz)
+        F.theta_flux, F.q_flux, F.drag_rho_ustar2 = float(theta_flux), float(q_flux), float(drag_rho_ustar2)
+        self._check(self.lib.set_forcing(self.handle, C.byref(F)), "set_forcing")
+
+    def clear_forcing(self):
+        self._check(self.lib.set_forcing(self.handle, None), "set_forcing")
 
     def get_field(self, name_or_id):
         fid = FIELD_IDS[name_or_id] if isinstance(name_or_id, str) else int(name_or_id)

@@ -43,6 +43,11 @@ struct bz_ctx {
     double *lam_x = nullptr, *lam_y = nullptr, *inv_beta = nullptr, *tfac = nullptr;
     long long* ky_base = nullptr;
     int* ky_kstride = nullptr;
+    // forcing (bz_forcing)
+    int forced = 0, subs_mask = 0;
+    double coriolis_f = 0, theta_flux = 0, q_flux = 0, drag = 0;
+    double* fstore = nullptr;            // ws[Nz+1] | ug | vg | q_tend | e_tend | sums[4Nz] | fcol[4Nz]
+    double *d_ws = nullptr, *d_ug = nullptr, *d_vg = nullptr, *d_qt = nullptr, *d_et = nullptr, *d_sums = nullptr, *d_fcol = nullptr;
     int lines_x = 1, lines_y = 1;
     cudaStream_t stream = nullptr;
     Comm comm;
@@ -352,13 +357,37 @@ static int fill_halos(bz_ctx* c, double* const* fields, int nf, int fam, bool ex
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// forcing: horizontal means → per-level forcing columns (compute_forcings!, update_atmosphere_model_state.jl:81-86)
+// ---------------------------------------------------------------------------------------------------------------
+static int update_column_forcing(bz_ctx* c, int set_index) {
+    const Layout& L = c->L;
+    ProfScope ps(c, 4);
+    if (c->d_ws && c->subs_mask) {
+        FieldSet U; U.n = NPROG;
+        for (int f = 0; f < NPROG; ++f) U.f[f] = c->set[set_index][f];
+        column_sums<<<L.Nz, 256, 0, c->stream>>>(L, U, c->d_sums);
+        c->launches++;
+        if (c->comm.n_ranks > 1) {
+            int rc = comm_allreduce_sum_device(c->comm, c->d_sums, (size_t)4 * L.Nz, c->stream);
+            if (rc) { bz_set_error(c, "allreduce: %s", c->comm.err); return rc; }
+        }
+    }
+    const double inv_n = 1.0 / ((double)c->cfg.Nx * (double)c->cfg.Ny);
+    column_forcing_kernel<<<1, 256, 0, c->stream>>>(L.Nz, L.dz, inv_n, c->col.rho, c->d_sums, c->d_ws, c->subs_mask, c->d_ug, c->d_vg,
+                                                     c->d_qt, c->coriolis_f, c->d_fcol);
+    c->launches++;
+    CUDA_TRY(c, cudaGetLastError());
+    return BZ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // stage kernel launch
 // ---------------------------------------------------------------------------------------------------------------
-template <int TX, int TY, bool HAS_Y, bool FLAT_X, int MICRO>
+template <int TX, int TY, bool HAS_Y, bool FLAT_X, int MICRO, bool FORCED>
 static int launch_stage_t(bz_ctx* c, const StageParams& P, int nz_chunks) {
     using SM = StageShared<TX, TY, HAS_Y>;
     static bool configured = false;
-    auto kern = stage_kernel<TX, TY, HAS_Y, FLAT_X, MICRO>;
+    auto kern = stage_kernel<TX, TY, HAS_Y, FLAT_X, MICRO, FORCED>;
     if (!configured) {
         CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SM)));
         configured = true;
@@ -386,11 +415,21 @@ static int launch_stage(bz_ctx* c, int in, double* const* out, int u0, double dt
     int chunks = c->z_chunks;
     P.k_chunk = (c->L.Nz + chunks - 1) / chunks;
     const bool moist = c->cfg.microphysics != BZ_MICROPHYSICS_NONE;
-    if (!c->L.flat_y) {
-        return moist ? launch_stage_t<32, 8, true, false, 1>(c, P, chunks) : launch_stage_t<32, 8, true, false, 0>(c, P, chunks);
+    if (c->forced) {
+        int rc = update_column_forcing(c, in);
+        if (rc) return rc;
+        for (int f = 0; f < 4; ++f) P.fcol[f] = c->d_fcol + (size_t)f * c->L.Nz;
+        P.e_tend = c->d_et;
+        P.coriolis_f = c->coriolis_f;
+        P.theta_flux_dz = c->theta_flux / c->L.dz; P.q_flux_dz = c->q_flux / c->L.dz; P.drag_dz = c->drag / c->L.dz;
     }
-    if (c->L.flat_x) return moist ? launch_stage_t<32, 1, false, true, 1>(c, P, chunks) : launch_stage_t<32, 1, false, true, 0>(c, P, chunks);
-    return moist ? launch_stage_t<128, 1, false, false, 1>(c, P, chunks) : launch_stage_t<128, 1, false, false, 0>(c, P, chunks);
+#define LAUNCH(TX, TY, HY, FX)                                                                                        \
+    (c->forced ? (moist ? launch_stage_t<TX, TY, HY, FX, 1, true>(c, P, chunks) : launch_stage_t<TX, TY, HY, FX, 0, true>(c, P, chunks)) \
+               : (moist ? launch_stage_t<TX, TY, HY, FX, 1, false>(c, P, chunks) : launch_stage_t<TX, TY, HY, FX, 0, false>(c, P, chunks)))
+    if (!c->L.flat_y) return LAUNCH(32, 8, true, false);
+    if (c->L.flat_x) return LAUNCH(32, 1, false, true);
+    return LAUNCH(128, 1, false, false);
+#undef LAUNCH
 }
 
 // compute_pressure_correction! + make_pressure_correction! on set[cur], then refresh all ghosts
@@ -454,7 +493,7 @@ void bz_destroy(bz_ctx* c) {
     cudaFree(c->phi); cudaFree(c->dense); cudaFree(c->scalar); cudaFree(c->col_store);
     if (c->W2 != c->W) cudaFree(c->W2);
     cudaFree(c->W); cudaFree(c->tw_x); cudaFree(c->tw_y); cudaFree(c->lam_x); cudaFree(c->lam_y);
-    cudaFree(c->inv_beta); cudaFree(c->tfac); cudaFree(c->ky_base); cudaFree(c->ky_kstride);
+    cudaFree(c->inv_beta); cudaFree(c->tfac); cudaFree(c->ky_base); cudaFree(c->ky_kstride); cudaFree(c->fstore);
     for (auto e : c->prof_ev) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -598,6 +637,36 @@ int bz_set_state(bz_ctx* c, const double* ru, const double* rv, const double* rw
         if (src[f] && (rc = upload_field(c, src[f], c->set[c->cur][f], f == BZ_RHO_W))) return rc;
     if ((rc = fill_halos(c, c->set[c->cur], NPROG, 4))) return rc;
     if (enforce && (rc = pressure_correct(c, 1.0))) return rc;
+    return BZ_OK;
+}
+
+int bz_set_forcing(bz_ctx* c, const bz_forcing* F) {
+    if (!c) return BZ_ERR_INVALID;
+    cudaSetDevice(c->cfg.device);
+    if (!F) { c->forced = 0; return BZ_OK; }
+    const int Nz = c->L.Nz;
+    if (c->L.flat_x && (F->coriolis_f != 0 || F->drag_rho_ustar2 != 0)) { bz_set_error(c, "Coriolis / drag need a non-Flat x"); return BZ_ERR_UNSUPPORTED; }
+    const size_t total = (size_t)(Nz + 1) + 4 * (size_t)Nz + 8 * (size_t)Nz;
+    if (!c->fstore) { int rc = dev_alloc(c, &c->fstore, total); if (rc) return rc; }
+    std::vector<double> h(total, 0.0);
+    double* base = c->fstore;
+    size_t off = 0;
+    auto put = [&](const double* src, size_t n, double** dev) {
+        if (src) { memcpy(&h[off], src, n * sizeof(double)); *dev = base + off; } else *dev = nullptr;
+        off += n;
+    };
+    put(F->subsidence_w, Nz + 1, &c->d_ws);
+    put(F->geostrophic_u, Nz, &c->d_ug);
+    put(F->geostrophic_v, Nz, &c->d_vg);
+    put(F->q_tendency, Nz, &c->d_qt);
+    put(F->e_tendency, Nz, &c->d_et);
+    c->d_sums = base + off; off += (size_t)4 * Nz;
+    c->d_fcol = base + off; off += (size_t)4 * Nz;
+    CUDA_TRY(c, cudaMemcpyAsync(c->fstore, h.data(), total * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    c->coriolis_f = F->coriolis_f; c->theta_flux = F->theta_flux; c->q_flux = F->q_flux; c->drag = F->drag_rho_ustar2;
+    c->subs_mask = F->subsidence_mask;
+    c->forced = 1;
     return BZ_OK;
 }
 

@@ -136,3 +136,47 @@ __global__ void unpack_x_faces(Layout L, FieldSet F, int i_dst, int w, const dou
         F.f[f][lidx(L, i_dst + c, j, k)] = buf[e];
     }
 }
+
+// Horizontal sums of the four forced prognostics per level (compute_forcing!(::SubsidenceForcing): the averages are
+// recomputed every update_state!). grid = Nz blocks; sums[f * Nz + k].
+__global__ void column_sums(Layout L, FieldSet U, double* __restrict__ sums) {
+    __shared__ double sh[4][256];
+    const int k = blockIdx.x;
+    const int map[4] = {0, 1, 3, 4};             // ρu, ρv, ρθ, ρq
+    double a[4] = {0.0, 0.0, 0.0, 0.0};
+    const int n = L.nx * L.Ny;
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+        long long idx = lidx(L, e % L.nx, e / L.nx, k);
+#pragma unroll
+        for (int f = 0; f < 4; ++f) a[f] += U.f[map[f]][idx];
+    }
+#pragma unroll
+    for (int f = 0; f < 4; ++f) sh[f][threadIdx.x] = a[f];
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) for (int f = 0; f < 4; ++f) sh[f][threadIdx.x] += sh[f][threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x < 4) sums[threadIdx.x * L.Nz + k] = sh[threadIdx.x][0];
+}
+
+// ρ × (subsidence + geostrophic + prescribed) specific forcing per level (src/Forcings/subsidence_forcing.jl:84-100,
+// geostrophic_forcings.jl:74-84, specific_forcing.jl:70-74). One block; fcol[f * Nz + k].
+__global__ void column_forcing_kernel(int Nz, double dz, double inv_n, const double* __restrict__ rho, const double* __restrict__ sums,
+                                      const double* __restrict__ ws, int mask, const double* __restrict__ ug, const double* __restrict__ vg,
+                                      const double* __restrict__ q_tend, double coriolis_f, double* __restrict__ fcol) {
+    for (int e = threadIdx.x; e < 4 * Nz; e += blockDim.x) {
+        const int f = e / Nz, k = e % Nz;
+        double F = 0.0;
+        if (ws && ((mask >> f) & 1)) {
+            auto mean = [&](int kk) { return sums[f * Nz + kk] * inv_n / rho[kk]; };
+            double up = (k + 1 < Nz) ? ws[k + 1] * ((mean(k + 1) - mean(k)) / dz) : 0.0;
+            double lo = (k > 0) ? ws[k] * ((mean(k) - mean(k - 1)) / dz) : 0.0;
+            F -= (k == Nz - 1) ? lo : ((k == 0) ? up : 0.5 * (up + lo));
+        }
+        if (f == 0 && vg) F += -coriolis_f * vg[k];
+        if (f == 1 && ug) F += coriolis_f * ug[k];
+        if (f == 3 && q_tend) F += q_tend[k];
+        fcol[e] = rho[k] * F;
+    }
+}

@@ -17,7 +17,7 @@
 
 typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId_t;
-enum { NCCL_FLOAT64 = 8, NCCL_MAX = 2 };      // ncclDataType_t / ncclRedOp_t values (nccl.h)
+enum { NCCL_FLOAT64 = 8, NCCL_SUM = 0, NCCL_MAX = 2 };      // ncclDataType_t / ncclRedOp_t values (nccl.h)
 
 struct NcclApi {
     void* lib = nullptr;
@@ -172,6 +172,11 @@ static int comm_transpose_forward(Comm& cm, const double2* W, double2* W2, int n
 }
 static int comm_transpose_backward(Comm& cm, const double2* W2, double2* W, int nx, const PoissonGeom& G, cudaStream_t s, int64_t*) {
     return comm_alltoall(cm, W2, W, nx, G, false, s);
+}
+
+static int comm_allreduce_sum_device(Comm& cm, double* dev, size_t n, cudaStream_t s) {
+    NCCL_TRY(cm, cm.api.AllReduce(dev, dev, n, NCCL_FLOAT64, NCCL_SUM, cm.comm, s));
+    return BZ_OK;
 }
 
 static int comm_allreduce_max(Comm& cm, double* host_value, double* dev_scalar, cudaStream_t s) {

@@ -39,6 +39,10 @@ struct StageParams {
     int nx_u;                         // ρu (and G_ρu) is produced for i < nx_u (nx, or nx + 1 on a multi-GPU slab)
     int k_chunk;                      // levels per z chunk (blockIdx.z selects the chunk)
     int use_tma;
+    // forcing / Coriolis / bottom flux BCs (bz_forcing); only read by the FORCED instantiation
+    const double* fcol[4];            // ρ × horizontally uniform specific forcing of u, v, θ, q per level (device, Nz each)
+    const double* e_tend;             // specific energy tendency per level or nullptr
+    double coriolis_f, theta_flux_dz, q_flux_dz, drag_dz;   // fluxes already divided by Δz
 };
 
 // ---- thermodynamics on the fly ---------------------------------------------------------------------------------
@@ -92,17 +96,21 @@ __device__ double saturation_adjust(const Thermo& th, double theta, double pr, d
 }
 
 // buoyancy_forceᶜᶜᶜ: -g ρᵣ (Rᵐᵣ Tᵣ / (Rᵐ T) - 1), reference moisture = 0 (anelastic_buoyancy.jl:36-72)
+// cpm_pi (optional): cᵖᵐ Π of the cell, for the Fρe / (cᵖᵐ Π) term of the ρθ tendency (potential_temperature_tendency.jl:93-104)
 template <int MICRO>
 __device__ __forceinline__ double buoyancy_center(const Thermo& th, const Columns& col, int k, double rho_k, double exner_dry_k, double Tr_k,
-                                                  double theta, double q) {
-    double T, Rm;
+                                                  double theta, double q, double* cpm_pi = nullptr) {
+    double T, Rm, qv = q, ql = 0.0;
     if (MICRO == BZ_MICROPHYSICS_NONE) {
         if (q == 0.0) { T = exner_dry_k * theta; Rm = th.Rd; }
         else { T = lipt_temperature(th, theta, col.log_p_pst[k], q, 0.0); Rm = (1.0 - q) * th.Rd + q * th.Rv; }
     } else {
-        double qv, ql;
         T = saturation_adjust(th, theta, col.p[k], col.log_p_pst[k], q, qv, ql);
         Rm = (1.0 - (qv + ql)) * th.Rd + qv * th.Rv;
+    }
+    if (cpm_pi) {
+        double cpm = (1.0 - (qv + ql)) * th.cpd + qv * th.cpv + ql * th.cl;
+        *cpm_pi = cpm * exp((Rm / cpm) * col.log_p_pst[k]);
     }
     double rho_p = rho_k * (th.Rd * Tr_k / (Rm * T) - 1.0);
     return -th.g * rho_p;
@@ -160,7 +168,7 @@ __device__ __forceinline__ double biased6c(double v0, double v1, double v2, doub
     return left ? v2 : v3;
 }
 
-template <int TX, int TY, bool HAS_Y, bool FLAT_X, int MICRO>
+template <int TX, int TY, bool HAS_Y, bool FLAT_X, int MICRO, bool FORCED>
 __global__ void __launch_bounds__(2 * TX * TY, 1) stage_kernel(const __grid_constant__ StageParams P) {
     using SM = StageShared<TX, TY, HAS_Y>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -299,7 +307,7 @@ __global__ void __launch_bounds__(2 * TX * TY, 1) stage_kernel(const __grid_cons
         const double* const Lk = Lp[2];
         const double* const Lt = Lp[3];                                // level of the top face / of cell k+1
 
-        double zt0 = 0.0, zt1 = 0.0, zt2 = 0.0, b_here = 0.0;
+        double zt0 = 0.0, zt1 = 0.0, zt2 = 0.0, b_here = 0.0, cpm_pi = 1.0;
 
         // One level of flux work. FULL: every z stencil is at full order (2 <= k <= Nz-4): all orders are compile-time.
         auto level = [&](auto full_tag, auto phase_tag) {
@@ -416,7 +424,7 @@ __global__ void __launch_bounds__(2 * TX * TY, 1) stage_kernel(const __grid_cons
                 if (role == 0) { zt0 = z_flux(K0{}); zt1 = z_flux(K1{}); }
                 else {
                     zt0 = z_flux(K2{}); zt1 = z_flux(K3{}); zt2 = z_flux(K4{});
-                    b_here = buoyancy_center<MICRO>(P.th, P.col, k, rho_k, ex_k, Tr_k, Lk[3 * PL], Lk[4 * PL]);
+                    b_here = buoyancy_center<MICRO>(P.th, P.col, k, rho_k, ex_k, Tr_k, Lk[3 * PL], Lk[4 * PL], (FORCED && P.e_tend) ? &cpm_pi : nullptr);
                 }
             }
 #undef XS
@@ -447,6 +455,25 @@ __global__ void __launch_bounds__(2 * TX * TY, 1) stage_kernel(const __grid_cons
                 if (HAS_Y) g += (S.fy[k & 1][f][ty + 1][tx] - S.fy[k & 1][f][ty][tx]) * rdy;
                 g = -(g + (zt[a] - zb[a]) * rdz);
                 if (f == 2) g = (k >= 1) ? g + 0.5 * (b_here + b_below) : 0.0;
+                if (FORCED) {
+                    // FPlane Coriolis, horizontally uniform forcings, prescribed energy tendency, bottom flux BCs (bz_forcing)
+                    if (f == 0) {
+                        double rv_fc = 0.25 * rho_k * ((Lk[PL - 1] + Lk[PL]) + (HAS_Y ? Lk[PL + SW - 1] + Lk[PL + SW] : Lk[PL - 1] + Lk[PL]));
+                        g += P.coriolis_f * rv_fc + P.fcol[0][k];
+                        if (k == 0 && P.drag_dz != 0.0) { double ru = rho_k * Lk[0]; g -= P.drag_dz * ru / sqrt(ru * ru + rv_fc * rv_fc); }
+                    } else if (f == 1) {
+                        double ru_cf = 0.25 * rho_k * ((Lk[0] + Lk[1]) + (HAS_Y ? Lk[-SW] + Lk[-SW + 1] : Lk[0] + Lk[1]));
+                        g += -P.coriolis_f * ru_cf + P.fcol[1][k];
+                        if (k == 0 && P.drag_dz != 0.0) { double rv = rho_k * Lk[PL]; g -= P.drag_dz * rv / sqrt(ru_cf * ru_cf + rv * rv); }
+                    } else if (f == 3) {
+                        g += P.fcol[2][k];
+                        if (P.e_tend) g += rho_k * P.e_tend[k] / cpm_pi;
+                        if (k == 0) g += P.theta_flux_dz;
+                    } else if (f == 4) {
+                        g += P.fcol[3][k];
+                        if (k == 0) g += P.q_flux_dz;
+                    }
+                }
                 double r;
                 if (P.mode == 1) r = g;
                 else {

@@ -141,6 +141,50 @@ class WENO:
     order: int = 5
 
 
+@dataclass
+class FPlane:
+    """Oceananigans FPlane(f=...)"""
+    f: float = 0.0
+
+
+class SubsidenceForcing:
+    """SubsidenceForcing(wˢ): wˢ a function of z or an array at the Nz+1 z-faces (src/Forcings/subsidence_forcing.jl)."""
+
+    def __init__(self, wˢ):
+        self.w = wˢ
+
+
+class GeostrophicForcing:
+    def __init__(self, velocity, direction):
+        self.velocity, self.direction = velocity, direction
+
+
+def geostrophic_forcings(uᵍ, vᵍ):
+    """geostrophic_forcings(uᵍ, vᵍ) → forcings keyed `u` (uses vᵍ) and `v` (uses uᵍ) (src/Forcings/geostrophic_forcings.jl:128-132)."""
+    return {"u": GeostrophicForcing(vᵍ, "x"), "v": GeostrophicForcing(uᵍ, "y")}
+
+
+class Forcing:
+    """Forcing(field): a prescribed horizontally uniform profile (function of z or array over the Nz centres)."""
+
+    def __init__(self, profile):
+        self.profile = profile
+
+
+class FluxBoundaryCondition:
+    """Bottom FluxBoundaryCondition with a constant value (examples/bomex.jl:77-84)."""
+
+    def __init__(self, value):
+        self.value = float(value)
+
+
+class DragFluxBoundaryCondition:
+    """Bottom momentum flux -ρ₀ u★² ρu / |ρ𝐮ₕ| (examples/bomex.jl:93-101); give the same object for ρu and ρv."""
+
+    def __init__(self, rho0, u_star):
+        self.rho0_ustar2 = float(rho0) * float(u_star) ** 2
+
+
 class SaturationAdjustment:
     """SaturationAdjustment(equilibrium=WarmPhaseEquilibrium()) (src/Microphysics/saturation_adjustment.jl:23-55)."""
 
@@ -173,7 +217,8 @@ class AtmosphereModel:
 
     def __init__(self, grid: RectilinearGrid, dynamics: AnelasticDynamics | None = None, advection: WENO | None = None,
                  microphysics=None, thermodynamic_constants: ThermodynamicConstants | None = None,
-                 timestepper: str = "SSPRungeKutta3"):
+                 timestepper: str = "SSPRungeKutta3", coriolis: FPlane | None = None, forcing: dict | None = None,
+                 boundary_conditions: dict | None = None):
         if timestepper != "SSPRungeKutta3":
             raise NotImplementedError("only :SSPRungeKutta3 is on the hot path")
         self.grid = grid
@@ -215,6 +260,59 @@ class AtmosphereModel:
         # local x-slab of this rank
         self.Nx_local = self.context.Nx_local
         self.i0 = cfg.rank * self.Nx_local
+        self.coriolis, self.forcing, self.boundary_conditions = coriolis, forcing, boundary_conditions
+        if coriolis is not None or forcing or boundary_conditions:
+            self._install_forcing()
+
+    def _profile(self, value, face=False):
+        z = self.grid.znodes(face=face)
+        return np.array([value(zz) for zz in z], dtype=np.float64) if callable(value) else np.asarray(value, dtype=np.float64)
+
+    def _install_forcing(self):
+        """forcing = (; u = (subsidence, geostrophic.u), θ = subsidence, qᵉ = (subsidence, Forcing(drying)), e = Forcing(cooling))
+        and boundary_conditions = (ρθ=…, ρqᵉ=…, ρu=…, ρv=…) as in examples/bomex.jl:119-208."""
+        kw = dict(coriolis_f=self.coriolis.f if self.coriolis else 0.0)
+        alias = {"θ": "θ", "θˡⁱ": "θ", "qᵉ": "q", "qᵗ": "q", "qᵛ": "q", "q": "q", "u": "u", "v": "v", "e": "e"}
+        subs_on, subs_w = [], None
+        for key, items in (self.forcing or {}).items():
+            name = alias.get(key)
+            if name is None:
+                raise ValueError(f"forcing key {key}: supply forcings under the specific names u, v, θ, qᵉ, e")
+            for item in (items if isinstance(items, (tuple, list)) else (items,)):
+                if isinstance(item, SubsidenceForcing):
+                    if name == "e":
+                        raise ValueError("SubsidenceForcing applies to u, v, θ, qᵉ")
+                    w = self._profile(item.w, face=True)
+                    if subs_w is not None and not np.array_equal(w, subs_w):
+                        raise NotImplementedError("one subsidence profile per model")
+                    subs_w = w
+                    subs_on.append(name)
+                elif isinstance(item, GeostrophicForcing):
+                    f = kw["coriolis_f"]
+                    if f == 0.0:
+                        raise ValueError("geostrophic forcing needs coriolis=FPlane(f)")
+                    kw["geostrophic_v" if item.direction == "x" else "geostrophic_u"] = self._profile(item.velocity)
+                elif isinstance(item, Forcing):
+                    if name == "q":
+                        kw["q_tendency"] = self._profile(item.profile)
+                    elif name == "e":
+                        kw["e_tendency"] = self._profile(item.profile)
+                    else:
+                        raise NotImplementedError("Forcing(field) is on the path for qᵉ and e only")
+                else:
+                    raise NotImplementedError(f"forcing of type {type(item).__name__}")
+        if subs_w is not None:
+            kw.update(subsidence_w=subs_w, subsidence_on=tuple(subs_on))
+        for key, bc in (self.boundary_conditions or {}).items():
+            if isinstance(bc, DragFluxBoundaryCondition):
+                kw["drag_rho_ustar2"] = bc.rho0_ustar2
+            elif key in ("ρθ", "ρθˡⁱ"):
+                kw["theta_flux"] = bc.value
+            elif key in ("ρqᵉ", "ρqᵗ", "ρqᵛ", "ρq"):
+                kw["q_flux"] = bc.value
+            else:
+                raise NotImplementedError(f"boundary condition on {key}")
+        self.context.set_forcing(**kw)
 
     # --- coordinates of the local slab -----------------------------------------------------------
     def _coords(self, loc):

@@ -96,6 +96,31 @@ typedef struct bz_config {
     int32_t reserved[6];
 } bz_config;
 
+/*
+ * bz_forcing — the forcing / Coriolis / bottom flux-BC terms of an LES case such as BOMEX (examples/bomex.jl:77-196), all
+ * zero in the bubble configurations. Pointers are HOST arrays read during the call (NULL = term absent):
+ *   SubsidenceForcing(wˢ) on u, v, θ, qᵉ   F_ϕ = -ℑzb(wˢ ∂z ϕ̄), ϕ̄ = horizontal mean, recomputed every update_state!
+ *                                          (src/Forcings/subsidence_forcing.jl:84-141); enters as ρ F_ϕ (specific_forcing.jl:70-74)
+ *   geostrophic_forcings(uᵍ, vᵍ)            F_u = -f vᵍ, F_v = +f uᵍ (src/Forcings/geostrophic_forcings.jl:74-84), × ρ
+ *   FPlane(f)                               -x_f_cross_U = +f ℑxy(ρv), -y_f_cross_U = -f ℑxy(ρu) (dynamics_kernel_functions.jl:79,99)
+ *   Forcing(field) under `qᵉ` and `e`       ρ·q_tendency;  ρ·e_tendency / (cᵖᵐ Π) into ρθ (potential_temperature_tendency.jl:97-104)
+ *   bottom FluxBoundaryConditions           G[i,j,1] += J/Δz (update_atmosphere_model_state.jl:418-434): constant J for ρθ, ρq;
+ *                                           J = -ρ₀u★² ρu/|ρ𝐮ₕ| (and ρv) with the other component interpolated to the face.
+ */
+typedef struct bz_forcing {
+    double coriolis_f;
+    const double* subsidence_w;        /* Nz+1 values at z-faces */
+    int32_t subsidence_mask;           /* bit 0: u, 1: v, 2: θ, 3: q */
+    int32_t reserved0;
+    const double* geostrophic_u;       /* Nz */
+    const double* geostrophic_v;       /* Nz */
+    const double* q_tendency;          /* Nz, specific (kg/kg/s) */
+    const double* e_tendency;          /* Nz, specific energy tendency (J/kg/s) */
+    double theta_flux;                 /* ρ₀ w'θ' */
+    double q_flux;                     /* ρ₀ w'q' */
+    double drag_rho_ustar2;            /* ρ₀ u★² */
+} bz_forcing;
+
 typedef struct bz_ctx bz_ctx;
 
 void        bz_default_config(bz_config* cfg);
@@ -121,6 +146,9 @@ int bz_set_reference_state(bz_ctx* ctx, const double* density, const double* pre
  * Δt = 1 → update_state!] so momentum is discretely divergence-free before the first step (:121-128,338,351). */
 int bz_set_state(bz_ctx* ctx, const double* rho_u, const double* rho_v, const double* rho_w,
                  const double* rho_theta, const double* rho_q, int enforce_mass_conservation);
+
+/* AtmosphereModel(grid; coriolis, forcing, boundary_conditions, ...): installs / replaces the terms above (NULL clears them). */
+int bz_set_forcing(bz_ctx* ctx, const bz_forcing* forcing);
 
 /* time_step!(model::AtmosphereModel{…,<:SSPRungeKutta3}, Δt) (src/TimeSteppers/ssp_runge_kutta_3.jl:209-278).
  * Asynchronous with respect to the device. bz_time_steps = many_time_steps! (benchmarking/src/timestepping.jl:11-16). */

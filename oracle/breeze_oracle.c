@@ -70,6 +70,13 @@ typedef struct orc_ctx {
     double *lower;        /* Nz-1 */
     double *diag;         /* Nx*Ny*Nz */
     fft_plan px, py;
+    /* forcing / Coriolis / bottom flux BCs (bz_forcing); all absent by default */
+    int stale;            /* tendencies must be rebuilt before the next stage (after set! / a change of forcing) */
+    int has_forcing;
+    double coriolis_f, theta_flux, q_flux, drag_rho_ustar2;
+    int subsidence_mask;
+    double *ws, *ug, *vg, *q_tend, *e_tend;      /* ws: Nz+1 faces; others Nz; NULL = absent */
+    double *mean[4];                              /* horizontal means of u, v, θ, q (Nz) */
     double time; int64_t iteration;
     char err[256];
 } orc_ctx;
@@ -562,6 +569,38 @@ static inline double flux_Ww(const orc_ctx* c, int i, int j, int k) {        /* 
     return wt * biased_interp(c->w + n1, SZ, red_center(k, c->Nz, 3), wt > 0);
 }
 
+/* compute_forcing!(::SubsidenceForcing): horizontal averages of the specific fields (subsidence_forcing.jl:137-141) */
+static void compute_forcing_means(orc_ctx* c, const double* qe) {
+    if (!c->has_forcing || !c->ws) return;
+    const double* src[4] = {c->u, c->v, c->theta, qe};
+    const double n = (double)c->Nx * c->Ny;
+    for (int f = 0; f < 4; ++f)
+        for (int k = 0; k < c->Nz; ++k) {
+            double s = 0;
+            for (int j = 0; j < c->Ny; ++j) for (int i = 0; i < c->Nx; ++i) s += src[f][IDX(c, i, j, k)];
+            c->mean[f][k] = s / n;
+        }
+}
+
+/* SubsidenceForcing kernel: -ℑzb(wˢ ∂z ϕ̄) with the one-sided top / bottom rule (subsidence_forcing.jl:84-100) */
+static inline double subsidence_tendency(const orc_ctx* c, const double* phibar, int k) {
+    const int Nz = c->Nz;
+    double up = (k + 1 < Nz) ? c->ws[k + 1] * ((phibar[k + 1] - phibar[k]) / c->dz) : 0.0;   /* face k+1 */
+    double lo = (k > 0) ? c->ws[k] * ((phibar[k] - phibar[k - 1]) / c->dz) : 0.0;            /* face k   */
+    double v = (k == Nz - 1) ? lo : ((k == 0) ? up : (up + lo) / 2);
+    return -v;
+}
+
+/* ρ × (sum of the specific forcings of field f = 0 u, 1 v, 2 θ, 3 q) at level k, horizontally uniform part */
+static inline double column_forcing(const orc_ctx* c, int f, int k) {
+    double F = 0;
+    if (c->ws && (c->subsidence_mask >> f & 1)) F += subsidence_tendency(c, c->mean[f], k);
+    if (f == 0 && c->vg) F += -c->coriolis_f * c->vg[k];
+    if (f == 1 && c->ug) F += c->coriolis_f * c->ug[k];
+    if (f == 3 && c->q_tend) F += c->q_tend[k];
+    return c->rho_r[k + c->Hz] * F;
+}
+
 /* compute_tendencies!: update_atmosphere_model_state.jl:294-387 → x/y/z_momentum_tendency
  * (dynamics_kernel_functions.jl:64-130), potential_temperature_tendency (potential_temperature_tendency.jl:66-106),
  * scalar_tendency (dynamics_kernel_functions.jl:132-159). Zero terms of the configs on the path (Coriolis, closure,
@@ -600,6 +639,32 @@ static void compute_tendencies(orc_ctx* c, const double* qe) {
                 }
                 c->G[BZ_RHO_THETA][n] = -div_rhoUc(c, c->theta, i, j, k);
                 c->G[BZ_RHO_Q][n] = -div_rhoUc(c, qe, i, j, k);
+                if (c->has_forcing) {
+                    const double f = c->coriolis_f;
+                    const double* ru = c->U[BZ_RHO_U]; const double* rv = c->U[BZ_RHO_V];
+                    /* FPlane: -x_f_cross_U = +f ℑxyᶠᶜᵃ(ρv), -y_f_cross_U = -f ℑxyᶜᶠᵃ(ρu) */
+                    double rv_fc = 0.25 * (rv[IDX(c, i - 1, j, k)] + rv[n] + rv[IDX(c, i - 1, j + 1, k)] + rv[IDX(c, i, j + 1, k)]);
+                    double ru_cf = 0.25 * (ru[IDX(c, i, j - 1, k)] + ru[IDX(c, i + 1, j - 1, k)] + ru[n] + ru[IDX(c, i + 1, j, k)]);
+                    c->G[BZ_RHO_U][n] += f * rv_fc + column_forcing(c, 0, k);
+                    c->G[BZ_RHO_V][n] += -f * ru_cf + column_forcing(c, 1, k);
+                    c->G[BZ_RHO_THETA][n] += column_forcing(c, 2, k);
+                    c->G[BZ_RHO_Q][n] += column_forcing(c, 3, k);
+                    if (c->e_tend) {   /* (Fρe) / (cᵖᵐ Π), Fρe = ρ e_tendency */
+                        double qv = c->qv[n], ql = c->ql[n];
+                        double Rm = mixture_gas_constant(c, qv, ql, 0), cpm = mixture_heat_capacity(c, qv, ql, 0);
+                        double Pi = pow(c->p_r[k + c->Hz] / c->cfg.standard_pressure, Rm / cpm);
+                        c->G[BZ_RHO_THETA][n] += c->rho_r[k + c->Hz] * c->e_tend[k] / (cpm * Pi);
+                    }
+                    if (k == 0) {      /* compute_flux_bc_tendencies!: bottom fluxes, G += J Az / V */
+                        c->G[BZ_RHO_THETA][n] += c->theta_flux / c->dz;
+                        c->G[BZ_RHO_Q][n] += c->q_flux / c->dz;
+                        if (c->drag_rho_ustar2 != 0) {
+                            double a = c->drag_rho_ustar2;
+                            c->G[BZ_RHO_U][n] += (-a * ru[n] / sqrt(ru[n] * ru[n] + rv_fc * rv_fc)) / c->dz;
+                            c->G[BZ_RHO_V][n] += (-a * rv[n] / sqrt(ru_cf * ru_cf + rv[n] * rv[n])) / c->dz;
+                        }
+                    }
+                }
             }
 }
 
@@ -823,6 +888,7 @@ static void update_state(orc_ctx* c, int with_tendencies) {
             qe[n] = c->U[BZ_RHO_Q][n] / c->rho_r[k + c->Hz];
         }
         fill_halos(c, qe, LOC_CENTER);
+        compute_forcing_means(c, qe);
         compute_tendencies(c, qe);
         free(qe);
     }
@@ -844,7 +910,7 @@ static void ssp_rk3_substep(orc_ctx* c, double dt, double alpha) {
 
 /* time_step!: ssp_runge_kutta_3.jl:209-278 */
 static void time_step(orc_ctx* c, double dt) {
-    if (c->iteration == 0) update_state(c, 1);     /* maybe_prepare_first_time_step! */
+    if (c->iteration == 0 || c->stale) { update_state(c, 1); c->stale = 0; }   /* maybe_prepare_first_time_step! */
     for (int f = 0; f < NPROG; ++f) memcpy(c->U0[f], c->U[f], c->n_padded * sizeof(double));   /* store_initial_state! */
     const double alphas[3] = {1.0, 1.0 / 4.0, 2.0 / 3.0};
     for (int s = 0; s < 3; ++s) {
@@ -916,6 +982,8 @@ void orc_destroy(orc_ctx* c) {
     free(c->u); free(c->v); free(c->w); free(c->theta); free(c->qv); free(c->ql); free(c->T); free(c->phi);
     free(c->rhs); free(c->sol); free(c->lam_x); free(c->lam_y); free(c->lower); free(c->diag);
     fft_plan_free(&c->px); fft_plan_free(&c->py);
+    free(c->ws); free(c->ug); free(c->vg); free(c->q_tend); free(c->e_tend);
+    for (int f = 0; f < 4; ++f) free(c->mean[f]);
     free(c);
 }
 
@@ -964,7 +1032,27 @@ int orc_set_state(orc_ctx* c, const double* ru, const double* rv, const double* 
         make_pressure_correction(c, 1.0);
         update_state(c, 0);
     }
-    c->iteration = 0;    /* tendencies are recomputed by the next time_step! */
+    c->stale = 1;        /* tendencies are recomputed by the next time_step! */
+    return BZ_OK;
+}
+
+static void replace_profile(double** dst, const double* src, int n) {
+    free(*dst); *dst = NULL;
+    if (src) { *dst = (double*)malloc(sizeof(double) * (size_t)n); memcpy(*dst, src, sizeof(double) * (size_t)n); }
+}
+
+int orc_set_forcing(orc_ctx* c, const bz_forcing* F) {
+    if (!F) { c->has_forcing = 0; c->stale = 1; return BZ_OK; }
+    c->has_forcing = 1;
+    c->coriolis_f = F->coriolis_f; c->theta_flux = F->theta_flux; c->q_flux = F->q_flux; c->drag_rho_ustar2 = F->drag_rho_ustar2;
+    c->subsidence_mask = F->subsidence_mask;
+    replace_profile(&c->ws, F->subsidence_w, c->Nz + 1);
+    replace_profile(&c->ug, F->geostrophic_u, c->Nz);
+    replace_profile(&c->vg, F->geostrophic_v, c->Nz);
+    replace_profile(&c->q_tend, F->q_tendency, c->Nz);
+    replace_profile(&c->e_tend, F->e_tendency, c->Nz);
+    for (int f = 0; f < 4; ++f) if (!c->mean[f]) c->mean[f] = (double*)calloc((size_t)c->Nz, sizeof(double));
+    c->stale = 1;          /* tendencies are recomputed by the next time_step! */
     return BZ_OK;
 }
 

@@ -280,3 +280,78 @@ def test_warm_phase_saturation_adjustment_constructive(oracle_arch):
     # unsaturated air is left alone
     model.set(θ=300.0, qᵗ=1e-3)
     assert np.all(model.field("qˡ") == 0.0) and np.allclose(model.field("qᵛ"), 1e-3)
+
+
+# ---- BOMEX-type forcing terms ------------------------------------------------------------------
+
+def _forced_model(arch, size=(16, 16, 12), **forcing_kw):
+    grid = bz.RectilinearGrid(arch, size=size, x=(0, 3200.0), y=(0, 3200.0), z=(0, 3000.0))
+    model = bz.AtmosphereModel(grid, dynamics=bz.AnelasticDynamics(bz.ReferenceState(grid, surface_pressure=101500.0, potential_temperature=299.1)))
+    model.context.set_forcing(**forcing_kw)
+    return model
+
+
+def test_geostrophic_balance_is_a_fixed_point(oracle_arch):
+    """-f×ρu and the geostrophic forcing cancel exactly when (u, v) = (uᵍ, vᵍ) is uniform (geostrophic_forcings.jl:74-84)."""
+    Nz = 12
+    m = _forced_model(oracle_arch, coriolis_f=1e-4, geostrophic_u=np.full(Nz, 7.0), geostrophic_v=np.full(Nz, -3.0))
+    m.set(u=7.0, v=-3.0, θ=299.1)
+    m.context.compute_tendencies()
+    rho = m.reference_profiles()[0][:, None, None]
+    assert np.max(np.abs(m.context.get_tendency("ρu"))) < 1e-15 * 1e-4 * 7 * 1e3
+    assert np.max(np.abs(m.context.get_tendency("ρv"))) < 1e-15 * 1e-4 * 7 * 1e3
+    # out of balance: G_ρu = f ρ (v - vᵍ), G_ρv = -f ρ (u - uᵍ)
+    m.set(u=8.0, v=-3.0, θ=299.1, enforce_mass_conservation=False)
+    m.context.compute_tendencies()
+    assert np.allclose(m.context.get_tendency("ρv"), -1e-4 * rho * 1.0, rtol=1e-12)
+
+
+def test_subsidence_forcing_matches_numpy(oracle_arch):
+    """F_ϕ = -ℑzb(wˢ ∂z ϕ̄) with the one-sided top/bottom rule (subsidence_forcing.jl:84-100), ρ-weighted (specific_forcing.jl:70-74)."""
+    Nz = 12
+    rng = np.random.default_rng(4)
+    ws = -0.01 * rng.random(Nz + 1)
+    m = _forced_model(oracle_arch, subsidence_w=ws, subsidence_on=("θ", "q"))
+    z = m.grid.znodes()
+    theta_prof = 299.0 + 3e-3 * z + 0.3 * np.sin(z / 400.0)
+    q_prof = 0.015 * np.exp(-z / 1500.0)
+    m.set(θ=theta_prof[:, None, None] * np.ones((Nz, 16, 16)), qᵗ=q_prof[:, None, None] * np.ones((Nz, 16, 16)))
+    m.context.compute_tendencies()
+    rho = m.reference_profiles()[0]
+    dz = m.grid.Δz
+    for name, prof in (("ρθ", theta_prof), ("ρq", q_prof)):
+        dphi = np.zeros(Nz + 1)
+        dphi[1:Nz] = ws[1:Nz] * (prof[1:] - prof[:-1]) / dz
+        F = -0.5 * (dphi[1:] + dphi[:-1])
+        F[0], F[-1] = -dphi[1], -dphi[Nz - 1]
+        G = m.context.get_tendency(name)
+        assert np.allclose(G[:, 3, 5], rho * F, rtol=1e-10, atol=1e-16)
+
+
+def test_bottom_fluxes_and_prescribed_tendencies(oracle_arch):
+    Nz = 12
+    cpd = 1005.0
+    e_t = np.full(Nz, cpd * (-2.0 / 86400))
+    m = _forced_model(oracle_arch, theta_flux=1.2 * 8e-3, q_flux=1.2 * 5.2e-5, q_tendency=np.full(Nz, -1.2e-8), e_tendency=e_t)
+    m.set(θ=299.1)
+    m.context.compute_tendencies()
+    rho, p, _ = m.reference_profiles()
+    Gt, Gq = m.context.get_tendency("ρθ"), m.context.get_tendency("ρq")
+    Pi = (p / 1e5) ** ((8.314462618 / 0.02897) / cpd)
+    expect_t = rho * e_t / (cpd * Pi)
+    expect_t[0] += 1.2 * 8e-3 / m.grid.Δz
+    expect_q = rho * -1.2e-8
+    expect_q[0] += 1.2 * 5.2e-5 / m.grid.Δz
+    assert np.allclose(Gt[:, 2, 2], expect_t, rtol=1e-12)
+    assert np.allclose(Gq[:, 2, 2], expect_q, rtol=1e-12)
+
+
+def test_bomex_case_runs(oracle_arch):
+    """BASELINE config 3 (BOMEX; reduced to 16×16×30 for the CPU suite): 20 steps stay finite, cloud-free start, drag decelerates."""
+    m = bz.cases.bomex_model(oracle_arch, size=(16, 16, 30), extent=1600.0)
+    u0 = m.field("u")[0].mean()
+    for _ in range(20):
+        m.time_step(2.0)
+    assert all(np.isfinite(m.field(n)).all() for n in ("ρu", "ρv", "ρw", "ρθ", "ρq", "T"))
+    assert abs(m.field("u")[0].mean()) < abs(u0)            # bottom drag acts on the lowest level
+    assert m.context.max_abs_divergence() < 1e-12
