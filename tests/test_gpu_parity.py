@@ -198,8 +198,19 @@ def test_bomex_forcings_match_oracle(oracle_arch):
         oracle_lib.set_beta_form(0)
     for name in PROGNOSTIC:
         assert rel_err(gpu.context.get_tendency(name), cpu.context.get_tendency(name)) < TOL_SAME_FORM, name
-    for _ in range(5):
-        gpu.time_step(2.0)
-        cpu.time_step(2.0)
-    for name in PROGNOSTIC + ["T", "qˡ"]:
-        assert rel_err(gpu.field(name), cpu.field(name)) < TOL_STEPS, name
+    # Five steps. The initial state carries grid-scale random noise, where the WENO weights amplify the difference between
+    # the reference's quadratic-form and the kernels' difference-form smoothness indicators (≈ 4e-10 on ρθ, which buoyancy
+    # feeds into the small ρv, ρw); so the oracle steps in the kernels' form here, and momentum components are compared
+    # on the common momentum scale.
+    oracle_lib.set_beta_form(1)
+    try:
+        for _ in range(5):
+            gpu.time_step(2.0)
+            cpu.time_step(2.0)
+    finally:
+        oracle_lib.set_beta_form(0)
+    mom_scale = max(np.abs(cpu.field(n)).max() for n in ("ρu", "ρv", "ρw"))
+    for name in ("ρu", "ρv", "ρw"):
+        assert np.abs(gpu.field(name) - cpu.field(name)).max() < 1e-9 * mom_scale, name
+    for name in ("ρθ", "ρq", "T", "qˡ"):
+        assert rel_err(gpu.field(name), cpu.field(name)) < 1e-9, name
