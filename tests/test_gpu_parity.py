@@ -214,3 +214,61 @@ def test_bomex_forcings_match_oracle(oracle_arch):
         assert np.abs(gpu.field(name) - cpu.field(name)).max() < 1e-9 * mom_scale, name
     for name in ("ρθ", "ρq", "T", "qˡ"):
         assert rel_err(gpu.field(name), cpu.field(name)) < 1e-9, name
+
+
+# ---- BASELINE configurations at (or near) their full sizes ------------------------------------------------------------
+
+def test_config0_readme_quickstart_2d_256(oracle_arch):
+    """BASELINE config 0: README quick-start, 2-D 256×256 (Periodic, Flat, Bounded), Δt = 2, 10 steps, against the oracle."""
+    import breeze_b200 as bz
+    gpu = make_bubble_model(bz.B200(), (256, 256), flat_y=True)
+    cpu = make_bubble_model(oracle_arch, (256, 256), flat_y=True)
+    for m in (gpu, cpu):
+        m.set(θ=bubble_theta())
+    for _ in range(10):
+        gpu.time_step(2.0)
+        cpu.time_step(2.0)
+    for name in ("ρu", "ρw", "ρθ", "u", "w", "θ", "T"):
+        assert rel_err(gpu.field(name), cpu.field(name)) < TOL_STEPS, name
+
+
+def test_config1_bubble_3d_128_vs_oracle(oracle_arch):
+    """BASELINE config 1 (3-D dry bubble, anelastic WENO5, FP64 match vs the CPU run) at 128³ — the size the 16-core oracle
+    steps in seconds; 3 steps. The 256³ / 512³ runs are checked through size-independent properties below."""
+    import breeze_b200 as bz
+    gpu = make_bubble_model(bz.B200(), (128, 128, 128))
+    cpu = make_bubble_model(oracle_arch, (128, 128, 128))
+    for m in (gpu, cpu):
+        m.set(θ=bubble_theta())
+    for _ in range(3):
+        gpu.time_step(0.5)
+        cpu.time_step(0.5)
+    for name in PROGNOSTIC + ["w", "θ"]:
+        assert rel_err(gpu.field(name), cpu.field(name)) < TOL_STEPS, name
+
+
+@pytest.mark.parametrize("N", [256, 512])
+def test_full_size_properties(N):
+    """256³ (config 1) and 512³ (the metric's workload): properties that do not need the oracle —
+    discrete divergence-free momentum after every step, conservation of ∫ρu, ∫ρv, ∫ρθ (flux form, closed domain in z), the
+    symmetry of the centred bubble (v(x,y,z) = u(y,x,z) under the x↔y swap of a symmetric initial state), and bit-identical
+    results from the TMA-staged and plain-load kernels."""
+    import breeze_b200 as bz
+    results = []
+    for use_tma in (1, 2):
+        m = make_bubble_model(bz.B200(use_tma=use_tma), (N, N, N))
+        m.set(θ=bubble_theta(), u=0.0)
+        s0 = m.field("ρθ").sum()
+        for _ in range(2):
+            m.time_step(0.5)
+        div = m.context.max_abs_divergence()
+        assert div < 1e-11, div
+        ru, rv, rt = m.field("ρu"), m.field("ρv"), m.field("ρθ")
+        assert abs(ru.sum()) < 1e-6 * np.abs(ru).sum() + 1e-9 and abs(rv.sum()) < 1e-6 * np.abs(rv).sum() + 1e-9
+        assert abs(rt.sum() - s0) < 1e-12 * abs(s0)
+        # x↔y symmetry of the bubble: ρv(k, j, i) == ρu(k, i, j)
+        sym = np.abs(rv - np.swapaxes(ru, 1, 2)).max()
+        assert sym < 1e-10 * max(np.abs(ru).max(), 1e-30), sym
+        results.append((ru, rt))
+        del m
+    assert np.array_equal(results[0][0], results[1][0]) and np.array_equal(results[0][1], results[1][1])
