@@ -243,18 +243,22 @@ static int setup_poisson(bz_ctx* c) {
     if (!L.flat_y) {
         int lines = 2048 / g.Ny; if (lines < 1) lines = 1;
         int half = (L.nx + 1) / 2; if (lines > half) lines = half;
+        while (lines & (lines - 1)) lines &= lines - 1;       // power of two (the kernels shift instead of dividing)
         c->lines_y = lines;
         size_t sm = fft_smem_bytes(g.Ny, lines);
-        CUDA_TRY(c, cudaFuncSetAttribute(poisson_forward_y, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        CUDA_TRY(c, cudaFuncSetAttribute(poisson_inverse_y, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        FFT_DISPATCH(g.Ny, {
+            CUDA_TRY(c, cudaFuncSetAttribute(poisson_forward_y<FN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            CUDA_TRY(c, cudaFuncSetAttribute(poisson_inverse_y<FN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        })
     }
     if (!L.flat_x) {
         int lines = 1024 / g.Nx; if (lines < 1) lines = 1;
         long long nl = (long long)G.Nz * G.nky_loc; if (nl < 1) nl = 1;
         if (lines > nl) lines = (int)nl;
+        while (lines & (lines - 1)) lines &= lines - 1;
         c->lines_x = lines;
         size_t sm = fft_smem_bytes(g.Nx, lines);
-        CUDA_TRY(c, cudaFuncSetAttribute(fft_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        FFT_DISPATCH(g.Nx, { CUDA_TRY(c, cudaFuncSetAttribute(fft_x_kernel<FN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); })
     }
     return setup_thomas(c);
 }
@@ -271,7 +275,7 @@ static int poisson_solve(bz_ctx* c, double dt) {
             int lines = c->lines_y;
             dim3 grid((L.nx + 2 * lines - 1) / (2 * lines), L.Nz);
             size_t sm = fft_smem_bytes(G.Ny, lines);
-            poisson_forward_y<<<grid, lines * G.Ny / 8, sm, c->stream>>>(L, G, U[0], U[1], U[2], dz_over_dt, c->W, c->tw_y, lines);
+            FFT_DISPATCH(G.Ny, (poisson_forward_y<FN><<<grid, lines * G.Ny / 8, sm, c->stream>>>(L, G, U[0], U[1], U[2], dz_over_dt, c->W, c->tw_y, lines)));
         } else {
             dim3 grid((L.nx + 127) / 128, L.Nz);
             poisson_pack_flat_y<<<grid, 128, 0, c->stream>>>(L, G, U[0], U[1], U[2], dz_over_dt, c->W);
@@ -288,7 +292,7 @@ static int poisson_solve(bz_ctx* c, double dt) {
         ProfScope ps(c, 1);
         int lines = c->lines_x;
         size_t sm = fft_smem_bytes(G.Nx, lines);
-        fft_x_kernel<<<(unsigned)((n_lines + lines - 1) / lines), lines * G.Nx / 8, sm, c->stream>>>(G, c->W2, n_lines, c->tw_x, lines, 0);
+        FFT_DISPATCH(G.Nx, (fft_x_kernel<FN><<<(unsigned)((n_lines + lines - 1) / lines), lines * G.Nx / 8, sm, c->stream>>>(G, c->W2, n_lines, c->tw_x, lines, 0)));
         c->launches++;
     }
     if (G.nky_loc > 0) {
@@ -302,7 +306,7 @@ static int poisson_solve(bz_ctx* c, double dt) {
         ProfScope ps(c, 3);
         int lines = c->lines_x;
         size_t sm = fft_smem_bytes(G.Nx, lines);
-        fft_x_kernel<<<(unsigned)((n_lines + lines - 1) / lines), lines * G.Nx / 8, sm, c->stream>>>(G, c->W2, n_lines, c->tw_x, lines, 1);
+        FFT_DISPATCH(G.Nx, (fft_x_kernel<FN><<<(unsigned)((n_lines + lines - 1) / lines), lines * G.Nx / 8, sm, c->stream>>>(G, c->W2, n_lines, c->tw_x, lines, 1)));
         c->launches++;
     }
     if (c->comm.n_ranks > 1) {
@@ -317,7 +321,7 @@ static int poisson_solve(bz_ctx* c, double dt) {
             int lines = c->lines_y;
             dim3 grid((L.nx + 2 * lines - 1) / (2 * lines), L.Nz);
             size_t sm = fft_smem_bytes(G.Ny, lines);
-            poisson_inverse_y<<<grid, lines * G.Ny / 8, sm, c->stream>>>(L, G, c->W, c->phi, c->tw_y, lines, scale);
+            FFT_DISPATCH(G.Ny, (poisson_inverse_y<FN><<<grid, lines * G.Ny / 8, sm, c->stream>>>(L, G, c->W, c->phi, c->tw_y, lines, scale)));
         } else {
             dim3 grid((L.nx + 127) / 128, L.Nz);
             poisson_unpack_flat_y<<<grid, 128, 0, c->stream>>>(L, G, c->W, c->phi, scale);

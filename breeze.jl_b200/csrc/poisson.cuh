@@ -85,55 +85,56 @@ __host__ __device__ __forceinline__ int line_pitch(int N) { return ((N + (N >> 4
 __host__ __device__ __forceinline__ int imag_offset(int N, int lines) { int o = lines * line_pitch(N); return o + ((2 - o) & 15); }
 __host__ __device__ __forceinline__ size_t fft_smem_bytes(int N, int lines) { return (size_t)(imag_offset(N, lines) + lines * line_pitch(N)) * sizeof(double); }
 
-// One Stockham pass of radix R over `lines` lines of length N held as re[l*LP + pidx(n)], im[l*LP + pidx(n)].
-// Each thread owns 8/R butterflies (8 complex values in registers): blockDim.x == lines * N / 8.
-template <int R>
-__device__ __forceinline__ void stockham_pass(double* re, double* im, int LP, int N, int Ns, const double2* __restrict__ tw) {
-    constexpr int ITEMS = 8 / R;
-    const int per_line = N / 8;                    // threads per line
-    const int l = threadIdx.x / per_line, t = threadIdx.x % per_line;
-    double* lre = re + (size_t)l * LP;
-    double* lim = im + (size_t)l * LP;
-    const int NR = N / R;
+// One Stockham pass of radix R over lines of compile-time length N held as re[l*LP + pidx(n)], im[l*LP + pidx(n)].
+// Each thread owns 8/R butterflies (8 complex values in registers): blockDim.x == lines * N / 8. N, R, Ns are
+// compile-time, so every index below folds to shifts and immediates (the run-time-N version spent 85 % of its
+// instructions on index arithmetic).
+template <int N, int R, int Ns>
+__device__ __forceinline__ void stockham_pass(double* __restrict__ re, double* __restrict__ im, const double2* __restrict__ tw) {
+    constexpr int ITEMS = 8 / R, PER_LINE = N / 8, NR = N / R, LP = ((N + (N >> 4) + 15) & ~15) + 4, STEP = N / (Ns * R);
+    const int l = threadIdx.x / PER_LINE, t = threadIdx.x % PER_LINE;
+    double* lre = re + l * LP;
+    double* lim = im + l * LP;
     cpx v[ITEMS][R];
-    int jj[ITEMS];
 #pragma unroll
     for (int it = 0; it < ITEMS; ++it) {
-        int j = t + it * per_line;                 // butterfly index in [0, N/R)
-        jj[it] = j;
+        const int j = t + it * PER_LINE;            // butterfly index in [0, N/R)
 #pragma unroll
         for (int r = 0; r < R; ++r) v[it][r] = {lre[pidx(j + r * NR)], lim[pidx(j + r * NR)]};
     }
     __syncthreads();
 #pragma unroll
     for (int it = 0; it < ITEMS; ++it) {
-        int j = jj[it];
-        int k = j & (Ns - 1);
+        const int j = t + it * PER_LINE;
+        const int k = j & (Ns - 1);
         if (Ns > 1) {
-            int step = N / (Ns * R);
 #pragma unroll
             for (int r = 1; r < R; ++r) {
-                double2 w = __ldg(&tw[r * k * step]);
+                double2 w = __ldg(&tw[r * k * STEP]);
                 v[it][r] = cmul(v[it][r], cpx{w.x, w.y});
             }
         }
         if (R == 8) dft8(v[it]);
         else if (R == 4) dft4(v[it][0], v[it][1], v[it][2], v[it][3]);
         else dft2(v[it][0], v[it][1]);
-        int j0 = (j - k) * R + k;
+        const int j0 = (j - k) * R + k;
 #pragma unroll
         for (int r = 0; r < R; ++r) { lre[pidx(j0 + r * Ns)] = v[it][r].x; lim[pidx(j0 + r * Ns)] = v[it][r].y; }
     }
     __syncthreads();
 }
 
-// Forward DFT (e^{-2πi nk/N}) of every line in shared memory; N = 2^m >= 8. Callers conjugate for the inverse.
-__device__ __forceinline__ void fft_lines_smem(double* re, double* im, int LP, int N, const double2* __restrict__ tw) {
-    int m = 31 - __clz(N);
-    int Ns = 1;
-    for (int p = 0; p < m / 3; ++p) { stockham_pass<8>(re, im, LP, N, Ns, tw); Ns *= 8; }
-    if (m % 3 == 2) stockham_pass<4>(re, im, LP, N, Ns, tw);
-    else if (m % 3 == 1) stockham_pass<2>(re, im, LP, N, Ns, tw);
+// Forward DFT (e^{-2πi nk/N}) of every line in shared memory; N = 2^m, 8 <= N <= 2048. Callers conjugate for the inverse.
+template <int N>
+__device__ __forceinline__ void fft_lines_smem(double* __restrict__ re, double* __restrict__ im, const double2* __restrict__ tw) {
+    constexpr int m = (N == 8) ? 3 : (N == 16) ? 4 : (N == 32) ? 5 : (N == 64) ? 6 : (N == 128) ? 7 : (N == 256) ? 8 : (N == 512) ? 9 : (N == 1024) ? 10 : 11;
+    static_assert((1 << m) == N, "N must be a power of two in [8, 2048]");
+    stockham_pass<N, 8, 1>(re, im, tw);
+    if (m >= 6) stockham_pass<N, 8, (m >= 6 ? 8 : 1)>(re, im, tw);
+    if (m >= 9) stockham_pass<N, 8, (m >= 9 ? 64 : 1)>(re, im, tw);
+    constexpr int done = (m / 3) * 3, Ns = 1 << done;
+    if (m % 3 == 2) stockham_pass<N, 4, (m % 3 == 2 ? Ns : 1)>(re, im, tw);
+    else if (m % 3 == 1) stockham_pass<N, 2, (m % 3 == 1 ? Ns : 1)>(re, im, tw);
 }
 
 // ---- source term ------------------------------------------------------------------------------------------------
@@ -151,15 +152,17 @@ __device__ __forceinline__ double source_term(const Layout& L, const double* __r
 
 // ---- pass 1: source term + real-to-complex FFT along y ----------------------------------------------------------
 // grid (ceil(nx / (2*lines)), Nz); block lines*Ny/8 <= 256 threads; smem 2*lines*line_pitch(Ny) doubles.
+template <int N>
 __global__ void __launch_bounds__(256, 3) poisson_forward_y(Layout L, PoissonGeom G, const double* __restrict__ ru, const double* __restrict__ rv,
                                   const double* __restrict__ rw, double dz_over_dt, double2* __restrict__ W,
                                   const double2* __restrict__ tw_y, int lines) {
     extern __shared__ double sm[];
-    const int N = G.Ny, LP = line_pitch(N);
+    constexpr int LP = ((N + (N >> 4) + 15) & ~15) + 4;
     double* re = sm;
     double* im = sm + imag_offset(N, lines);
     const int k = blockIdx.y;
-    const int XB = 2 * lines;
+    const int XB = 2 * lines;                        // lines is a power of two
+    const int xb_shift = 31 - __clz(XB);
     const int ib = blockIdx.x * XB;
     // blockDim.x == lines * N / 8 and XB == 2 * lines: every thread evaluates 16 source-term values, 8 at a time so that
     // their loads are in flight together
@@ -168,27 +171,27 @@ __global__ void __launch_bounds__(256, 3) poisson_forward_y(Layout L, PoissonGeo
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
             int e = threadIdx.x + (half * 8 + it) * blockDim.x;
-            int c = e % XB, y = e / XB;
+            int c = e & (XB - 1), y = e >> xb_shift;
             int i = ib + c;
             v[it] = (i < L.nx) ? source_term(L, ru, rv, rw, i, y, k, dz_over_dt) : 0.0;
         }
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
             int e = threadIdx.x + (half * 8 + it) * blockDim.x;
-            int c = e % XB, y = e / XB;
-            ((c & 1) ? im : re)[(size_t)(c >> 1) * LP + pidx(y)] = v[it];
+            int c = e & (XB - 1), y = e >> xb_shift;
+            ((c & 1) ? im : re)[(c >> 1) * LP + pidx(y)] = v[it];
         }
     }
     __syncthreads();
-    fft_lines_smem(re, im, LP, N, tw_y);
+    fft_lines_smem<N>(re, im, tw_y);
     // untangle the two real transforms: A = (Z[ky] + conj Z[N-ky])/2, B = (Z[ky] - conj Z[N-ky])/(2i)
     for (int e = threadIdx.x; e < G.nky * XB; e += blockDim.x) {
-        int c = e % XB, ky = e / XB;
+        int c = e & (XB - 1), ky = e >> xb_shift;
         int i = ib + c;
         if (i >= L.nx) continue;
         int l = c >> 1, km = (N - ky) & (N - 1);
-        double zr = re[(size_t)l * LP + pidx(ky)], zi = im[(size_t)l * LP + pidx(ky)];
-        double yr = re[(size_t)l * LP + pidx(km)], yi = im[(size_t)l * LP + pidx(km)];
+        double zr = re[l * LP + pidx(ky)], zi = im[l * LP + pidx(ky)];
+        double yr = re[l * LP + pidx(km)], yi = im[l * LP + pidx(km)];
         double2 o = (c & 1) ? make_double2(0.5 * (zi + yi), -0.5 * (zr - yr)) : make_double2(0.5 * (zr + yr), 0.5 * (zi - yi));
         W[w_index(G, k, ky, i)] = o;
     }
@@ -202,14 +205,16 @@ __global__ void poisson_pack_flat_y(Layout L, PoissonGeom G, const double* __res
 }
 
 // ---- pass 5: complex-to-real inverse FFT along y → φ (padded field interior) -------------------------------------
+template <int N>
 __global__ void __launch_bounds__(256, 3) poisson_inverse_y(Layout L, PoissonGeom G, const double2* __restrict__ W, double* __restrict__ phi,
                                   const double2* __restrict__ tw_y, int lines, double scale) {
     extern __shared__ double sm[];
-    const int N = G.Ny, LP = line_pitch(N);
+    constexpr int LP = ((N + (N >> 4) + 15) & ~15) + 4;
     double* re = sm;
     double* im = sm + imag_offset(N, lines);
     const int k = blockIdx.y;
-    const int XB = 2 * lines;
+    const int XB = 2 * lines;                        // lines is a power of two
+    const int xb_shift = 31 - __clz(XB);
     const int ib = blockIdx.x * XB;
     // rebuild the packed spectrum Z = A + iB (Hermitian halves), conjugated for the inverse-by-forward trick
     // (N/2 + 1) * lines <= 5 * blockDim.x elements; loads are batched ahead of their use
@@ -221,7 +226,7 @@ __global__ void __launch_bounds__(256, 3) poisson_inverse_y(Layout L, PoissonGeo
             int e = threadIdx.x + it * blockDim.x;
             A[it] = make_double2(0.0, 0.0); B[it] = make_double2(0.0, 0.0);
             if (e < total) {
-                int l = e % lines, ky = e / lines;
+                int l = e & (lines - 1), ky = e >> (xb_shift - 1);
                 int i = ib + 2 * l;
                 if (i < L.nx) A[it] = W[w_index(G, k, ky, i)];
                 if (i + 1 < L.nx) B[it] = W[w_index(G, k, ky, i + 1)];
@@ -231,25 +236,25 @@ __global__ void __launch_bounds__(256, 3) poisson_inverse_y(Layout L, PoissonGeo
         for (int it = 0; it < 5; ++it) {
             int e = threadIdx.x + it * blockDim.x;
             if (e < total) {
-                int l = e % lines, ky = e / lines;
+                int l = e & (lines - 1), ky = e >> (xb_shift - 1);
                 // Z[ky] = A + iB, Z[N-ky] = conj(A) + i conj(B); store conj(Z)
-                re[(size_t)l * LP + pidx(ky)] = A[it].x - B[it].y;
-                im[(size_t)l * LP + pidx(ky)] = -(A[it].y + B[it].x);
+                re[l * LP + pidx(ky)] = A[it].x - B[it].y;
+                im[l * LP + pidx(ky)] = -(A[it].y + B[it].x);
                 if (ky > 0 && ky < N / 2) {
-                    re[(size_t)l * LP + pidx(N - ky)] = A[it].x + B[it].y;
-                    im[(size_t)l * LP + pidx(N - ky)] = -(B[it].x - A[it].y);
+                    re[l * LP + pidx(N - ky)] = A[it].x + B[it].y;
+                    im[l * LP + pidx(N - ky)] = -(B[it].x - A[it].y);
                 }
             }
         }
     }
     __syncthreads();
-    fft_lines_smem(re, im, LP, N, tw_y);
+    fft_lines_smem<N>(re, im, tw_y);
     for (int e = threadIdx.x; e < N * XB; e += blockDim.x) {
-        int c = e % XB, y = e / XB;
+        int c = e & (XB - 1), y = e >> xb_shift;
         int i = ib + c;
         if (i >= L.nx) continue;
         int l = c >> 1;
-        double v = (c & 1) ? -im[(size_t)l * LP + pidx(y)] : re[(size_t)l * LP + pidx(y)];
+        double v = (c & 1) ? -im[l * LP + pidx(y)] : re[l * LP + pidx(y)];
         phi[lidx(L, i, y, k)] = v * scale;
     }
 }
@@ -261,40 +266,44 @@ __global__ void poisson_unpack_flat_y(Layout L, PoissonGeom G, const double2* __
 
 // ---- passes 2 / 4: complex FFT along x, in place; one line = Nx contiguous complex numbers ----------------------
 // grid ceil(n_lines / lines); block lines*Nx/8 <= 256 threads; smem 2*lines*line_pitch(Nx) doubles.
+template <int N>
 __global__ void __launch_bounds__(256, 3) fft_x_kernel(PoissonGeom G, double2* __restrict__ W, long long n_lines, const double2* __restrict__ tw_x, int lines, int inverse) {
-    const int Nx = G.Nx;
     extern __shared__ double sm[];
-    const int N = Nx, LP = line_pitch(N);
+    constexpr int LP = ((N + (N >> 4) + 15) & ~15) + 4;
     double* re = sm;
     double* im = sm + imag_offset(N, lines);
-    const long long l0 = (long long)blockIdx.x * lines;
+    const int l0 = blockIdx.x * lines;                  // first line of this CTA; line = k * nky_loc + ky_loc (fits an int)
     const double sgn = inverse ? -1.0 : 1.0;
+    const int k0 = l0 / G.nky_loc, r0 = l0 - k0 * G.nky_loc;    // one division per CTA; lines advance (k, ky) incrementally
+    const int xmask = (1 << G.nx_shift) - 1;
+    auto w2_of = [&](int l, int x) -> size_t {          // offset of element x of the CTA's line l in the peer-blocked W2
+        int ky = r0 + l, k = k0;
+        while (ky >= G.nky_loc) { ky -= G.nky_loc; ++k; }
+        const int p = x >> G.nx_shift;
+        return ((((size_t)p * G.Nz + k) * G.nky_loc + ky) << G.nx_shift) + (x & xmask);
+    };
     // blockDim.x == lines * N / 8: every thread moves exactly 8 elements; all 8 loads are issued before the first use
-    {
-        double2 v[8];
+    double2 v[8];
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            int e = threadIdx.x + it * blockDim.x;
-            int l = e / N;
-            int line = (int)l0 + l;                                    // line = k * nky_loc + ky_loc (fits an int)
-            int kk = line / G.nky_loc;
-            v[it] = (line < n_lines) ? W[w2_index(G, kk, line - kk * G.nky_loc, e - l * N)] : make_double2(0.0, 0.0);
-        }
+    for (int it = 0; it < 8; ++it) {
+        const int e = threadIdx.x + it * blockDim.x;
+        const int l = e / N, x = e % N;
+        v[it] = (l0 + l < n_lines) ? W[w2_of(l, x)] : make_double2(0.0, 0.0);
+    }
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            int e = threadIdx.x + it * blockDim.x;
-            int x = e % N, l = e / N;
-            re[(size_t)l * LP + pidx(x)] = v[it].x;
-            im[(size_t)l * LP + pidx(x)] = sgn * v[it].y;
-        }
+    for (int it = 0; it < 8; ++it) {
+        const int e = threadIdx.x + it * blockDim.x;
+        const int l = e / N, x = e % N;
+        re[l * LP + pidx(x)] = v[it].x;
+        im[l * LP + pidx(x)] = sgn * v[it].y;
     }
     __syncthreads();
-    fft_lines_smem(re, im, LP, N, tw_x);
-    for (int e = threadIdx.x; e < N * lines; e += blockDim.x) {
-        int x = e % N, l = e / N;
-        int line = (int)l0 + l;
-        int kk = line / G.nky_loc;
-        if (line < n_lines) W[w2_index(G, kk, line - kk * G.nky_loc, x)] = make_double2(re[(size_t)l * LP + pidx(x)], sgn * im[(size_t)l * LP + pidx(x)]);
+    fft_lines_smem<N>(re, im, tw_x);
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int e = threadIdx.x + it * blockDim.x;
+        const int l = e / N, x = e % N;
+        if (l0 + l < n_lines) W[w2_of(l, x)] = make_double2(re[l * LP + pidx(x)], sgn * im[l * LP + pidx(x)]);
     }
 }
 
@@ -390,3 +399,13 @@ __global__ void remove_mean_mode(PoissonGeom G, double2* __restrict__ W) {
     double mr = sr[0] / G.Nz, mi = si[0] / G.Nz;
     for (int k = threadIdx.x; k < G.Nz; k += blockDim.x) { double2 v = W[k * stride]; W[k * stride] = make_double2(v.x - mr, v.y - mi); }
 }
+
+// Host-side dispatch on the (power-of-two) line length.
+#define FFT_DISPATCH(n, CALL)                                                                                    \
+    switch (n) {                                                                                                  \
+        case 8: { constexpr int FN = 8; CALL; break; }       case 16: { constexpr int FN = 16; CALL; break; }     \
+        case 32: { constexpr int FN = 32; CALL; break; }     case 64: { constexpr int FN = 64; CALL; break; }     \
+        case 128: { constexpr int FN = 128; CALL; break; }   case 256: { constexpr int FN = 256; CALL; break; }   \
+        case 512: { constexpr int FN = 512; CALL; break; }   case 1024: { constexpr int FN = 1024; CALL; break; } \
+        case 2048: { constexpr int FN = 2048; CALL; break; } default: break;                                      \
+    }
