@@ -124,6 +124,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--use-tma", type=int, default=0)
     ap.add_argument("--z-chunks", type=int, default=0)
+    ap.add_argument("--no-peer-memory", action="store_true", help="multi-GPU: NCCL send/recv instead of CUDA-IPC peer loads")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -172,6 +173,8 @@ def main():
     N = args.size
     grid = bz.RectilinearGrid(arch, size=(N, N, N), x=(-10e3, 10e3), y=(-10e3, 10e3), z=(0, 10e3))
     model = bz.AtmosphereModel(grid, dynamics=bz.AnelasticDynamics(bz.ReferenceState(grid, potential_temperature=300)), advection=bz.WENO(order=5))
+    if world > 1 and not args.no_peer_memory:
+        bz.enable_peer_memory(model)
     model.set(θ=bubble)
     ctx = model.context
     cells = N ** 3
@@ -265,7 +268,7 @@ def main():
         out = {
             "metric": METRIC, "value": value, "unit": "Mcell-updates/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload, "grid": [N, N, N], "parallelism": f"x-slabs x{world}", "l2": "inputs larger than L2 (5 fields x %.2f GB per rank)" % (cells_local * 8 / 1e9),
+            "config": {"workload": workload, "grid": [N, N, N], "parallelism": f"x-slabs x{world}" + ("" if world == 1 else (", NCCL send/recv" if args.no_peer_memory else ", CUDA-IPC peer loads + NCCL barrier")), "l2": "inputs larger than L2 (5 fields x %.2f GB per rank)" % (cells_local * 8 / 1e9),
                        "staging": "tma" if args.use_tma != 2 else "plain", "device_bytes": ctx.device_bytes()},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": "stage_kernel (fused WENO5 tendencies + RK update)", "kernel_ms": stage_ms, "peak_source": peak_src,

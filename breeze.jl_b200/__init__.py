@@ -9,6 +9,6 @@ from .abi import BreezeError, Context, Library, bz_config, bz_forcing, load_cuda
 from .model import (B200, DragFluxBoundaryCondition, FluxBoundaryCondition, Forcing, FPlane, GeostrophicForcing, SubsidenceForcing,
                     geostrophic_forcings, AnelasticDynamics, AtmosphereModel, Bounded, Flat, Periodic, RectilinearGrid, ReferenceState,
                     SaturationAdjustment, Simulation, ThermodynamicConstants, TimeStepWizard, WENO,
-                    conjure_time_step_wizard_, many_time_steps_, run_, set_, time_step_)
+                    conjure_time_step_wizard_, enable_peer_memory, many_time_steps_, run_, set_, time_step_)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -99,6 +99,8 @@ CUDA_ONLY_SYMBOLS = {
     "stream": (_vp, [_vp]),
     "device_bytes": (C.c_int64, [_vp]),
     "nccl_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
+    "ipc_export": (C.c_int, [_vp, C.POINTER(C.c_uint8)]),
+    "ipc_attach": (C.c_int, [_vp, C.POINTER(C.c_uint8)]),
 }
 
 
@@ -273,6 +275,18 @@ class Context:
         n = np.zeros(8, dtype=np.int64)
         self._check(self.lib.profile_read(self.handle, _as_dp(ms), n.ctypes.data_as(C.POINTER(C.c_int64))), "profile_read")
         return ms, n
+
+    def ipc_export(self) -> bytes:
+        buf = (C.c_uint8 * 64)()
+        self._check(self.lib.ipc_export(self.handle, buf), "ipc_export")
+        return bytes(buf)
+
+    def ipc_attach(self, handles: bytes):
+        n = max(1, self.cfg.n_ranks)
+        if len(handles) != 64 * n:
+            raise BreezeError(f"ipc_attach: expected {64 * n} bytes of handles, got {len(handles)}")
+        buf = (C.c_uint8 * len(handles)).from_buffer_copy(handles)
+        self._check(self.lib.ipc_attach(self.handle, buf), "ipc_attach")
 
     def kernel_launch_count(self):
         return int(self.lib.kernel_launch_count(self.handle))

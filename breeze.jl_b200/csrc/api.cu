@@ -32,6 +32,10 @@ struct bz_ctx {
     CUtensorMap tmap[3][NPROG];
     int cur = 0;                         // index of the set holding the current state
     double* phi = nullptr;
+    // One device allocation ("arena") holds the 15 prognostic buffers, φ and the spectral arrays, so that a single CUDA IPC
+    // handle exposes them to the neighbouring ranks (peer loads over NVLink replace NCCL transfers, comm.cuh).
+    double* arena = nullptr;
+    size_t arena_bytes = 0, off_W = 0, off_W2 = 0;      // byte offsets of W / W2 inside the arena (fields: (s*5+f)*L.n, φ: 15*L.n doubles)
     double* G[NPROG] = {};               // tendencies, allocated on first bz_compute_tendencies
     double* dense = nullptr;             // nx*Ny*(Nz+1) staging buffer for host transfers
     double* scalar = nullptr;            // device scalar for reductions
@@ -43,6 +47,8 @@ struct bz_ctx {
     double *lam_x = nullptr, *lam_y = nullptr, *inv_beta = nullptr, *tfac = nullptr;
     long long* ky_base = nullptr;
     int* ky_kstride = nullptr;
+    int* ky_owner = nullptr;
+    long long* ky_base2 = nullptr;
     // forcing (bz_forcing)
     int forced = 0, subs_mask = 0;
     double coriolis_f = 0, theta_flux = 0, q_flux = 0, drag = 0;
@@ -186,12 +192,6 @@ static int setup_poisson(bz_ctx* c) {
     const Layout& L = c->L;
     const bz_config& g = c->cfg;
     PoissonGeom& G = c->PG;
-    G.Nx = g.Nx; G.Ny = g.Ny; G.Nz = g.Nz;
-    G.nky = L.flat_y ? 1 : g.Ny / 2 + 1;
-    comm_split_ky(c->comm, G.nky, &G.ky0, &G.nky_loc);
-    G.P = c->comm.n_ranks;
-    G.nx_shift = 0;
-    while ((1 << G.nx_shift) < L.nx) ++G.nx_shift;
     // twiddles and eigenvalues (Oceananigans poisson_eigenvalues: λ = (2 sin(π i / N) / Δ)², Flat: 0)
     std::vector<double2> twx(g.Nx), twy(g.Ny);
     std::vector<double> lx(g.Nx), ly(G.nky);
@@ -216,12 +216,21 @@ static int setup_poisson(bz_ctx* c) {
     if ((rc = dev_alloc(c, &c->lam_y, G.nky))) return rc;
     if ((rc = dev_alloc(c, &c->ky_base, G.nky))) return rc;
     if ((rc = dev_alloc(c, &c->ky_kstride, G.nky))) return rc;
+    if ((rc = dev_alloc(c, &c->ky_owner, G.nky))) return rc;
+    if ((rc = dev_alloc(c, &c->ky_base2, G.nky))) return rc;
     {
-        std::vector<long long> kb(G.nky); std::vector<int> ks(G.nky);
+        std::vector<long long> kb(G.nky), kb2(G.nky); std::vector<int> ks(G.nky), ko(G.nky);
         for (int p = 0; p < G.P; ++p) {
             int st, cnt; ky_block(G.nky, G.P, p, &st, &cnt);
-            for (int ky = st; ky < st + cnt; ++ky) { kb[ky] = (long long)st * L.nx * G.Nz + (long long)(ky - st) * L.nx; ks[ky] = cnt * L.nx; }
+            for (int ky = st; ky < st + cnt; ++ky) {
+                kb[ky] = (long long)st * L.nx * G.Nz + (long long)(ky - st) * L.nx; ks[ky] = cnt * L.nx;
+                ko[ky] = p; kb2[ky] = ((long long)c->comm.rank * G.Nz * cnt + (ky - st)) * L.nx;
+            }
         }
+        CUDA_TRY(c, cudaMemcpyAsync(c->ky_owner, ko.data(), sizeof(int) * G.nky, cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(c, cudaMemcpyAsync(c->ky_base2, kb2.data(), sizeof(long long) * G.nky, cudaMemcpyHostToDevice, c->stream));
+        G.ky_owner = c->ky_owner; G.ky_base2 = c->ky_base2;
+        G.off_W = (long long)c->off_W; G.off_W2 = (long long)c->off_W2; G.rank = c->comm.rank;
         CUDA_TRY(c, cudaMemcpyAsync(c->ky_base, kb.data(), sizeof(long long) * G.nky, cudaMemcpyHostToDevice, c->stream));
         CUDA_TRY(c, cudaMemcpyAsync(c->ky_kstride, ks.data(), sizeof(int) * G.nky, cudaMemcpyHostToDevice, c->stream));
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
@@ -232,11 +241,7 @@ static int setup_poisson(bz_ctx* c) {
     CUDA_TRY(c, cudaMemcpyAsync(c->lam_x, lx.data(), sizeof(double) * g.Nx, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(c, cudaMemcpyAsync(c->lam_y, ly.data(), sizeof(double) * G.nky, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    size_t nW = (size_t)L.nx * G.nky * G.Nz;                  // x-slab layout
-    size_t nW2 = (size_t)G.Nx * G.nky_loc * G.Nz;             // transposed layout
-    if ((rc = dev_alloc(c, &c->W, nW))) return rc;
-    if (c->comm.n_ranks > 1) { if ((rc = dev_alloc(c, &c->W2, nW2 > 0 ? nW2 : 1))) return rc; }
-    else c->W2 = c->W;
+    size_t nW2 = (size_t)G.Nx * G.nky_loc * G.Nz;             // transposed layout (W, W2 live in the arena)
     if ((rc = dev_alloc(c, &c->inv_beta, nW2 > 0 ? nW2 : 1))) return rc;
     if ((rc = dev_alloc(c, &c->tfac, nW2 > 0 ? nW2 : 1))) return rc;
     // launch shapes: each thread owns 8 points of a line
@@ -282,9 +287,12 @@ static int poisson_solve(bz_ctx* c, double dt) {
         }
         c->launches++;
     }
+    const bool pull = c->comm.p2p && !L.flat_y;        // peer-memory path: the transposes are peer loads inside fft_x / inverse_y
+    PeerBases peers;
+    for (int p = 0; p < 8; ++p) peers.base[p] = c->comm.peer_base[p];
     if (c->comm.n_ranks > 1) {
         ProfScope ps(c, 5);
-        int rc = comm_transpose_forward(c->comm, c->W, c->W2, L.nx, G, c->stream, &c->launches);
+        int rc = pull ? comm_barrier(c->comm, c->stream) : comm_transpose_forward(c->comm, c->W, c->W2, L.nx, G, c->stream, &c->launches);
         if (rc) { bz_set_error(c, "transpose: %s", c->comm.err); return rc; }
     }
     const long long n_lines = (long long)G.Nz * G.nky_loc;
@@ -292,7 +300,7 @@ static int poisson_solve(bz_ctx* c, double dt) {
         ProfScope ps(c, 1);
         int lines = c->lines_x;
         size_t sm = fft_smem_bytes(G.Nx, lines);
-        FFT_DISPATCH(G.Nx, (fft_x_kernel<FN><<<(unsigned)((n_lines + lines - 1) / lines), lines * G.Nx / 8, sm, c->stream>>>(G, c->W2, n_lines, c->tw_x, lines, 0)));
+        FFT_DISPATCH(G.Nx, (fft_x_kernel<FN><<<(unsigned)((n_lines + lines - 1) / lines), lines * G.Nx / 8, sm, c->stream>>>(G, c->W2, n_lines, c->tw_x, lines, 0, peers, pull ? 1 : 0)));
         c->launches++;
     }
     if (G.nky_loc > 0) {
@@ -306,12 +314,12 @@ static int poisson_solve(bz_ctx* c, double dt) {
         ProfScope ps(c, 3);
         int lines = c->lines_x;
         size_t sm = fft_smem_bytes(G.Nx, lines);
-        FFT_DISPATCH(G.Nx, (fft_x_kernel<FN><<<(unsigned)((n_lines + lines - 1) / lines), lines * G.Nx / 8, sm, c->stream>>>(G, c->W2, n_lines, c->tw_x, lines, 1)));
+        FFT_DISPATCH(G.Nx, (fft_x_kernel<FN><<<(unsigned)((n_lines + lines - 1) / lines), lines * G.Nx / 8, sm, c->stream>>>(G, c->W2, n_lines, c->tw_x, lines, 1, peers, 0)));
         c->launches++;
     }
     if (c->comm.n_ranks > 1) {
         ProfScope ps(c, 5);
-        int rc = comm_transpose_backward(c->comm, c->W2, c->W, L.nx, G, c->stream, &c->launches);
+        int rc = pull ? comm_barrier(c->comm, c->stream) : comm_transpose_backward(c->comm, c->W2, c->W, L.nx, G, c->stream, &c->launches);
         if (rc) { bz_set_error(c, "transpose: %s", c->comm.err); return rc; }
     }
     {
@@ -321,7 +329,7 @@ static int poisson_solve(bz_ctx* c, double dt) {
             int lines = c->lines_y;
             dim3 grid((L.nx + 2 * lines - 1) / (2 * lines), L.Nz);
             size_t sm = fft_smem_bytes(G.Ny, lines);
-            FFT_DISPATCH(G.Ny, (poisson_inverse_y<FN><<<grid, lines * G.Ny / 8, sm, c->stream>>>(L, G, c->W, c->phi, c->tw_y, lines, scale)));
+            FFT_DISPATCH(G.Ny, (poisson_inverse_y<FN><<<grid, lines * G.Ny / 8, sm, c->stream>>>(L, G, c->W, c->phi, c->tw_y, lines, scale, peers, pull ? 1 : 0)));
         } else {
             dim3 grid((L.nx + 127) / 128, L.Nz);
             poisson_unpack_flat_y<<<grid, 128, 0, c->stream>>>(L, G, c->W, c->phi, scale);
@@ -344,7 +352,8 @@ static int fill_halos(bz_ctx* c, double* const* fields, int nf, int fam, bool ex
     int mode = 3;
     if (c->comm.n_ranks > 1) {
         if (exchange_x) {
-            int rc = comm_exchange_x_halos(c->comm, L, F, c->stream, &c->launches);
+            int rc = c->comm.p2p ? comm_pull_x_halos(c->comm, L, F, 0, c->stream, &c->launches)
+                                 : comm_exchange_x_halos(c->comm, L, F, c->stream, &c->launches);
             if (rc) { bz_set_error(c, "halo exchange: %s", c->comm.err); return rc; }
         }
         mode = 2;
@@ -445,7 +454,9 @@ static int pressure_correct(bz_ctx* c, double dt) {
         double* uv[1] = {U[1]};                                                          // comes from the right neighbour's first column
         if ((rc = fill_halos(c, uv, 1, 4, false))) return rc;
         ProfScope ps(c, 5);
-        if ((rc = comm_exchange_u_face(c->comm, c->L, U[0], c->stream, &c->launches))) { bz_set_error(c, "face exchange: %s", c->comm.err); return rc; }
+        if (c->comm.p2p) { FieldSet Fu; Fu.n = 1; Fu.f[0] = U[0]; rc = comm_pull_x_halos(c->comm, c->L, Fu, 1, c->stream, &c->launches); }
+        else rc = comm_exchange_u_face(c->comm, c->L, U[0], c->stream, &c->launches);
+        if (rc) { bz_set_error(c, "face exchange: %s", c->comm.err); return rc; }
     }
     if ((rc = poisson_solve(c, dt))) return rc;
     double* ph[1] = {c->phi};
@@ -492,12 +503,11 @@ void bz_destroy(bz_ctx* c) {
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     comm_destroy(c->comm);
-    for (int s = 0; s < 3; ++s) for (int f = 0; f < NPROG; ++f) cudaFree(c->set[s][f]);
+    cudaFree(c->arena);
     for (int f = 0; f < NPROG; ++f) cudaFree(c->G[f]);
-    cudaFree(c->phi); cudaFree(c->dense); cudaFree(c->scalar); cudaFree(c->col_store);
-    if (c->W2 != c->W) cudaFree(c->W2);
-    cudaFree(c->W); cudaFree(c->tw_x); cudaFree(c->tw_y); cudaFree(c->lam_x); cudaFree(c->lam_y);
-    cudaFree(c->inv_beta); cudaFree(c->tfac); cudaFree(c->ky_base); cudaFree(c->ky_kstride); cudaFree(c->fstore);
+    cudaFree(c->dense); cudaFree(c->scalar); cudaFree(c->col_store);
+    cudaFree(c->tw_x); cudaFree(c->tw_y); cudaFree(c->lam_x); cudaFree(c->lam_y);
+    cudaFree(c->inv_beta); cudaFree(c->tfac); cudaFree(c->ky_base); cudaFree(c->ky_kstride); cudaFree(c->ky_owner); cudaFree(c->ky_base2); cudaFree(c->fstore);
     for (auto e : c->prof_ev) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -554,8 +564,27 @@ int bz_create(const bz_config* cfg, bz_ctx** out) {
     TRYCUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     rc = comm_init(c->comm, cfg, c->stream);
     if (rc) { bz_set_error(nullptr, "comm_init: %s", c->comm.err); bz_destroy(c); return rc; }
-    for (int s = 0; s < 3; ++s) for (int f = 0; f < NPROG; ++f) TRY(dev_alloc(c, &c->set[s][f], (size_t)L.n));
-    TRY(dev_alloc(c, &c->phi, (size_t)L.n));
+    {
+        PoissonGeom& G = c->PG;
+        G.Nx = cfg->Nx; G.Ny = cfg->Ny; G.Nz = cfg->Nz;
+        G.nky = fy ? 1 : cfg->Ny / 2 + 1;
+        comm_split_ky(c->comm, G.nky, &G.ky0, &G.nky_loc);
+        G.P = c->comm.n_ranks;
+        G.nx_shift = 0;
+        while ((1 << G.nx_shift) < L.nx) ++G.nx_shift;
+        const size_t nW = (size_t)L.nx * G.nky * G.Nz, nW2 = (size_t)G.Nx * G.nky_loc * G.Nz;
+        const size_t field_bytes = (size_t)16 * L.n * sizeof(double);
+        c->off_W = (field_bytes + 255) & ~(size_t)255;
+        c->off_W2 = (c->off_W + nW * sizeof(double2) + 255) & ~(size_t)255;
+        c->arena_bytes = (P > 1) ? c->off_W2 + (nW2 > 0 ? nW2 : 1) * sizeof(double2) : c->off_W2;
+        TRYCUDA(cudaMalloc((void**)&c->arena, c->arena_bytes));
+        TRYCUDA(cudaMemsetAsync(c->arena, 0, c->arena_bytes, c->stream));
+        c->bytes += (int64_t)c->arena_bytes;
+        for (int s = 0; s < 3; ++s) for (int f = 0; f < NPROG; ++f) c->set[s][f] = c->arena + (size_t)(s * NPROG + f) * L.n;
+        c->phi = c->arena + (size_t)15 * L.n;
+        c->W = (double2*)((char*)c->arena + c->off_W);
+        c->W2 = (P > 1) ? (double2*)((char*)c->arena + c->off_W2) : c->W;
+    }
     TRY(dev_alloc(c, &c->dense, (size_t)L.nx * L.Ny * (L.Nz + 1)));
     TRY(dev_alloc(c, &c->scalar, 8));
     TRY(dev_alloc(c, &c->col_store, (size_t)8 * (L.Nz + 1)));
@@ -829,6 +858,21 @@ int bz_profile_read(bz_ctx* c, double* ms, int64_t* n) {
 int bz_nccl_unique_id(uint8_t* out128) {
     if (!out128) return BZ_ERR_INVALID;
     return comm_unique_id(out128, g_err);
+}
+
+int bz_ipc_export(bz_ctx* c, uint8_t* out64) {
+    if (!c || !out64) return BZ_ERR_INVALID;
+    cudaSetDevice(c->cfg.device);
+    return comm_ipc_export(c->arena, out64, c->err);
+}
+
+int bz_ipc_attach(bz_ctx* c, const uint8_t* handles) {
+    if (!c || !handles) return BZ_ERR_INVALID;
+    cudaSetDevice(c->cfg.device);
+    cudaStreamSynchronize(c->stream);
+    int rc = comm_ipc_attach(c->comm, c->arena, handles);
+    if (rc) bz_set_error(c, "%s", c->comm.err);
+    return rc;
 }
 
 int64_t bz_kernel_launch_count(const bz_ctx* c) { return c ? c->launches : 0; }

@@ -38,8 +38,15 @@ struct Comm {
     double* halo_send = nullptr;    // [2][nf][HX][Ny][Nz]
     double* halo_recv = nullptr;
     size_t halo_cap = 0;
+    // Peer memory (CUDA IPC): every rank maps the other ranks' arenas; halo ghosts and the FFT transposes are then peer
+    // LOADS issued by the consuming kernels over NVLink, ordered by a tiny NCCL all-reduce used as a stream barrier.
+    int p2p = 0;
+    char* peer_base[8] = {};        // arena base of every rank in THIS process' address space (own arena at [rank])
+    double* token = nullptr;
     char err[256] = {};
 };
+
+struct PeerPtrs { const char* base[8]; };
 
 #define NCCL_TRY(cm, call)                                                                                  \
     do {                                                                                                    \
@@ -95,14 +102,16 @@ static int comm_init(Comm& cm, const bz_config* cfg, cudaStream_t) {
 static void comm_destroy(Comm& cm) {
     if (cm.comm && cm.api.CommDestroy) cm.api.CommDestroy(cm.comm);
     cm.comm = nullptr;
-    cudaFree(cm.halo_send); cudaFree(cm.halo_recv);
-    cm.halo_send = cm.halo_recv = nullptr;
+    for (int p = 0; p < cm.n_ranks && cm.p2p; ++p) if (p != cm.rank && cm.peer_base[p]) cudaIpcCloseMemHandle(cm.peer_base[p]);
+    cm.p2p = 0;
+    cudaFree(cm.halo_send); cudaFree(cm.halo_recv); cudaFree(cm.token);
+    cm.halo_send = cm.halo_recv = nullptr; cm.token = nullptr;
 }
 
 static int comm_alloc_buffers(Comm& cm, const Layout& L, const PoissonGeom&, int64_t* bytes) {
     if (cm.n_ranks == 1) return BZ_OK;
     cm.halo_cap = (size_t)2 * (NPROG + 1) * L.HX * L.Ny * L.Nz;
-    if (cudaMalloc(&cm.halo_send, cm.halo_cap * 8) || cudaMalloc(&cm.halo_recv, cm.halo_cap * 8)) {
+    if (cudaMalloc(&cm.halo_send, cm.halo_cap * 8) || cudaMalloc(&cm.halo_recv, cm.halo_cap * 8) || cudaMalloc(&cm.token, 64) || cudaMemset(cm.token, 0, 64)) {
         snprintf(cm.err, 256, "cudaMalloc of communication buffers failed"); return BZ_ERR_NOMEM;
     }
     *bytes += (int64_t)(2 * cm.halo_cap * 8);
@@ -172,6 +181,66 @@ static int comm_transpose_forward(Comm& cm, const double2* W, double2* W2, int n
 }
 static int comm_transpose_backward(Comm& cm, const double2* W2, double2* W, int nx, const PoissonGeom& G, cudaStream_t s, int64_t*) {
     return comm_alltoall(cm, W2, W, nx, G, false, s);
+}
+
+// Stream barrier across ranks: when it completes on this rank's stream, every rank's earlier work on its stream is complete.
+static int comm_barrier(Comm& cm, cudaStream_t s) {
+    NCCL_TRY(cm, cm.api.AllReduce(cm.token, cm.token, 1, NCCL_FLOAT64, NCCL_MAX, cm.comm, s));
+    return BZ_OK;
+}
+
+static int comm_ipc_export(void* arena, uint8_t* out64, char* err) {
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, arena);
+    if (e != cudaSuccess) { snprintf(err, 256, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e)); return BZ_ERR_CUDA; }
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(out64, &h, 64);
+    return BZ_OK;
+}
+
+// handles: n_ranks × 64 bytes, rank-ordered (all_gather of bz_ipc_export).
+static int comm_ipc_attach(Comm& cm, void* own_arena, const uint8_t* handles) {
+    if (cm.n_ranks == 1) return BZ_OK;
+    if (cm.n_ranks > 8) { snprintf(cm.err, 256, "peer memory path supports up to 8 ranks"); return BZ_ERR_UNSUPPORTED; }
+    for (int p = 0; p < cm.n_ranks; ++p) {
+        if (p == cm.rank) { cm.peer_base[p] = (char*)own_arena; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)64 * p, 64);
+        void* ptr = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) { snprintf(cm.err, 256, "cudaIpcOpenMemHandle(rank %d): %s", p, cudaGetErrorString(e)); return BZ_ERR_CUDA; }
+        cm.peer_base[p] = (char*)ptr;
+    }
+    cm.p2p = 1;
+    return BZ_OK;
+}
+
+// Ghost columns pulled straight from the neighbours' interiors (peer loads). mode 0: both sides, HX columns;
+// mode 1: only the first ghost column on the right (ρu at i = nx for the divergence).
+__global__ void halo_pull_x(Layout L, FieldSet F, const char* my_base, const char* left_base, const char* right_base, int mode) {
+    const int ncol = mode == 0 ? 2 * L.HX : 1;
+    const long long per_field = (long long)ncol * L.Ny * L.Nz;
+    const long long total = per_field * F.n;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        int f = (int)(e / per_field); long long r = e % per_field;
+        int c = (int)(r % ncol), j = (int)((r / ncol) % L.Ny), k = (int)(r / ((long long)ncol * L.Ny));
+        int i_dst, i_src; const char* peer;
+        if (mode == 0 && c < L.HX) { i_dst = c - L.HX; i_src = L.nx - L.HX + c; peer = left_base; }
+        else { int cc = mode == 0 ? c - L.HX : 0; i_dst = L.nx + cc; i_src = cc; peer = right_base; }
+        const double* src = reinterpret_cast<const double*>(peer + (reinterpret_cast<const char*>(F.f[f]) - my_base));
+        F.f[f][lidx(L, i_dst, j, k)] = __ldcv(src + lidx(L, i_src, j, k));
+    }
+}
+
+static int comm_pull_x_halos(Comm& cm, const Layout& L, const FieldSet& F, int mode, cudaStream_t s, int64_t* launches) {
+    const int P = cm.n_ranks, left = (cm.rank + P - 1) % P, right = (cm.rank + 1) % P;
+    int rc = comm_barrier(cm, s);
+    if (rc) return rc;
+    const long long total = (long long)F.n * (mode == 0 ? 2 * L.HX : 1) * L.Ny * L.Nz;
+    const int blocks = (int)((total + 255) / 256) > 148 * 8 ? 148 * 8 : (int)((total + 255) / 256);
+    halo_pull_x<<<blocks, 256, 0, s>>>(L, F, cm.peer_base[cm.rank], cm.peer_base[left], cm.peer_base[right], mode);
+    *launches += 1;
+    return BZ_OK;
 }
 
 static int comm_allreduce_sum_device(Comm& cm, double* dev, size_t n, cudaStream_t s) {

@@ -28,7 +28,14 @@ struct PoissonGeom {
     int nx_shift;  // log2(nx)
     const long long* ky_base;   // per ky: offset of (k = 0, ky, i = 0) in the peer-blocked W   (device, nky entries)
     const int* ky_kstride;      // per ky: level stride of its block = count_p * nx              (device, nky entries)
+    // peer-memory path (CUDA IPC): the all-to-all transposes become peer loads inside the consuming FFT kernels
+    const int* ky_owner;        // per ky: rank that owns it in the transposed layout
+    const long long* ky_base2;  // per ky: offset of (k = 0, ky, i = 0) of THIS rank's block in the owner's W2
+    long long off_W, off_W2;    // byte offsets of W / W2 in every rank's arena
+    int rank;
 };
+
+struct PeerBases { const char* base[8]; };   // arena base address of every rank, mapped into this process
 
 // Peer-blocked layouts of the two spectral arrays. The all-to-all of the distributed FFT then moves CONTIGUOUS blocks
 // straight between them (no pack / unpack passes); with one rank both reduce to the plain [k][ky][x] order.
@@ -207,7 +214,7 @@ __global__ void poisson_pack_flat_y(Layout L, PoissonGeom G, const double* __res
 // ---- pass 5: complex-to-real inverse FFT along y → φ (padded field interior) -------------------------------------
 template <int N>
 __global__ void __launch_bounds__(256, 3) poisson_inverse_y(Layout L, PoissonGeom G, const double2* __restrict__ W, double* __restrict__ phi,
-                                  const double2* __restrict__ tw_y, int lines, double scale) {
+                                  const double2* __restrict__ tw_y, int lines, double scale, PeerBases peers, int pull) {
     extern __shared__ double sm[];
     constexpr int LP = ((N + (N >> 4) + 15) & ~15) + 4;
     double* re = sm;
@@ -228,8 +235,15 @@ __global__ void __launch_bounds__(256, 3) poisson_inverse_y(Layout L, PoissonGeo
             if (e < total) {
                 int l = e & (lines - 1), ky = e >> (xb_shift - 1);
                 int i = ib + 2 * l;
-                if (i < L.nx) A[it] = W[w_index(G, k, ky, i)];
-                if (i + 1 < L.nx) B[it] = W[w_index(G, k, ky, i + 1)];
+                if (pull) {   // transposed spectrum read straight from its owner's W2 over NVLink (replaces the backward all-to-all)
+                    const double2* src = reinterpret_cast<const double2*>(peers.base[__ldg(&G.ky_owner[ky])] + G.off_W2)
+                                         + __ldg(&G.ky_base2[ky]) + (long long)k * __ldg(&G.ky_kstride[ky]);
+                    if (i < L.nx) A[it] = __ldcv(src + i);
+                    if (i + 1 < L.nx) B[it] = __ldcv(src + i + 1);
+                } else {
+                    if (i < L.nx) A[it] = W[w_index(G, k, ky, i)];
+                    if (i + 1 < L.nx) B[it] = W[w_index(G, k, ky, i + 1)];
+                }
             }
         }
 #pragma unroll
@@ -267,7 +281,8 @@ __global__ void poisson_unpack_flat_y(Layout L, PoissonGeom G, const double2* __
 // ---- passes 2 / 4: complex FFT along x, in place; one line = Nx contiguous complex numbers ----------------------
 // grid ceil(n_lines / lines); block lines*Nx/8 <= 256 threads; smem 2*lines*line_pitch(Nx) doubles.
 template <int N>
-__global__ void __launch_bounds__(256, 3) fft_x_kernel(PoissonGeom G, double2* __restrict__ W, long long n_lines, const double2* __restrict__ tw_x, int lines, int inverse) {
+__global__ void __launch_bounds__(256, 3) fft_x_kernel(PoissonGeom G, double2* __restrict__ W, long long n_lines, const double2* __restrict__ tw_x, int lines, int inverse,
+                                                       PeerBases peers, int pull) {
     extern __shared__ double sm[];
     constexpr int LP = ((N + (N >> 4) + 15) & ~15) + 4;
     double* re = sm;
@@ -288,7 +303,15 @@ __global__ void __launch_bounds__(256, 3) fft_x_kernel(PoissonGeom G, double2* _
     for (int it = 0; it < 8; ++it) {
         const int e = threadIdx.x + it * blockDim.x;
         const int l = e / N, x = e % N;
-        v[it] = (l0 + l < n_lines) ? W[w2_of(l, x)] : make_double2(0.0, 0.0);
+        if (l0 + l >= n_lines) v[it] = make_double2(0.0, 0.0);
+        else if (pull) {   // x-slab spectrum read straight from the rank that owns these columns (replaces the forward all-to-all)
+            int ky = r0 + l, k = k0;
+            while (ky >= G.nky_loc) { ky -= G.nky_loc; ++k; }
+            const int p = x >> G.nx_shift;
+            const double2* src = reinterpret_cast<const double2*>(peers.base[p] + G.off_W)
+                                 + (((long long)G.ky0 * G.Nz + (long long)k * G.nky_loc + ky) << G.nx_shift) + (x & xmask);
+            v[it] = __ldcv(src);
+        } else v[it] = W[w2_of(l, x)];
     }
 #pragma unroll
     for (int it = 0; it < 8; ++it) {

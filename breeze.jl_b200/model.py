@@ -375,6 +375,21 @@ class AtmosphereModel:
         self.context.time_step(Δt)
 
 
+def enable_peer_memory(model: AtmosphereModel):
+    """Multi-GPU: map the neighbouring ranks' device arenas (CUDA IPC) so that ghost cells and the FFT transposes become peer
+    loads over NVLink inside the consuming kernels. Needs an initialised torch.distributed process group (one rank per GPU);
+    a no-op on one rank."""
+    ctx = model.context
+    if ctx.cfg.n_ranks <= 1:
+        return
+    import torch
+    import torch.distributed as dist
+    mine = torch.tensor(list(ctx.ipc_export()), dtype=torch.uint8, device="cuda")
+    parts = [torch.empty_like(mine) for _ in range(ctx.cfg.n_ranks)]
+    dist.all_gather(parts, mine)
+    ctx.ipc_attach(b"".join(bytes(p.cpu().tolist()) for p in parts))
+
+
 def set_(model: AtmosphereModel, **kw):
     model.set(**kw)
 

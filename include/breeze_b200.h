@@ -184,6 +184,13 @@ int bz_synchronize(bz_ctx* ctx);
  * (torch.distributed broadcast in bench.py); every rank then puts it in bz_config.nccl_unique_id. */
 int bz_nccl_unique_id(uint8_t* out128);
 
+/* Peer memory over NVLink (optional, n_ranks > 1, one process per GPU): every rank exports ONE CUDA IPC handle of its
+ * device arena (64 bytes); the rank-ordered concatenation of all handles (all_gather) is attached on every rank. From then
+ * on ghost cells and the two transposes of the distributed FFT are peer LOADS issued by the consuming kernels, ordered by
+ * a one-element NCCL all-reduce used as a stream barrier; without it the same exchanges run as NCCL send/recv. */
+int bz_ipc_export(bz_ctx* ctx, uint8_t* out64);
+int bz_ipc_attach(bz_ctx* ctx, const uint8_t* handles /* n_ranks * 64 bytes */);
+
 /* Instrumentation for bench.py: CUDA-event time (ms) accumulated per kernel family since the last reset, and the
  * number of kernels this library launched. Families: 0 stage(tendency+RK), 1 Poisson forward (div+FFT), 2 Thomas,
  * 3 Poisson inverse, 4 projection(+halo), 5 halo exchange / transposes. Profiling adds event records only when enabled. */

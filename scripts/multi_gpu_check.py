@@ -25,9 +25,14 @@ dist.broadcast(buf, 0)
 uid = bytes(buf.cpu().tolist())
 
 
+P2P = os.environ.get("BZ_P2P", "1") == "1"
+
+
 def build(arch):
     grid = bz.RectilinearGrid(arch, size=(N, N // 2, N // 2), x=(-10e3, 10e3), y=(-5e3, 5e3), z=(0, 10e3))
     m = bz.AtmosphereModel(grid, dynamics=bz.AnelasticDynamics(bz.ReferenceState(grid, potential_temperature=300)))
+    if P2P:
+        bz.enable_peer_memory(m)
     m.set(θ=lambda x, y, z: 300 + 2 * np.cos(np.pi / 2 * np.minimum(1, np.sqrt((x - 3000) ** 2 + y ** 2 + (z - 2000) ** 2) / 2000)) ** 2,
           u=lambda x, y, z: 5 + np.sin(2 * np.pi * x / 20e3) * np.cos(2 * np.pi * y / 10e3) + 0 * z,
           v=lambda x, y, z: -2 + np.cos(2 * np.pi * x / 20e3) + 0 * y + 0 * z,
@@ -57,6 +62,6 @@ if rank == 0:
         worst = max(worst, np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
     t1, d1 = ref.context.cell_advection_timescale(), ref.context.max_abs_divergence()
     ok = worst < 1e-11 and abs(tau - t1) < 1e-9 * t1
-    print(f"MULTI_GPU_{'OK' if ok else 'FAIL'} ranks={world} max_rel={worst:.3e} tau={tau:.6f}/{t1:.6f} div={div:.2e}/{d1:.2e}")
+    print(f"MULTI_GPU_{'OK' if ok else 'FAIL'} p2p={int(P2P)} ranks={world} max_rel={worst:.3e} tau={tau:.6f}/{t1:.6f} div={div:.2e}/{d1:.2e}")
 dist.barrier()
 dist.destroy_process_group()

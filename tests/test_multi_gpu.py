@@ -14,11 +14,13 @@ def _ngpu():
     return torch.cuda.device_count()
 
 
+@pytest.mark.parametrize("p2p", [1, 0])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_slabs_match_single_gpu(world):
+def test_slabs_match_single_gpu(world, p2p):
+    """p2p = 1: ghost cells and FFT transposes as CUDA-IPC peer loads; p2p = 0: NCCL send/recv."""
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-           "--master-port", str(29600 + world), os.path.join(ROOT, "scripts", "multi_gpu_check.py"), "64", "3"]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+           "--master-port", str(29600 + 10 * world + p2p), os.path.join(ROOT, "scripts", "multi_gpu_check.py"), "64", "3"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, BZ_P2P=str(p2p)))
     assert "MULTI_GPU_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
