@@ -331,16 +331,16 @@ __global__ void __launch_bounds__(2 * TX * TY, 1) stage_kernel(const __grid_cons
                 const double u_i = XS(0, 0);
                 if (kind == 0) {          // FUu at centre i-1
                     double ut = rho_k * sym4(XS(0, -2), XS(0, -1), u_i, XS(0, 1), 2);
-                    return ut * biased6c<3>(XS(0, -3), XS(0, -2), XS(0, -1), u_i, XS(0, 1), XS(0, 2), ut > 0.0);
+                    return ut * biased6c<3>(XS(0, -3), XS(0, -2), XS(0, -1), u_i, XS(0, 1), XS(0, 2), positive(ut));
                 } else if (kind == 1) {   // FUv at (face i, face j)
                     double ut = HAS_Y ? rho_k * sym4(cell[-2 * SW], cell[-SW], u_i, cell[SW], 2) : rho_k * u_i;
-                    return ut * biased6c<3>(XS(1, -3), XS(1, -2), XS(1, -1), XS(1, 0), XS(1, 1), XS(1, 2), ut > 0.0);
+                    return ut * biased6c<3>(XS(1, -3), XS(1, -2), XS(1, -1), XS(1, 0), XS(1, 1), XS(1, 2), positive(ut));
                 } else if (kind == 2) {   // FUw at (face i, z-face k); the wall face k = 0 carries no w tendency
                     if (!FULL && k < 1) return 0.0;
                     double ut = sz(r_m2 * Lp[0][zoff], r_m1 * Lp[1][zoff], rho_k * u_i, r_p1 * Lp[3][zoff], Rf_k2);
-                    return ut * biased6c<3>(XS(2, -3), XS(2, -2), XS(2, -1), XS(2, 0), XS(2, 1), XS(2, 2), ut > 0.0);
+                    return ut * biased6c<3>(XS(2, -3), XS(2, -2), XS(2, -1), XS(2, 0), XS(2, 1), XS(2, 2), positive(ut));
                 } else {                  // tracer mass flux ρ u ĉ
-                    return rho_k * u_i * biased6c<3>(XS(kind, -3), XS(kind, -2), XS(kind, -1), XS(kind, 0), XS(kind, 1), XS(kind, 2), u_i > 0.0);
+                    return rho_k * u_i * biased6c<3>(XS(kind, -3), XS(kind, -2), XS(kind, -1), XS(kind, 0), XS(kind, 1), XS(kind, 2), positive(u_i));
                 }
             };
             // Y-type fluxes: through y-face j (or at centre j-1 for ρv) of the cell whose plane element is `row`
@@ -349,16 +349,16 @@ __global__ void __launch_bounds__(2 * TX * TY, 1) stage_kernel(const __grid_cons
                 const double v_j = YS(1, 0);
                 if (kind == 0) {          // FVu at (face i, face j)
                     double vt = FLAT_X ? rho_k * v_j : rho_k * sym4(row[PL - 2], row[PL - 1], v_j, row[PL + 1], 2);
-                    return vt * biased6c<3>(YS(0, -3), YS(0, -2), YS(0, -1), YS(0, 0), YS(0, 1), YS(0, 2), vt > 0.0);
+                    return vt * biased6c<3>(YS(0, -3), YS(0, -2), YS(0, -1), YS(0, 0), YS(0, 1), YS(0, 2), positive(vt));
                 } else if (kind == 1) {   // FVv at centre j-1
                     double vt = rho_k * sym4(YS(1, -2), YS(1, -1), v_j, YS(1, 1), 2);
-                    return vt * biased6c<3>(YS(1, -3), YS(1, -2), YS(1, -1), v_j, YS(1, 1), YS(1, 2), vt > 0.0);
+                    return vt * biased6c<3>(YS(1, -3), YS(1, -2), YS(1, -1), v_j, YS(1, 1), YS(1, 2), positive(vt));
                 } else if (kind == 2) {   // FVw at (face j, z-face k)
                     if (!FULL && k < 1) return 0.0;
                     double vt = sz(r_m2 * Lp[0][PL + zoff], r_m1 * Lp[1][PL + zoff], rho_k * v_j, r_p1 * Lp[3][PL + zoff], Rf_k2);
-                    return vt * biased6c<3>(YS(2, -3), YS(2, -2), YS(2, -1), YS(2, 0), YS(2, 1), YS(2, 2), vt > 0.0);
+                    return vt * biased6c<3>(YS(2, -3), YS(2, -2), YS(2, -1), YS(2, 0), YS(2, 1), YS(2, 2), positive(vt));
                 } else {
-                    return rho_k * v_j * biased6c<3>(YS(kind, -3), YS(kind, -2), YS(kind, -1), YS(kind, 0), YS(kind, 1), YS(kind, 2), v_j > 0.0);
+                    return rho_k * v_j * biased6c<3>(YS(kind, -3), YS(kind, -2), YS(kind, -1), YS(kind, 0), YS(kind, 1), YS(kind, 2), positive(v_j));
                 }
             };
             // Z-type fluxes through the top face k+1 (or at centre k for ρw)
@@ -367,15 +367,15 @@ __global__ void __launch_bounds__(2 * TX * TY, 1) stage_kernel(const __grid_cons
                 const double w_top = Lt[2 * PL];                           // 0 on the top wall (zero plane)
                 if (kind == 0) {          // FWu at (face i, z-face k+1)
                     double wt = FLAT_X ? rho_ft * w_top : rho_ft * sym4(Lt[2 * PL - 2], Lt[2 * PL - 1], w_top, Lt[2 * PL + 1], 2);
-                    return wt * bz(ZS(0, -2), ZS(0, -1), ZS(0, 0), ZS(0, 1), ZS(0, 2), ZS(0, 3), Rf_top, wt > 0.0);
+                    return wt * bz(ZS(0, -2), ZS(0, -1), ZS(0, 0), ZS(0, 1), ZS(0, 2), ZS(0, 3), Rf_top, positive(wt));
                 } else if (kind == 1) {   // FWv at (face j, z-face k+1)
                     double wt = HAS_Y ? rho_ft * sym4(Lt[2 * PL - 2 * SW], Lt[2 * PL - SW], w_top, Lt[2 * PL + SW], 2) : rho_ft * w_top;
-                    return wt * bz(ZS(1, -2), ZS(1, -1), ZS(1, 0), ZS(1, 1), ZS(1, 2), ZS(1, 3), Rf_top, wt > 0.0);
+                    return wt * bz(ZS(1, -2), ZS(1, -1), ZS(1, 0), ZS(1, 1), ZS(1, 2), ZS(1, 3), Rf_top, positive(wt));
                 } else if (kind == 2) {   // FWw at centre k: faces k-1 .. k+2 (advecting), k-2 .. k+3 (advected)
                     double wt = sz(f_m1 * ZS(2, -1), f_0 * ZS(2, 0), rho_ft * w_top, f_p2 * ZS(2, 2), Rc2);
-                    return wt * bz(ZS(2, -2), ZS(2, -1), ZS(2, 0), w_top, ZS(2, 2), ZS(2, 3), Rc3, wt > 0.0);
+                    return wt * bz(ZS(2, -2), ZS(2, -1), ZS(2, 0), w_top, ZS(2, 2), ZS(2, 3), Rc3, positive(wt));
                 } else {                  // tracer mass flux ℑz(ρ) w ĉ
-                    return rho_ft * w_top * bz(ZS(kind, -2), ZS(kind, -1), ZS(kind, 0), ZS(kind, 1), ZS(kind, 2), ZS(kind, 3), Rf_top, w_top > 0.0);
+                    return rho_ft * w_top * bz(ZS(kind, -2), ZS(kind, -1), ZS(kind, 0), ZS(kind, 1), ZS(kind, 2), ZS(kind, 3), Rf_top, positive(w_top));
                 }
             };
             using K0 = std::integral_constant<int, 0>; using K1 = std::integral_constant<int, 1>; using K2 = std::integral_constant<int, 2>;

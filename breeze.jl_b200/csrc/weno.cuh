@@ -18,15 +18,26 @@
 __device__ __forceinline__ double fast_rcp(double x) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+#ifdef BZ_RCP_TWO_NEWTON
     double e = fma(-x, r, 1.0);
     r = fma(r, e, r);
     e = fma(-x, r, 1.0);
     r = fma(r, e, r);
+#else
+    // one cubically convergent step: r (1 + e + e²), e = 1 - x r  (MUFU.RCP64H is good to ~2⁻²³ ⇒ ≤ 1 ulp after it)
+    double e = fma(-x, r, 1.0);
+    e = fma(e, e, e);
+    r = fma(r, e, r);
+#endif
     return r;
 }
 
+// sign test on the high word (integer pipe instead of DSETP on the FP64 pipe); differs from `x > 0` only for
+// x = ±0, where the flux it selects for is multiplied by that zero
+__device__ __forceinline__ bool positive(double x) { return __double2hiint(x) >= 0; }
+
 // Left-biased value at the face between c and d from the five cells a b c | d e (a = ψ[i-3] … e = ψ[i+1]).
-// Written with explicit fma() for the minimal FP64 instruction count (46 + one reciprocal):
+// Written with explicit fma() for the minimal FP64 instruction count (43 + one reciprocal):
 //   β' = β / 0.75 = (13/3) s² + t²  (ε scaled alike: the weights only see the ratios τ/(β+ε));
 //   Σ ω_r q_r = q₁ + ω₀ (q₀ - q₁) + ω₂ (q₂ - q₁)  with  q₀ - q₁ = (s₁ - s₀)/6,  q₂ - q₁ = (s₂ - s₁)/3
 // (s_r are the second differences already formed for β), so only the central candidate polynomial is evaluated.
@@ -35,17 +46,19 @@ __device__ __forceinline__ double weno5z(double a, double b, double c, double d,
     double s0 = fma(-2.0, d, c) + e, t0 = fma(3.0, c, fma(-4.0, d, e));   // stencil (c, d, e)
     double s1 = fma(-2.0, c, b) + d, t1 = b - d;                          // stencil (b, c, d)
     double s2 = fma(-2.0, b, a) + c, t2 = fma(3.0, c, fma(-4.0, b, a));   // stencil (a, b, c)
-    double b0 = fma(s0 * K, s0, t0 * t0);
-    double b1 = fma(s1 * K, s1, t1 * t1);
-    double b2 = fma(s2 * K, s2, t2 * t2);
-    double tau = fabs(b0 - b2);
+    // b_r = β'_r + ε' in one chain; τ = |b0 - b2| only enters squared
+    double b0 = fma(s0 * K, s0, fma(t0, t0, EPSP));
+    double b1 = fma(s1 * K, s1, fma(t1, t1, EPSP));
+    double b2 = fma(s2 * K, s2, fma(t2, t2, EPSP));
+    double tau = b0 - b2;
     double tt = tau * tau;
-    b0 += EPSP; b1 += EPSP; b2 += EPSP;
     double q0 = b0 * b0, q1 = b1 * b1, q2 = b2 * b2;
-    // un-normalised weights × Π b_s² (the common factor cancels in the ratio); optimal weights (3, 6, 1)/10 applied below
-    double w0 = (q0 + tt) * (q1 * q2);
-    double w1 = (q1 + tt) * (q0 * q2);
-    double w2 = (q2 + tt) * (q0 * q1);
+    // un-normalised weights × Π b_s² (the common factor cancels in the ratio):  (q_r + τ²) Π_{s≠r} q_s = Π q + τ² Π_{s≠r} q_s
+    double m12 = q1 * q2, m02 = q0 * q2, m01 = q0 * q1;
+    double pq = q0 * m12;
+    double w0 = fma(tt, m12, pq);
+    double w1 = fma(tt, m02, pq);
+    double w2 = fma(tt, m01, pq);
     double qc = fma(-1.0 / 6.0, b, fma(5.0 / 6.0, c, (1.0 / 3.0) * d));   // central candidate (stencil b, c, d)
     double num = fma(0.5 * w0, s1 - s0, ((1.0 / 3.0) * w2) * (s2 - s1));  // 3 w0 (q0 - qc) + w2 (q2 - qc)
     double den = fma(3.0, w0, fma(6.0, w1, w2));
