@@ -11,4 +11,8 @@ from .model import (B200, DragFluxBoundaryCondition, FluxBoundaryCondition, Forc
                     SaturationAdjustment, Simulation, ThermodynamicConstants, TimeStepWizard, WENO,
                     conjure_time_step_wizard_, enable_peer_memory, many_time_steps_, run_, set_, time_step_)
 
+from .compressible import (CompressibleAtmosphereModel, CompressibleContext, CompressibleDynamics, ConstantSubstepSize, MonolithicFirstStage,
+                           NoDivergenceDamping, ProportionalSubsteps, SplitExplicitTimeDiscretization, ThermalDivergenceDamping,
+                           bzc_config, compressible_library)
+
 __all__ = [n for n in dir() if not n.startswith("_")]

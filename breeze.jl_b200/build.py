@@ -7,8 +7,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(CSRC, "libbreeze_b200.so")
 SOURCES = ["api.cu"]
-HEADERS = ["common.cuh", "weno.cuh", "stage_kernel.cuh", "poisson.cuh", "aux_kernels.cuh", "comm.cuh",
-           os.path.join("..", "..", "include", "breeze_b200.h")]
+HEADERS = ["common.cuh", "weno.cuh", "stage_kernel.cuh", "poisson.cuh", "aux_kernels.cuh", "comm.cuh", "compressible.cuh",
+           "compressible_api.cuh", os.path.join("..", "..", "include", "breeze_b200.h"),
+           os.path.join("..", "..", "include", "breeze_b200_compressible.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--use_fast_math=false" if False else "-Xcompiler", "-O2"]

@@ -880,3 +880,6 @@ void* bz_stream(bz_ctx* c) { return c ? (void*)c->stream : nullptr; }
 int64_t bz_device_bytes(const bz_ctx* c) { return c ? c->bytes : 0; }
 
 }  // extern "C"
+
+// second hot-path family: compressible WS-RK3 with acoustic substepping (include/breeze_b200_compressible.h)
+#include "compressible_api.cuh"

@@ -1,0 +1,403 @@
+// compressible.cuh — kernels of the compressible split-explicit path (include/breeze_b200_compressible.h):
+// Wicker–Skamarock RK3 with linearized acoustic substepping, dry air.
+//
+// Reference kernels replaced (paths relative to the reference repository):
+//   per stage   _compute_linearization_exner_and_theta!, _compute_linearization_mixture_eos!    acoustic_substepping.jl:372-415
+//               compute_x/y/z_momentum_tendency! (SlowTendencyMode), _compute_density_tendency!,
+//               compute_potential_temperature_tendency!                                         acoustic_substep_helpers.jl:55-149
+//               _assemble_slow_vertical_momentum_tendency!                                      acoustic_substepping.jl:724-748
+//               _zero_stage_workspaces!, _initialize_stage_perturbations!, …_with_rewind!        :805-833
+//   per substep _explicit_horizontal_step! (A), _build_predictors! + _build_vertical_rhs! (B),
+//               solve!(BatchedTridiagonalSolver) (C), _post_solve_recovery! (D),
+//               _thermal_divergence_damping! (E) and 7 halo fills                                :859-1144,1442-1552
+//   stage end   _finalize_time_averaged_velocity!, _recover_full_state!, _compute_velocities!,
+//               _compute_auxiliary_thermodynamic_variables!, _compute_temperature_and_pressure!   :1230-1293, compressible_time_stepping.jl:191-235
+//
+// B200 design. The substep loop is HBM-bound (1- to 7-point stencils + a column recurrence), so it is cut to TWO launches per
+// substep with no halo passes at all (periodic neighbours are addressed by wrapped indices):
+//   acoustic_horizontal   E of the previous substep fused with A of this one (both only touch (ρu)′, (ρv)′ pointwise)
+//   acoustic_column       one thread per (i, j) column, x fastest across the warp (coalesced 256-byte rows): the upward march
+//                         builds the predictors ρ′★, (ρθ)′★, the face right-hand side and runs the forward elimination of
+//                         the tridiagonal system with coefficients formed on the fly from Cᴸ = γRᵐᴸ Πᴸ and θᴸ; the downward
+//                         march back-substitutes (ρw)′ and recovers ρ′, (ρθ)′ and the ⟨ρ𝐮′⟩ accumulators. Face values of the
+//                         level below / above are carried in registers, so every field is read once per march.
+// Fields use the layout of common.cuh (4 ghost cells in x / y, none in z) with Nz + 1 levels allocated; only the WENO5 slow
+// tendency kernel reads ghost cells (filled once per stage). z-face level 0 is the bottom wall, level Nz the top wall.
+#pragma once
+#include "common.cuh"
+#include "weno.cuh"
+
+struct CEos { double Rd, cpd, pst, g; };
+
+// ---- periodic neighbours by wrapped index (interior addressing, no ghost cells needed) -----------------------------
+__device__ __forceinline__ long long cxm(const Layout& L, long long n, int i) { return i > 0 ? n - 1 : n + (L.nx - 1); }
+__device__ __forceinline__ long long cxp(const Layout& L, long long n, int i) { return i < L.nx - 1 ? n + 1 : n - (L.nx - 1); }
+__device__ __forceinline__ long long cym(const Layout& L, long long n, int j) { return j > 0 ? n - L.PX : n + (long long)(L.Ny - 1) * L.PX; }
+__device__ __forceinline__ long long cyp(const Layout& L, long long n, int j) { return j < L.Ny - 1 ? n + L.PX : n - (long long)(L.Ny - 1) * L.PX; }
+
+// ---- update_state!: velocities, θ, and the joint (T, p) diagnosis ---------------------------------------------------
+// temperature(::LiquidIceDensityState) with NewtonSolver(reltol=0, abstol=1e-4, maxiter=8) (dynamic_states.jl:201-232); p = ρ Rᵈ T
+__device__ __forceinline__ void c_temperature_pressure(const CEos& e, double rho, double theta, double& T, double& p) {
+    const double Rm = e.Rd, cpm = e.cpd;
+    const double kap = Rm / cpm, gam = cpm / (cpm - Rm);
+    T = pow(theta, gam) * pow(rho * Rm / e.pst, gam - 1.0) + 0.0;
+    double dT = T; int iter = 0;
+    while (fabs(dT) > 1e-4 && iter < 8) {
+        double Phi = pow(rho * Rm * T / e.pst, kap) * theta;
+        dT = -(T - Phi - 0.0) / (1.0 - kap * Phi / T);
+        T += dT;
+        ++iter;
+    }
+    p = rho * Rm * T;
+}
+
+// grid (x blocks, Ny, Nz + 1); ρ needs valid x / y ghost cells
+__global__ void c_update_state(Layout L, CEos e, const double* __restrict__ rho, const double* __restrict__ ru, const double* __restrict__ rv,
+                               const double* __restrict__ rw, const double* __restrict__ rth, double* __restrict__ u, double* __restrict__ v,
+                               double* __restrict__ w, double* __restrict__ theta, double* __restrict__ T, double* __restrict__ p) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, k = blockIdx.z;
+    if (i >= L.nx) return;
+    long long n = lidx(L, i, j, k);
+    if (k < L.Nz) {
+        double r = rho[n];
+        double rx = L.flat_x ? r : (r + rho[n - 1]) / 2;
+        double ry = L.flat_y ? r : (r + rho[n - L.PX]) / 2;
+        u[n] = ru[n] / rx;
+        v[n] = rv[n] / ry;
+        double th = rth[n] / r;
+        theta[n] = th;
+        double Tn, pn;
+        c_temperature_pressure(e, r, th, Tn, pn);
+        T[n] = Tn; p[n] = pn;
+    }
+    w[n] = (k == 0 || k == L.Nz) ? 0.0 : rw[n] / ((rho[n] + rho[n - L.plane]) / 2);
+}
+
+// refresh_linearization_basic_state!: Πᴸ = (p/pˢᵗ)^κ, θᴸ = ρθ/ρ, Cᴸ = γᵐRᵐᴸ Πᴸ (dry: γᵐRᵐ = cᵖᵈ Rᵈ / (cᵖᵈ - Rᵈ))
+__global__ void c_linearize(Layout L, CEos e, const double* __restrict__ p, const double* __restrict__ rho, const double* __restrict__ rth,
+                            double* __restrict__ PiL, double* __restrict__ thL, double* __restrict__ CL) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, k = blockIdx.z;
+    if (i >= L.nx) return;
+    long long n = lidx(L, i, j, k);
+    double Pi = pow(p[n] / e.pst, e.Rd / e.cpd);
+    double r = rho[n];
+    double rh = (r == 0.0) ? 1.0 : r;
+    double gR = e.cpd * e.Rd / (e.cpd - e.Rd);
+    PiL[n] = Pi;
+    thL[n] = rth[n] / rh;
+    CL[n] = gR * Pi;
+}
+
+// ---- slow tendencies (WENO5, 3-D coupling density) ------------------------------------------------------------------
+struct CSlowArgs {
+    const double *rho, *ru, *rv, *rw, *u, *v, *w, *theta, *p;
+    const double *p_r, *rho_r;           // Nz each or nullptr (reference_state = nothing)
+    double *Grho, *Gru, *Grv, *Grw, *Grth, *Gs_rw;
+};
+
+// biased reconstruction at the "face" between f[n - s] and f[n]; in x / y the ghost cells make R = 3 always valid,
+// in z the buffer R shrinks next to the walls (weno.cuh red_face / red_center) and only in-range levels are read
+__device__ __forceinline__ double c_biased(const double* __restrict__ f, long long n, long long s, int R, bool left) {
+    if (R >= 3) return biased6c<3>(f[n - 3 * s], f[n - 2 * s], f[n - s], f[n], f[n + s], f[n + 2 * s], left);
+    if (R == 2) return left ? weno3z(f[n - 2 * s], f[n - s], f[n]) : weno3z(f[n + s], f[n], f[n - s]);
+    return left ? f[n - s] : f[n];
+}
+__device__ __forceinline__ double c_sym(const double* __restrict__ a, long long n, long long s, int R) {
+    if (R >= 2) return ((7.0 / 12.0) * (a[n - s] + a[n])) - ((1.0 / 12.0) * (a[n - 2 * s] + a[n + s]));
+    return 0.5 * (a[n - s] + a[n]);
+}
+
+__global__ void __launch_bounds__(128) c_slow_tendencies(Layout L, CSlowArgs A, double g) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, k = blockIdx.z;
+    if (i >= L.nx) return;
+    const long long n = lidx(L, i, j, k);
+    const long long SX = 1, SY = L.PX, SZ = L.plane;
+    const int Nz = L.Nz;
+    const bool fx_ = L.flat_x, fy_ = L.flat_y;
+    const double Ax = L.dy * L.dz, Ay = L.dx * L.dz, Az = L.dx * L.dy, Vinv = 1.0 / (L.dx * L.dy * L.dz);
+    // advecting mass fluxes: centred-4 interpolation of the area-weighted momentum; advected velocity: WENO5-Z
+    auto symx = [&](const double* a, long long m) { return fx_ ? a[m] : c_sym(a, m, SX, 2); };
+    auto symy = [&](const double* a, long long m) { return fy_ ? a[m] : c_sym(a, m, SY, 2); };
+    auto Fuu = [&](long long m1) { double t = Ax * c_sym(A.ru, m1, SX, 2); return t * c_biased(A.u, m1, SX, 3, t > 0); };          // centre i (m1 = i + 1)
+    auto Fvu = [&](long long m) { double t = Ay * symx(A.rv, m); return t * c_biased(A.u, m, SY, 3, t > 0); };                      // (face i, face j)
+    auto Fwu = [&](long long m, int kk) { if (kk == 0 || kk == Nz) return 0.0; double t = Az * symx(A.rw, m); return t * c_biased(A.u, m, SZ, red_face(kk, Nz, 3), t > 0); };
+    auto Fuv = [&](long long m) { double t = Ax * symy(A.ru, m); return t * c_biased(A.v, m, SX, 3, t > 0); };
+    auto Fvv = [&](long long m1) { double t = Ay * c_sym(A.rv, m1, SY, 2); return t * c_biased(A.v, m1, SY, 3, t > 0); };
+    auto Fwv = [&](long long m, int kk) { if (kk == 0 || kk == Nz) return 0.0; double t = Az * symy(A.rw, m); return t * c_biased(A.v, m, SZ, red_face(kk, Nz, 3), t > 0); };
+    auto Fuw = [&](long long m, int kk) { double t = Ax * c_sym(A.ru, m, SZ, red_face(kk, Nz, 2)); return t * c_biased(A.w, m, SX, 3, t > 0); };
+    auto Fvw = [&](long long m, int kk) { double t = Ay * c_sym(A.rv, m, SZ, red_face(kk, Nz, 2)); return t * c_biased(A.w, m, SY, 3, t > 0); };
+    auto Fww = [&](long long m1, int kc) { double t = Az * c_sym(A.rw, m1, SZ, red_center(kc, Nz, 2)); return t * c_biased(A.w, m1, SZ, red_center(kc, Nz, 3), t > 0); };
+    auto Tx = [&](long long m) { double t = A.u[m]; return ((A.rho[m] + A.rho[m - SX]) / 2) * (Ax * t * c_biased(A.theta, m, SX, 3, t > 0)); };
+    auto Ty = [&](long long m) { double t = A.v[m]; return ((A.rho[m] + A.rho[m - SY]) / 2) * (Ay * t * c_biased(A.theta, m, SY, 3, t > 0)); };
+    auto Tz = [&](long long m, int kk) { if (kk == 0 || kk == Nz) return 0.0; double t = A.w[m];
+                                         return ((A.rho[m] + A.rho[m - SZ]) / 2) * (Az * t * c_biased(A.theta, m, SZ, red_face(kk, Nz, 3), t > 0)); };
+    {
+        double fx = fx_ ? 0.0 : Fuu(n + SX) - Fuu(n);
+        double fy = fy_ ? 0.0 : Fvu(n + SY) - Fvu(n);
+        double fz = Fwu(n + SZ, k + 1) - Fwu(n, k);
+        A.Gru[n] = -(Vinv * (fx + fy + fz));
+    }
+    {
+        double fx = fx_ ? 0.0 : Fuv(n + SX) - Fuv(n);
+        double fy = fy_ ? 0.0 : Fvv(n + SY) - Fvv(n);
+        double fz = Fwv(n + SZ, k + 1) - Fwv(n, k);
+        A.Grv[n] = -(Vinv * (fx + fy + fz));
+    }
+    double Gw = 0.0;
+    if (k >= 1) {
+        double fx = fx_ ? 0.0 : Fuw(n + SX, k) - Fuw(n, k);
+        double fy = fy_ ? 0.0 : Fvw(n + SY, k) - Fvw(n, k);
+        double fz = Fww(n + SZ, k) - Fww(n, k - 1);
+        Gw = -(Vinv * (fx + fy + fz));
+    }
+    A.Grw[n] = Gw;
+    {
+        double dxu = fx_ ? 0.0 : Ax * A.ru[n + SX] - Ax * A.ru[n];
+        double dyv = fy_ ? 0.0 : Ay * A.rv[n + SY] - Ay * A.rv[n];
+        double dzw = Az * A.rw[n + SZ] - Az * A.rw[n];
+        A.Grho[n] = -(Vinv * (dxu + dyv + dzw));
+    }
+    {
+        double fx = fx_ ? 0.0 : Tx(n + SX) - Tx(n);
+        double fy = fy_ ? 0.0 : Ty(n + SY) - Ty(n);
+        double fz = Tz(n + SZ, k + 1) - Tz(n, k);
+        A.Grth[n] = -(Vinv * (fx + fy + fz));
+    }
+    // _assemble_slow_vertical_momentum_tendency!: Gˢρw = (Gρw - ∂z(pᴸ - pᵣ) - g ℑz(ρᴸ - ρᵣ)) (k > 1)
+    double Gs = 0.0;
+    if (k >= 1) {
+        if (A.p_r) {
+            double dpk = A.p[n] - A.p_r[k], dpm = A.p[n - SZ] - A.p_r[k - 1];
+            double drk = A.rho[n] - A.rho_r[k], drm = A.rho[n - SZ] - A.rho_r[k - 1];
+            Gs = Gw - (dpk - dpm) * L.rdz - g * ((drk + drm) / 2);
+        } else {
+            Gs = Gw - (A.p[n] - A.p[n - SZ]) * L.rdz - g * ((A.rho[n] + A.rho[n - SZ]) / 2);
+        }
+    }
+    A.Gs_rw[n] = Gs;
+}
+
+// ---- stage start: rewind-initialised perturbations, zeroed accumulators ----------------------------------------------
+struct CFields5 { double* f[5]; };      // ρ, ρu, ρv, ρw, ρθ
+struct CConst5 { const double* f[5]; };
+
+__global__ void c_init_perturbations(Layout L, CConst5 U0, CConst5 U, CFields5 P, double* __restrict__ avg_u, double* __restrict__ avg_v,
+                                     double* __restrict__ avg_w) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, k = blockIdx.z;      // k = 0..Nz
+    if (i >= L.nx) return;
+    long long n = lidx(L, i, j, k);
+    if (k < L.Nz) {
+#pragma unroll
+        for (int f = 0; f < 5; ++f) {
+            double v = U0.f[f][n] - U.f[f][n];
+            if (f == 3 && k == 0) v = 0.0;                   // impenetrable bottom wall (halo fill of the z-face field)
+            P.f[f][n] = v;
+        }
+        avg_u[n] = 0.0; avg_v[n] = 0.0;
+    } else {
+        P.f[3][n] = 0.0;                                      // top wall
+    }
+    avg_w[n] = 0.0;
+}
+
+// ---- substep, horizontal part: E (damping of the previous substep) fused with A (explicit step of this substep) ------
+struct CHorizArgs {
+    double *ru_p, *rv_p;
+    const double *rth_p, *rth_old, *thL, *CL, *p, *Gru, *Grv;
+    double kx, ky;            // κˣ, κʸ of the damping (0: none)
+    double dtau, factor;      // A: Δτ and the perturbation-PGF gate (1 / 0)
+    int do_damp, do_step;
+};
+
+__global__ void c_acoustic_horizontal(Layout L, CHorizArgs A) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, k = blockIdx.z;
+    if (i >= L.nx) return;
+    const long long n = lidx(L, i, j, k);
+    const long long nxm = cxm(L, n, i), nym = cym(L, n, j);
+    double ru = A.ru_p[n], rv = A.rv_p[n];
+    const double rt = A.rth_p[n];
+    if (A.do_damp) {          // _thermal_divergence_damping!
+        double d0 = rt - A.rth_old[n];
+        double th = A.thL[n];
+        if (!L.flat_x) {
+            double dxd = (d0 - (A.rth_p[nxm] - A.rth_old[nxm])) * L.rdx;
+            ru -= A.kx * dxd / ((th + A.thL[nxm]) / 2);
+        }
+        if (!L.flat_y) {
+            double dyd = (d0 - (A.rth_p[nym] - A.rth_old[nym])) * L.rdy;
+            rv -= A.ky * dyd / ((th + A.thL[nym]) / 2);
+        }
+    }
+    if (A.do_step) {          // _explicit_horizontal_step!
+        double pn = A.p[n], cp = A.CL[n] * rt;
+        double dxp = 0.0, dyp = 0.0;
+        if (!L.flat_x) dxp = (pn - A.p[nxm]) * L.rdx + A.factor * ((cp - A.CL[nxm] * A.rth_p[nxm]) * L.rdx);
+        if (!L.flat_y) dyp = (pn - A.p[nym]) * L.rdy + A.factor * ((cp - A.CL[nym] * A.rth_p[nym]) * L.rdy);
+        ru += A.dtau * (A.Gru[n] - dxp);
+        rv += A.dtau * (A.Grv[n] - dyp);
+    }
+    A.ru_p[n] = ru; A.rv_p[n] = rv;
+}
+
+// ---- substep, vertical part: B + C + D in one column kernel ------------------------------------------------------------
+struct CColumnArgs {
+    double *rho_p, *rth_p, *rw_p;              // perturbation prognostics (in / out)
+    const double *ru_p, *rv_p;                 // after step A
+    double *rho_s, *rth_s, *rth_old, *tfac;    // predictors, stashed (ρθ)′, Thomas factors
+    double *avg_u, *avg_v, *avg_w;
+    const double *Grho, *Grth, *Gs_rw, *thL, *CL;
+    double dtau, dtm, dts, dm, ds, g, fth, fw;
+};
+
+// one thread per column; blockDim.x columns along x per block, blockIdx.y = j
+__global__ void __launch_bounds__(128) c_acoustic_column(Layout L, CColumnArgs A) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    if (i >= L.nx) return;
+    const int Nz = L.Nz;
+    const long long SZ = L.plane;
+    const long long n0 = lidx(L, i, j, 0);
+    const long long oxm = cxm(L, n0, i) - n0, oxp = cxp(L, n0, i) - n0, oym = cym(L, n0, j) - n0, oyp = cyp(L, n0, j) - n0;
+    const double Ax = L.dy * L.dz, Ay = L.dx * L.dz, Vinv = 1.0 / (L.dx * L.dy * L.dz);
+    const double rdz = L.rdz, rdzc = L.rdz, rdzf = L.rdz;
+    const double dtm2 = A.dtm * A.dtm;
+    const double tiny = 10.0 * 2.220446049250313e-16;
+    const bool fx_ = L.flat_x, fy_ = L.flat_y;
+
+    // ---- upward march: predictors (B), face right-hand side, forward elimination (C) --------------------------------
+    // carried from the level below (face k lies between cells k-1 and k)
+    double C_m = 0.0, rs_m = 0.0, ts_m = 0.0, rp_m = 0.0, tp_m = 0.0;   // Cᴸ, ρ′★, (ρθ)′★, old ρ′, old (ρθ)′ at cell k-1
+    double w_m = 0.0, w_0 = 0.0;                                         // old (ρw)′ at faces k-1, k (face 0 is the wall)
+    double th_0 = A.thL[n0];
+    double thf_m = th_0, thf_0 = th_0;                                   // ℑbz θᴸ at faces k-1, k (one-sided on the walls)
+    double cu_prev = 0.0, beta = 1.0, phi_prev = 0.0;
+    for (int k = 0; k < Nz; ++k) {
+        const long long n = n0 + (long long)k * SZ;
+        const bool top = (k + 1 == Nz);
+        const double w_p = top ? 0.0 : A.rw_p[n + SZ];                   // old (ρw)′ at face k+1 (top wall: 0)
+        const double th_p = top ? th_0 : A.thL[n + SZ];
+        const double thf_p = top ? th_0 : (th_p + th_0) / 2;             // face k+1
+        const double C_0 = A.CL[n];
+        const double rp_0 = A.rho_p[n], tp_0 = A.rth_p[n];
+        // Step B — _build_predictors!
+        A.rth_old[n] = tp_0;
+        const double ru_0 = A.ru_p[n], rv_0 = A.rv_p[n];
+        double dxM = 0.0, dxT = 0.0, dyM = 0.0, dyT = 0.0;
+        if (!fx_) {
+            double ru_e = A.ru_p[n + oxp];
+            dxM = Ax * ru_e - Ax * ru_0;
+            dxT = Ax * ((A.thL[n + oxp] + th_0) / 2) * ru_e - Ax * ((th_0 + A.thL[n + oxm]) / 2) * ru_0;
+        }
+        if (!fy_) {
+            double rv_n = A.rv_p[n + oyp];
+            dyM = Ay * rv_n - Ay * rv_0;
+            dyT = Ay * ((A.thL[n + oyp] + th_0) / 2) * rv_n - Ay * ((th_0 + A.thL[n + oym]) / 2) * rv_0;
+        }
+        const double divM = Vinv * (dxM + dyM), divT = Vinv * (dxT + dyT);
+        const double dzw = (w_p - w_0) * rdz;
+        const double dzT = (thf_p * w_p - thf_0 * w_0) * rdz;
+        const double rs_0 = rp_0 + A.dtau * (A.Grho[n] - divM) - A.dts * dzw;
+        const double ts_0 = tp_0 + A.dtau * (A.fth * A.Grth[n] - divT) - A.dts * dzT;
+        A.rho_s[n] = rs_0; A.rth_s[n] = ts_0;
+        // _build_vertical_rhs! at face k, then row k of the forward elimination. Row 0 is the wall: b = 1, c = 0, rhs = 0.
+        double phi, cu;
+        if (k == 0) {
+            beta = 1.0;
+            phi = 0.0;
+            cu = 0.0;
+        } else {
+            double dp_s = (C_0 * ts_0 - C_m * ts_m) * rdz;
+            double dp_o = (C_0 * tp_0 - C_m * tp_m) * rdz;
+            double Gp = A.dts * dp_o + A.dtm * dp_s;
+            double Gb = A.g * (A.dts * ((rp_0 + rp_m) / 2) + A.dtm * ((rs_0 + rs_m) / 2));
+            double d2 = ((w_p - w_0) * rdz - (w_0 - w_m) * rdz) * rdz;
+            double Gd = -A.ds * d2;
+            double rhs = w_0 + A.dtau * A.fw * A.Gs_rw[n] - Gp - Gb - Gd;
+            // get_coefficient(::AcousticTridiagLower / Diagonal / Upper) for row k
+            double al = -dtm2 * C_m * thf_m * rdzc * rdzf + dtm2 * A.g * rdzc / 2 - A.dm * rdzc * rdzf;
+            double b = 1.0 + (dtm2 * thf_0 * (C_0 * rdzc + C_m * rdzc) * rdzf + dtm2 * A.g * (rdzc - rdzc) / 2 + A.dm * (rdzc + rdzc) * rdzf);
+            cu = -dtm2 * C_0 * thf_p * rdzc * rdzf - dtm2 * A.g * rdzc / 2 - A.dm * rdzc * rdzf;
+            double t = cu_prev / beta;
+            A.tfac[n] = t;
+            beta = b - al * t;
+            phi = (fabs(beta) > tiny) ? (rhs - al * phi_prev) / beta : w_0;
+        }
+        A.rw_p[n] = phi;
+        // roll
+        cu_prev = cu; phi_prev = phi;
+        C_m = C_0; rs_m = rs_0; ts_m = ts_0; rp_m = rp_0; tp_m = tp_0;
+        w_m = w_0; w_0 = w_p;
+        thf_m = thf_0; thf_0 = thf_p; th_0 = th_p;
+    }
+
+    // ---- downward march: back substitution (C), recovery of ρ′, (ρθ)′ and the ⟨ρ𝐮′⟩ accumulators (D) -----------------
+    double w_top = 0.0;                                                  // final (ρw)′ at face k+1 (top wall: 0)
+    double th_up = 0.0;                                                  // θᴸ at cell k+1
+    double th_k = A.thL[n0 + (long long)(Nz - 1) * SZ];
+    for (int k = Nz - 1; k >= 0; --k) {
+        const long long n = n0 + (long long)k * SZ;
+        double w_k = A.rw_p[n];
+        if (k < Nz - 1) { w_k -= A.tfac[n + SZ] * w_top; A.rw_p[n] = w_k; }
+        const double th_dn = (k > 0) ? A.thL[n - SZ] : th_k;
+        const double thf_p = (k + 1 < Nz) ? (th_up + th_k) / 2 : th_k;
+        const double thf_0 = (k > 0) ? (th_k + th_dn) / 2 : th_k;
+        const double dzw = (w_top - w_k) * rdz;
+        const double dzT = (thf_p * w_top - thf_0 * w_k) * rdz;
+        A.rho_p[n] = A.rho_s[n] - A.dtm * dzw;
+        A.rth_p[n] = A.rth_s[n] - A.dtm * dzT;
+        A.avg_u[n] += A.ru_p[n];
+        A.avg_v[n] += A.rv_p[n];
+        A.avg_w[n] += w_k;
+        w_top = w_k; th_up = th_k; th_k = th_dn;
+    }
+}
+
+// ---- stage end ------------------------------------------------------------------------------------------------------
+// _finalize_time_averaged_velocity! (ρᴸ needs valid x / y ghost cells; still the stage-entry density here)
+__global__ void c_finalize_average(Layout L, const double* __restrict__ rho, const double* __restrict__ ru, const double* __restrict__ rv,
+                                   const double* __restrict__ rw, double* __restrict__ avg_u, double* __restrict__ avg_v,
+                                   double* __restrict__ avg_w, double inv_n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, k = blockIdx.z;
+    if (i >= L.nx) return;
+    long long n = lidx(L, i, j, k);
+    double r = rho[n];
+    double rx = L.flat_x ? r : (r + rho[n - 1]) / 2;
+    double ry = L.flat_y ? r : (r + rho[n - L.PX]) / 2;
+    double rz = (k > 0) ? (r + rho[n - L.plane]) / 2 : r;
+    rx = (rx == 0.0) ? 1.0 : rx; ry = (ry == 0.0) ? 1.0 : ry; rz = (rz == 0.0) ? 1.0 : rz;
+    avg_u[n] = (ru[n] + avg_u[n] * inv_n) / rx;
+    avg_v[n] = (rv[n] + avg_v[n] * inv_n) / ry;
+    avg_w[n] = (k > 0) ? (rw[n] + avg_w[n] * inv_n) / rz : 0.0;
+}
+
+// _recover_full_state!: U ← Uᴸ + U′ in place
+__global__ void c_recover(Layout L, CFields5 U, CConst5 P) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, k = blockIdx.z;
+    if (i >= L.nx) return;
+    long long n = lidx(L, i, j, k);
+#pragma unroll
+    for (int f = 0; f < 5; ++f) U.f[f][n] = U.f[f][n] + P.f[f][n];
+}
+
+// seed_time_averaged_velocities! / store_initial_state!: plain copies of n doubles
+__global__ void c_copy(const double* __restrict__ src, double* __restrict__ dst, long long n) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) dst[e] = src[e];
+}
+
+// dense interior (x fastest, nz_out levels) <-> padded field with Nz + 1 levels allocated
+__global__ void c_extract(Layout L, const double* __restrict__ src, double* __restrict__ dst) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, k = blockIdx.z;
+    if (i >= L.nx) return;
+    dst[((size_t)k * L.Ny + j) * L.nx + i] = src[lidx(L, i, j, k)];
+}
+__global__ void c_scatter(Layout L, const double* __restrict__ src, double* __restrict__ dst, int zface) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, k = blockIdx.z;
+    if (i >= L.nx) return;
+    double v = src[((size_t)k * L.Ny + j) * L.nx + i];
+    if (zface && (k == 0 || k == L.Nz)) v = 0.0;           // impenetrable walls
+    dst[lidx(L, i, j, k)] = v;
+}
+__global__ void c_fill(Layout L, double* __restrict__ dst, const double* __restrict__ column, double value, int nz) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, k = blockIdx.z;
+    if (i >= L.nx || k >= nz) return;
+    dst[lidx(L, i, j, k)] = column ? column[k] : value;
+}

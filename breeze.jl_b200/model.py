@@ -213,7 +213,17 @@ def _evaluate(value, grid: RectilinearGrid, xs, ys, zs, shape):
 class AtmosphereModel:
     """AtmosphereModel(grid; dynamics, advection, microphysics, thermodynamic_constants)
     for the configurations on the hot path: AnelasticDynamics, WENO(order=5), SSPRungeKutta3,
-    LiquidIcePotentialTemperature formulation, closure = nothing."""
+    LiquidIcePotentialTemperature formulation, closure = nothing.
+
+    `dynamics = CompressibleDynamics(SplitExplicitTimeDiscretization(...))` dispatches to the AcousticRungeKutta3 model of
+    breeze_b200.compressible (the reference selects the stepper from the dynamics type, dynamics_interface.jl:71)."""
+
+    def __new__(cls, grid=None, dynamics=None, *args, **kw):
+        from .compressible import CompressibleAtmosphereModel, CompressibleDynamics
+        if isinstance(dynamics, CompressibleDynamics):
+            kw.pop("timestepper", None)
+            return CompressibleAtmosphereModel(grid, dynamics, *args, **kw)
+        return super().__new__(cls)
 
     def __init__(self, grid: RectilinearGrid, dynamics: AnelasticDynamics | None = None, advection: WENO | None = None,
                  microphysics=None, thermodynamic_constants: ThermodynamicConstants | None = None,

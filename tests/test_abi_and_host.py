@@ -13,9 +13,9 @@ from breeze_b200 import abi
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared_symbols():
-    text = open(os.path.join(ROOT, "include", "breeze_b200.h")).read()
-    return sorted(set(re.findall(r"\b(bz_[a-z_0-9]+)\s*\(", text)) - {"bz_ctx", "bz_config"})
+def _declared_symbols(header="breeze_b200.h", prefix="bz_"):
+    text = open(os.path.join(ROOT, "include", header)).read()
+    return sorted(set(re.findall(r"\b(" + prefix + r"[a-z_0-9]+)\s*\(", text)) - {prefix + "ctx", prefix + "config"})
 
 
 def test_cuda_library_exports_every_declared_symbol():
@@ -23,6 +23,50 @@ def test_cuda_library_exports_every_declared_symbol():
     for name in _declared_symbols():
         assert hasattr(lib.dll, name), name
     assert lib.abi_version() == abi.BZ_ABI_VERSION
+
+
+def test_cuda_library_exports_every_compressible_symbol():
+    """include/breeze_b200_compressible.h: every declared bzc_* entry point is exported and bound by the host mirror."""
+    lib = abi.load_cuda_library()
+    declared = _declared_symbols("breeze_b200_compressible.h", "bzc_")
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib.dll, name), name
+    clib = bz.compressible_library(lib)
+    cfg = bz.bzc_config()
+    clib.default_config(C.byref(cfg))
+    assert cfg.forward_weight == 0.65 and cfg.acoustic_cfl == 0.5 and cfg.damping_coefficient == 0.1 and cfg.base.abi_version == 1
+    assert C.sizeof(bz.bzc_config) == C.sizeof(abi.bz_config) + 4 * 6 + 8 * 6 + 4 * 8
+    h = C.c_void_p()
+    import torch
+    if not torch.cuda.is_available():
+        assert clib.create(C.byref(cfg), C.byref(h)) != 0
+        assert b"no CPU fallback" in clib.last_error(None)
+
+
+def test_oracle_exports_the_compressible_abi(oracle_arch):
+    from breeze_b200 import compressible
+    lib = oracle_arch.library()
+    for name in compressible.ABI_SYMBOLS:
+        assert hasattr(lib.dll, "orcc_" + name), name
+
+
+def test_compressible_argument_validation(oracle_arch):
+    with pytest.raises(ValueError):
+        bz.CompressibleDynamics(reference_state="none")
+    with pytest.raises(ValueError):
+        bz.CompressibleDynamics(reference_state=None, reference_potential_temperature=300.0)
+    with pytest.raises(ValueError):
+        bz.SplitExplicitTimeDiscretization(acoustic_cfl=0)
+    with pytest.raises(ValueError):
+        bz.SplitExplicitTimeDiscretization(damping=(bz.ThermalDivergenceDamping(), bz.NoDivergenceDamping()))
+    grid = bz.RectilinearGrid(oracle_arch, size=(8, 8, 8), x=(0, 1e3), y=(0, 1e3), z=(0, 1e3))
+    m = bz.AtmosphereModel(grid, dynamics=bz.CompressibleDynamics())
+    assert isinstance(m, bz.CompressibleAtmosphereModel)
+    with pytest.raises(ValueError):
+        m.set(qᵗ=0.01)
+    with pytest.raises(bz.BreezeError):
+        m.context.set_state(rho=np.zeros((3, 3, 3)))
 
 
 def test_oracle_exports_the_same_abi(oracle_arch):

@@ -1,0 +1,222 @@
+"""GPU parity tests of the compressible split-explicit path: libbreeze_b200.so (bzc_*, through the C ABI) against the CPU
+oracle (orcc_*) on identical inputs, plus the reference's rest-state contracts evaluated directly on the CUDA path.
+
+Tolerances (FP64; both sides evaluate the same scheme, the CUDA side with FMA contraction, device pow, and the
+difference-form / single-reciprocal WENO5-Z of weno.cuh):
+  * update_state! diagnostics (u, v, w, θ, T, p) and the linearization (Πᴸ, θᴸ)          : 1e-13 relative to the max-norm
+  * one slow-tendency evaluation vs the oracle with the same (difference-form) indicators : 1e-11
+  * one acoustic substep loop (perturbation fields, recovered state)                      : 1e-10
+  * N = 5 WS-RK3 steps of a moving warm bubble                                            : 1e-9
+"""
+import numpy as np
+import pytest
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL_DIAG = 1e-13
+TOL_TENDENCY = 1e-11
+TOL_LOOP = 1e-10
+TOL_STEPS = 1e-9
+PROGNOSTIC = ["ρ", "ρu", "ρv", "ρw", "ρθ"]
+RD = 8.314462618 / 0.02897
+
+
+def _model(arch, size, flat_y=False, theta_ref=300.0, **td):
+    import breeze_b200 as bz
+    if flat_y:
+        grid = bz.RectilinearGrid(arch, size=size, x=(-5e3, 5e3), z=(0, 10e3), topology=(bz.Periodic, bz.Flat, bz.Bounded))
+    else:
+        grid = bz.RectilinearGrid(arch, size=size, x=(-5e3, 5e3), y=(-5e3, 5e3), z=(0, 10e3))
+    dyn = bz.CompressibleDynamics(bz.SplitExplicitTimeDiscretization(**td), reference_potential_temperature=theta_ref)
+    return bz.AtmosphereModel(grid, dynamics=dyn)
+
+
+def _pair(oracle_arch, size, flat_y=False, seed=0, noise=1.0, **td):
+    import breeze_b200 as bz
+    rng = np.random.default_rng(seed)
+    models = [_model(a, size, flat_y, **td) for a in (bz.B200(), oracle_arch)]
+    g = models[0].grid
+    shp_c, shp_w = (g.Nz, g.Ny, g.Nx), (g.Nz + 1, g.Ny, g.Nx)
+    _, rho_r, _ = models[1].reference_profiles()
+    rho = rho_r[:, None, None] * (1 + 1e-3 * noise * rng.standard_normal(shp_c))
+    u = 3.0 + noise * rng.standard_normal(shp_c)
+    v = (-2.0 + noise * rng.standard_normal(shp_c)) * (0.0 if flat_y else 1.0)
+    w = 0.5 * noise * rng.standard_normal(shp_w)
+
+    def theta(*xyz):
+        x, z = xyz[0], xyz[-1]
+        r2 = x ** 2 + (z - 3000.0) ** 2 + (xyz[1] ** 2 if len(xyz) == 3 else 0.0)
+        return 300.0 + 2.0 * np.cos(np.pi / 2 * np.minimum(1.0, np.sqrt(r2) / 2000.0)) ** 2
+
+    for m in models:
+        m.set(ρ=rho, θ=theta, u=u, v=v, w=w)
+    return models
+
+
+def test_reference_state_identical(oracle_arch):
+    import breeze_b200 as bz
+    gpu, cpu = _model(bz.B200(), (8, 8, 40)), _model(oracle_arch, (8, 8, 40))
+    for a, b in zip(gpu.reference_profiles(), cpu.reference_profiles()):
+        assert np.array_equal(a, b)
+    th = lambda z: 250.0 * np.exp(9.80665 * z / (1005.0 * 250.0))      # noqa: E731
+    gpu, cpu = _model(bz.B200(), (8, 8, 40), theta_ref=th), _model(oracle_arch, (8, 8, 40), theta_ref=th)
+    for a, b in zip(gpu.reference_profiles(), cpu.reference_profiles()):
+        assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("size,flat_y", [((32, 16, 24), False), ((64, 40), True), ((12, 20, 9), False)])
+def test_update_state_matches_oracle(oracle_arch, size, flat_y):
+    gpu, cpu = _pair(oracle_arch, size, flat_y)
+    for name in PROGNOSTIC:
+        assert np.array_equal(gpu.field(name), cpu.field(name)), name
+    for name in ["u", "v", "w", "θ", "T", "p"]:
+        assert rel_err(gpu.field(name), cpu.field(name)) < TOL_DIAG, name
+
+
+@pytest.mark.parametrize("size,flat_y", [((32, 16, 24), False), ((64, 40), True), ((12, 20, 9), False)])
+@pytest.mark.parametrize("reference", ["auto", None])
+def test_slow_tendencies_match_oracle(oracle_arch, size, flat_y, reference):
+    import breeze_b200 as bz
+    import oracle_lib
+    if reference is None:
+        models = []
+        for a in (bz.B200(), oracle_arch):
+            kw = dict(x=(-5e3, 5e3), z=(0, 10e3))
+            kw.update(dict(topology=(bz.Periodic, bz.Flat, bz.Bounded)) if flat_y else dict(y=(-5e3, 5e3)))
+            models.append(bz.AtmosphereModel(bz.RectilinearGrid(a, size=size, **kw), dynamics=bz.CompressibleDynamics(reference_state=None)))
+        g = models[0].grid
+        rng = np.random.default_rng(3)
+        shp = (g.Nz, g.Ny, g.Nx)
+        rho = 1.1 * np.exp(-g.znodes() / 8000.0)[:, None, None] * (1 + 1e-3 * rng.standard_normal(shp))
+        th = 300.0 + 0.01 * g.znodes()[:, None, None] + 0.5 * rng.standard_normal(shp)
+        w = 0.3 * rng.standard_normal((g.Nz + 1, g.Ny, g.Nx))
+        for m in models:
+            m.set(ρ=rho, θ=th, u=2.0 + 0 * rho, w=w)
+        gpu, cpu = models
+    else:
+        gpu, cpu = _pair(oracle_arch, size, flat_y, seed=1)
+    oracle_lib.set_beta_form(1)
+    try:
+        gpu.context.compute_slow_tendencies()
+        cpu.context.compute_slow_tendencies()
+        for name in ["Πᴸ", "θᴸ", "γRᵐᴸ"]:
+            assert rel_err(gpu.field(name), cpu.field(name)) < TOL_DIAG, name
+        for name in ["Gρ", "Gρu", "Gρv", "Gρw", "Gρθ", "Gˢρw"]:
+            assert rel_err(gpu.field(name), cpu.field(name)) < TOL_TENDENCY, name
+    finally:
+        oracle_lib.set_beta_form(0)
+
+
+@pytest.mark.parametrize("size,flat_y", [((32, 16, 24), False), ((64, 40), True)])
+@pytest.mark.parametrize("td", [dict(substeps=6), dict(substeps=4, forward_weight=0.55, damping="none"),
+                                dict(substeps=6, damping="vertical"), dict(substeps=3, apply_first_substep_pressure_gradient=True)])
+@pytest.mark.parametrize("beta", [1.0 / 3.0, 1.0])
+def test_acoustic_substep_loop_matches_oracle(oracle_arch, size, flat_y, td, beta):
+    import breeze_b200 as bz
+    import oracle_lib
+    td = dict(td)
+    d = td.pop("damping", None)
+    if d == "none":
+        td["damping"] = bz.NoDivergenceDamping()
+    elif d == "vertical":
+        td["damping"] = bz.ThermalDivergenceDamping(coefficient=0.12, damp_vertical=True)
+    gpu, cpu = _pair(oracle_arch, size, flat_y, seed=2, noise=0.2, **td)
+    oracle_lib.set_beta_form(1)
+    try:
+        for m in (gpu, cpu):
+            m.context.compute_slow_tendencies()
+            m.context.acoustic_substep_loop(1.2, beta)        # Δτ ≤ 0.4 s: acoustic Courant number < 1 at Δx = 156 m
+    finally:
+        oracle_lib.set_beta_form(0)
+    for name in ["ρ′", "ρθ′", "ρu′", "ρv′", "ρw′", "⟨u⟩", "⟨v⟩", "⟨w⟩"] + PROGNOSTIC + ["u", "v", "w", "p"]:
+        assert np.isfinite(cpu.field(name)).all(), name
+        assert rel_err(gpu.field(name), cpu.field(name)) < TOL_LOOP, name
+
+
+@pytest.mark.parametrize("size,flat_y,dt", [((32, 32, 24), False, 2.0), ((64, 40), True, 1.0)])
+def test_bubble_steps_match_oracle(oracle_arch, size, flat_y, dt):
+    import oracle_lib
+    gpu, cpu = _pair(oracle_arch, size, flat_y, seed=5, noise=0.0)
+    oracle_lib.set_beta_form(1)
+    try:
+        for m in (gpu, cpu):
+            for _ in range(5):
+                m.time_step(dt)
+    finally:
+        oracle_lib.set_beta_form(0)
+    assert gpu.clock == cpu.clock
+    for name in PROGNOSTIC + ["u", "w", "θ", "p"]:
+        assert rel_err(gpu.field(name), cpu.field(name)) < TOL_STEPS, name
+    assert np.abs(gpu.field("w")).max() > 1e-3                # the bubble does move
+
+
+# ---- the reference's rest-state contracts on the CUDA path itself (test/substepper_rest_state.jl) ------------------------
+def _rest_model(Nx=8, Ny=8, Nz=32, Lz=10e3, **td):
+    import breeze_b200 as bz
+    grid = bz.RectilinearGrid(bz.B200(), size=(Nx, Ny, Nz), x=(0, 100e3), y=(0, 100e3), z=(0, Lz))
+    th = lambda z: 250.0 * np.exp(9.80665 * z / (1005.0 * 250.0))      # noqa: E731
+    dyn = bz.CompressibleDynamics(bz.SplitExplicitTimeDiscretization(**td), reference_potential_temperature=th,
+                                  surface_pressure=1e5, standard_pressure=1e5)
+    m = bz.AtmosphereModel(grid, dynamics=dyn)
+    p, rho, pi = m.reference_profiles()
+    shape = m.context.shape(0)
+    m.context.set_state(rho=np.broadcast_to(rho[:, None, None], shape).copy(),
+                        rho_theta=np.broadcast_to((p / (RD * pi))[:, None, None], shape).copy(),
+                        rho_u=np.zeros(shape), rho_v=np.zeros(shape), rho_w=np.zeros(m.context.shape(3)))
+    return m
+
+
+def test_rest_state_pressure_and_slow_tendency_on_gpu():
+    """T2, T3 (test/substepper_rest_state.jl:183-215): EoS pressure within 100 ulp of p_ref; Gˢρw <= 1e-12 at rest."""
+    m = _rest_model(Nx=16, Ny=16, Nz=64, Lz=30e3)
+    p, rho, _ = m.reference_profiles()
+    assert np.abs(m.field("p") - p[:, None, None]).max() <= 100 * np.finfo(float).eps * p.max()
+    assert np.abs(m.field("ρ") - rho[:, None, None]).max() == 0
+    m.context.compute_slow_tendencies()
+    assert np.abs(m.field("Gˢρw")).max() <= 1e-12
+
+
+@pytest.mark.parametrize("dt,td", [(0.5, {}), (20.0, {})])
+def test_rest_atmosphere_drift_on_gpu(dt, td):
+    """T4 (test/substepper_rest_state.jl:263-303): max|w| <= 1e-10 m/s over 200 outer steps."""
+    m = _rest_model(**td)
+    envelope = 0.0
+    for n in range(1, 201):
+        m.time_step(dt)
+        if n % 10 == 0:
+            w = np.abs(m.field("w")).max()
+            assert np.isfinite(w)
+            envelope = max(envelope, w)
+    assert envelope <= 1e-10
+
+
+def test_mass_conservation_and_walls_on_gpu(oracle_arch):
+    """S4, S5 (test/substepper_structural.jl:211-247)."""
+    gpu, _ = _pair(oracle_arch, (32, 32, 24), seed=7, noise=0.0)
+    M0 = gpu.field("ρ").sum()
+    for _ in range(3):
+        gpu.time_step(2.0)
+    assert abs(gpu.field("ρ").sum() - M0) / M0 <= 1e-12
+    rw = gpu.field("ρw")
+    assert np.abs(rw[-1]).max() == 0 and np.abs(rw[0]).max() == 0
+
+
+def test_config4_shape_runs_and_counts_launches():
+    """BASELINE config 4 shape (256 x 256 x 64, 6 substeps per full step): two launches per substep."""
+    import breeze_b200 as bz
+    grid = bz.RectilinearGrid(bz.B200(), size=(256, 256, 64), x=(0, 168e3), y=(0, 168e3), z=(0, 20e3))
+    dyn = bz.CompressibleDynamics(bz.SplitExplicitTimeDiscretization(substeps=6), reference_potential_temperature=300.0)
+    m = bz.AtmosphereModel(grid, dynamics=dyn)
+    _, rho, _ = m.reference_profiles()
+    m.set(ρ=np.broadcast_to(rho[:, None, None], m.context.shape(0)).copy(),
+          θ=lambda x, y, z: 300.0 + 3.0 * np.exp(-((x - 84e3) ** 2 + (y - 84e3) ** 2) / 10e3 ** 2 - (z - 1500.0) ** 2 / 1500.0 ** 2), u=10.0)
+    n0 = m.context.kernel_launch_count()
+    for _ in range(3):
+        m.time_step(6.0)
+    m.context.synchronize()
+    per_step = (m.context.kernel_launch_count() - n0) / 3
+    substeps = 2 + 3 + 6
+    assert per_step <= 2 * substeps + 3 * 12
+    assert np.isfinite(m.field("w")).all() and np.abs(m.field("w")).max() > 1e-4
