@@ -249,6 +249,15 @@ struct CColumnArgs {
     double dtau, dtm, dts, dm, ds, g, fth, fw;
 };
 
+// Everything one level of the upward march reads from HBM. The column recurrence is latency-bound unless many loads are in
+// flight per thread, so the march is software-pipelined: the loads of level k + D - 1 are issued (into a register ring of D
+// LevelIn) before level k is computed and stored — the DRAM round trips of D - 1 levels overlap with the recurrence.
+#ifndef BZ_COL_DEPTH
+#define BZ_COL_DEPTH 6            // ring of prefetched levels per thread: loads run BZ_COL_DEPTH - 1 levels ahead of the recurrence
+#endif
+struct CLevelIn { double rp, tp, ru0, rue, rv0, rvn, th_e, th_w, th_n, th_s, th_up, Grho, Grth, C, w_up, Gs; };
+struct CLevelDown { double w, t_up, th_dn, rs, ts, ru, rv, au, av, aw; };
+
 // one thread per column; blockDim.x columns along x per block, blockIdx.y = j
 __global__ void __launch_bounds__(128) c_acoustic_column(Layout L, CColumnArgs A) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
@@ -262,44 +271,56 @@ __global__ void __launch_bounds__(128) c_acoustic_column(Layout L, CColumnArgs A
     const double dtm2 = A.dtm * A.dtm;
     const double tiny = 10.0 * 2.220446049250313e-16;
     const bool fx_ = L.flat_x, fy_ = L.flat_y;
+    const double* __restrict__ ru_p = A.ru_p; const double* __restrict__ rv_p = A.rv_p;
+    const double* __restrict__ thL = A.thL; const double* __restrict__ CL = A.CL;
+    const double* __restrict__ Grho = A.Grho; const double* __restrict__ Grth = A.Grth; const double* __restrict__ Gs_rw = A.Gs_rw;
+
+    auto load_up = [&](int k, CLevelIn& q) {
+        const long long n = n0 + (long long)k * SZ;
+        const bool top = (k + 1 == Nz);
+        q.rp = A.rho_p[n]; q.tp = A.rth_p[n];
+        q.ru0 = __ldg(ru_p + n); q.rv0 = __ldg(rv_p + n);
+        q.rue = fx_ ? 0.0 : __ldg(ru_p + n + oxp); q.rvn = fy_ ? 0.0 : __ldg(rv_p + n + oyp);
+        q.th_e = fx_ ? 0.0 : __ldg(thL + n + oxp); q.th_w = fx_ ? 0.0 : __ldg(thL + n + oxm);
+        q.th_n = fy_ ? 0.0 : __ldg(thL + n + oyp); q.th_s = fy_ ? 0.0 : __ldg(thL + n + oym);
+        q.th_up = top ? 0.0 : __ldg(thL + n + SZ);
+        q.Grho = __ldg(Grho + n); q.Grth = __ldg(Grth + n); q.C = __ldg(CL + n);
+        q.w_up = top ? 0.0 : A.rw_p[n + SZ];                  // old (ρw)′ at face k+1 (not yet overwritten: row k+1 comes later)
+        q.Gs = __ldg(Gs_rw + n);
+    };
 
     // ---- upward march: predictors (B), face right-hand side, forward elimination (C) --------------------------------
     // carried from the level below (face k lies between cells k-1 and k)
     double C_m = 0.0, rs_m = 0.0, ts_m = 0.0, rp_m = 0.0, tp_m = 0.0;   // Cᴸ, ρ′★, (ρθ)′★, old ρ′, old (ρθ)′ at cell k-1
     double w_m = 0.0, w_0 = 0.0;                                         // old (ρw)′ at faces k-1, k (face 0 is the wall)
-    double th_0 = A.thL[n0];
+    double th_0 = __ldg(thL + n0);
     double thf_m = th_0, thf_0 = th_0;                                   // ℑbz θᴸ at faces k-1, k (one-sided on the walls)
     double cu_prev = 0.0, beta = 1.0, phi_prev = 0.0;
-    for (int k = 0; k < Nz; ++k) {
+    auto process_up = [&](int k, const CLevelIn& cur) {
         const long long n = n0 + (long long)k * SZ;
         const bool top = (k + 1 == Nz);
-        const double w_p = top ? 0.0 : A.rw_p[n + SZ];                   // old (ρw)′ at face k+1 (top wall: 0)
-        const double th_p = top ? th_0 : A.thL[n + SZ];
+        const double w_p = cur.w_up;
+        const double th_p = top ? th_0 : cur.th_up;
         const double thf_p = top ? th_0 : (th_p + th_0) / 2;             // face k+1
-        const double C_0 = A.CL[n];
-        const double rp_0 = A.rho_p[n], tp_0 = A.rth_p[n];
+        const double C_0 = cur.C;
+        const double rp_0 = cur.rp, tp_0 = cur.tp;
         // Step B — _build_predictors!
-        A.rth_old[n] = tp_0;
-        const double ru_0 = A.ru_p[n], rv_0 = A.rv_p[n];
         double dxM = 0.0, dxT = 0.0, dyM = 0.0, dyT = 0.0;
         if (!fx_) {
-            double ru_e = A.ru_p[n + oxp];
-            dxM = Ax * ru_e - Ax * ru_0;
-            dxT = Ax * ((A.thL[n + oxp] + th_0) / 2) * ru_e - Ax * ((th_0 + A.thL[n + oxm]) / 2) * ru_0;
+            dxM = Ax * cur.rue - Ax * cur.ru0;
+            dxT = Ax * ((cur.th_e + th_0) / 2) * cur.rue - Ax * ((th_0 + cur.th_w) / 2) * cur.ru0;
         }
         if (!fy_) {
-            double rv_n = A.rv_p[n + oyp];
-            dyM = Ay * rv_n - Ay * rv_0;
-            dyT = Ay * ((A.thL[n + oyp] + th_0) / 2) * rv_n - Ay * ((th_0 + A.thL[n + oym]) / 2) * rv_0;
+            dyM = Ay * cur.rvn - Ay * cur.rv0;
+            dyT = Ay * ((cur.th_n + th_0) / 2) * cur.rvn - Ay * ((th_0 + cur.th_s) / 2) * cur.rv0;
         }
         const double divM = Vinv * (dxM + dyM), divT = Vinv * (dxT + dyT);
         const double dzw = (w_p - w_0) * rdz;
         const double dzT = (thf_p * w_p - thf_0 * w_0) * rdz;
-        const double rs_0 = rp_0 + A.dtau * (A.Grho[n] - divM) - A.dts * dzw;
-        const double ts_0 = tp_0 + A.dtau * (A.fth * A.Grth[n] - divT) - A.dts * dzT;
-        A.rho_s[n] = rs_0; A.rth_s[n] = ts_0;
+        const double rs_0 = rp_0 + A.dtau * (cur.Grho - divM) - A.dts * dzw;
+        const double ts_0 = tp_0 + A.dtau * (A.fth * cur.Grth - divT) - A.dts * dzT;
         // _build_vertical_rhs! at face k, then row k of the forward elimination. Row 0 is the wall: b = 1, c = 0, rhs = 0.
-        double phi, cu;
+        double phi, cu, t = 0.0;
         if (k == 0) {
             beta = 1.0;
             phi = 0.0;
@@ -311,43 +332,85 @@ __global__ void __launch_bounds__(128) c_acoustic_column(Layout L, CColumnArgs A
             double Gb = A.g * (A.dts * ((rp_0 + rp_m) / 2) + A.dtm * ((rs_0 + rs_m) / 2));
             double d2 = ((w_p - w_0) * rdz - (w_0 - w_m) * rdz) * rdz;
             double Gd = -A.ds * d2;
-            double rhs = w_0 + A.dtau * A.fw * A.Gs_rw[n] - Gp - Gb - Gd;
+            double rhs = w_0 + A.dtau * A.fw * cur.Gs - Gp - Gb - Gd;
             // get_coefficient(::AcousticTridiagLower / Diagonal / Upper) for row k
             double al = -dtm2 * C_m * thf_m * rdzc * rdzf + dtm2 * A.g * rdzc / 2 - A.dm * rdzc * rdzf;
             double b = 1.0 + (dtm2 * thf_0 * (C_0 * rdzc + C_m * rdzc) * rdzf + dtm2 * A.g * (rdzc - rdzc) / 2 + A.dm * (rdzc + rdzc) * rdzf);
             cu = -dtm2 * C_0 * thf_p * rdzc * rdzf - dtm2 * A.g * rdzc / 2 - A.dm * rdzc * rdzf;
-            double t = cu_prev / beta;
-            A.tfac[n] = t;
+            t = cu_prev / beta;
             beta = b - al * t;
             phi = (fabs(beta) > tiny) ? (rhs - al * phi_prev) / beta : w_0;
         }
+        A.rth_old[n] = tp_0;
+        A.rho_s[n] = rs_0; A.rth_s[n] = ts_0;
+        A.tfac[n] = t;
         A.rw_p[n] = phi;
         // roll
         cu_prev = cu; phi_prev = phi;
         C_m = C_0; rs_m = rs_0; ts_m = ts_0; rp_m = rp_0; tp_m = tp_0;
         w_m = w_0; w_0 = w_p;
         thf_m = thf_0; thf_0 = thf_p; th_0 = th_p;
+    };
+    {
+        CLevelIn ring[BZ_COL_DEPTH];
+#pragma unroll
+        for (int d = 0; d < BZ_COL_DEPTH - 1; ++d) if (d < Nz) load_up(d, ring[d]);
+        for (int k0 = 0; k0 < Nz; k0 += BZ_COL_DEPTH) {
+#pragma unroll
+            for (int d = 0; d < BZ_COL_DEPTH; ++d) {
+                const int k = k0 + d;
+                if (k < Nz) {
+                    if (k + BZ_COL_DEPTH - 1 < Nz) load_up(k + BZ_COL_DEPTH - 1, ring[(d + BZ_COL_DEPTH - 1) % BZ_COL_DEPTH]);   // in flight while levels k … are computed
+                    process_up(k, ring[d]);
+                }
+            }
+        }
     }
 
     // ---- downward march: back substitution (C), recovery of ρ′, (ρθ)′ and the ⟨ρ𝐮′⟩ accumulators (D) -----------------
+    auto load_down = [&](int k, CLevelDown& q) {
+        const long long n = n0 + (long long)k * SZ;
+        q.w = A.rw_p[n];
+        q.t_up = (k < Nz - 1) ? A.tfac[n + SZ] : 0.0;
+        q.th_dn = (k > 0) ? __ldg(thL + n - SZ) : 0.0;
+        q.rs = A.rho_s[n]; q.ts = A.rth_s[n];
+        q.ru = __ldg(ru_p + n); q.rv = __ldg(rv_p + n);
+        q.au = A.avg_u[n]; q.av = A.avg_v[n]; q.aw = A.avg_w[n];
+    };
     double w_top = 0.0;                                                  // final (ρw)′ at face k+1 (top wall: 0)
     double th_up = 0.0;                                                  // θᴸ at cell k+1
-    double th_k = A.thL[n0 + (long long)(Nz - 1) * SZ];
-    for (int k = Nz - 1; k >= 0; --k) {
+    double th_k = __ldg(thL + n0 + (long long)(Nz - 1) * SZ);
+    auto process_down = [&](int k, const CLevelDown& dc) {
         const long long n = n0 + (long long)k * SZ;
-        double w_k = A.rw_p[n];
-        if (k < Nz - 1) { w_k -= A.tfac[n + SZ] * w_top; A.rw_p[n] = w_k; }
-        const double th_dn = (k > 0) ? A.thL[n - SZ] : th_k;
+        double w_k = dc.w;
+        if (k < Nz - 1) w_k -= dc.t_up * w_top;
+        const double th_dn = (k > 0) ? dc.th_dn : th_k;
         const double thf_p = (k + 1 < Nz) ? (th_up + th_k) / 2 : th_k;
         const double thf_0 = (k > 0) ? (th_k + th_dn) / 2 : th_k;
         const double dzw = (w_top - w_k) * rdz;
         const double dzT = (thf_p * w_top - thf_0 * w_k) * rdz;
-        A.rho_p[n] = A.rho_s[n] - A.dtm * dzw;
-        A.rth_p[n] = A.rth_s[n] - A.dtm * dzT;
-        A.avg_u[n] += A.ru_p[n];
-        A.avg_v[n] += A.rv_p[n];
-        A.avg_w[n] += w_k;
+        A.rw_p[n] = w_k;
+        A.rho_p[n] = dc.rs - A.dtm * dzw;
+        A.rth_p[n] = dc.ts - A.dtm * dzT;
+        A.avg_u[n] = dc.au + dc.ru;
+        A.avg_v[n] = dc.av + dc.rv;
+        A.avg_w[n] = dc.aw + w_k;
         w_top = w_k; th_up = th_k; th_k = th_dn;
+    };
+    {
+        CLevelDown ring[BZ_COL_DEPTH];
+#pragma unroll
+        for (int d = 0; d < BZ_COL_DEPTH - 1; ++d) if (Nz - 1 - d >= 0) load_down(Nz - 1 - d, ring[d]);
+        for (int k0 = Nz - 1; k0 >= 0; k0 -= BZ_COL_DEPTH) {
+#pragma unroll
+            for (int d = 0; d < BZ_COL_DEPTH; ++d) {
+                const int k = k0 - d;
+                if (k >= 0) {
+                    if (k - (BZ_COL_DEPTH - 1) >= 0) load_down(k - (BZ_COL_DEPTH - 1), ring[(d + BZ_COL_DEPTH - 1) % BZ_COL_DEPTH]);
+                    process_down(k, ring[d]);
+                }
+            }
+        }
     }
 }
 
