@@ -2,7 +2,8 @@
 
 1. reference_known_answers.json — every number the reference itself pins for this path (doctests / test files), copied with
    its file:line. The reference (Julia) cannot run in this project, so these are transcribed, not generated.
-2. oracle_bubble_16x8x12.npz, oracle_bomex_16x8x12.npz — the CPU oracle's state after a few steps of two small seeded cases.
+2. oracle_bubble_16x8x12.npz, oracle_bomex_16x8x12.npz, oracle_compressible_16x8x12.npz — the CPU oracle's state after a few
+   steps of small seeded cases (anelastic bubble, BOMEX-type forcing, compressible WS-RK3 with acoustic substepping).
    They freeze the oracle (so an accidental change of the checker is caught on CPU) and give the GPU tests a committed target
    that does not depend on re-running the oracle.
 
@@ -30,6 +31,10 @@ KNOWN = {
     "projection_divergence_bound": {"formula": "max|div| < Nx*Ny*Nz*eps for 32^3 random momentum, rho_r = 1",
                                     "source": "test/anelastic_pressure_solver_nonhydrostatic.jl:40-46"},
     "secant_sqrt2": {"value": 1.4142135624, "source": "src/Solvers.jl:225-241"},
+    "explicit_horizontal_step_frozen_pgf": {"formula": "p = 2x + 3y, dtau = 0.5, perturbation PGF gated off => rho_u' = -1, rho_v' = -1.5 exactly",
+                                            "source": "test/acoustic_substepping_components.jl:58-93"},
+    "rest_state_contracts": {"formula": "hydrostatic residual <= 1e-9; |p - p_ref| <= 100 ulp; |Gs_rho_w| <= 1e-12; max|w| <= 1e-10 over 200 steps at dt in {0.5, 20}",
+                             "source": "test/substepper_rest_state.jl:159-303"},
     "acoustic_substeps_dx1km_dt12": {"formula": "ceil(12*sqrt(1.4*287*300)/(0.5*1000))", "source": "test/acoustic_substepping_components.jl:269-316"},
 }
 
@@ -53,7 +58,24 @@ def bomex_case(arch):
     return m
 
 
+def compressible_case(arch):
+    """Moving warm bubble, compressible dynamics, WS-RK3 with 6 acoustic substeps per step (default ω = 0.65, Klemp damping 0.1)."""
+    import breeze_b200 as bz
+    grid = bz.RectilinearGrid(arch, size=(16, 8, 12), x=(-5e3, 5e3), y=(-2.5e3, 2.5e3), z=(0, 10e3))
+    dyn = bz.CompressibleDynamics(bz.SplitExplicitTimeDiscretization(substeps=6), reference_potential_temperature=300.0)
+    m = bz.AtmosphereModel(grid, dynamics=dyn)
+    _, rho, _ = m.reference_profiles()
+    rng = np.random.default_rng(20261018)
+    shape = m.context.shape(0)
+    m.set(ρ=rho[:, None, None] * (1 + 1e-4 * rng.standard_normal(shape)), u=3.0 + 0.3 * rng.standard_normal(shape), v=-1.0,
+          θ=lambda x, y, z: 300.0 + 2.0 * np.cos(np.pi / 2 * np.minimum(1.0, np.sqrt(x ** 2 + y ** 2 + (z - 3000.0) ** 2) / 2500.0)) ** 2)
+    for _ in range(3):
+        m.time_step(3.0)
+    return m
+
+
 FIELDS = ["ρu", "ρv", "ρw", "ρθ", "ρq", "T", "φ"]
+COMPRESSIBLE_FIELDS = ["ρ", "ρu", "ρv", "ρw", "ρθ", "T", "p", "⟨w⟩"]
 
 if __name__ == "__main__":
     from oracle_lib import CPUOracle
@@ -62,3 +84,6 @@ if __name__ == "__main__":
         m = case(CPUOracle())
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **{f: m.field(f) for f in FIELDS})
         print(name, {f: float(np.abs(m.field(f)).max()) for f in FIELDS})
+    m = compressible_case(CPUOracle())
+    np.savez_compressed(os.path.join(HERE, "oracle_compressible_16x8x12.npz"), **{f: m.field(f) for f in COMPRESSIBLE_FIELDS})
+    print("oracle_compressible_16x8x12", {f: float(np.abs(m.field(f)).max()) for f in COMPRESSIBLE_FIELDS})
