@@ -196,16 +196,14 @@ def bench_compressible(args, steps, warmup, with_cpu=True, with_e2e=True):
         shapes = [ctx.shape(f) for f in range(5)]
         pin_in = [torch.empty(sh, dtype=torch.float64).pin_memory() for sh in shapes]
         pin_out = [torch.empty(sh, dtype=torch.float64).pin_memory() for sh in shapes]
-        for f, t in enumerate(pin_in):
-            t.numpy()[...] = ctx.get_field(f)
+        ctx.get_state([t.numpy() for t in pin_in])
         nbytes = sum(int(np.prod(sh)) * 8 for sh in shapes)
         t0 = time.perf_counter()
         k = 3
         for _ in range(k):
             ctx.set_state(*[t.numpy() for t in pin_in])
             ctx.time_step(dt)
-            for f, t in enumerate(pin_out):
-                t.numpy()[...] = ctx.get_field(f)
+            ctx.get_state([t.numpy() for t in pin_out])
             pin_in, pin_out = pin_out, pin_in
         ctx.synchronize()
         out["e2e"] = {"value": cells / ((time.perf_counter() - t0) / k) / 1e6, "unit": "Mcell-updates/s", "h2d_bytes_per_step": nbytes,

@@ -59,6 +59,7 @@ ABI_SYMBOLS = {
     "stage_substep_count_and_size": (C.c_int, [_vp, C.c_double, C.c_double, C.POINTER(C.c_int32), _dp]),
     "acoustic_substep_loop": (C.c_int, [_vp, C.c_double, C.c_double]),
     "get_field": (C.c_int, [_vp, C.c_int, _dp]),
+    "get_state": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _dp]),
     "get_clock": (C.c_int, [_vp, _dp, C.POINTER(C.c_int64)]),
     "synchronize": (C.c_int, [_vp]),
 }
@@ -180,6 +181,13 @@ class CompressibleContext:
         fid = FIELD_IDS[name_or_id] if isinstance(name_or_id, str) else int(name_or_id)
         out = np.empty(self.shape(fid))
         self._check(self.lib.get_field(self.handle, fid, _as_dp(out)), "get_field")
+        return out
+
+    def get_state(self, out=None):
+        """The five prognostics (ρ, ρu, ρv, ρw, ρθ) in one call, into `out` (e.g. pinned buffers) when given."""
+        if out is None:
+            out = [np.empty(self.shape(f)) for f in range(5)]
+        self._check(self.lib.get_state(self.handle, *[_as_dp(a) for a in out]), "get_state")
         return out
 
     def clock(self):

@@ -107,13 +107,28 @@ __device__ __forceinline__ double c_sym(const double* __restrict__ a, long long 
     return 0.5 * (a[n - s] + a[n]);
 }
 
-__global__ void __launch_bounds__(128) c_slow_tendencies(Layout L, CSlowArgs A, double g) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, k = blockIdx.z;
-    if (i >= L.nx) return;
-    const long long n = lidx(L, i, j, k);
-    const long long SX = 1, SY = L.PX, SZ = L.plane;
+// Every face flux is evaluated ONCE: a block owns 31 x TY columns and marches up a chunk of levels. Each thread evaluates the
+// fluxes through the LOW x face, the LOW y face and the TOP z face of its cell; the high x face comes from lane + 1 by warp
+// shuffle (tiles overlap by one column: lane 31 only supplies fluxes), the high y face from the row above through shared memory
+// (the last row evaluates its own), the bottom z face is carried in registers from the level below.
+#ifndef CS_TY
+#define CS_TY 8
+#endif
+#define CS_TX 31
+#ifndef CS_MINB
+#define CS_MINB 4             // 64 registers per thread: 4 CTAs of 256 threads per SM (A/B: 2 → 697 us, 3 → 570 us, 4 → 494 us at 256x256x64)
+#endif
+__global__ void __launch_bounds__(32 * CS_TY, CS_MINB) c_slow_tendencies(Layout L, CSlowArgs A, double g, int k_chunk) {
+    __shared__ double sfy[4][CS_TY][32];
+    const int lane = threadIdx.x, ty = threadIdx.y;
+    const int i = blockIdx.x * CS_TX + lane, j = blockIdx.y * CS_TY + ty;
     const int Nz = L.Nz;
+    const int kb = blockIdx.z * k_chunk, ke = min(Nz, kb + k_chunk);
+    const long long SX = 1, SY = L.PX, SZ = L.plane;
     const bool fx_ = L.flat_x, fy_ = L.flat_y;
+    const bool col_ok = (i <= L.nx) && (j < L.Ny) && (fx_ ? i < L.nx : true);       // i = nx: only the low-x-face fluxes are needed
+    const bool own = (lane < CS_TX) && (i < L.nx) && (j < L.Ny);
+    const bool last_row = (ty == CS_TY - 1) || (j == L.Ny - 1);
     const double Ax = L.dy * L.dz, Ay = L.dx * L.dz, Az = L.dx * L.dy, Vinv = 1.0 / (L.dx * L.dy * L.dz);
     // advecting mass fluxes: centred-4 interpolation of the area-weighted momentum; advected velocity: WENO5-Z
     auto symx = [&](const double* a, long long m) { return fx_ ? a[m] : c_sym(a, m, SX, 2); };
@@ -124,57 +139,67 @@ __global__ void __launch_bounds__(128) c_slow_tendencies(Layout L, CSlowArgs A, 
     auto Fuv = [&](long long m) { double t = Ax * symy(A.ru, m); return t * c_biased(A.v, m, SX, 3, t > 0); };
     auto Fvv = [&](long long m1) { double t = Ay * c_sym(A.rv, m1, SY, 2); return t * c_biased(A.v, m1, SY, 3, t > 0); };
     auto Fwv = [&](long long m, int kk) { if (kk == 0 || kk == Nz) return 0.0; double t = Az * symy(A.rw, m); return t * c_biased(A.v, m, SZ, red_face(kk, Nz, 3), t > 0); };
-    auto Fuw = [&](long long m, int kk) { double t = Ax * c_sym(A.ru, m, SZ, red_face(kk, Nz, 2)); return t * c_biased(A.w, m, SX, 3, t > 0); };
-    auto Fvw = [&](long long m, int kk) { double t = Ay * c_sym(A.rv, m, SZ, red_face(kk, Nz, 2)); return t * c_biased(A.w, m, SY, 3, t > 0); };
+    auto Fuw = [&](long long m, int kk) { if (kk == 0) return 0.0; double t = Ax * c_sym(A.ru, m, SZ, red_face(kk, Nz, 2)); return t * c_biased(A.w, m, SX, 3, t > 0); };
+    auto Fvw = [&](long long m, int kk) { if (kk == 0) return 0.0; double t = Ay * c_sym(A.rv, m, SZ, red_face(kk, Nz, 2)); return t * c_biased(A.w, m, SY, 3, t > 0); };
     auto Fww = [&](long long m1, int kc) { double t = Az * c_sym(A.rw, m1, SZ, red_center(kc, Nz, 2)); return t * c_biased(A.w, m1, SZ, red_center(kc, Nz, 3), t > 0); };
     auto Tx = [&](long long m) { double t = A.u[m]; return ((A.rho[m] + A.rho[m - SX]) / 2) * (Ax * t * c_biased(A.theta, m, SX, 3, t > 0)); };
     auto Ty = [&](long long m) { double t = A.v[m]; return ((A.rho[m] + A.rho[m - SY]) / 2) * (Ay * t * c_biased(A.theta, m, SY, 3, t > 0)); };
     auto Tz = [&](long long m, int kk) { if (kk == 0 || kk == Nz) return 0.0; double t = A.w[m];
                                          return ((A.rho[m] + A.rho[m - SZ]) / 2) * (Az * t * c_biased(A.theta, m, SZ, red_face(kk, Nz, 3), t > 0)); };
-    {
-        double fx = fx_ ? 0.0 : Fuu(n + SX) - Fuu(n);
-        double fy = fy_ ? 0.0 : Fvu(n + SY) - Fvu(n);
-        double fz = Fwu(n + SZ, k + 1) - Fwu(n, k);
-        A.Gru[n] = -(Vinv * (fx + fy + fz));
+    const long long n0 = lidx(L, min(i, L.nx), min(j, L.Ny - 1), 0);
+    // z-type fluxes through the bottom face of the chunk's first level (Fww: at centre kb - 1)
+    double zb_u = 0.0, zb_v = 0.0, zb_w = 0.0, zb_t = 0.0;
+    if (own && kb > 0) {
+        const long long n = n0 + (long long)kb * SZ;
+        zb_u = Fwu(n, kb); zb_v = Fwv(n, kb); zb_w = Fww(n, kb - 1); zb_t = Tz(n, kb);
     }
-    {
-        double fx = fx_ ? 0.0 : Fuv(n + SX) - Fuv(n);
-        double fy = fy_ ? 0.0 : Fvv(n + SY) - Fvv(n);
-        double fz = Fwv(n + SZ, k + 1) - Fwv(n, k);
-        A.Grv[n] = -(Vinv * (fx + fy + fz));
-    }
-    double Gw = 0.0;
-    if (k >= 1) {
-        double fx = fx_ ? 0.0 : Fuw(n + SX, k) - Fuw(n, k);
-        double fy = fy_ ? 0.0 : Fvw(n + SY, k) - Fvw(n, k);
-        double fz = Fww(n + SZ, k) - Fww(n, k - 1);
-        Gw = -(Vinv * (fx + fy + fz));
-    }
-    A.Grw[n] = Gw;
-    {
-        double dxu = fx_ ? 0.0 : Ax * A.ru[n + SX] - Ax * A.ru[n];
-        double dyv = fy_ ? 0.0 : Ay * A.rv[n + SY] - Ay * A.rv[n];
-        double dzw = Az * A.rw[n + SZ] - Az * A.rw[n];
-        A.Grho[n] = -(Vinv * (dxu + dyv + dzw));
-    }
-    {
-        double fx = fx_ ? 0.0 : Tx(n + SX) - Tx(n);
-        double fy = fy_ ? 0.0 : Ty(n + SY) - Ty(n);
-        double fz = Tz(n + SZ, k + 1) - Tz(n, k);
-        A.Grth[n] = -(Vinv * (fx + fy + fz));
-    }
-    // _assemble_slow_vertical_momentum_tendency!: Gˢρw = (Gρw - ∂z(pᴸ - pᵣ) - g ℑz(ρᴸ - ρᵣ)) (k > 1)
-    double Gs = 0.0;
-    if (k >= 1) {
-        if (A.p_r) {
-            double dpk = A.p[n] - A.p_r[k], dpm = A.p[n - SZ] - A.p_r[k - 1];
-            double drk = A.rho[n] - A.rho_r[k], drm = A.rho[n - SZ] - A.rho_r[k - 1];
-            Gs = Gw - (dpk - dpm) * L.rdz - g * ((drk + drm) / 2);
-        } else {
-            Gs = Gw - (A.p[n] - A.p[n - SZ]) * L.rdz - g * ((A.rho[n] + A.rho[n - SZ]) / 2);
+    for (int k = kb; k < ke; ++k) {
+        const long long n = n0 + (long long)k * SZ;
+        // low-x-face fluxes of this column (every lane of a valid row, including the overlap lane)
+        double xu = 0.0, xv = 0.0, xw = 0.0, xt = 0.0;
+        if (col_ok && !fx_) { xu = Fuu(n); xv = Fuv(n); xw = Fuw(n, k); xt = Tx(n); }
+        const double xu_e = __shfl_down_sync(0xffffffffu, xu, 1), xv_e = __shfl_down_sync(0xffffffffu, xv, 1);
+        const double xw_e = __shfl_down_sync(0xffffffffu, xw, 1), xt_e = __shfl_down_sync(0xffffffffu, xt, 1);
+        // low-y-face fluxes → shared memory; the last row of the tile evaluates its own high face
+        double yu = 0.0, yv = 0.0, yw = 0.0, yt = 0.0;
+        if (own && !fy_) { yu = Fvu(n); yv = Fvv(n); yw = Fvw(n, k); yt = Ty(n); }
+        __syncthreads();                                   // the previous level's readers are done
+        sfy[0][ty][lane] = yu; sfy[1][ty][lane] = yv; sfy[2][ty][lane] = yw; sfy[3][ty][lane] = yt;
+        __syncthreads();
+        if (!own) continue;                                // (no barrier below this point inside the level)
+        double yu_n = 0.0, yv_n = 0.0, yw_n = 0.0, yt_n = 0.0;
+        if (!fy_) {
+            if (last_row) { yu_n = Fvu(n + SY); yv_n = Fvv(n + SY); yw_n = Fvw(n + SY, k); yt_n = Ty(n + SY); }
+            else { yu_n = sfy[0][ty + 1][lane]; yv_n = sfy[1][ty + 1][lane]; yw_n = sfy[2][ty + 1][lane]; yt_n = sfy[3][ty + 1][lane]; }
         }
+        // top-z-face fluxes (Fww: at centre k)
+        const double zt_u = Fwu(n + SZ, k + 1), zt_v = Fwv(n + SZ, k + 1), zt_w = Fww(n + SZ, k), zt_t = Tz(n + SZ, k + 1);
+        // Fuu / Fvv live at centres: this thread's "low" value is centre i-1 (j-1), the neighbour's is centre i (j)
+        A.Gru[n] = -(Vinv * ((fx_ ? 0.0 : xu_e - xu) + (fy_ ? 0.0 : yu_n - yu) + (zt_u - zb_u)));
+        A.Grv[n] = -(Vinv * ((fx_ ? 0.0 : xv_e - xv) + (fy_ ? 0.0 : yv_n - yv) + (zt_v - zb_v)));
+        const double Gw = (k >= 1) ? -(Vinv * ((fx_ ? 0.0 : xw_e - xw) + (fy_ ? 0.0 : yw_n - yw) + (zt_w - zb_w))) : 0.0;
+        A.Grw[n] = Gw;
+        {
+            double dxu = fx_ ? 0.0 : Ax * A.ru[n + SX] - Ax * A.ru[n];
+            double dyv = fy_ ? 0.0 : Ay * A.rv[n + SY] - Ay * A.rv[n];
+            double dzw = Az * A.rw[n + SZ] - Az * A.rw[n];
+            A.Grho[n] = -(Vinv * (dxu + dyv + dzw));
+        }
+        A.Grth[n] = -(Vinv * ((fx_ ? 0.0 : xt_e - xt) + (fy_ ? 0.0 : yt_n - yt) + (zt_t - zb_t)));
+        // _assemble_slow_vertical_momentum_tendency!: Gˢρw = (Gρw - ∂z(pᴸ - pᵣ) - g ℑz(ρᴸ - ρᵣ)) (k > 1)
+        double Gs = 0.0;
+        if (k >= 1) {
+            if (A.p_r) {
+                double dpk = A.p[n] - A.p_r[k], dpm = A.p[n - SZ] - A.p_r[k - 1];
+                double drk = A.rho[n] - A.rho_r[k], drm = A.rho[n - SZ] - A.rho_r[k - 1];
+                Gs = Gw - (dpk - dpm) * L.rdz - g * ((drk + drm) / 2);
+            } else {
+                Gs = Gw - (A.p[n] - A.p[n - SZ]) * L.rdz - g * ((A.rho[n] + A.rho[n - SZ]) / 2);
+            }
+        }
+        A.Gs_rw[n] = Gs;
+        zb_u = zt_u; zb_v = zt_v; zb_w = zt_w; zb_t = zt_t;
     }
-    A.Gs_rw[n] = Gs;
 }
 
 // ---- stage start: rewind-initialised perturbations, zeroed accumulators ----------------------------------------------

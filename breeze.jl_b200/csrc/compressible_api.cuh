@@ -157,7 +157,15 @@ static int c_stage_tendencies(bzc_ctx* c) {
     A.u = c->u; A.v = c->v; A.w = c->w; A.theta = c->theta; A.p = c->p;
     A.p_r = c->has_ref ? c->d_cols : nullptr; A.rho_r = c->has_ref ? c->d_cols + L.Nz : nullptr;
     A.Grho = c->G[CF_RHO]; A.Gru = c->G[CF_RU]; A.Grv = c->G[CF_RV]; A.Grw = c->G[CF_RW]; A.Grth = c->G[CF_RTH]; A.Gs_rw = c->Gs_rw;
-    c_slow_tendencies<<<c_grid(L, L.Nz), 128, 0, c->stream>>>(L, A, c->eos.g);
+    {
+        const int gx = (L.nx + CS_TX - 1) / CS_TX, gy = (L.Ny + CS_TY - 1) / CS_TY;
+        int chunks = (2 * 148 * 8 + gx * gy - 1) / (gx * gy);                    // enough CTAs for ~2 waves of 8 resident CTAs per SM
+        const int max_chunks = (L.Nz + 7) / 8;                                    // at least 8 levels per chunk: the carried-flux replay stays < 7 %
+        if (chunks > max_chunks) chunks = max_chunks;
+        if (chunks < 1) chunks = 1;
+        const int k_chunk = (L.Nz + chunks - 1) / chunks;
+        c_slow_tendencies<<<dim3(gx, gy, (L.Nz + k_chunk - 1) / k_chunk), dim3(32, CS_TY), 0, c->stream>>>(L, A, c->eos.g, k_chunk);
+    }
     c->launches++;
     CC_TRY(c, cudaGetLastError());
     return BZ_OK;
@@ -400,15 +408,15 @@ int bzc_set_state(bzc_ctx* c, const double* rho, const double* ru, const double*
     cudaSetDevice(c->cfg.base.device);
     const Layout& L = c->L;
     const double* src[5] = {rho, ru, rv, rw, rth};
-    for (int f = 0; f < 5; ++f) {
+    for (int f = 0; f < 5; ++f) {                       // staged through the perturbation fields (scratch between steps): no sync per field
         if (!src[f]) continue;
         const int nz = (f == CF_RW) ? L.Nz + 1 : L.Nz;
-        CC_TRY(c, cudaMemcpyAsync(c->dense, src[f], (size_t)L.nx * L.Ny * nz * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-        c_scatter<<<c_grid(L, nz), 128, 0, c->stream>>>(L, c->dense, c->U[f], f == CF_RW);
+        CC_TRY(c, cudaMemcpyAsync(c->P[f], src[f], (size_t)L.nx * L.Ny * nz * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        c_scatter<<<c_grid(L, nz), 128, 0, c->stream>>>(L, c->P[f], c->U[f], f == CF_RW);
         c->launches++;
-        CC_TRY(c, cudaGetLastError());
-        CC_TRY(c, cudaStreamSynchronize(c->stream));
     }
+    CC_TRY(c, cudaGetLastError());
+    CC_TRY(c, cudaStreamSynchronize(c->stream));        // the caller's buffers are free again
     int rc = c_update_state_host(c);
     if (rc) return rc;
     return c_store_initial_state(c);
@@ -492,6 +500,24 @@ int bzc_get_field(bzc_ctx* c, int f, double* out) {
     c->launches++;
     CC_TRY(c, cudaGetLastError());
     CC_TRY(c, cudaMemcpyAsync(out, c->dense, count * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CC_TRY(c, cudaStreamSynchronize(c->stream));
+    return BZ_OK;
+}
+
+int bzc_get_state(bzc_ctx* c, double* rho, double* ru, double* rv, double* rw, double* rth) {
+    if (!c) return BZ_ERR_INVALID;
+    cudaSetDevice(c->cfg.base.device);
+    const Layout& L = c->L;
+    double* dst[5] = {rho, ru, rv, rw, rth};
+    // the perturbation fields are scratch between steps: stage the five dense copies there and download them back to back
+    for (int f = 0; f < 5; ++f) {
+        if (!dst[f]) continue;
+        const int nz = (f == CF_RW) ? L.Nz + 1 : L.Nz;
+        c_extract<<<c_grid(L, nz), 128, 0, c->stream>>>(L, c->U[f], c->P[f]);
+        c->launches++;
+        CC_TRY(c, cudaMemcpyAsync(dst[f], c->P[f], (size_t)L.nx * L.Ny * nz * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    }
+    CC_TRY(c, cudaGetLastError());
     CC_TRY(c, cudaStreamSynchronize(c->stream));
     return BZ_OK;
 }

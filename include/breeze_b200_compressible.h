@@ -100,6 +100,8 @@ int bzc_stage_substep_count_and_size(bzc_ctx* ctx, double dt, double beta, int32
 int bzc_acoustic_substep_loop(bzc_ctx* ctx, double dt, double beta);
 
 int bzc_get_field(bzc_ctx* ctx, int field, double* host_out);
+/* interior of the five prognostics → HOST in one call (any pointer may be NULL); synchronises once */
+int bzc_get_state(bzc_ctx* ctx, double* rho, double* rho_u, double* rho_v, double* rho_w, double* rho_theta);
 int bzc_get_clock(bzc_ctx* ctx, double* time, int64_t* iteration);
 int bzc_synchronize(bzc_ctx* ctx);
 

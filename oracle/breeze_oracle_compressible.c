@@ -841,6 +841,11 @@ int orcc_get_field(orcc_ctx* c, int f, double* out) {
     copy_out(c, out, src, zf ? c->Nz + 1 : c->Nz);
     return BZ_OK;
 }
+int orcc_get_state(orcc_ctx* c, double* rho, double* ru, double* rv, double* rw, double* rth) {
+    double* dst[NPROGC] = {rho, ru, rv, rw, rth};
+    for (int f = 0; f < NPROGC; ++f) if (dst[f]) copy_out(c, dst[f], c->U[f], f == C_RW ? c->Nz + 1 : c->Nz);
+    return BZ_OK;
+}
 int orcc_get_clock(orcc_ctx* c, double* t, int64_t* it) { if (t) *t = c->time; if (it) *it = c->iteration; return BZ_OK; }
 int orcc_synchronize(orcc_ctx* c) { (void)c; return BZ_OK; }
 
