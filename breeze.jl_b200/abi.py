@@ -16,10 +16,12 @@ import numpy as np
 BZ_ABI_VERSION = 1
 BZ_PERIODIC, BZ_FLAT = 0, 1
 BZ_MICROPHYSICS_NONE, BZ_MICROPHYSICS_WARM_SATURATION_ADJUSTMENT = 0, 1
+BZ_FORMULATION_POTENTIAL_TEMPERATURE, BZ_FORMULATION_STATIC_ENERGY = 0, 1
 
 FIELD_IDS = {
     "ρu": 0, "ρv": 1, "ρw": 2, "ρθ": 3, "ρqᵛ": 4, "ρqᵉ": 4, "ρq": 4,
     "u": 5, "v": 6, "w": 7, "θ": 8, "qᵛ": 9, "T": 10, "φ": 11, "qˡ": 12,
+    "ρe": 3, "e": 8,          # StaticEnergyFormulation: the thermodynamic slots carry ρe / e
     # ASCII aliases
     "rho_u": 0, "rho_v": 1, "rho_w": 2, "rho_theta": 3, "rho_q": 4,
     "theta": 8, "qv": 9, "phi": 11, "ql": 12,
@@ -47,7 +49,7 @@ class bz_config(C.Structure):
         ("advection_order", C.c_int32), ("microphysics", C.c_int32),
         ("n_ranks", C.c_int32), ("rank", C.c_int32), ("device", C.c_int32), ("reserved0", C.c_int32),
         ("nccl_unique_id", C.c_uint8 * 128),
-        ("use_tma", C.c_int32), ("z_chunks", C.c_int32), ("reserved", C.c_int32 * 6),
+        ("use_tma", C.c_int32), ("z_chunks", C.c_int32), ("formulation", C.c_int32), ("reserved", C.c_int32 * 5),
     ]
 
 

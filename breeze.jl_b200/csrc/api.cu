@@ -439,6 +439,11 @@ static int launch_stage(bz_ctx* c, int in, double* const* out, int u0, double dt
 #define LAUNCH(TX, TY, HY, FX)                                                                                        \
     (c->forced ? (moist ? launch_stage_t<TX, TY, HY, FX, 1, true>(c, P, chunks) : launch_stage_t<TX, TY, HY, FX, 0, true>(c, P, chunks)) \
                : (moist ? launch_stage_t<TX, TY, HY, FX, 1, false>(c, P, chunks) : launch_stage_t<TX, TY, HY, FX, 0, false>(c, P, chunks)))
+    if (c->cfg.formulation == BZ_FORMULATION_STATIC_ENERGY) {       // StaticEnergyFormulation: no microphysics, no forcings (bz_create / bz_set_forcing)
+        if (!c->L.flat_y) return launch_stage_t<32, 8, true, false, BZ_THERMO_STATIC_ENERGY, false>(c, P, chunks);
+        if (c->L.flat_x) return launch_stage_t<32, 1, false, true, BZ_THERMO_STATIC_ENERGY, false>(c, P, chunks);
+        return launch_stage_t<128, 1, false, false, BZ_THERMO_STATIC_ENERGY, false>(c, P, chunks);
+    }
     if (!c->L.flat_y) return LAUNCH(32, 8, true, false);
     if (c->L.flat_x) return LAUNCH(32, 1, false, true);
     return LAUNCH(128, 1, false, false);
@@ -520,6 +525,9 @@ int bz_create(const bz_config* cfg, bz_ctx** out) {
     if (cfg->abi_version != BZ_ABI_VERSION) FAIL(BZ_ERR_INVALID, "abi_version %d != %d", cfg->abi_version, BZ_ABI_VERSION);
     if (cfg->Nx < 1 || cfg->Ny < 1 || cfg->Nz < 2) FAIL(BZ_ERR_INVALID, "grid size must be positive (Nz >= 2)");
     if (cfg->advection_order != 5) FAIL(BZ_ERR_UNSUPPORTED, "only WENO(order=5) is on the path");
+    if (cfg->formulation != BZ_FORMULATION_POTENTIAL_TEMPERATURE && cfg->formulation != BZ_FORMULATION_STATIC_ENERGY) FAIL(BZ_ERR_INVALID, "unknown formulation %d", cfg->formulation);
+    if (cfg->formulation == BZ_FORMULATION_STATIC_ENERGY && cfg->microphysics != BZ_MICROPHYSICS_NONE)
+        FAIL(BZ_ERR_UNSUPPORTED, "StaticEnergyFormulation is on the path without microphysics only");
     const int fx = cfg->topology_x == BZ_FLAT, fy = cfg->topology_y == BZ_FLAT;
     if ((fx && cfg->Nx != 1) || (fy && cfg->Ny != 1)) FAIL(BZ_ERR_INVALID, "a Flat dimension must have size 1");
     if (fx && !fy) FAIL(BZ_ERR_UNSUPPORTED, "(Flat, Periodic, Bounded) is not supported; use (Periodic, Flat, Bounded)");
@@ -557,6 +565,7 @@ int bz_create(const bz_config* cfg, bz_ctx** out) {
     th.Ll = cfg->liquid_reference_latent_heat; th.Li = cfg->ice_reference_latent_heat; th.pst = cfg->standard_pressure;
     th.Tr_energy = cfg->energy_reference_temperature; th.Ttr = cfg->triple_point_temperature; th.ptr = cfg->triple_point_pressure;
     th.microphysics = cfg->microphysics;
+    th.z0 = cfg->z0; th.dz = L.dz;
 
     int rc = BZ_OK;
 #define TRY(x) do { rc = (x); if (rc) { strncpy(g_err, c->err, 511); bz_destroy(c); return rc; } } while (0)
@@ -611,7 +620,12 @@ int bz_create(const bz_config* cfg, bz_ctx** out) {
     {
         std::vector<double> h((size_t)L.nx * L.Ny * L.Nz);
         for (int k = 0; k < L.Nz; ++k)
-            for (size_t a = 0; a < (size_t)L.nx * L.Ny; ++a) h[(size_t)k * L.nx * L.Ny + a] = c->h_rho[k] * cfg->potential_temperature;
+        {
+            double th0 = cfg->potential_temperature;
+            if (cfg->formulation == BZ_FORMULATION_STATIC_ENERGY)       // set!(model, θ = θ₀) → e = cᵖᵈ Π θ₀ + g z (static_energy_tendency.jl:113-146)
+                th0 = c->th.cpd * (pow(c->h_p[k] / cfg->standard_pressure, c->th.Rd / c->th.cpd) * th0) + c->th.g * (cfg->z0 + (k + 0.5) * L.dz);
+            for (size_t a = 0; a < (size_t)L.nx * L.Ny; ++a) h[(size_t)k * L.nx * L.Ny + a] = c->h_rho[k] * th0;
+        }
         TRYCUDA(cudaMemcpyAsync(c->dense, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
         dim3 grid((L.nx + 127) / 128, L.Ny, L.Nz);
         scatter_interior<<<grid, 128, 0, c->stream>>>(L, c->dense, c->set[0][BZ_RHO_THETA], 0);
@@ -677,6 +691,7 @@ int bz_set_forcing(bz_ctx* c, const bz_forcing* F) {
     if (!c) return BZ_ERR_INVALID;
     cudaSetDevice(c->cfg.device);
     if (!F) { c->forced = 0; return BZ_OK; }
+    if (c->cfg.formulation == BZ_FORMULATION_STATIC_ENERGY) { bz_set_error(c, "forcings are on the path for the potential-temperature formulation only"); return BZ_ERR_UNSUPPORTED; }
     const int Nz = c->L.Nz;
     if (c->L.flat_x && (F->coriolis_f != 0 || F->drag_rho_ustar2 != 0)) { bz_set_error(c, "Coriolis / drag need a non-Flat x"); return BZ_ERR_UNSUPPORTED; }
     const size_t total = (size_t)(Nz + 1) + 4 * (size_t)Nz + 8 * (size_t)Nz;
@@ -774,7 +789,8 @@ int bz_get_field(bz_ctx* c, int f, double* out) {
     else if (f >= BZ_U && f <= BZ_QL) {
         FieldSet U; U.n = NPROG;
         for (int a = 0; a < NPROG; ++a) U.f[a] = c->set[c->cur][a];
-        if (c->cfg.microphysics == BZ_MICROPHYSICS_NONE) diagnose_field<0><<<grid, 128, 0, c->stream>>>(L, c->col, c->th, U, f, c->dense, nz_out);
+        if (c->cfg.formulation == BZ_FORMULATION_STATIC_ENERGY) diagnose_field<BZ_THERMO_STATIC_ENERGY><<<grid, 128, 0, c->stream>>>(L, c->col, c->th, U, f, c->dense, nz_out);
+        else if (c->cfg.microphysics == BZ_MICROPHYSICS_NONE) diagnose_field<0><<<grid, 128, 0, c->stream>>>(L, c->col, c->th, U, f, c->dense, nz_out);
         else diagnose_field<1><<<grid, 128, 0, c->stream>>>(L, c->col, c->th, U, f, c->dense, nz_out);
     } else return BZ_ERR_INVALID;
     c->launches++;

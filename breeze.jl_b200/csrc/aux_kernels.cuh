@@ -77,7 +77,8 @@ __global__ void diagnose_field(Layout L, Columns col, Thermo th, FieldSet U, int
             default: {
                 double theta = U.f[3][n] / col.rho[k], q = U.f[4][n] / col.rho[k];
                 double qv = q, ql = 0.0, T;
-                if (MICRO == BZ_MICROPHYSICS_NONE) T = (q == 0.0) ? col.exner_dry[k] * theta : lipt_temperature(th, theta, col.log_p_pst[k], q, 0.0);
+                if (MICRO == BZ_THERMO_STATIC_ENERGY) T = (theta - th.g * (th.z0 + (k + 0.5) * th.dz)) / ((1.0 - q) * th.cpd + q * th.cpv);
+                else if (MICRO == BZ_MICROPHYSICS_NONE) T = (q == 0.0) ? col.exner_dry[k] * theta : lipt_temperature(th, theta, col.log_p_pst[k], q, 0.0);
                 else T = saturation_adjust(th, theta, col.p[k], col.log_p_pst[k], q, qv, ql);
                 v = which == BZ_T ? T : (which == BZ_QV ? qv : ql);
             }

@@ -50,8 +50,12 @@ struct Columns {
 struct Thermo {
     double Rd, Rv, cpd, cpv, cl, ci, g, Ll, Li, pst;
     double Tr_energy, Ttr, ptr;
+    double z0, dz;           // heights of the cell centres z_k = z0 + (k + 1/2) dz (StaticEnergyFormulation: T = (e - g z)/cᵖᵐ)
     int microphysics;
 };
+
+// third value of the stage kernel's MICRO template parameter: StaticEnergyFormulation without microphysics
+#define BZ_THERMO_STATIC_ENERGY 2
 
 #define CUDA_TRY(ctx, call)                                                                       \
     do {                                                                                          \

@@ -101,7 +101,11 @@ template <int MICRO>
 __device__ __forceinline__ double buoyancy_center(const Thermo& th, const Columns& col, int k, double rho_k, double exner_dry_k, double Tr_k,
                                                   double theta, double q, double* cpm_pi = nullptr) {
     double T, Rm, qv = q, ql = 0.0;
-    if (MICRO == BZ_MICROPHYSICS_NONE) {
+    if (MICRO == BZ_THERMO_STATIC_ENERGY) {
+        // `theta` carries the specific static energy e; temperature(::StaticEnergyState) = (e - g z)/cᵖᵐ (dynamic_states.jl:283-298)
+        T = (theta - th.g * (th.z0 + (k + 0.5) * th.dz)) / ((1.0 - q) * th.cpd + q * th.cpv);
+        Rm = (1.0 - q) * th.Rd + q * th.Rv;
+    } else if (MICRO == BZ_MICROPHYSICS_NONE) {
         if (q == 0.0) { T = exner_dry_k * theta; Rm = th.Rd; }
         else { T = lipt_temperature(th, theta, col.log_p_pst[k], q, 0.0); Rm = (1.0 - q) * th.Rd + q * th.Rv; }
     } else {
@@ -259,6 +263,7 @@ __global__ void __launch_bounds__(2 * TX * TY, 1) stage_kernel(const __grid_cons
 
     // carried from the level below: z-type fluxes through the bottom face (role 0: ρu, ρv; role 1: ρw, θ, q), buoyancy below
     double zb0 = 0.0, zb1 = 0.0, zb2 = 0.0, b_below = 0.0;
+    double b_carry = 0.0;                        // StaticEnergyFormulation: buoyancy of the level above, evaluated one level ahead
 
     const double rdx = L.rdx, rdy = L.rdy, rdz = L.rdz;
     const bool own_cell = (j < L.Ny);
@@ -307,7 +312,7 @@ __global__ void __launch_bounds__(2 * TX * TY, 1) stage_kernel(const __grid_cons
         const double* const Lk = Lp[2];
         const double* const Lt = Lp[3];                                // level of the top face / of cell k+1
 
-        double zt0 = 0.0, zt1 = 0.0, zt2 = 0.0, b_here = 0.0, cpm_pi = 1.0;
+        double zt0 = 0.0, zt1 = 0.0, zt2 = 0.0, b_here = 0.0, cpm_pi = 1.0, b_above = 0.0;
 
         // One level of flux work. FULL: every z stencil is at full order (2 <= k <= Nz-4): all orders are compile-time.
         auto level = [&](auto full_tag, auto phase_tag) {
@@ -424,6 +429,11 @@ __global__ void __launch_bounds__(2 * TX * TY, 1) stage_kernel(const __grid_cons
                 if (role == 0) { zt0 = z_flux(K0{}); zt1 = z_flux(K1{}); }
                 else {
                     zt0 = z_flux(K2{}); zt1 = z_flux(K3{}); zt2 = z_flux(K4{});
+                    if (MICRO == BZ_THERMO_STATIC_ENERGY) {
+                        // the ρe tendency needs the buoyancy at k-1, k, k+1 (static_energy_tendency.jl:60-63): evaluate it one level ahead
+                        b_here = (k == kstart) ? buoyancy_center<MICRO>(P.th, P.col, k, rho_k, ex_k, Tr_k, Lk[3 * PL], Lk[4 * PL]) : b_carry;
+                        b_above = (k + 1 < Nz) ? buoyancy_center<MICRO>(P.th, P.col, k + 1, r_p1, nx_ex, nx_Tr, Lt[3 * PL], Lt[4 * PL]) : 0.0;
+                    } else
                     b_here = buoyancy_center<MICRO>(P.th, P.col, k, rho_k, ex_k, Tr_k, Lk[3 * PL], Lk[4 * PL], (FORCED && P.e_tend) ? &cpm_pi : nullptr);
                 }
             }
@@ -455,6 +465,8 @@ __global__ void __launch_bounds__(2 * TX * TY, 1) stage_kernel(const __grid_cons
                 if (HAS_Y) g += (S.fy[k & 1][f][ty + 1][tx] - S.fy[k & 1][f][ty][tx]) * rdy;
                 g = -(g + (zt[a] - zb[a]) * rdz);
                 if (f == 2) g = (k >= 1) ? g + 0.5 * (b_here + b_below) : 0.0;
+                if (MICRO == BZ_THERMO_STATIC_ENERGY && f == 3)      // - ℑzᵃᵃᶜ(w ℑzᵃᵃᶠ(ρb)); w = 0 on both walls (zero plane above the top)
+                    g -= 0.5 * (Lk[2 * PL] * (0.5 * (b_here + b_below)) + Lt[2 * PL] * (0.5 * (b_above + b_here)));
                 if (FORCED) {
                     // FPlane Coriolis, horizontally uniform forcings, prescribed energy tendency, bottom flux BCs (bz_forcing)
                     if (f == 0) {
@@ -484,7 +496,7 @@ __global__ void __launch_bounds__(2 * TX * TY, 1) stage_kernel(const __grid_cons
                 P.out[f][n] = r;
             }
         }
-        zb0 = zt0; zb1 = zt1; zb2 = zt2; b_below = b_here;
+        zb0 = zt0; zb1 = zt1; zb2 = zt2; b_below = b_here; b_carry = b_above;
         // fx / fy are double-buffered by level parity: the next level writes the other buffer, and the barrier after that
         // orders it against this level's readers
     }

@@ -228,9 +228,14 @@ class AtmosphereModel:
     def __init__(self, grid: RectilinearGrid, dynamics: AnelasticDynamics | None = None, advection: WENO | None = None,
                  microphysics=None, thermodynamic_constants: ThermodynamicConstants | None = None,
                  timestepper: str = "SSPRungeKutta3", coriolis: FPlane | None = None, forcing: dict | None = None,
-                 boundary_conditions: dict | None = None):
+                 boundary_conditions: dict | None = None, formulation: str = "LiquidIcePotentialTemperature"):
         if timestepper != "SSPRungeKutta3":
             raise NotImplementedError("only :SSPRungeKutta3 is on the hot path")
+        if formulation not in ("LiquidIcePotentialTemperature", "StaticEnergy"):
+            raise ValueError(f"formulation must be :LiquidIcePotentialTemperature or :StaticEnergy, got {formulation!r}")
+        if formulation == "StaticEnergy" and (microphysics is not None or forcing or boundary_conditions):
+            raise NotImplementedError("StaticEnergyFormulation is on the path without microphysics / forcings only")
+        self.formulation = formulation
         self.grid = grid
         self.architecture = grid.architecture
         if dynamics is None:
@@ -260,6 +265,7 @@ class AtmosphereModel:
         arch = self.architecture
         cfg.n_ranks, cfg.rank, cfg.device = getattr(arch, "n_ranks", 1), getattr(arch, "rank", 0), getattr(arch, "device", 0)
         cfg.use_tma, cfg.z_chunks = getattr(arch, "use_tma", 0), getattr(arch, "z_chunks", 0)
+        cfg.formulation = abi.BZ_FORMULATION_STATIC_ENERGY if formulation == "StaticEnergy" else abi.BZ_FORMULATION_POTENTIAL_TEMPERATURE
         uid = getattr(arch, "nccl_unique_id", None)
         if uid is not None:
             for n, b in enumerate(uid[:128]):
@@ -339,13 +345,37 @@ class AtmosphereModel:
     def set(self, enforce_mass_conservation=True, **kw):
         """set!(model; θ, u, v, w, qᵗ, ρu, ρv, ρw, ρθ, ρqᵛ, ...) (set_atmosphere_model.jl:198-360)."""
         ctx, g = self.context, self.grid
-        rho, _, _ = ctx.reference_state()
+        rho, p_ref, _ = ctx.reference_state()
         rho_c = rho[:, None, None]
         rho_f = np.empty(g.Nz + 1)
         rho_f[1:-1] = 0.5 * (rho[1:] + rho[:-1])
         rho_f[0], rho_f[-1] = rho[0], rho[-1]          # wall faces: only ever multiply w = 0
         rho_f = rho_f[:, None, None]
         args = dict(rho_u=None, rho_v=None, rho_w=None, rho_theta=None, rho_q=None)
+        energy = self.formulation == "StaticEnergy"
+        if energy:
+            # set_thermodynamic_variable!(::StaticEnergyModel, …) (static_energy_tendency.jl:76-190): θ or T → e = cᵖᵐ T + g z,
+            # T = Π θ with the moisture set in the same call (vapour only)
+            allowed = {"θ", "θˡⁱ", "T", "e", "ρe"}
+            given = [k for k in kw if k in allowed]
+            if len(given) > 1:
+                raise ValueError(f"set! one thermodynamic variable at a time, got {given}")
+            if given and given[0] != "ρe":
+                name = given[0]
+                xs, ys, zs = self._coords("c")
+                val = _evaluate(kw.pop(name), g, xs, ys, zs, ctx.shape(3))
+                qname = next((k for k in ("qᵗ", "qᵛ", "qᵉ", "qt", "qv") if k in kw), None)
+                q = _evaluate(kw[qname], g, xs, ys, zs, ctx.shape(3)) if qname else ctx.get_field("ρq") / rho_c
+                c = self.thermodynamic_constants
+                Rd, Rv = c.molar_gas_constant / c.dry_air_molar_mass, c.molar_gas_constant / c.vapor_molar_mass
+                Rm, cpm = (1 - q) * Rd + q * Rv, (1 - q) * c.dry_air_heat_capacity + q * c.vapor_heat_capacity
+                if name in ("θ", "θˡⁱ"):
+                    val = (p_ref[:, None, None] / self.dynamics.reference_state.standard_pressure) ** (Rm / cpm) * val
+                if name != "e":
+                    val = cpm * val + c.gravitational_acceleration * zs[:, None, None]
+                kw["ρθ"] = val * rho_c                       # the thermodynamic slot of the ABI carries ρe
+            elif given:
+                kw["ρθ"] = kw.pop("ρe")
         aliases = {"θ": "theta", "θˡⁱ": "theta", "qᵗ": "q", "qᵛ": "q", "qᵉ": "q", "ρθ": "rho_theta", "ρθˡⁱ": "rho_theta",
                    "ρqᵗ": "rho_q", "ρqᵛ": "rho_q", "ρqᵉ": "rho_q", "ρu": "rho_u", "ρv": "rho_v", "ρw": "rho_w",
                    "qt": "q", "qv": "q"}

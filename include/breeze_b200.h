@@ -42,6 +42,11 @@ enum { BZ_PERIODIC = 0, BZ_FLAT = 1 };
  * (src/Microphysics/saturation_adjustment.jl:23,55) */
 enum { BZ_MICROPHYSICS_NONE = 0, BZ_MICROPHYSICS_WARM_SATURATION_ADJUSTMENT = 1 };
 
+/* thermodynamic formulation: LiquidIcePotentialTemperatureFormulation (prognostic ρθ) or StaticEnergyFormulation (prognostic ρe,
+ * e = cᵖᵐ T + g z - ℒˡqˡ - ℒⁱqⁱ; src/StaticEnergyFormulations/, src/Thermodynamics/dynamic_states.jl:283-312). With the static-energy
+ * formulation the BZ_RHO_THETA slot carries ρe, BZ_THETA returns e, and microphysics must be NONE. */
+enum { BZ_FORMULATION_POTENTIAL_TEMPERATURE = 0, BZ_FORMULATION_STATIC_ENERGY = 1 };
+
 /* Field selectors for bz_get_field / bz_get_tendency. */
 enum { BZ_RHO_U = 0, BZ_RHO_V = 1, BZ_RHO_W = 2, BZ_RHO_THETA = 3, BZ_RHO_Q = 4,   /* prognostic      */
        BZ_U = 5, BZ_V = 6, BZ_W = 7, BZ_THETA = 8, BZ_QV = 9, BZ_T = 10,            /* diagnostic      */
@@ -93,7 +98,8 @@ typedef struct bz_config {
     /* tuning knobs (0 = library default); never change results beyond FP64 round-off */
     int32_t use_tma;              /* stage kernel operand staging: 0 default, 1 TMA, 2 plain loads */
     int32_t z_chunks;             /* split the z march of the stage kernel into this many chunks   */
-    int32_t reserved[6];
+    int32_t formulation;          /* BZ_FORMULATION_* (AtmosphereModel(...; formulation = :StaticEnergy)); default 0 */
+    int32_t reserved[5];
 } bz_config;
 
 /*

@@ -364,7 +364,13 @@ static void compute_auxiliary_thermodynamics(orc_ctx* c) {
                 c->theta[n] = theta;
                 double qve = c->U[BZ_RHO_Q][n] / rho;
                 double pr = c->p_r[k + Hz];
-                if (c->cfg.microphysics == BZ_MICROPHYSICS_NONE) {
+                if (c->cfg.formulation == BZ_FORMULATION_STATIC_ENERGY) {
+                    /* StaticEnergyFormulation (static_energy_formulation.jl:60-88): e = ρe/ρ, held in c->theta;
+                     * temperature(::StaticEnergyState) = (e - g z + ℒˡqˡ + ℒⁱqⁱ)/cᵖᵐ (dynamic_states.jl:283-298), vapour only */
+                    double z = c->cfg.z0 + (k + 0.5) * c->dz;
+                    c->qv[n] = qve; c->ql[n] = 0;
+                    c->T[n] = (theta - c->g * z + 0.0 + 0.0) / mixture_heat_capacity(c, qve, 0, 0);
+                } else if (c->cfg.microphysics == BZ_MICROPHYSICS_NONE) {
                     c->qv[n] = qve; c->ql[n] = 0;
                     c->T[n] = lipt_temperature(c, theta, pr, qve, 0, 0);
                 } else {
@@ -561,6 +567,12 @@ static void compute_tendencies(orc_ctx* c, const double* qe) {
                     c->G[BZ_RHO_W][n] = 0.0;
                 }
                 c->G[BZ_RHO_THETA][n] = -div_rhoUc(c, c->theta, i, j, k);
+                if (c->cfg.formulation == BZ_FORMULATION_STATIC_ENERGY) {
+                    /* static_energy_tendency (static_energy_tendency.jl:39-72): - ℑzᵃᵃᶜ(w · ℑzᵃᵃᶠ(buoyancy_forceᶜᶜᶜ)); w = 0 on the walls */
+                    double bf_lo = (k > 0) ? c->w[n] * (0.5 * (buoyancy_ccc(c, i, j, k) + buoyancy_ccc(c, i, j, k - 1))) : 0.0;
+                    double bf_hi = (k + 1 < c->Nz) ? c->w[IDX(c, i, j, k + 1)] * (0.5 * (buoyancy_ccc(c, i, j, k + 1) + buoyancy_ccc(c, i, j, k))) : 0.0;
+                    c->G[BZ_RHO_THETA][n] -= 0.5 * (bf_lo + bf_hi);
+                }
                 c->G[BZ_RHO_Q][n] = -div_rhoUc(c, qe, i, j, k);
                 if (c->has_forcing) {
                     const double f = c->coriolis_f;
@@ -857,6 +869,8 @@ int orc_create(const bz_config* cfg, orc_ctx** out) {
     if (cfg->abi_version != BZ_ABI_VERSION) { set_err(NULL, "abi_version mismatch"); return BZ_ERR_INVALID; }
     if (cfg->Nx < 1 || cfg->Ny < 1 || cfg->Nz < 1) { set_err(NULL, "grid size must be positive"); return BZ_ERR_INVALID; }
     if (cfg->advection_order != 5) { set_err(NULL, "only WENO(order=5) is on the path"); return BZ_ERR_UNSUPPORTED; }
+    if (cfg->formulation == BZ_FORMULATION_STATIC_ENERGY && cfg->microphysics != BZ_MICROPHYSICS_NONE) {
+        set_err(NULL, "StaticEnergyFormulation is on the path without microphysics only"); return BZ_ERR_UNSUPPORTED; }
     if ((cfg->topology_x == BZ_FLAT && cfg->Nx != 1) || (cfg->topology_y == BZ_FLAT && cfg->Ny != 1)) {
         set_err(NULL, "a Flat dimension must have size 1"); return BZ_ERR_INVALID; }
     orc_ctx* c = (orc_ctx*)calloc(1, sizeof(orc_ctx));
@@ -891,8 +905,15 @@ int orc_create(const bz_config* cfg, orc_ctx** out) {
     build_reference_state(c);
     build_solver(c);
     /* initialize_model_thermodynamics!: θ = θ₀ (anelastic_time_stepping.jl:15-19) */
-    for (int k = 0; k < c->Nz; ++k) for (int j = 0; j < c->Ny; ++j) for (int i = 0; i < c->Nx; ++i)
-        c->U[BZ_RHO_THETA][IDX(c, i, j, k)] = c->rho_r[k + c->Hz] * cfg->potential_temperature;
+    for (int k = 0; k < c->Nz; ++k) for (int j = 0; j < c->Ny; ++j) for (int i = 0; i < c->Nx; ++i) {
+        double th = cfg->potential_temperature;
+        if (cfg->formulation == BZ_FORMULATION_STATIC_ENERGY) {
+            /* set!(model, θ = θ₀) → _energy_density_from_potential_temperature! (static_energy_tendency.jl:113-146): e = cᵖᵐ Π θ + g z */
+            double T = lipt_temperature(c, th, c->p_r[k + c->Hz], 0, 0, 0);
+            th = mixture_heat_capacity(c, 0, 0, 0) * T + c->g * (cfg->z0 + (k + 0.5) * c->dz) - 0.0 - 0.0;
+        }
+        c->U[BZ_RHO_THETA][IDX(c, i, j, k)] = c->rho_r[k + c->Hz] * th;
+    }
     update_state(c, 0);
     *out = c;
     return BZ_OK;
@@ -966,6 +987,7 @@ static void replace_profile(double** dst, const double* src, int n) {
 
 int orc_set_forcing(orc_ctx* c, const bz_forcing* F) {
     if (!F) { c->has_forcing = 0; c->stale = 1; return BZ_OK; }
+    if (c->cfg.formulation == BZ_FORMULATION_STATIC_ENERGY) { set_err(c, "forcings are on the path for the potential-temperature formulation only"); return BZ_ERR_UNSUPPORTED; }
     c->has_forcing = 1;
     c->coriolis_f = F->coriolis_f; c->theta_flux = F->theta_flux; c->q_flux = F->q_flux; c->drag_rho_ustar2 = F->drag_rho_ustar2;
     c->subsidence_mask = F->subsidence_mask;
