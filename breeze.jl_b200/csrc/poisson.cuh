@@ -96,6 +96,10 @@ __host__ __device__ __forceinline__ size_t fft_smem_bytes(int N, int lines) { re
 // Each thread owns 8/R butterflies (8 complex values in registers): blockDim.x == lines * N / 8. N, R, Ns are
 // compile-time, so every index below folds to shifts and immediates (the run-time-N version spent 85 % of its
 // instructions on index arithmetic).
+// padded offset of a compile-time displacement D from an element whose padded index is already known: when D is a multiple
+// of 16 the padding term folds to a constant (pidx(n + D) = pidx(n) + D + D/16)
+template <int D> __device__ __forceinline__ int pidx_plus(int n, int pn) { return (D % 16 == 0) ? pn + D + D / 16 : pidx(n + D); }
+
 template <int N, int R, int Ns>
 __device__ __forceinline__ void stockham_pass(double* __restrict__ re, double* __restrict__ im, const double2* __restrict__ tw) {
     constexpr int ITEMS = 8 / R, PER_LINE = N / 8, NR = N / R, LP = ((N + (N >> 4) + 15) & ~15) + 4, STEP = N / (Ns * R);
@@ -106,8 +110,12 @@ __device__ __forceinline__ void stockham_pass(double* __restrict__ re, double* _
 #pragma unroll
     for (int it = 0; it < ITEMS; ++it) {
         const int j = t + it * PER_LINE;            // butterfly index in [0, N/R)
+        const int pj = pidx(j);
 #pragma unroll
-        for (int r = 0; r < R; ++r) v[it][r] = {lre[pidx(j + r * NR)], lim[pidx(j + r * NR)]};
+        for (int r = 0; r < R; ++r) {
+            const int o = (NR % 16 == 0) ? pj + r * (NR + NR / 16) : pidx(j + r * NR);
+            v[it][r] = {lre[o], lim[o]};
+        }
     }
     __syncthreads();
 #pragma unroll
@@ -125,8 +133,12 @@ __device__ __forceinline__ void stockham_pass(double* __restrict__ re, double* _
         else if (R == 4) dft4(v[it][0], v[it][1], v[it][2], v[it][3]);
         else dft2(v[it][0], v[it][1]);
         const int j0 = (j - k) * R + k;
+        const int pj0 = pidx(j0);
 #pragma unroll
-        for (int r = 0; r < R; ++r) { lre[pidx(j0 + r * Ns)] = v[it][r].x; lim[pidx(j0 + r * Ns)] = v[it][r].y; }
+        for (int r = 0; r < R; ++r) {
+            const int o = (Ns % 16 == 0) ? pj0 + r * (Ns + Ns / 16) : pidx(j0 + r * Ns);
+            lre[o] = v[it][r].x; lim[o] = v[it][r].y;
+        }
     }
     __syncthreads();
 }
@@ -299,6 +311,15 @@ __global__ void __launch_bounds__(256, 3) fft_x_kernel(PoissonGeom G, double2* _
     };
     // blockDim.x == lines * N / 8: every thread moves exactly 8 elements; all 8 loads are issued before the first use
     double2 v[8];
+    const long long chunk = (n_lines - l0 < lines ? n_lines - l0 : lines) * (long long)N;   // valid elements of this CTA's lines
+    if (G.P == 1) {                                     // one rank: the CTA's lines are ONE contiguous chunk of W
+        const double2* __restrict__ src = W + (size_t)l0 * N;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int e = threadIdx.x + it * blockDim.x;
+            v[it] = (e < chunk) ? src[e] : make_double2(0.0, 0.0);
+        }
+    } else {
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
         const int e = threadIdx.x + it * blockDim.x;
@@ -313,6 +334,7 @@ __global__ void __launch_bounds__(256, 3) fft_x_kernel(PoissonGeom G, double2* _
             v[it] = __ldcv(src);
         } else v[it] = W[w2_of(l, x)];
     }
+    }
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
         const int e = threadIdx.x + it * blockDim.x;
@@ -322,11 +344,21 @@ __global__ void __launch_bounds__(256, 3) fft_x_kernel(PoissonGeom G, double2* _
     }
     __syncthreads();
     fft_lines_smem<N>(re, im, tw_x);
+    if (G.P == 1) {
+        double2* __restrict__ dst = W + (size_t)l0 * N;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int e = threadIdx.x + it * blockDim.x;
+            const int l = e / N, x = e % N;
+            if (e < chunk) dst[e] = make_double2(re[l * LP + pidx(x)], sgn * im[l * LP + pidx(x)]);
+        }
+    } else {
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
         const int e = threadIdx.x + it * blockDim.x;
         const int l = e / N, x = e % N;
         if (l0 + l < n_lines) W[w2_of(l, x)] = make_double2(re[l * LP + pidx(x)], sgn * im[l * LP + pidx(x)]);
+    }
     }
 }
 
