@@ -394,11 +394,28 @@ __global__ void __launch_bounds__(2 * TX * TY, 1) stage_kernel(const __grid_cons
             const int xoff = ((lane + YO) * SW + (TX + 4 + xs)) - toff;
             const double* const xedge = Lk + xoff;
             constexpr int XE0 = HAS_Y ? 3 : 1, XE1 = HAS_Y ? 2 : 1;
+            // Same x flux with the kind chosen at run time (only the advecting factor differs between kinds; the reconstruction is one
+            // instruction stream), so that ONE warp evaluates the x-edge column of four kinds at once: lane → (kind, row).
+            auto x_flux_rt = [&](int kind, const double* cell, int zoff) -> double {
+                const double u_i = cell[0];
+                double ut;
+                if (kind == 0) ut = rho_k * sym4(cell[-2], cell[-1], u_i, cell[1], 2);
+                else if (kind == 1) ut = HAS_Y ? rho_k * sym4(cell[-2 * SW], cell[-SW], u_i, cell[SW], 2) : rho_k * u_i;
+                else if (kind == 2) ut = (!FULL && k < 1) ? 0.0 : sz(r_m2 * Lp[0][zoff], r_m1 * Lp[1][zoff], rho_k * u_i, r_p1 * Lp[3][zoff], Rf_k2);
+                else ut = rho_k * u_i;
+                const double* f = cell + kind * PL;
+                return ut * biased6c<3>(f[-3], f[-2], f[-1], f[0], f[1], f[2], positive(kind >= 3 ? u_i : ut));
+            };
+#ifndef BZ_EDGE_UNBALANCED
+            constexpr bool BALANCED = HAS_Y && TY == 8 && !FLAT_X;   // all tile-edge fluxes on the lighter role (role 1: 7.3 vs 8 flux units per level)
+#else
+            constexpr bool BALANCED = false;
+#endif
             if (PHASE == 0) {
                 if (role == 0) {
                     if (!FLAT_X) {
                         FX[0][ty][tx] = x_flux(K0{}, Lk, 0); FX[1][ty][tx] = x_flux(K1{}, Lk, 0); FX[3][ty][tx] = x_flux(K3{}, Lk, 0);
-                        if (lane < TY) {
+                        if (!BALANCED && lane < TY) {
                             if (wrp == XE0) FX[0][lane][TX] = x_flux(K0{}, xedge, xoff);
                             else if (wrp == XE0 + 1) FX[1][lane][TX] = x_flux(K1{}, xedge, xoff);
                             else if (wrp == XE0 + 2) FX[3][lane][TX] = x_flux(K3{}, xedge, xoff);
@@ -407,22 +424,39 @@ __global__ void __launch_bounds__(2 * TX * TY, 1) stage_kernel(const __grid_cons
                     if (HAS_Y) {
                         FY[0][ty][tx] = y_flux(K0{}, Lk, 0); FY[1][ty][tx] = y_flux(K1{}, Lk, 0); FY[3][ty][tx] = y_flux(K3{}, Lk, 0);
                         // the extra row of y-faces above the tile: one flux kind per warp (rows 0..2 of this role)
-                        if (ty == 0) FY[0][TY][tx] = y_flux(K0{}, edge, ezoff);
-                        else if (ty == 1) FY[1][TY][tx] = y_flux(K1{}, edge, ezoff);
-                        else if (ty == 2) FY[3][TY][tx] = y_flux(K3{}, edge, ezoff);
+                        if (!BALANCED) {
+                            if (ty == 0) FY[0][TY][tx] = y_flux(K0{}, edge, ezoff);
+                            else if (ty == 1) FY[1][TY][tx] = y_flux(K1{}, edge, ezoff);
+                            else if (ty == 2) FY[3][TY][tx] = y_flux(K3{}, edge, ezoff);
+                        }
                     }
                 } else {
                     if (!FLAT_X) {
                         FX[2][ty][tx] = x_flux(K2{}, Lk, 0); FX[4][ty][tx] = x_flux(K4{}, Lk, 0);
-                        if (lane < TY) {
+                        if (BALANCED) {
+                            // x-edge column: warp 0 takes kinds 0..3 (lane = kind * TY + row), warp 1 takes kind 4
+                            if (wrp == 0 || (wrp == 1 && lane < TY)) {
+                                const int kind = (wrp == 0) ? (lane >> 3) : 4, row = lane & (TY - 1);
+                                const int xo = ((row + YO) * SW + (TX + 4 + xs)) - toff;
+                                FX[kind][row][TX] = x_flux_rt(kind, Lk + xo, xo);
+                            }
+                        } else if (lane < TY) {
                             if (wrp == XE1) FX[2][lane][TX] = x_flux(K2{}, xedge, xoff);
                             else if (wrp == XE1 + 1) FX[4][lane][TX] = x_flux(K4{}, xedge, xoff);
                         }
                     }
                     if (HAS_Y) {
                         FY[2][ty][tx] = y_flux(K2{}, Lk, 0); FY[4][ty][tx] = y_flux(K4{}, Lk, 0);
-                        if (ty == 0) FY[2][TY][tx] = y_flux(K2{}, edge, ezoff);
-                        else if (ty == 1) FY[4][TY][tx] = y_flux(K4{}, edge, ezoff);
+                        if (BALANCED) {                      // y-edge row: one kind per warp, warps 2..6
+                            if (ty == 2) FY[0][TY][tx] = y_flux(K0{}, edge, ezoff);
+                            else if (ty == 3) FY[1][TY][tx] = y_flux(K1{}, edge, ezoff);
+                            else if (ty == 4) FY[2][TY][tx] = y_flux(K2{}, edge, ezoff);
+                            else if (ty == 5) FY[3][TY][tx] = y_flux(K3{}, edge, ezoff);
+                            else if (ty == 6) FY[4][TY][tx] = y_flux(K4{}, edge, ezoff);
+                        } else {
+                            if (ty == 0) FY[2][TY][tx] = y_flux(K2{}, edge, ezoff);
+                            else if (ty == 1) FY[4][TY][tx] = y_flux(K4{}, edge, ezoff);
+                        }
                     }
                 }
             } else {
