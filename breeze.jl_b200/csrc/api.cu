@@ -612,7 +612,10 @@ int bz_create(const bz_config* cfg, bz_ctx** out) {
     {
         int gx = fy ? (L.nx + 127) / 128 : (L.nx + 31) / 32, gy = fy ? 1 : (L.Ny + 7) / 8;
         int want = (20 * 148 + gx * gy - 1) / (gx * gy);   // ~20 waves of CTAs keep the tail of the last wave small
-        int maxc = L.Nz / 64 > 1 ? L.Nz / 64 : 1;
+        // large grids: chunks of >= 64 levels (the one replayed level and the prologue stay < 2 %); grids with fewer CTAs than two per SM
+        // (e.g. BOMEX 128 x 128 x 75: 64 columns of tiles) trade a 6 % replay for filling the machine with chunks of >= 16 levels
+        const int min_levels = (gx * gy >= 2 * 148) ? 64 : 16;
+        int maxc = L.Nz / min_levels > 1 ? L.Nz / min_levels : 1;
         c->z_chunks = cfg->z_chunks > 0 ? cfg->z_chunks : (want < 1 ? 1 : (want > maxc ? maxc : want));
         if (c->z_chunks > L.Nz) c->z_chunks = L.Nz;
     }
