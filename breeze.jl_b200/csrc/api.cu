@@ -611,12 +611,20 @@ int bz_create(const bz_config* cfg, bz_ctx** out) {
     }
     {
         int gx = fy ? (L.nx + 127) / 128 : (L.nx + 31) / 32, gy = fy ? 1 : (L.Ny + 7) / 8;
-        int want = (20 * 148 + gx * gy - 1) / (gx * gy);   // ~20 waves of CTAs keep the tail of the last wave small
-        // large grids: chunks of >= 64 levels (the one replayed level and the prologue stay < 2 %); grids with fewer CTAs than two per SM
-        // (e.g. BOMEX 128 x 128 x 75: 64 columns of tiles) trade a 6 % replay for filling the machine with chunks of >= 16 levels
-        const int min_levels = (gx * gy >= 2 * 148) ? 64 : 16;
-        int maxc = L.Nz / min_levels > 1 ? L.Nz / min_levels : 1;
-        c->z_chunks = cfg->z_chunks > 0 ? cfg->z_chunks : (want < 1 ? 1 : (want > maxc ? maxc : want));
+        // z-chunks (blockIdx.z): one CTA per SM, so the step time is waves x levels per CTA. Model: ceil(tiles * ch / 148) waves of
+        // ceil(Nz / ch) + 5 levels (prologue planes + the one replayed level); the smallest chunk count that minimises it wins.
+        // Measured optima (scripts/zchunk_sweep.py): 512^3 -> 1 (13.10 ms; 3: 13.18, 6: 13.35), 256^3 -> 4, 128^3 -> 2.
+        int best_ch = 1;
+        {
+            const long long tiles = (long long)gx * gy;
+            const int max_ch = L.Nz / 16 > 1 ? L.Nz / 16 : 1;
+            double best = 1e300;
+            for (int ch = 1; ch <= max_ch; ++ch) {
+                double cost = (double)((tiles * ch + 147) / 148) * ((L.Nz + ch - 1) / ch + 5);
+                if (cost < best) { best = cost; best_ch = ch; }
+            }
+        }
+        c->z_chunks = cfg->z_chunks > 0 ? cfg->z_chunks : best_ch;
         if (c->z_chunks > L.Nz) c->z_chunks = L.Nz;
     }
     // initialize_model_thermodynamics!: θ = θ₀ (anelastic_time_stepping.jl:15-19)
