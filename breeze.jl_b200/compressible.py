@@ -25,9 +25,10 @@ FIELD_IDS = {
     "ρ": 0, "ρᵈ": 0, "ρu": 1, "ρv": 2, "ρw": 3, "ρθ": 4, "u": 5, "v": 6, "w": 7, "θ": 8, "T": 9, "p": 10,
     "Gρ": 11, "Gρu": 12, "Gρv": 13, "Gρw": 14, "Gρθ": 15, "Gˢρw": 16, "Πᴸ": 17, "θᴸ": 18, "γRᵐᴸ": 19,
     "ρ′": 20, "ρθ′": 21, "ρu′": 22, "ρv′": 23, "ρw′": 24, "⟨u⟩": 25, "⟨v⟩": 26, "⟨w⟩": 27,
+    "ρqᵛ": 28, "qᵛ": 29, "ρᵗ": 30, "Gρqᵛ": 31,          # ρᵗ: total density ρᵈ + ρqᵛ (dynamics.total_density)
 }
 Z_FACE_FIELDS = {3, 7, 16, 24, 27}
-PROGNOSTIC = ("ρ", "ρu", "ρv", "ρw", "ρθ")
+PROGNOSTIC = ("ρ", "ρu", "ρv", "ρw", "ρθ", "ρqᵛ")
 
 
 class bzc_config(C.Structure):
@@ -52,14 +53,14 @@ ABI_SYMBOLS = {
     "last_error": (C.c_char_p, [_vp]),
     "set_reference_potential_temperature": (C.c_int, [_vp, _dp]),
     "get_reference_state": (C.c_int, [_vp, _dp, _dp, _dp]),
-    "set_state": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _dp]),
+    "set_state": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _dp, _dp]),
     "time_step": (C.c_int, [_vp, C.c_double]),
     "time_steps": (C.c_int, [_vp, C.c_double, C.c_int]),
     "compute_slow_tendencies": (C.c_int, [_vp]),
     "stage_substep_count_and_size": (C.c_int, [_vp, C.c_double, C.c_double, C.POINTER(C.c_int32), _dp]),
     "acoustic_substep_loop": (C.c_int, [_vp, C.c_double, C.c_double]),
     "get_field": (C.c_int, [_vp, C.c_int, _dp]),
-    "get_state": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _dp]),
+    "get_state": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _dp, _dp]),
     "get_clock": (C.c_int, [_vp, _dp, C.POINTER(C.c_int64)]),
     "synchronize": (C.c_int, [_vp]),
 }
@@ -147,15 +148,16 @@ class CompressibleContext:
         self._check(self.lib.get_reference_state(self.handle, _as_dp(p), _as_dp(rho), _as_dp(pi)), "get_reference_state")
         return p, rho, pi
 
-    def set_state(self, rho=None, rho_u=None, rho_v=None, rho_w=None, rho_theta=None):
+    def set_state(self, rho=None, rho_u=None, rho_v=None, rho_w=None, rho_theta=None, rho_qv=None):
+        """`rho` is the DRY density ρᵈ; a context that never receives `rho_qv` stays dry."""
         arrs = []
-        for fid, a in enumerate((rho, rho_u, rho_v, rho_w, rho_theta)):
+        for fid, a in enumerate((rho, rho_u, rho_v, rho_w, rho_theta, rho_qv)):
             if a is None:
                 arrs.append(None)
                 continue
             a = np.ascontiguousarray(a, dtype=np.float64)
-            if a.shape != self.shape(fid):
-                raise BreezeError(f"field {PROGNOSTIC[fid]}: expected shape {self.shape(fid)}, got {a.shape}")
+            if a.shape != self.shape(fid if fid < 5 else 0):
+                raise BreezeError(f"field {PROGNOSTIC[fid]}: expected shape {self.shape(fid if fid < 5 else 0)}, got {a.shape}")
             arrs.append(a)
         self._check(self.lib.set_state(self.handle, *[_as_dp(a) for a in arrs]), "set_state")
 
@@ -184,10 +186,11 @@ class CompressibleContext:
         return out
 
     def get_state(self, out=None):
-        """The five prognostics (ρ, ρu, ρv, ρw, ρθ) in one call, into `out` (e.g. pinned buffers) when given."""
+        """The prognostics (ρᵈ, ρu, ρv, ρw, ρθ[, ρqᵛ]) in one call, into `out` (e.g. pinned buffers) when given."""
         if out is None:
             out = [np.empty(self.shape(f)) for f in range(5)]
-        self._check(self.lib.get_state(self.handle, *[_as_dp(a) for a in out]), "get_state")
+        ptrs = [_as_dp(a) for a in out] + [None] * (6 - len(out))
+        self._check(self.lib.get_state(self.handle, *ptrs), "get_state")
         return out
 
     def clock(self):
@@ -290,12 +293,13 @@ class CompressibleDynamics:
 
 class CompressibleAtmosphereModel:
     """AtmosphereModel(grid; dynamics = CompressibleDynamics(SplitExplicitTimeDiscretization(...)), advection = WENO(order=5))
-    stepped by AcousticRungeKutta3 (dry air)."""
+    stepped by AcousticRungeKutta3 (dry or vapour-laden air, microphysics = nothing)."""
 
     def __init__(self, grid, dynamics: CompressibleDynamics, advection=None, thermodynamic_constants=None, microphysics=None):
         from .model import Flat, ThermodynamicConstants, WENO
         if microphysics is not None:
-            raise NotImplementedError("the compressible path is dry")
+            raise NotImplementedError("the compressible path carries vapour only (microphysics = nothing)")
+        self._moist = False
         self.grid, self.architecture, self.dynamics = grid, grid.architecture, dynamics
         self.thermodynamic_constants = thermodynamic_constants or ThermodynamicConstants()
         self.advection = advection or WENO(order=5)
@@ -339,17 +343,49 @@ class CompressibleAtmosphereModel:
         variable and velocities weighted by it (ρθ = ρᵈ θ; set_velocity!: ρu = ℑ(ρᵈ) u with periodic / zero-gradient halos)."""
         from .model import Flat, _evaluate
         ctx, g = self.context, self.grid
-        names = {"ρᵈ": "ρ", "θˡⁱ": "θ", "ρθˡⁱ": "ρθ", "rho": "ρ", "theta": "θ"}
-        kw = {names.get(k, k): v for k, v in kw.items()}
+        # Python NFKC-normalises identifiers, so a keyword written qᵛ arrives as "qv" (and ρᵈ as "ρd"): normalise every key alike
+        import unicodedata
+        nf = lambda t: unicodedata.normalize("NFKC", t)                     # noqa: E731
+        canon = {nf(t): t for t in ("ρ", "ρᵈ", "θ", "u", "v", "w", "ρu", "ρv", "ρw", "ρθ", "qᵛ", "qᵗ", "qᵉ", "ρqᵛ", "ρqᵗ")}
+        canon.update({nf("θˡⁱ"): "θ", nf("ρθˡⁱ"): "ρθ", "rho": "ρ", "theta": "θ"})
+        kw = {canon.get(nf(k), k): v for k, v in kw.items()}
         for k in kw:
-            if k not in ("ρ", "θ", "u", "v", "w", "ρu", "ρv", "ρw", "ρθ"):
+            if k not in ("ρ", "ρᵈ", "θ", "u", "v", "w", "ρu", "ρv", "ρw", "ρθ", "qᵛ", "qᵗ", "qᵉ", "ρqᵛ", "ρqᵗ"):
                 raise ValueError(f"Cannot set! {k} in AtmosphereModel because {k} is neither a prognostic variable, "
                                  "a settable thermodynamic variable, nor a settable diagnostic variable!")
         xs, ys, zs, zf = g.xnodes(), g.ynodes(), g.znodes(), g.znodes(face=True)
         xf, yf = g.xnodes(face=True), g.ynodes(face=True)
         cshape, wshape = ctx.shape(0), ctx.shape(3)
-        rho = _evaluate(kw["ρ"], g, xs, ys, zs, cshape) if "ρ" in kw else ctx.get_field("ρ")
-        args = dict(rho=rho if "ρ" in kw else None)
+        # establish_densities! (compressible_time_stepping.jl:89-137): `ρ` is the TOTAL density (ρᵈ = ρ − ρqᵛ), `ρᵈ` the dry one
+        # (ρ = ρᵈ/(1 − qᵛ)); moisture as a mass fraction of the total density (qᵛ / qᵗ) or as a density (ρqᵛ)
+        moist_given = [k for k in ("qᵛ", "qᵗ", "qᵉ", "ρqᵛ", "ρqᵗ") if k in kw]
+        if len(moist_given) > 1:
+            raise ValueError(f"set! one moisture variable at a time, got {moist_given}")
+        total = _evaluate(kw["ρ"], g, xs, ys, zs, cshape) if "ρ" in kw else None
+        dry = _evaluate(kw["ρᵈ"], g, xs, ys, zs, cshape) if "ρᵈ" in kw else None
+        if total is not None and dry is not None:
+            raise ValueError("set! either the total density ρ or the dry density ρᵈ")
+        rqv = None
+        if moist_given:
+            mval = _evaluate(kw[moist_given[0]], g, xs, ys, zs, cshape)
+            if moist_given[0].startswith("ρ"):
+                rqv = mval
+                if total is not None:
+                    dry = total - rqv
+            else:
+                if total is not None:
+                    rqv, dry = total * mval, total - total * mval
+                else:
+                    if dry is None:
+                        dry = ctx.get_field("ρ")
+                    tot = dry / (1 - mval)
+                    rqv = tot * mval
+        elif total is not None:
+            dry = total - (ctx.get_field("ρqᵛ") if self._moist else 0.0)
+        rho = dry if dry is not None else ctx.get_field("ρ")         # coupling density ρᵈ: ρθ = ρᵈ θ, ρu = ℑ(ρᵈ) u
+        args = dict(rho=dry, rho_qv=rqv)
+        if rqv is not None:
+            self._moist = True
         for comp, axis, coords in (("u", 2, (xf, ys, zs)), ("v", 1, (xs, yf, zs)), ("w", 0, (xs, ys, zf))):
             if "ρ" + comp in kw:
                 args["rho_" + comp] = _evaluate(kw["ρ" + comp], g, *coords, wshape if comp == "w" else cshape)

@@ -27,7 +27,7 @@
 #include "common.cuh"
 #include "weno.cuh"
 
-struct CEos { double Rd, cpd, pst, g; };
+struct CEos { double Rd, cpd, pst, g, Rv, cpv; };
 
 // ---- periodic neighbours by wrapped index (interior addressing, no ghost cells needed) -----------------------------
 __device__ __forceinline__ long long cxm(const Layout& L, long long n, int i) { return i > 0 ? n - 1 : n + (L.nx - 1); }
@@ -37,8 +37,10 @@ __device__ __forceinline__ long long cyp(const Layout& L, long long n, int j) { 
 
 // ---- update_state!: velocities, θ, and the joint (T, p) diagnosis ---------------------------------------------------
 // temperature(::LiquidIceDensityState) with NewtonSolver(reltol=0, abstol=1e-4, maxiter=8) (dynamic_states.jl:201-232); p = ρ Rᵈ T
-__device__ __forceinline__ void c_temperature_pressure(const CEos& e, double rho, double theta, double& T, double& p) {
-    const double Rm = e.Rd, cpm = e.cpd;
+__device__ __forceinline__ void c_temperature_pressure(const CEos& e, double rho, double theta, double qv, double& T, double& p) {
+    // mixture constants of MoistureMassFractions(qᵛ, 0, 0); qᵛ = 0 reproduces Rᵈ, cᵖᵈ bit for bit
+    const double qd = 1.0 - qv;
+    const double Rm = qd * e.Rd + qv * e.Rv, cpm = qd * e.cpd + qv * e.cpv;
     const double kap = Rm / cpm, gam = cpm / (cpm - Rm);
     T = pow(theta, gam) * pow(rho * Rm / e.pst, gam - 1.0) + 0.0;
     double dT = T; int iter = 0;
@@ -51,10 +53,11 @@ __device__ __forceinline__ void c_temperature_pressure(const CEos& e, double rho
     p = rho * Rm * T;
 }
 
-// grid (x blocks, Ny, Nz + 1); ρ needs valid x / y ghost cells
+// grid (x blocks, Ny, Nz + 1); ρᵈ needs valid x / y ghost cells. rqv == nullptr: dry air (ρ = ρᵈ, qᵛ = 0; rho_tot / qv are not written).
 __global__ void c_update_state(Layout L, CEos e, const double* __restrict__ rho, const double* __restrict__ ru, const double* __restrict__ rv,
-                               const double* __restrict__ rw, const double* __restrict__ rth, double* __restrict__ u, double* __restrict__ v,
-                               double* __restrict__ w, double* __restrict__ theta, double* __restrict__ T, double* __restrict__ p) {
+                               const double* __restrict__ rw, const double* __restrict__ rth, const double* __restrict__ rqv,
+                               double* __restrict__ u, double* __restrict__ v, double* __restrict__ w, double* __restrict__ theta,
+                               double* __restrict__ T, double* __restrict__ p, double* __restrict__ rho_tot, double* __restrict__ qv) {
     int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, k = blockIdx.z;
     if (i >= L.nx) return;
     long long n = lidx(L, i, j, k);
@@ -64,10 +67,16 @@ __global__ void c_update_state(Layout L, CEos e, const double* __restrict__ rho,
         double ry = L.flat_y ? r : (r + rho[n - L.PX]) / 2;
         u[n] = ru[n] / rx;
         v[n] = rv[n] / ry;
-        double th = rth[n] / r;
+        double th = rth[n] / r;                       // θ = ρθ / ρᵈ (coupling density)
         theta[n] = th;
+        double rt = r, q = 0.0;
+        if (rqv) {                                     // compute_total_density!: ρ = ρᵈ + ρqᵛ; qᵛ is a mass fraction of the total
+            const double m = rqv[n];
+            rt = r + m; q = m / rt;
+            rho_tot[n] = rt; qv[n] = q;
+        }
         double Tn, pn;
-        c_temperature_pressure(e, r, th, Tn, pn);
+        c_temperature_pressure(e, rt, th, q, Tn, pn);
         T[n] = Tn; p[n] = pn;
     }
     w[n] = (k == 0 || k == L.Nz) ? 0.0 : rw[n] / ((rho[n] + rho[n - L.plane]) / 2);
@@ -75,14 +84,17 @@ __global__ void c_update_state(Layout L, CEos e, const double* __restrict__ rho,
 
 // refresh_linearization_basic_state!: Πᴸ = (p/pˢᵗ)^κ, θᴸ = ρθ/ρ, Cᴸ = γᵐRᵐᴸ Πᴸ (dry: γᵐRᵐ = cᵖᵈ Rᵈ / (cᵖᵈ - Rᵈ))
 __global__ void c_linearize(Layout L, CEos e, const double* __restrict__ p, const double* __restrict__ rho, const double* __restrict__ rth,
-                            double* __restrict__ PiL, double* __restrict__ thL, double* __restrict__ CL) {
+                            const double* __restrict__ qv, double* __restrict__ PiL, double* __restrict__ thL, double* __restrict__ CL) {
     int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, k = blockIdx.z;
     if (i >= L.nx) return;
     long long n = lidx(L, i, j, k);
     double Pi = pow(p[n] / e.pst, e.Rd / e.cpd);
     double r = rho[n];
     double rh = (r == 0.0) ? 1.0 : r;
-    double gR = e.cpd * e.Rd / (e.cpd - e.Rd);
+    const double q = qv ? qv[n] : 0.0;               // _compute_linearization_mixture_eos!: γᵐRᵐ = cᵖᵐ Rᵐ / (cᵖᵐ - Rᵐ)
+    const double qd = 1.0 - q;
+    const double Rm = qd * e.Rd + q * e.Rv, cpm = qd * e.cpd + q * e.cpv;
+    double gR = cpm * Rm / (cpm - Rm);
     PiL[n] = Pi;
     thL[n] = rth[n] / rh;
     CL[n] = gR * Pi;
@@ -91,6 +103,7 @@ __global__ void c_linearize(Layout L, CEos e, const double* __restrict__ p, cons
 // ---- slow tendencies (WENO5, 3-D coupling density) ------------------------------------------------------------------
 struct CSlowArgs {
     const double *rho, *ru, *rv, *rw, *u, *v, *w, *theta, *p;
+    const double *rho_tot;               // total density ρᵈ + ρqᵛ for the buoyancy (= rho for dry air)
     const double *p_r, *rho_r;           // Nz each or nullptr (reference_state = nothing)
     double *Grho, *Gru, *Grv, *Grw, *Grth, *Gs_rw;
 };
@@ -191,10 +204,10 @@ __global__ void __launch_bounds__(32 * CS_TY, CS_MINB) c_slow_tendencies(Layout 
         if (k >= 1) {
             if (A.p_r) {
                 double dpk = A.p[n] - A.p_r[k], dpm = A.p[n - SZ] - A.p_r[k - 1];
-                double drk = A.rho[n] - A.rho_r[k], drm = A.rho[n - SZ] - A.rho_r[k - 1];
+                double drk = A.rho_tot[n] - A.rho_r[k], drm = A.rho_tot[n - SZ] - A.rho_r[k - 1];
                 Gs = Gw - (dpk - dpm) * L.rdz - g * ((drk + drm) / 2);
             } else {
-                Gs = Gw - (A.p[n] - A.p[n - SZ]) * L.rdz - g * ((A.rho[n] + A.rho[n - SZ]) / 2);
+                Gs = Gw - (A.p[n] - A.p[n - SZ]) * L.rdz - g * ((A.rho_tot[n] + A.rho_tot[n - SZ]) / 2);
             }
         }
         A.Gs_rw[n] = Gs;
@@ -457,13 +470,35 @@ __global__ void c_finalize_average(Layout L, const double* __restrict__ rho, con
     avg_w[n] = (k > 0) ? (rw[n] + avg_w[n] * inv_n) / rz : 0.0;
 }
 
-// _recover_full_state!: U ← Uᴸ + U′ in place
-__global__ void c_recover(Layout L, CFields5 U, CConst5 P) {
+// _recover_full_state!: U ← Uᴸ + U′ in place; with moisture also scalar_rk3_substep!: ρqᵛ ← ρqᵛ⁰ + βΔt Gⁿ.ρqᵛ
+__global__ void c_recover(Layout L, CFields5 U, CConst5 P, double* __restrict__ rqv, const double* __restrict__ rqv0,
+                          const double* __restrict__ Grqv, double dt_stage) {
     int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, k = blockIdx.z;
     if (i >= L.nx) return;
     long long n = lidx(L, i, j, k);
 #pragma unroll
     for (int f = 0; f < 5; ++f) U.f[f][n] = U.f[f][n] + P.f[f][n];
+    if (rqv) rqv[n] = rqv0[n] + dt_stage * Grqv[n];
+}
+
+// compute_scalar_tendency! for the moisture density (update_atmosphere_model_state.jl:343, dynamics_kernel_functions.jl:132-159):
+// Gⁿ.ρqᵛ = -div_ρUc(ρ_total, ⟨𝐮⟩, qᵛ) with the acoustic-mean transport velocities. ρ_total, qᵛ, ⟨𝐮⟩ need valid ghost cells.
+__global__ void __launch_bounds__(128) c_moisture_tendency(Layout L, const double* __restrict__ rho, const double* __restrict__ q,
+                                                           const double* __restrict__ au, const double* __restrict__ av,
+                                                           const double* __restrict__ aw, double* __restrict__ G) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, k = blockIdx.z;
+    if (i >= L.nx) return;
+    const long long n = lidx(L, i, j, k), SX = 1, SY = L.PX, SZ = L.plane;
+    const int Nz = L.Nz;
+    const double Ax = L.dy * L.dz, Ay = L.dx * L.dz, Az = L.dx * L.dy, Vinv = 1.0 / (L.dx * L.dy * L.dz);
+    auto Fx = [&](long long m) { double t = au[m]; return ((rho[m] + rho[m - SX]) / 2) * (Ax * t * c_biased(q, m, SX, 3, t > 0)); };
+    auto Fy = [&](long long m) { double t = av[m]; return ((rho[m] + rho[m - SY]) / 2) * (Ay * t * c_biased(q, m, SY, 3, t > 0)); };
+    auto Fz = [&](long long m, int kk) { if (kk == 0 || kk == Nz) return 0.0; double t = aw[m];
+                                         return ((rho[m] + rho[m - SZ]) / 2) * (Az * t * c_biased(q, m, SZ, red_face(kk, Nz, 3), t > 0)); };
+    double fx = L.flat_x ? 0.0 : Fx(n + SX) - Fx(n);
+    double fy = L.flat_y ? 0.0 : Fy(n + SY) - Fy(n);
+    double fz = Fz(n + SZ, k + 1) - Fz(n, k);
+    G[n] = -(Vinv * (fx + fy + fz));
 }
 
 // seed_time_averaged_velocities! / store_initial_state!: plain copies of n doubles

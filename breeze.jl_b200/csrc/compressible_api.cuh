@@ -23,6 +23,8 @@ struct bzc_ctx {
     double *rho_s = nullptr, *rth_s = nullptr, *rth_old = nullptr, *tfac = nullptr;
     double *avg[3] = {};
     double* Gs_rw = nullptr;
+    int moist = 0;                                     // set once bzc_set_state receives a moisture density
+    double *rqv = nullptr, *rqv0 = nullptr, *Grqv = nullptr, *qv = nullptr, *rho_tot = nullptr;
     double* dense = nullptr;
     cudaStream_t stream = nullptr;
     double time = 0.0;
@@ -130,16 +132,29 @@ static int c_update_state_host(bzc_ctx* c) {
     int rc;
     if ((rc = c_fill_ghosts(c, c->U, 5))) return rc;
     c_update_state<<<c_grid(L, L.Nz + 1), 128, 0, c->stream>>>(L, c->eos, c->U[CF_RHO], c->U[CF_RU], c->U[CF_RV], c->U[CF_RW], c->U[CF_RTH],
-                                                                c->u, c->v, c->w, c->theta, c->T, c->p);
+                                                                c->moist ? c->rqv : nullptr, c->u, c->v, c->w, c->theta, c->T, c->p,
+                                                                c->rho_tot, c->qv);
     c->launches++;
     CC_TRY(c, cudaGetLastError());
-    double* diag[5] = {c->u, c->v, c->w, c->theta, c->p};
-    return c_fill_ghosts(c, diag, 5);
+    double* diag[7] = {c->u, c->v, c->w, c->theta, c->p, c->rho_tot, c->qv};
+    return c_fill_ghosts(c, diag, c->moist ? 7 : 5);
+}
+
+// update_state!(compute_tendencies = true) for the moisture density: consumed by the NEXT stage's scalar_rk3_substep!
+static int c_moisture_tendency_host(bzc_ctx* c) {
+    if (!c->moist) return BZ_OK;
+    const Layout& L = c->L;
+    int rc;
+    if ((rc = c_fill_ghosts(c, c->avg, 3))) return rc;
+    c_moisture_tendency<<<c_grid(L, L.Nz), 128, 0, c->stream>>>(L, c->rho_tot, c->qv, c->avg[0], c->avg[1], c->avg[2], c->Grqv);
+    c->launches++;
+    CC_TRY(c, cudaGetLastError());
+    return BZ_OK;
 }
 
 static int c_linearize_host(bzc_ctx* c) {
     const Layout& L = c->L;
-    c_linearize<<<c_grid(L, L.Nz), 128, 0, c->stream>>>(L, c->eos, c->p, c->U[CF_RHO], c->U[CF_RTH], c->PiL, c->thL, c->CL);
+    c_linearize<<<c_grid(L, L.Nz), 128, 0, c->stream>>>(L, c->eos, c->p, c->U[CF_RHO], c->U[CF_RTH], c->moist ? c->qv : nullptr, c->PiL, c->thL, c->CL);
     c->launches++;
     CC_TRY(c, cudaGetLastError());
     return BZ_OK;
@@ -155,6 +170,7 @@ static int c_stage_tendencies(bzc_ctx* c) {
     CSlowArgs A;
     A.rho = c->U[CF_RHO]; A.ru = c->U[CF_RU]; A.rv = c->U[CF_RV]; A.rw = c->U[CF_RW];
     A.u = c->u; A.v = c->v; A.w = c->w; A.theta = c->theta; A.p = c->p;
+    A.rho_tot = c->moist ? c->rho_tot : c->U[CF_RHO];
     A.p_r = c->has_ref ? c->d_cols : nullptr; A.rho_r = c->has_ref ? c->d_cols + L.Nz : nullptr;
     A.Grho = c->G[CF_RHO]; A.Gru = c->G[CF_RU]; A.Grv = c->G[CF_RV]; A.Grw = c->G[CF_RW]; A.Grth = c->G[CF_RTH]; A.Gs_rw = c->Gs_rw;
     {
@@ -250,7 +266,7 @@ static int c_substep_loop(bzc_ctx* c, double dt, double beta) {
     CProfScope ps(c, 4);
     c_finalize_average<<<c_grid(L, L.Nz), 128, 0, c->stream>>>(L, c->U[CF_RHO], c->U[CF_RU], c->U[CF_RV], c->U[CF_RW], c->avg[0], c->avg[1],
                                                                 c->avg[2], 1.0 / (double)n_tau);
-    c_recover<<<c_grid(L, L.Nz), 128, 0, c->stream>>>(L, Um, Pc);
+    c_recover<<<c_grid(L, L.Nz), 128, 0, c->stream>>>(L, Um, Pc, c->moist ? c->rqv : nullptr, c->rqv0, c->Grqv, beta * dt);
     c->launches += 2;
     CC_TRY(c, cudaGetLastError());
     return BZ_OK;
@@ -259,6 +275,7 @@ static int c_substep_loop(bzc_ctx* c, double dt, double beta) {
 static int c_store_initial_state(bzc_ctx* c) {
     for (int f = 0; f < 5; ++f)
         CC_TRY(c, cudaMemcpyAsync(c->U0[f], c->U[f], c->fsize * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    if (c->moist) CC_TRY(c, cudaMemcpyAsync(c->rqv0, c->rqv, c->fsize * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     return BZ_OK;
 }
 
@@ -274,6 +291,7 @@ static int c_time_step(bzc_ctx* c, double dt) {
         if ((rc = c_substep_loop(c, dt, betas[s]))) return rc;
         CProfScope ps(c, 4);
         if ((rc = c_update_state_host(c))) return rc;
+        if ((rc = c_moisture_tendency_host(c))) return rc;
     }
     c->time += dt; c->iteration += 1;
     return BZ_OK;
@@ -310,7 +328,7 @@ int bzc_create(const bzc_config* cfg, bzc_ctx** out) {
     const bz_config* b = &cfg->base;
 #define FAIL(code, ...) do { bzc_set_error(nullptr, __VA_ARGS__); return (code); } while (0)
     if (b->abi_version != BZ_ABI_VERSION) FAIL(BZ_ERR_INVALID, "abi_version %d != %d", b->abi_version, BZ_ABI_VERSION);
-    if (b->microphysics != BZ_MICROPHYSICS_NONE) FAIL(BZ_ERR_UNSUPPORTED, "the compressible path is dry");
+    if (b->microphysics != BZ_MICROPHYSICS_NONE) FAIL(BZ_ERR_UNSUPPORTED, "the compressible path carries vapour only (microphysics = nothing)");
     if (b->n_ranks > 1) FAIL(BZ_ERR_UNSUPPORTED, "the compressible path runs on one GPU");
     if (b->advection_order != 5) FAIL(BZ_ERR_UNSUPPORTED, "only WENO(order=5) is on the path");
     const int fx = b->topology_x == BZ_FLAT, fy = b->topology_y == BZ_FLAT;
@@ -339,11 +357,12 @@ int bzc_create(const bzc_config* cfg, bzc_ctx** out) {
     L.rdx = fx ? 0.0 : 1.0 / L.dx; L.rdy = fy ? 0.0 : 1.0 / L.dy; L.rdz = 1.0 / L.dz;
     c->eos.Rd = b->molar_gas_constant / b->dry_air_molar_mass; c->eos.cpd = b->dry_air_heat_capacity;
     c->eos.pst = b->standard_pressure; c->eos.g = b->gravitational_acceleration;
+    c->eos.Rv = b->molar_gas_constant / b->vapor_molar_mass; c->eos.cpv = b->vapor_heat_capacity;
     c->has_ref = cfg->reference_state == BZC_REFERENCE_EXNER;
     c->fsize = (size_t)L.plane * (L.Nz + 1);
 #define TRYCUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { bzc_set_error(nullptr, "%s: %s", #x, cudaGetErrorString(e_)); bzc_destroy(c); return BZ_ERR_CUDA; } } while (0)
     TRYCUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    const int nfields = 5 * 4 + 6 + 3 + 4 + 3 + 1;         // U, U0, G, P | u v w θ T p | Πᴸ θᴸ Cᴸ | ρ′★ (ρθ)′★ (ρθ)′ˢ⁻ tfac | ⟨u v w⟩ | Gˢρw
+    const int nfields = 5 * 4 + 6 + 3 + 4 + 3 + 1 + 5;     // U, U0, G, P | u v w θ T p | Πᴸ θᴸ Cᴸ | ρ′★ (ρθ)′★ (ρθ)′ˢ⁻ tfac | ⟨u v w⟩ | Gˢρw | moisture
     const size_t abytes = (size_t)nfields * c->fsize * sizeof(double);
     TRYCUDA(cudaMalloc((void**)&c->arena, abytes));
     TRYCUDA(cudaMemsetAsync(c->arena, 0, abytes, c->stream));
@@ -360,6 +379,7 @@ int bzc_create(const bzc_config* cfg, bzc_ctx** out) {
         c->rho_s = take(); c->rth_s = take(); c->rth_old = take(); c->tfac = take();
         for (int a = 0; a < 3; ++a) c->avg[a] = take();
         c->Gs_rw = take();
+        c->rqv = take(); c->rqv0 = take(); c->Grqv = take(); c->qv = take(); c->rho_tot = take();
     }
     TRYCUDA(cudaMalloc((void**)&c->dense, (size_t)L.nx * L.Ny * (L.Nz + 1) * sizeof(double)));
     TRYCUDA(cudaMalloc((void**)&c->d_cols, (size_t)2 * L.Nz * sizeof(double)));
@@ -403,11 +423,17 @@ int bzc_get_reference_state(bzc_ctx* c, double* p, double* rho, double* pi) {
     return BZ_OK;
 }
 
-int bzc_set_state(bzc_ctx* c, const double* rho, const double* ru, const double* rv, const double* rw, const double* rth) {
+int bzc_set_state(bzc_ctx* c, const double* rho, const double* ru, const double* rv, const double* rw, const double* rth, const double* rqv) {
     if (!c) return BZ_ERR_INVALID;
     cudaSetDevice(c->cfg.base.device);
     const Layout& L = c->L;
     const double* src[5] = {rho, ru, rv, rw, rth};
+    if (rqv) {                                          // staged through ρ′★ (scratch between steps)
+        CC_TRY(c, cudaMemcpyAsync(c->rho_s, rqv, (size_t)L.nx * L.Ny * L.Nz * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        c_scatter<<<c_grid(L, L.Nz), 128, 0, c->stream>>>(L, c->rho_s, c->rqv, 0);
+        c->launches++;
+        c->moist = 1;
+    }
     for (int f = 0; f < 5; ++f) {                       // staged through the perturbation fields (scratch between steps): no sync per field
         if (!src[f]) continue;
         const int nz = (f == CF_RW) ? L.Nz + 1 : L.Nz;
@@ -419,7 +445,13 @@ int bzc_set_state(bzc_ctx* c, const double* rho, const double* ru, const double*
     CC_TRY(c, cudaStreamSynchronize(c->stream));        // the caller's buffers are free again
     int rc = c_update_state_host(c);
     if (rc) return rc;
-    return c_store_initial_state(c);
+    if ((rc = c_store_initial_state(c))) return rc;
+    if (c->moist) {   // maybe_prepare_first_time_step!: seed ⟨𝐮⟩ with the velocities, then the first moisture tendency
+        const double* vel[3] = {c->u, c->v, c->w};
+        for (int a = 0; a < 3; ++a) CC_TRY(c, cudaMemcpyAsync(c->avg[a], vel[a], c->fsize * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        rc = c_moisture_tendency_host(c);
+    }
+    return rc;
 }
 
 int bzc_time_step(bzc_ctx* c, double dt) {
@@ -453,8 +485,9 @@ int bzc_acoustic_substep_loop(bzc_ctx* c, double dt, double beta) {
     cudaSetDevice(c->cfg.base.device);
     int rc = c_substep_loop(c, dt, beta);
     if (rc) return rc;
-    // fill_halo_regions! + compute_velocities! at the end of the loop (:1584-1587); θ, T, p are refreshed by the next update_state!
-    return c_update_state_host(c);
+    // fill_halo_regions! + compute_velocities! at the end of the loop (:1584-1587), then update_state! as in time_step!
+    if ((rc = c_update_state_host(c))) return rc;
+    return c_moisture_tendency_host(c);
 }
 
 int bzc_get_field(bzc_ctx* c, int f, double* out) {
@@ -482,7 +515,7 @@ int bzc_get_field(bzc_ctx* c, int f, double* out) {
         case BZC_SLOW_RHO_W: src = c->Gs_rw; zf = 1; break;
         case BZC_EXNER_L: src = c->PiL; break;
         case BZC_THETA_L: src = c->thL; break;
-        case BZC_GAMMA_R_L: is_const = true; constant = c->eos.cpd * c->eos.Rd / (c->eos.cpd - c->eos.Rd); break;
+        case BZC_GAMMA_R_L: is_const = true; constant = c->eos.cpd * c->eos.Rd / (c->eos.cpd - c->eos.Rd); break;   // (moist: Cᴸ/Πᴸ, below)
         case BZC_RHO_PERT: src = c->P[CF_RHO]; break;
         case BZC_RHO_THETA_PERT: src = c->P[CF_RTH]; break;
         case BZC_RHO_U_PERT: src = c->P[CF_RU]; break;
@@ -491,11 +524,26 @@ int bzc_get_field(bzc_ctx* c, int f, double* out) {
         case BZC_AVG_U: src = c->avg[0]; break;
         case BZC_AVG_V: src = c->avg[1]; break;
         case BZC_AVG_W: src = c->avg[2]; zf = 1; break;
+        case BZC_RHO_QV: src = c->rqv; break;
+        case BZC_QV: src = c->qv; break;
+        case BZC_TOTAL_RHO: src = c->moist ? c->rho_tot : c->U[CF_RHO]; break;
+        case BZC_G_RHO_QV: src = c->Grqv; break;
         default: bzc_set_error(c, "unknown field %d", f); return BZ_ERR_INVALID;
     }
     const int nz = zf ? L.Nz + 1 : L.Nz;
     const size_t count = (size_t)L.nx * L.Ny * nz;
-    if (is_const) { for (size_t e = 0; e < count; ++e) out[e] = constant; return BZ_OK; }
+    if (is_const && !c->moist) { for (size_t e = 0; e < count; ++e) out[e] = constant; return BZ_OK; }
+    if (is_const) {                                     // moist: γᵐRᵐᴸ = Cᴸ / Πᴸ (Cᴸ is what the kernels store)
+        std::vector<double> pi(count);
+        int rc = bzc_get_field(c, BZC_EXNER_L, pi.data());
+        if (rc) return rc;
+        c_extract<<<c_grid(L, nz), 128, 0, c->stream>>>(L, c->CL, c->dense);
+        c->launches++;
+        CC_TRY(c, cudaMemcpyAsync(out, c->dense, count * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CC_TRY(c, cudaStreamSynchronize(c->stream));
+        for (size_t e = 0; e < count; ++e) out[e] /= pi[e];
+        return BZ_OK;
+    }
     c_extract<<<c_grid(L, nz), 128, 0, c->stream>>>(L, src, c->dense);
     c->launches++;
     CC_TRY(c, cudaGetLastError());
@@ -504,7 +552,7 @@ int bzc_get_field(bzc_ctx* c, int f, double* out) {
     return BZ_OK;
 }
 
-int bzc_get_state(bzc_ctx* c, double* rho, double* ru, double* rv, double* rw, double* rth) {
+int bzc_get_state(bzc_ctx* c, double* rho, double* ru, double* rv, double* rw, double* rth, double* rqv) {
     if (!c) return BZ_ERR_INVALID;
     cudaSetDevice(c->cfg.base.device);
     const Layout& L = c->L;
@@ -516,6 +564,11 @@ int bzc_get_state(bzc_ctx* c, double* rho, double* ru, double* rv, double* rw, d
         c_extract<<<c_grid(L, nz), 128, 0, c->stream>>>(L, c->U[f], c->P[f]);
         c->launches++;
         CC_TRY(c, cudaMemcpyAsync(dst[f], c->P[f], (size_t)L.nx * L.Ny * nz * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (rqv) {
+        c_extract<<<c_grid(L, L.Nz), 128, 0, c->stream>>>(L, c->rqv, c->rho_s);
+        c->launches++;
+        CC_TRY(c, cudaMemcpyAsync(rqv, c->rho_s, (size_t)L.nx * L.Ny * L.Nz * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     }
     CC_TRY(c, cudaGetLastError());
     CC_TRY(c, cudaStreamSynchronize(c->stream));

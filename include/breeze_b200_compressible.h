@@ -5,8 +5,9 @@
  *   time_step!(model::CompressibleAcousticModel, Δt)           src/TimeSteppers/acoustic_runge_kutta_3.jl:264-319
  *   acoustic_rk3_substep!                                       :172-208
  *   acoustic_rk3_substep_loop!                                  src/CompressibleEquations/acoustic_substepping.jl:1404-1590
- * for dry air (no moisture / tracers), WENO(order=5), LiquidIcePotentialTemperature formulation, no closure, no sponge,
- * (Periodic | Flat, Periodic | Flat, Bounded) uniform grids.
+ * for dry or vapour-laden air (microphysics = nothing: the moisture density ρqᵛ is transported by the acoustic-mean velocities, enters
+ * the mixture EOS, the linearized PGF coefficient γᵐRᵐ and — through the total density — the buoyancy), WENO(order=5),
+ * LiquidIcePotentialTemperature formulation, no closure, no sponge, (Periodic | Flat, Periodic | Flat, Bounded) uniform grids.
  *
  * Same conventions as breeze_b200.h (plain pointers, HOST arrays interior-only with x fastest, 0 / negative return
  * codes, bzc_last_error for text). The CPU oracle exports the same ABI with prefix orcc_.
@@ -35,7 +36,8 @@ enum { BZC_RHO = 0, BZC_RHO_U = 1, BZC_RHO_V = 2, BZC_RHO_W = 3, BZC_RHO_THETA =
        BZC_EXNER_L = 17, BZC_THETA_L = 18, BZC_GAMMA_R_L = 19,                               /* Πᴸ, θᴸ, γᵐRᵐᴸ                  */
        BZC_RHO_PERT = 20, BZC_RHO_THETA_PERT = 21, BZC_RHO_U_PERT = 22, BZC_RHO_V_PERT = 23, BZC_RHO_W_PERT = 24,
        BZC_AVG_U = 25, BZC_AVG_V = 26, BZC_AVG_W = 27,                                       /* time-averaged velocities        */
-       BZC_N_FIELDS = 28 };
+       BZC_RHO_QV = 28, BZC_QV = 29, BZC_TOTAL_RHO = 30, BZC_G_RHO_QV = 31,                  /* moisture: ρqᵛ, qᵛ, ρ = ρᵈ + ρqᵛ, Gⁿ.ρqᵛ */
+       BZC_N_FIELDS = 32 };
 
 /*
  * bzc_config — RectilinearGrid + ThermodynamicConstants (the `base` part; base.microphysics must be NONE, base.n_ranks 1)
@@ -77,11 +79,13 @@ int bzc_set_reference_potential_temperature(bzc_ctx* ctx, const double* theta_r)
 /* ExnerReferenceState fields at cell centres (Nz each, any pointer may be NULL); BZ_ERR_STATE when reference_state = nothing. */
 int bzc_get_reference_state(bzc_ctx* ctx, double* pressure, double* density, double* exner);
 
-/* set!(model; ρ, ρu, ρv, ρw, ρθ) for the prognostic fields themselves (set_atmosphere_model.jl:198-360; NULL keeps a field),
- * followed by update_state!(model; compute_tendencies=false) (update_atmosphere_model_state.jl:41-68): halos, velocities,
- * θ, and the joint T, p diagnosis of compressible_time_stepping.jl:167-235. rho_w has Nz+1 levels. */
+/* set!(model; ρᵈ, ρu, ρv, ρw, ρθ, ρqᵛ) for the prognostic fields themselves (set_atmosphere_model.jl:198-360; NULL keeps a field;
+ * `rho` is the DRY density, the host side splits a given total density as establish_densities! does, compressible_time_stepping.jl:89-137),
+ * followed by update_state! (update_atmosphere_model_state.jl:41-68): total density, halos, velocities, θ, qᵛ and the joint T, p
+ * diagnosis of compressible_time_stepping.jl:167-235; with moisture also the first scalar tendency from the seeded transport velocity
+ * (maybe_prepare_first_time_step!, acoustic_runge_kutta_3.jl:240-256). rho_w has Nz+1 levels. A context that never receives rho_qv is dry. */
 int bzc_set_state(bzc_ctx* ctx, const double* rho, const double* rho_u, const double* rho_v, const double* rho_w,
-                  const double* rho_theta);
+                  const double* rho_theta, const double* rho_qv);
 
 /* time_step!(model::CompressibleAcousticModel, Δt) (acoustic_runge_kutta_3.jl:264-319); asynchronous w.r.t. the device. */
 int bzc_time_step(bzc_ctx* ctx, double dt);
@@ -101,7 +105,7 @@ int bzc_acoustic_substep_loop(bzc_ctx* ctx, double dt, double beta);
 
 int bzc_get_field(bzc_ctx* ctx, int field, double* host_out);
 /* interior of the five prognostics → HOST in one call (any pointer may be NULL); synchronises once */
-int bzc_get_state(bzc_ctx* ctx, double* rho, double* rho_u, double* rho_v, double* rho_w, double* rho_theta);
+int bzc_get_state(bzc_ctx* ctx, double* rho, double* rho_u, double* rho_v, double* rho_w, double* rho_theta, double* rho_qv);
 int bzc_get_clock(bzc_ctx* ctx, double* time, int64_t* iteration);
 int bzc_synchronize(bzc_ctx* ctx);
 

@@ -51,6 +51,9 @@ typedef struct orcc_ctx {
     double* U0[NPROGC];
     double* G[NPROGC];                            /* Gⁿ.ρᵈ, ρu, ρv, ρw, ρθ */
     double *u, *v, *w, *theta, *T, *p;
+    /* moisture (vapour only, microphysics = nothing): prognostic ρqᵛ, its U⁰ and Gⁿ, qᵛ = ρqᵛ/ρ, total density ρ = ρᵈ + ρqᵛ */
+    int moist;
+    double *rqv, *rqv0, *Grqv, *qv, *rho_tot;
     /* AcousticSubstepper fields (acoustic_substepping.jl:91-134) */
     double *PiL, *thL, *gRL;
     double *rho_p, *rth_p, *ru_p, *rv_p, *rw_p;
@@ -172,8 +175,10 @@ static void build_exner_reference(orcc_ctx* c) {
 
 /* temperature(::LiquidIceDensityState) + p = ρ Rᵐ T: dynamic_states.jl:201-232 (NewtonSolver(reltol=0, abstol=1e-4, maxiter=8),
  * Solvers.jl:82), compressible_time_stepping.jl:215-235. Dry air: L = 0. */
-static inline void temperature_and_pressure(const orcc_ctx* c, double rho, double theta, double* T_out, double* p_out) {
-    const double Rm = c->Rd, cpm = c->cpd;
+static inline void temperature_and_pressure(const orcc_ctx* c, double rho, double theta, double qv, double* T_out, double* p_out) {
+    /* mixture_gas_constant / mixture_heat_capacity of MoistureMassFractions(qᵛ, 0, 0) (thermodynamics_constants.jl:341-377) */
+    const double qd = 1 - qv - 0.0 - 0.0;
+    const double Rm = qd * c->Rd + qv * c->Rv, cpm = qd * c->cpd + qv * c->cpv + 0.0 + 0.0;
     const double kap = Rm / cpm, gam = cpm / (cpm - Rm), L = 0.0, pst = c->pst;
     double T = pow(theta, gam) * pow(rho * Rm / pst, gam - 1) + L;
     double dT = T; int iter = 0;
@@ -209,17 +214,24 @@ static void compute_velocities(orcc_ctx* c) {
 }
 
 static void update_state(orcc_ctx* c) {
+    /* compute_total_density!: ρ = ρᵈ + ρqᵛ (compressible_time_stepping.jl:49-67, microphysics_interface.jl:635-659) */
+    FOR_CELLS(c->Nz) { size_t n = IDX(c, i, j, k); c->rho_tot[n] = c->U[C_RHO][n] + c->rqv[n]; }
+    fill_halos(c, c->rho_tot, LOC_CENTER);
     fill_halos(c, c->U[C_RTH], LOC_CENTER);
+    fill_halos(c, c->rqv, LOC_CENTER);
     compute_velocities(c);
     /* _compute_auxiliary_thermodynamic_variables! (θ = ρθ/ρᵈ, potential_temperature_formulation.jl) and
      * _compute_temperature_and_pressure! (compressible_time_stepping.jl:191-213) */
     FOR_CELLS(c->Nz) {
         size_t n = IDX(c, i, j, k);
-        double rho = c->U[C_RHO][n];
+        double rho = c->U[C_RHO][n];                 /* coupling density ρᵈ: θ = ρθ/ρᵈ */
         double th = c->U[C_RTH][n] / rho;
         c->theta[n] = th;
-        temperature_and_pressure(c, rho, th, &c->T[n], &c->p[n]);
+        double qv = c->rqv[n] / c->rho_tot[n];       /* mass fraction of the TOTAL density */
+        c->qv[n] = qv;
+        temperature_and_pressure(c, c->rho_tot[n], th, qv, &c->T[n], &c->p[n]);
     }
+    fill_halos(c, c->qv, LOC_CENTER);
     fill_halos(c, c->theta, LOC_CENTER);
     fill_halos(c, c->T, LOC_CENTER);
     fill_halos(c, c->p, LOC_CENTER);
@@ -236,10 +248,11 @@ static void refresh_linearization_basic_state(orcc_ctx* c) {
         double rho = c->U[C_RHO][n];
         double rh = (rho == 0) ? 1.0 : rho;
         c->thL[n] = c->U[C_RTH][n] / rh;
-        /* _compute_linearization_mixture_eos! with qᵛ = qˡ = qⁱ = 0 */
-        double qd = 1 - 0.0 - 0.0 - 0.0;
-        double Rm = qd * c->Rd + 0.0 * c->Rv;
-        double cpm = qd * c->cpd + 0.0 * c->cpv;
+        /* _compute_linearization_mixture_eos! with q = (qᵛ, 0, 0) */
+        double qvl = c->qv[n];
+        double qd = 1 - qvl - 0.0 - 0.0;
+        double Rm = qd * c->Rd + qvl * c->Rv;
+        double cpm = qd * c->cpd + qvl * c->cpv + 0.0 + 0.0;
         double cvm = cpm - Rm;
         c->gRL[n] = cpm * Rm / cvm;
     }
@@ -365,6 +378,38 @@ static void compute_slow_tendencies(orcc_ctx* c) {
     }
 }
 
+/* compute_scalar_tendency! for the moisture density inside update_state!(compute_tendencies=true)
+ * (update_atmosphere_model_state.jl:343, dynamics_kernel_functions.jl:132-159): -div_ρUc(ρ_total, ⟨𝐮⟩, qᵛ) with the acoustic-mean
+ * transport velocities (acoustic_runge_kutta_3.jl:352-358) */
+static void compute_moisture_tendency(orcc_ctx* c) {
+    if (!c->moist) return;
+    const double V = c->dx * c->dy * c->dz, Ax = c->dy * c->dz, Ay = c->dx * c->dz, Az = c->dx * c->dy;
+    const double* rho = c->rho_tot; const double* q = c->qv;
+    FOR_CELLS(c->Nz) {
+        size_t n = IDX(c, i, j, k);
+        double fx = 0.0, fy = 0.0, fz;
+        if (!c->flat_x) {
+            double ue = c->avg_u[n + SX], uw = c->avg_u[n];
+            double Fe = ((rho[n + SX] + rho[n]) / 2) * (Ax * ue * biased_interp(q + n + SX, SX, 3, ue > 0));
+            double Fw = ((rho[n] + rho[n - SX]) / 2) * (Ax * uw * biased_interp(q + n, SX, 3, uw > 0));
+            fx = Fe - Fw;
+        }
+        if (!c->flat_y) {
+            double vn = c->avg_v[n + SY], vs = c->avg_v[n];
+            double Fn = ((rho[n + SY] + rho[n]) / 2) * (Ay * vn * biased_interp(q + n + SY, SY, 3, vn > 0));
+            double Fs = ((rho[n] + rho[n - SY]) / 2) * (Ay * vs * biased_interp(q + n, SY, 3, vs > 0));
+            fy = Fn - Fs;
+        }
+        {
+            double Ft = 0.0, Fb = 0.0;
+            if (k + 1 < c->Nz) { double wt = c->avg_w[n + SZ]; Ft = ((rho[n + SZ] + rho[n]) / 2) * (Az * wt * biased_interp(q + n + SZ, SZ, red_face(k + 1, c->Nz, 3), wt > 0)); }
+            if (k > 0) { double wb = c->avg_w[n]; Fb = ((rho[n] + rho[n - SZ]) / 2) * (Az * wb * biased_interp(q + n, SZ, red_face(k, c->Nz, 3), wb > 0)); }
+            fz = Ft - Fb;
+        }
+        c->Grqv[n] = -((1 / V) * (fx + fy + fz));
+    }
+}
+
 /* assemble_slow_vertical_momentum_tendency!: acoustic_substepping.jl:689-748 */
 static void assemble_slow_vertical_momentum_tendency(orcc_ctx* c) {
     const double g = c->g, rdz = 1 / c->dz;
@@ -374,10 +419,10 @@ static void assemble_slow_vertical_momentum_tendency(orcc_ctx* c) {
         double v;
         if (c->has_ref) {
             double dp_k = c->p[n] - c->p_r[k + Hz], dp_m = c->p[n - SZ] - c->p_r[k - 1 + Hz];
-            double dr_k = c->U[C_RHO][n] - c->rho_r[k + Hz], dr_m = c->U[C_RHO][n - SZ] - c->rho_r[k - 1 + Hz];
+            double dr_k = c->rho_tot[n] - c->rho_r[k + Hz], dr_m = c->rho_tot[n - SZ] - c->rho_r[k - 1 + Hz];
             v = c->G[C_RW][n] - (dp_k - dp_m) * rdz - g * ((dr_k + dr_m) / 2);
         } else {
-            v = c->G[C_RW][n] - (c->p[n] - c->p[n - SZ]) * rdz - g * ((c->U[C_RHO][n] + c->U[C_RHO][n - SZ]) / 2);
+            v = c->G[C_RW][n] - (c->p[n] - c->p[n - SZ]) * rdz - g * ((c->rho_tot[n] + c->rho_tot[n - SZ]) / 2);
         }
         c->Gs_rw[n] = v * (k > 0);
     }
@@ -679,6 +724,13 @@ static void stage_tendencies(orcc_ctx* c) {
 
 static void store_initial_state(orcc_ctx* c) {
     for (int f = 0; f < NPROGC; ++f) memcpy(c->U0[f], c->U[f], c->n_padded * sizeof(double));
+    memcpy(c->rqv0, c->rqv, c->n_padded * sizeof(double));
+}
+
+/* scalar_rk3_substep! (acoustic_runge_kutta_3.jl:214-223): ρqᵛ = ρqᵛ⁰ + βΔt Gⁿ.ρqᵛ, Gⁿ from the preceding update_state! */
+static void scalar_rk3_substep(orcc_ctx* c, double dt_stage) {
+    if (!c->moist) return;
+    FOR_CELLS(c->Nz) { size_t n = IDX(c, i, j, k); c->rqv[n] = c->rqv0[n] + dt_stage * c->Grqv[n]; }
 }
 
 /* time_step!(model::CompressibleAcousticModel, Δt): acoustic_runge_kutta_3.jl:264-319. The full (non-slow) tendencies that
@@ -694,7 +746,9 @@ static void time_step(orcc_ctx* c, double dt) {
     for (int s = 0; s < 3; ++s) {
         stage_tendencies(c);
         acoustic_substep_loop(c, dt, betas[s]);
+        scalar_rk3_substep(c, betas[s] * dt);
         update_state(c);
+        compute_moisture_tendency(c);                    /* update_state!(compute_tendencies = true): consumed by the NEXT stage */
     }
     c->time += dt; c->iteration += 1;
 }
@@ -711,6 +765,7 @@ void orcc_destroy(orcc_ctx* c) {
                       &c->Gs_rw, &c->rhs, &c->scratch};
     for (size_t a = 0; a < sizeof(all) / sizeof(all[0]); ++a) free(*all[a]);
     for (int f = 0; f < NPROGC; ++f) { free(c->U[f]); free(c->U0[f]); free(c->G[f]); }
+    free(c->rqv); free(c->rqv0); free(c->Grqv); free(c->qv); free(c->rho_tot);
     free(c);
 }
 
@@ -739,6 +794,7 @@ int orcc_create(const bzc_config* cfg, orcc_ctx** out) {
     size_t nz = (size_t)c->Nz + 2 * c->Hz + 1;
     c->p_r = calloc(nz, 8); c->rho_r = calloc(nz, 8); c->pi_r = calloc(nz, 8); c->theta_r = calloc(nz, 8);
     for (int f = 0; f < NPROGC; ++f) { c->U[f] = new_field(c); c->U0[f] = new_field(c); c->G[f] = new_field(c); }
+    c->rqv = new_field(c); c->rqv0 = new_field(c); c->Grqv = new_field(c); c->qv = new_field(c); c->rho_tot = new_field(c);
     double** fs[] = {&c->u, &c->v, &c->w, &c->theta, &c->T, &c->p, &c->PiL, &c->thL, &c->gRL, &c->rho_p, &c->rth_p, &c->ru_p, &c->rv_p, &c->rw_p,
                      &c->rho_s, &c->rth_s, &c->rth_old, &c->avg_u, &c->avg_v, &c->avg_w, &c->Gs_rw, &c->rhs, &c->scratch};
     for (size_t a = 0; a < sizeof(fs) / sizeof(fs[0]); ++a) *fs[a] = new_field(c);
@@ -780,11 +836,17 @@ static void copy_out(const orcc_ctx* c, double* dst, const double* src, int nzl)
         dst[(size_t)i + (size_t)c->Nx * ((size_t)j + (size_t)c->Ny * k)] = src[IDX(c, i, j, k)];
 }
 
-int orcc_set_state(orcc_ctx* c, const double* rho, const double* ru, const double* rv, const double* rw, const double* rth) {
+int orcc_set_state(orcc_ctx* c, const double* rho, const double* ru, const double* rv, const double* rw, const double* rth, const double* rqv) {
     const double* src[NPROGC] = {rho, ru, rv, rw, rth};
     for (int f = 0; f < NPROGC; ++f) if (src[f]) copy_in(c, c->U[f], src[f], f == C_RW ? c->Nz + 1 : c->Nz);
+    if (rqv) { copy_in(c, c->rqv, rqv, c->Nz); c->moist = 1; }
     update_state(c);
     store_initial_state(c);
+    /* maybe_prepare_first_time_step! (acoustic_runge_kutta_3.jl:240-256): seed ⟨𝐮⟩ with the velocities, then the first tendencies */
+    memcpy(c->avg_u, c->u, c->n_padded * sizeof(double));
+    memcpy(c->avg_v, c->v, c->n_padded * sizeof(double));
+    memcpy(c->avg_w, c->w, c->n_padded * sizeof(double));
+    compute_moisture_tendency(c);
     return BZ_OK;
 }
 
@@ -803,7 +865,13 @@ int orcc_stage_substep_count_and_size(orcc_ctx* c, double dt, double beta, int32
     if (d_tau) *d_tau = d;
     return BZ_OK;
 }
-int orcc_acoustic_substep_loop(orcc_ctx* c, double dt, double beta) { acoustic_substep_loop(c, dt, beta); update_state(c); return BZ_OK; }
+int orcc_acoustic_substep_loop(orcc_ctx* c, double dt, double beta) {
+    acoustic_substep_loop(c, dt, beta);
+    scalar_rk3_substep(c, beta * dt);
+    update_state(c);
+    compute_moisture_tendency(c);
+    return BZ_OK;
+}
 
 int orcc_get_field(orcc_ctx* c, int f, double* out) {
     const double* src = NULL; int zf = 0;
@@ -836,14 +904,19 @@ int orcc_get_field(orcc_ctx* c, int f, double* out) {
         case BZC_AVG_U: src = c->avg_u; break;
         case BZC_AVG_V: src = c->avg_v; break;
         case BZC_AVG_W: src = c->avg_w; zf = 1; break;
+        case BZC_RHO_QV: src = c->rqv; break;
+        case BZC_QV: src = c->qv; break;
+        case BZC_TOTAL_RHO: src = c->rho_tot; break;
+        case BZC_G_RHO_QV: src = c->Grqv; break;
         default: set_err(c, "unknown field %d", f); return BZ_ERR_INVALID;
     }
     copy_out(c, out, src, zf ? c->Nz + 1 : c->Nz);
     return BZ_OK;
 }
-int orcc_get_state(orcc_ctx* c, double* rho, double* ru, double* rv, double* rw, double* rth) {
+int orcc_get_state(orcc_ctx* c, double* rho, double* ru, double* rv, double* rw, double* rth, double* rqv) {
     double* dst[NPROGC] = {rho, ru, rv, rw, rth};
     for (int f = 0; f < NPROGC; ++f) if (dst[f]) copy_out(c, dst[f], c->U[f], f == C_RW ? c->Nz + 1 : c->Nz);
+    if (rqv) copy_out(c, rqv, c->rqv, c->Nz);
     return BZ_OK;
 }
 int orcc_get_clock(orcc_ctx* c, double* t, int64_t* it) { if (t) *t = c->time; if (it) *it = c->iteration; return BZ_OK; }

@@ -64,7 +64,9 @@ def test_compressible_argument_validation(oracle_arch):
     m = bz.AtmosphereModel(grid, dynamics=bz.CompressibleDynamics())
     assert isinstance(m, bz.CompressibleAtmosphereModel)
     with pytest.raises(ValueError):
-        m.set(qᵗ=0.01)
+        m.set(qˡ=0.01)
+    with pytest.raises(ValueError):
+        m.set(ρ=1.0, ρᵈ=1.0)
     with pytest.raises(bz.BreezeError):
         m.context.set_state(rho=np.zeros((3, 3, 3)))
 

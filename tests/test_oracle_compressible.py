@@ -211,3 +211,56 @@ def test_warm_bubble_rises_and_stays_symmetric():
     th = m.field("θ")
     assert np.abs(th - th[:, :, ::-1]).max() < 1e-9 and np.abs(th - th[:, ::-1, :]).max() < 1e-9
     assert abs(m.field("ρu").sum()) < 1e-9 * np.abs(m.field("ρw")).sum()
+
+
+# ---- moisture (vapour only, microphysics = nothing) --------------------------------------------------------------------------
+def moist_bubble(arch=None, q0=0.01, size=(16, 16, 16), explicit_zero=False):
+    grid = bz.RectilinearGrid(arch or CPUOracle(), size=size, x=(-5e3, 5e3), y=(-5e3, 5e3), z=(0, 10e3))
+    m = bz.AtmosphereModel(grid, dynamics=bz.CompressibleDynamics(bz.SplitExplicitTimeDiscretization(substeps=6),
+                                                                  reference_potential_temperature=300.0))
+    _, rho, _ = m.reference_profiles()
+    kw = dict(ρ=np.broadcast_to(rho[:, None, None], m.context.shape(0)).copy(), u=2.0, v=-1.0,
+              θ=lambda x, y, z: 300.0 + 2.0 * np.cos(np.pi / 2 * np.minimum(1.0, np.sqrt(x ** 2 + y ** 2 + (z - 3000.0) ** 2) / 2000.0)) ** 2)
+    if q0 or explicit_zero:
+        kw["qᵛ"] = lambda x, y, z: q0 * np.exp(-z / 2500.0) * (1 + 0.2 * np.sin(2 * np.pi * x / 10e3)) + 0 * y
+    m.set(**kw)
+    return m
+
+
+def test_set_splits_total_density_and_mixture_eos():
+    """establish_densities! (compressible_time_stepping.jl:89-137): `ρ` given ⇒ ρᵈ = ρ − ρ qᵛ; `ρᵈ` given ⇒ ρ = ρᵈ / (1 − qᵛ);
+    p = ρ Rᵐ T with the mixture gas constant and the TOTAL density (:215-235)."""
+    m = moist_bubble(q0=0.012)
+    rho_t, rho_d, rqv, qv = m.field("ρᵗ"), m.field("ρ"), m.field("ρqᵛ"), m.field("qᵛ")
+    _, rho_ref, _ = m.reference_profiles()
+    assert np.abs(rho_t - rho_ref[:, None, None]).max() < 1e-15 * rho_ref.max() * 4
+    assert np.abs(rho_d + rqv - rho_t).max() < 1e-15 and np.abs(rqv / rho_t - qv).max() < 1e-17
+    Rm = (1 - qv) * RD + qv * (8.314462618 / 0.018015)
+    assert np.abs(m.field("p") - rho_t * Rm * m.field("T")).max() < 1e-9
+    m2 = moist_bubble(q0=0.0)
+    m2.set(ρᵈ=rho_d, qᵛ=qv)
+    assert np.abs(m2.field("ρᵗ") - rho_t).max() < 1e-15 and np.abs(m2.field("ρqᵛ") - rqv).max() < 1e-17
+
+
+def test_zero_moisture_reproduces_the_dry_path_bit_for_bit():
+    """qᵛ ≡ 0 through the moist code path: γᵐRᵐ, the mixture EOS and ρ = ρᵈ + 0 collapse to the dry values exactly
+    (acoustic_substepping.jl:411-413)."""
+    dry, wet = moist_bubble(q0=0.0), moist_bubble(q0=0.0, explicit_zero=True)
+    for m in (dry, wet):
+        for _ in range(3):
+            m.time_step(3.0)
+    for name in ("ρ", "ρu", "ρv", "ρw", "ρθ", "T", "p"):
+        assert np.array_equal(dry.field(name), wet.field(name)), name
+    assert np.abs(wet.field("ρqᵛ")).max() == 0
+
+
+def test_vapour_mass_is_conserved_and_moves_with_the_flow():
+    m = moist_bubble(q0=0.012)
+    M0, D0 = m.field("ρqᵛ").sum(), m.field("ρ").sum()
+    q_start = m.field("ρqᵛ").copy()
+    for _ in range(5):
+        m.time_step(3.0)
+    assert abs(m.field("ρqᵛ").sum() - M0) / M0 < 1e-13
+    assert abs(m.field("ρ").sum() - D0) / D0 < 1e-13
+    assert np.abs(m.field("ρqᵛ") - q_start).max() > 1e-6                     # u = 2 m/s carries the x-modulated vapour
+    assert np.isfinite(m.field("w")).all() and m.field("qᵛ").min() > 0
