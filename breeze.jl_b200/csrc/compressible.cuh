@@ -3,10 +3,12 @@
 //
 // Reference kernels replaced (paths relative to the reference repository):
 //   per stage   _compute_linearization_exner_and_theta!, _compute_linearization_mixture_eos!    acoustic_substepping.jl:372-415
+//               (folded into the update_state kernel that produces the stage-entry state)
 //               compute_x/y/z_momentum_tendency! (SlowTendencyMode), _compute_density_tendency!,
 //               compute_potential_temperature_tendency!                                         acoustic_substep_helpers.jl:55-149
 //               _assemble_slow_vertical_momentum_tendency!                                      acoustic_substepping.jl:724-748
 //               _zero_stage_workspaces!, _initialize_stage_perturbations!, …_with_rewind!        :805-833
+//               (folded into the first substep's two kernels: U′ = U⁰ - U_stage on the fly)
 //   per substep _explicit_horizontal_step! (A), _build_predictors! + _build_vertical_rhs! (B),
 //               solve!(BatchedTridiagonalSolver) (C), _post_solve_recovery! (D),
 //               _thermal_divergence_damping! (E) and 7 halo fills                                :859-1144,1442-1552
@@ -57,7 +59,8 @@ __device__ __forceinline__ void c_temperature_pressure(const CEos& e, double rho
 __global__ void c_update_state(Layout L, CEos e, const double* __restrict__ rho, const double* __restrict__ ru, const double* __restrict__ rv,
                                const double* __restrict__ rw, const double* __restrict__ rth, const double* __restrict__ rqv,
                                double* __restrict__ u, double* __restrict__ v, double* __restrict__ w, double* __restrict__ theta,
-                               double* __restrict__ T, double* __restrict__ p, double* __restrict__ rho_tot, double* __restrict__ qv) {
+                               double* __restrict__ T, double* __restrict__ p, double* __restrict__ rho_tot, double* __restrict__ qv,
+                               double* __restrict__ PiL, double* __restrict__ CL) {
     int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, k = blockIdx.z;
     if (i >= L.nx) return;
     long long n = lidx(L, i, j, k);
@@ -78,26 +81,17 @@ __global__ void c_update_state(Layout L, CEos e, const double* __restrict__ rho,
         double Tn, pn;
         c_temperature_pressure(e, rt, th, q, Tn, pn);
         T[n] = Tn; p[n] = pn;
+        // refresh_linearization_basic_state! of the NEXT stage reads exactly this state (nothing touches it in between), so the
+        // stage-entry cache is written here: Πᴸ = (p/pˢᵗ)^(Rᵈ/cᵖᵈ), Cᴸ = γᵐRᵐᴸ Πᴸ; θᴸ = ρθ/ρᵈ is the θ field itself
+        {
+            const double Pi = pow(pn / e.pst, e.Rd / e.cpd);
+            const double qd = 1.0 - q;
+            const double Rm = qd * e.Rd + q * e.Rv, cpm = qd * e.cpd + q * e.cpv;
+            PiL[n] = Pi;
+            CL[n] = (cpm * Rm / (cpm - Rm)) * Pi;
+        }
     }
     w[n] = (k == 0 || k == L.Nz) ? 0.0 : rw[n] / ((rho[n] + rho[n - L.plane]) / 2);
-}
-
-// refresh_linearization_basic_state!: Πᴸ = (p/pˢᵗ)^κ, θᴸ = ρθ/ρ, Cᴸ = γᵐRᵐᴸ Πᴸ (dry: γᵐRᵐ = cᵖᵈ Rᵈ / (cᵖᵈ - Rᵈ))
-__global__ void c_linearize(Layout L, CEos e, const double* __restrict__ p, const double* __restrict__ rho, const double* __restrict__ rth,
-                            const double* __restrict__ qv, double* __restrict__ PiL, double* __restrict__ thL, double* __restrict__ CL) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, k = blockIdx.z;
-    if (i >= L.nx) return;
-    long long n = lidx(L, i, j, k);
-    double Pi = pow(p[n] / e.pst, e.Rd / e.cpd);
-    double r = rho[n];
-    double rh = (r == 0.0) ? 1.0 : r;
-    const double q = qv ? qv[n] : 0.0;               // _compute_linearization_mixture_eos!: γᵐRᵐ = cᵖᵐ Rᵐ / (cᵖᵐ - Rᵐ)
-    const double qd = 1.0 - q;
-    const double Rm = qd * e.Rd + q * e.Rv, cpm = qd * e.cpd + q * e.cpv;
-    double gR = cpm * Rm / (cpm - Rm);
-    PiL[n] = Pi;
-    thL[n] = rth[n] / rh;
-    CL[n] = gR * Pi;
 }
 
 // ---- slow tendencies (WENO5, 3-D coupling density) ------------------------------------------------------------------
@@ -215,28 +209,8 @@ __global__ void __launch_bounds__(32 * CS_TY, CS_MINB) c_slow_tendencies(Layout 
     }
 }
 
-// ---- stage start: rewind-initialised perturbations, zeroed accumulators ----------------------------------------------
 struct CFields5 { double* f[5]; };      // ρ, ρu, ρv, ρw, ρθ
 struct CConst5 { const double* f[5]; };
-
-__global__ void c_init_perturbations(Layout L, CConst5 U0, CConst5 U, CFields5 P, double* __restrict__ avg_u, double* __restrict__ avg_v,
-                                     double* __restrict__ avg_w) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, k = blockIdx.z;      // k = 0..Nz
-    if (i >= L.nx) return;
-    long long n = lidx(L, i, j, k);
-    if (k < L.Nz) {
-#pragma unroll
-        for (int f = 0; f < 5; ++f) {
-            double v = U0.f[f][n] - U.f[f][n];
-            if (f == 3 && k == 0) v = 0.0;                   // impenetrable bottom wall (halo fill of the z-face field)
-            P.f[f][n] = v;
-        }
-        avg_u[n] = 0.0; avg_v[n] = 0.0;
-    } else {
-        P.f[3][n] = 0.0;                                      // top wall
-    }
-    avg_w[n] = 0.0;
-}
 
 // ---- substep, horizontal part: E (damping of the previous substep) fused with A (explicit step of this substep) ------
 struct CHorizArgs {
@@ -245,15 +219,21 @@ struct CHorizArgs {
     double kx, ky;            // κˣ, κʸ of the damping (0: none)
     double dtau, factor;      // A: Δτ and the perturbation-PGF gate (1 / 0)
     int do_damp, do_step;
+    // first substep of a stage (initialize_stage_perturbations!, acoustic_substepping.jl:765-842): the perturbations are the rewind
+    // U⁰ - U_stage, formed on the fly instead of by a separate pass; null otherwise
+    const double *ru0, *ru, *rv0, *rv, *rth0, *rth;
 };
 
+template <bool FIRST>
 __global__ void c_acoustic_horizontal(Layout L, CHorizArgs A) {
     int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, k = blockIdx.z;
     if (i >= L.nx) return;
     const long long n = lidx(L, i, j, k);
     const long long nxm = cxm(L, n, i), nym = cym(L, n, j);
-    double ru = A.ru_p[n], rv = A.rv_p[n];
-    const double rt = A.rth_p[n];
+    constexpr bool first = FIRST;
+    auto rth_at = [&](long long m) { return first ? A.rth0[m] - A.rth[m] : A.rth_p[m]; };
+    double ru = first ? A.ru0[n] - A.ru[n] : A.ru_p[n], rv = first ? A.rv0[n] - A.rv[n] : A.rv_p[n];
+    const double rt = rth_at(n);
     if (A.do_damp) {          // _thermal_divergence_damping!
         double d0 = rt - A.rth_old[n];
         double th = A.thL[n];
@@ -269,8 +249,8 @@ __global__ void c_acoustic_horizontal(Layout L, CHorizArgs A) {
     if (A.do_step) {          // _explicit_horizontal_step!
         double pn = A.p[n], cp = A.CL[n] * rt;
         double dxp = 0.0, dyp = 0.0;
-        if (!L.flat_x) dxp = (pn - A.p[nxm]) * L.rdx + A.factor * ((cp - A.CL[nxm] * A.rth_p[nxm]) * L.rdx);
-        if (!L.flat_y) dyp = (pn - A.p[nym]) * L.rdy + A.factor * ((cp - A.CL[nym] * A.rth_p[nym]) * L.rdy);
+        if (!L.flat_x) dxp = (pn - A.p[nxm]) * L.rdx + A.factor * ((cp - A.CL[nxm] * rth_at(nxm)) * L.rdx);
+        if (!L.flat_y) dyp = (pn - A.p[nym]) * L.rdy + A.factor * ((cp - A.CL[nym] * rth_at(nym)) * L.rdy);
         ru += A.dtau * (A.Gru[n] - dxp);
         rv += A.dtau * (A.Grv[n] - dyp);
     }
@@ -285,6 +265,9 @@ struct CColumnArgs {
     double *avg_u, *avg_v, *avg_w;
     const double *Grho, *Grth, *Gs_rw, *thL, *CL;
     double dtau, dtm, dts, dm, ds, g, fth, fw;
+    // first substep of a stage: ρ′, (ρθ)′, (ρw)′ are the rewind U⁰ - U_stage formed on the fly and the ⟨ρ𝐮′⟩ accumulators start from
+    // zero (_zero_stage_workspaces!, _initialize_stage_perturbations!, _initialize_perturbation_with_rewind!); null otherwise
+    const double *rho0, *rho, *rth0, *rth, *rw0, *rw;
 };
 
 // Everything one level of the upward march reads from HBM. The column recurrence is latency-bound unless many loads are in
@@ -297,6 +280,7 @@ struct CLevelIn { double rp, tp, ru0, rue, rv0, rvn, th_e, th_w, th_n, th_s, th_
 struct CLevelDown { double w, t_up, th_dn, rs, ts, ru, rv, au, av, aw; };
 
 // one thread per column; blockDim.x columns along x per block, blockIdx.y = j
+template <bool FIRST>
 __global__ void __launch_bounds__(128) c_acoustic_column(Layout L, CColumnArgs A) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
     if (i >= L.nx) return;
@@ -312,18 +296,19 @@ __global__ void __launch_bounds__(128) c_acoustic_column(Layout L, CColumnArgs A
     const double* __restrict__ ru_p = A.ru_p; const double* __restrict__ rv_p = A.rv_p;
     const double* __restrict__ thL = A.thL; const double* __restrict__ CL = A.CL;
     const double* __restrict__ Grho = A.Grho; const double* __restrict__ Grth = A.Grth; const double* __restrict__ Gs_rw = A.Gs_rw;
+    constexpr bool first = FIRST;
 
     auto load_up = [&](int k, CLevelIn& q) {
         const long long n = n0 + (long long)k * SZ;
         const bool top = (k + 1 == Nz);
-        q.rp = A.rho_p[n]; q.tp = A.rth_p[n];
+        q.rp = first ? A.rho0[n] - A.rho[n] : A.rho_p[n]; q.tp = first ? A.rth0[n] - A.rth[n] : A.rth_p[n];
         q.ru0 = __ldg(ru_p + n); q.rv0 = __ldg(rv_p + n);
         q.rue = fx_ ? 0.0 : __ldg(ru_p + n + oxp); q.rvn = fy_ ? 0.0 : __ldg(rv_p + n + oyp);
         q.th_e = fx_ ? 0.0 : __ldg(thL + n + oxp); q.th_w = fx_ ? 0.0 : __ldg(thL + n + oxm);
         q.th_n = fy_ ? 0.0 : __ldg(thL + n + oyp); q.th_s = fy_ ? 0.0 : __ldg(thL + n + oym);
         q.th_up = top ? 0.0 : __ldg(thL + n + SZ);
         q.Grho = __ldg(Grho + n); q.Grth = __ldg(Grth + n); q.C = __ldg(CL + n);
-        q.w_up = top ? 0.0 : A.rw_p[n + SZ];                  // old (ρw)′ at face k+1 (not yet overwritten: row k+1 comes later)
+        q.w_up = top ? 0.0 : (first ? A.rw0[n + SZ] - A.rw[n + SZ] : A.rw_p[n + SZ]);   // old (ρw)′ at face k+1 (row k+1 comes later)
         q.Gs = __ldg(Gs_rw + n);
     };
 
@@ -413,7 +398,7 @@ __global__ void __launch_bounds__(128) c_acoustic_column(Layout L, CColumnArgs A
         q.th_dn = (k > 0) ? __ldg(thL + n - SZ) : 0.0;
         q.rs = A.rho_s[n]; q.ts = A.rth_s[n];
         q.ru = __ldg(ru_p + n); q.rv = __ldg(rv_p + n);
-        q.au = A.avg_u[n]; q.av = A.avg_v[n]; q.aw = A.avg_w[n];
+        q.au = first ? 0.0 : A.avg_u[n]; q.av = first ? 0.0 : A.avg_v[n]; q.aw = first ? 0.0 : A.avg_w[n];
     };
     double w_top = 0.0;                                                  // final (ρw)′ at face k+1 (top wall: 0)
     double th_up = 0.0;                                                  // θᴸ at cell k+1

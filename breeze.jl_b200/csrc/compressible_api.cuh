@@ -133,7 +133,7 @@ static int c_update_state_host(bzc_ctx* c) {
     if ((rc = c_fill_ghosts(c, c->U, 5))) return rc;
     c_update_state<<<c_grid(L, L.Nz + 1), 128, 0, c->stream>>>(L, c->eos, c->U[CF_RHO], c->U[CF_RU], c->U[CF_RV], c->U[CF_RW], c->U[CF_RTH],
                                                                 c->moist ? c->rqv : nullptr, c->u, c->v, c->w, c->theta, c->T, c->p,
-                                                                c->rho_tot, c->qv);
+                                                                c->rho_tot, c->qv, c->PiL, c->CL);
     c->launches++;
     CC_TRY(c, cudaGetLastError());
     double* diag[7] = {c->u, c->v, c->w, c->theta, c->p, c->rho_tot, c->qv};
@@ -152,20 +152,11 @@ static int c_moisture_tendency_host(bzc_ctx* c) {
     return BZ_OK;
 }
 
-static int c_linearize_host(bzc_ctx* c) {
-    const Layout& L = c->L;
-    c_linearize<<<c_grid(L, L.Nz), 128, 0, c->stream>>>(L, c->eos, c->p, c->U[CF_RHO], c->U[CF_RTH], c->moist ? c->qv : nullptr, c->PiL, c->thL, c->CL);
-    c->launches++;
-    CC_TRY(c, cudaGetLastError());
-    return BZ_OK;
-}
-
 // prepare_acoustic_cache! + compute_slow_momentum_tendencies! + compute_slow_scalar_tendencies! +
 // assemble_slow_vertical_momentum_tendency! (acoustic_runge_kutta_3.jl:181-188, acoustic_substepping.jl:1431)
 static int c_stage_tendencies(bzc_ctx* c) {
     const Layout& L = c->L;
-    int rc;
-    { CProfScope ps(c, 1); if ((rc = c_linearize_host(c))) return rc; }
+    // prepare_acoustic_cache!: Πᴸ, θᴸ (= θ), Cᴸ were written by the update_state! that produced this stage-entry state
     CProfScope ps(c, 0);
     CSlowArgs A;
     A.rho = c->U[CF_RHO]; A.ru = c->U[CF_RU]; A.rv = c->U[CF_RV]; A.rw = c->U[CF_RW];
@@ -216,13 +207,12 @@ static int c_substep_loop(bzc_ctx* c, double dt, double beta) {
     int n_tau; double dtau;
     c_stage_substeps(c, beta, dt, &n_tau, &dtau);
     const double om = c->cfg.forward_weight, dtm = om * dtau, dts = (1 - om) * dtau;
-    CConst5 U0c, Uc, Pc; CFields5 Pm, Um;
-    for (int f = 0; f < 5; ++f) { U0c.f[f] = c->U0[f]; Uc.f[f] = c->U[f]; Pc.f[f] = c->P[f]; Pm.f[f] = c->P[f]; Um.f[f] = c->U[f]; }
-    {
-        CProfScope ps(c, 1);
-        c_init_perturbations<<<c_grid(L, L.Nz + 1), 128, 0, c->stream>>>(L, U0c, Uc, Pm, c->avg[0], c->avg[1], c->avg[2]);
-        c->launches++;
-    }
+    CConst5 Pc; CFields5 Um;
+    for (int f = 0; f < 5; ++f) { Pc.f[f] = c->P[f]; Um.f[f] = c->U[f]; }
+    // initialize_stage_perturbations!: no separate pass — the first substep's kernels form U⁰ - U_stage on the fly (compressible.cuh);
+    // the top wall face of (ρw)′ (level Nz, never written by the kernels) is reset because the perturbation fields double as staging
+    // buffers of bzc_set_state / bzc_get_state
+    CC_TRY(c, cudaMemsetAsync(c->P[CF_RW] + (size_t)L.plane * L.Nz, 0, (size_t)L.plane * sizeof(double), c->stream));
     double dm = 0, ds = 0;                                 // implicit_damping_factors (:1003-1011)
     const bool thermal = c->cfg.damping == BZC_THERMAL_DIVERGENCE_DAMPING;
     if (thermal && c->cfg.damp_vertical) { double base = c->cfg.damping_coefficient * (L.dz * L.dz); dm = om * base; ds = (1 - om) * base; }
@@ -250,14 +240,21 @@ static int c_substep_loop(bzc_ctx* c, double dt, double beta) {
         H.do_step = substep <= n_tau;
         const int apply = c->cfg.apply_first_substep_pressure_gradient | (substep != 1) | (n_tau == 1);
         H.factor = apply ? 1.0 : 0.0;
+        const bool first = (substep == 1);
+        H.ru0 = first ? c->U0[CF_RU] : nullptr; H.ru = c->U[CF_RU]; H.rv0 = c->U0[CF_RV]; H.rv = c->U[CF_RV];
+        H.rth0 = c->U0[CF_RTH]; H.rth = c->U[CF_RTH];
+        K.rho0 = first ? c->U0[CF_RHO] : nullptr; K.rho = c->U[CF_RHO]; K.rth0 = c->U0[CF_RTH]; K.rth = c->U[CF_RTH];
+        K.rw0 = c->U0[CF_RW]; K.rw = c->U[CF_RW];
         if (H.do_damp || H.do_step) {
             CProfScope ps(c, 2);
-            c_acoustic_horizontal<<<c_grid(L, L.Nz), 128, 0, c->stream>>>(L, H);
+            if (first) c_acoustic_horizontal<true><<<c_grid(L, L.Nz), 128, 0, c->stream>>>(L, H);
+            else c_acoustic_horizontal<false><<<c_grid(L, L.Nz), 128, 0, c->stream>>>(L, H);
             c->launches++;
         }
         if (substep <= n_tau) {
             CProfScope ps(c, 3);
-            c_acoustic_column<<<dim3((L.nx + cb - 1) / cb, L.Ny), cb, 0, c->stream>>>(L, K);
+            if (first) c_acoustic_column<true><<<dim3((L.nx + cb - 1) / cb, L.Ny), cb, 0, c->stream>>>(L, K);
+            else c_acoustic_column<false><<<dim3((L.nx + cb - 1) / cb, L.Ny), cb, 0, c->stream>>>(L, K);
             c->launches++;
         }
     }
@@ -362,7 +359,7 @@ int bzc_create(const bzc_config* cfg, bzc_ctx** out) {
     c->fsize = (size_t)L.plane * (L.Nz + 1);
 #define TRYCUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { bzc_set_error(nullptr, "%s: %s", #x, cudaGetErrorString(e_)); bzc_destroy(c); return BZ_ERR_CUDA; } } while (0)
     TRYCUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    const int nfields = 5 * 4 + 6 + 3 + 4 + 3 + 1 + 5;     // U, U0, G, P | u v w θ T p | Πᴸ θᴸ Cᴸ | ρ′★ (ρθ)′★ (ρθ)′ˢ⁻ tfac | ⟨u v w⟩ | Gˢρw | moisture
+    const int nfields = 5 * 4 + 6 + 2 + 4 + 3 + 1 + 5;     // U, U0, G, P | u v w θ T p | Πᴸ Cᴸ | ρ′★ (ρθ)′★ (ρθ)′ˢ⁻ tfac | ⟨u v w⟩ | Gˢρw | moisture
     const size_t abytes = (size_t)nfields * c->fsize * sizeof(double);
     TRYCUDA(cudaMalloc((void**)&c->arena, abytes));
     TRYCUDA(cudaMemsetAsync(c->arena, 0, abytes, c->stream));
@@ -375,7 +372,8 @@ int bzc_create(const bzc_config* cfg, bzc_ctx** out) {
         for (int f = 0; f < 5; ++f) c->G[f] = take();
         for (int f = 0; f < 5; ++f) c->P[f] = take();
         c->u = take(); c->v = take(); c->w = take(); c->theta = take(); c->T = take(); c->p = take();
-        c->PiL = take(); c->thL = take(); c->CL = take();
+        c->PiL = take(); c->CL = take();
+        c->thL = c->theta;                              // θᴸ = ρθᴸ/ρᴸ is the diagnosed θ of the stage-entry state
         c->rho_s = take(); c->rth_s = take(); c->rth_old = take(); c->tfac = take();
         for (int a = 0; a < 3; ++a) c->avg[a] = take();
         c->Gs_rw = take();
