@@ -220,7 +220,7 @@ def bench_compressible(args, steps, warmup, with_cpu=True, with_e2e=True):
 # ---------------------------------------------------------------------------------------------------------------------
 # BASELINE config 3: BOMEX shallow-cumulus LES 128 x 128 x 75 (moist, warm-phase saturation adjustment, forcings, flux BCs)
 # ---------------------------------------------------------------------------------------------------------------------
-def bench_bomex(args, steps, warmup):
+def bench_bomex(args, steps, warmup, with_cpu=True):
     import torch
     import breeze_b200 as bz
     size, extent, dt = (128, 128, 75), 12800.0, 1.0
@@ -259,6 +259,8 @@ def bench_bomex(args, steps, warmup):
         "gpu_launches": int(ctx.kernel_launch_count() - n0),
         "checks": {"max_abs_divergence": ctx.max_abs_divergence(), "max_cloud_liquid": float(m.field("qˡ").max())},
     }
+    if not with_cpu:
+        return out
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_lib
     cm = bz.cases.bomex_model(oracle_lib.CPUOracle(), size=(64, 64, 75), extent=6400.0)
@@ -481,6 +483,12 @@ def main():
                 out["config4_compressible"]["workload"] = c4["config"]["workload"]
             except Exception as e:                       # never lose the headline line
                 out["config4_compressible"] = {"error": str(e)}
+            try:
+                c3 = bench_bomex(args, 20, 3, with_cpu=False)
+                out["config3_bomex"] = {k: c3[k] for k in ("value", "unit", "ms_per_step", "breakdown_ms_per_step", "gpu_launches", "checks")}
+                out["config3_bomex"]["workload"] = c3["config"]["workload"]
+            except Exception as e:
+                out["config3_bomex"] = {"error": str(e)}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -126,7 +126,7 @@ __device__ __forceinline__ double c_sym(const double* __restrict__ a, long long 
 #define CS_MINB 4             // 64 registers per thread: 4 CTAs of 256 threads per SM (A/B: 2 → 697 us, 3 → 570 us, 4 → 494 us at 256x256x64)
 #endif
 __global__ void __launch_bounds__(32 * CS_TY, CS_MINB) c_slow_tendencies(Layout L, CSlowArgs A, double g, int k_chunk) {
-    __shared__ double sfy[4][CS_TY][32];
+    __shared__ double sfy[2][4][CS_TY + 1][32];          // double-buffered by level parity: one CTA barrier per level
     const int lane = threadIdx.x, ty = threadIdx.y;
     const int i = blockIdx.x * CS_TX + lane, j = blockIdx.y * CS_TY + ty;
     const int Nz = L.Nz;
@@ -135,7 +135,9 @@ __global__ void __launch_bounds__(32 * CS_TY, CS_MINB) c_slow_tendencies(Layout 
     const bool fx_ = L.flat_x, fy_ = L.flat_y;
     const bool col_ok = (i <= L.nx) && (j < L.Ny) && (fx_ ? i < L.nx : true);       // i = nx: only the low-x-face fluxes are needed
     const bool own = (lane < CS_TX) && (i < L.nx) && (j < L.Ny);
-    const bool last_row = (ty == CS_TY - 1) || (j == L.Ny - 1);
+    const bool yrow_ok = (lane < CS_TX) && (i < L.nx) && (j <= L.Ny);             // j = Ny: the ghost row supplies the high face of row Ny - 1
+    const int j_top = blockIdx.y * CS_TY + CS_TY;                                 // the row of y faces just above a full tile: one flux kind per warp
+    const bool top_ok = (ty < 4) && (j_top <= L.Ny) && (lane < CS_TX) && (i < L.nx);
     const double Ax = L.dy * L.dz, Ay = L.dx * L.dz, Az = L.dx * L.dy, Vinv = 1.0 / (L.dx * L.dy * L.dz);
     // advecting mass fluxes: centred-4 interpolation of the area-weighted momentum; advected velocity: WENO5-Z
     auto symx = [&](const double* a, long long m) { return fx_ ? a[m] : c_sym(a, m, SX, 2); };
@@ -153,7 +155,8 @@ __global__ void __launch_bounds__(32 * CS_TY, CS_MINB) c_slow_tendencies(Layout 
     auto Ty = [&](long long m) { double t = A.v[m]; return ((A.rho[m] + A.rho[m - SY]) / 2) * (Ay * t * c_biased(A.theta, m, SY, 3, t > 0)); };
     auto Tz = [&](long long m, int kk) { if (kk == 0 || kk == Nz) return 0.0; double t = A.w[m];
                                          return ((A.rho[m] + A.rho[m - SZ]) / 2) * (Az * t * c_biased(A.theta, m, SZ, red_face(kk, Nz, 3), t > 0)); };
-    const long long n0 = lidx(L, min(i, L.nx), min(j, L.Ny - 1), 0);
+    const long long n0 = lidx(L, min(i, L.nx), min(j, L.Ny), 0);
+    const long long n0_top = lidx(L, min(i, L.nx), min(j_top, L.Ny), 0);
     // z-type fluxes through the bottom face of the chunk's first level (Fww: at centre kb - 1)
     double zb_u = 0.0, zb_v = 0.0, zb_w = 0.0, zb_t = 0.0;
     if (own && kb > 0) {
@@ -167,18 +170,19 @@ __global__ void __launch_bounds__(32 * CS_TY, CS_MINB) c_slow_tendencies(Layout 
         if (col_ok && !fx_) { xu = Fuu(n); xv = Fuv(n); xw = Fuw(n, k); xt = Tx(n); }
         const double xu_e = __shfl_down_sync(0xffffffffu, xu, 1), xv_e = __shfl_down_sync(0xffffffffu, xv, 1);
         const double xw_e = __shfl_down_sync(0xffffffffu, xw, 1), xt_e = __shfl_down_sync(0xffffffffu, xt, 1);
-        // low-y-face fluxes → shared memory; the last row of the tile evaluates its own high face
+        // low-y-face fluxes → shared memory (this level's buffer); the extra row above a full tile is spread one kind per warp
         double yu = 0.0, yv = 0.0, yw = 0.0, yt = 0.0;
-        if (own && !fy_) { yu = Fvu(n); yv = Fvv(n); yw = Fvw(n, k); yt = Ty(n); }
-        __syncthreads();                                   // the previous level's readers are done
-        sfy[0][ty][lane] = yu; sfy[1][ty][lane] = yv; sfy[2][ty][lane] = yw; sfy[3][ty][lane] = yt;
-        __syncthreads();
-        if (!own) continue;                                // (no barrier below this point inside the level)
-        double yu_n = 0.0, yv_n = 0.0, yw_n = 0.0, yt_n = 0.0;
-        if (!fy_) {
-            if (last_row) { yu_n = Fvu(n + SY); yv_n = Fvv(n + SY); yw_n = Fvw(n + SY, k); yt_n = Ty(n + SY); }
-            else { yu_n = sfy[0][ty + 1][lane]; yv_n = sfy[1][ty + 1][lane]; yw_n = sfy[2][ty + 1][lane]; yt_n = sfy[3][ty + 1][lane]; }
+        if (yrow_ok && !fy_) { yu = Fvu(n); yv = Fvv(n); yw = Fvw(n, k); yt = Ty(n); }
+        auto& S = sfy[k & 1];
+        S[0][ty][lane] = yu; S[1][ty][lane] = yv; S[2][ty][lane] = yw; S[3][ty][lane] = yt;
+        if (top_ok && !fy_) {
+            const long long nt = n0_top + (long long)k * SZ;
+            S[ty][CS_TY][lane] = (ty == 0) ? Fvu(nt) : (ty == 1) ? Fvv(nt) : (ty == 2) ? Fvw(nt, k) : Ty(nt);
         }
+        __syncthreads();                                   // the only barrier of the level (the other buffer is written next level)
+        if (!own) continue;
+        double yu_n = 0.0, yv_n = 0.0, yw_n = 0.0, yt_n = 0.0;
+        if (!fy_) { yu_n = S[0][ty + 1][lane]; yv_n = S[1][ty + 1][lane]; yw_n = S[2][ty + 1][lane]; yt_n = S[3][ty + 1][lane]; }
         // top-z-face fluxes (Fww: at centre k)
         const double zt_u = Fwu(n + SZ, k + 1), zt_v = Fwv(n + SZ, k + 1), zt_w = Fww(n + SZ, k), zt_t = Tz(n + SZ, k + 1);
         // Fuu / Fvv live at centres: this thread's "low" value is centre i-1 (j-1), the neighbour's is centre i (j)
