@@ -14,7 +14,8 @@ module BreezeB200Ext
 using Breeze, Oceananigans
 using Breeze.AtmosphereModels: AtmosphereModel, prognostic_fields
 using Breeze.AnelasticEquations: AnelasticDynamics
-using Breeze.TimeSteppers: SSPRungeKutta3
+using Breeze.TimeSteppers: SSPRungeKutta3, AcousticRungeKutta3
+using Breeze.CompressibleEquations: CompressibleDynamics, ThermalDivergenceDamping
 import Oceananigans.TimeSteppers: time_step!, update_state!
 import Oceananigans.Fields: set!
 
