@@ -156,7 +156,7 @@ def bench_compressible(args, steps, warmup, with_cpu=True, with_e2e=True):
     for _ in range(max(warmup, 3)):
         ctx.time_step(dt)
     ctx.synchronize()
-    ctx.profile_enable(True); ctx.profile_read()
+    # timed region: K steps between two CUDA events on the launching stream, no per-kernel events inside
     n0 = ctx.kernel_launch_count()
     sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
     sampler.start()
@@ -170,6 +170,10 @@ def bench_compressible(args, steps, warmup, with_cpu=True, with_e2e=True):
     ms = e0.elapsed_time(e1) / steps
     clocks = sampler.stop()
     launches = ctx.kernel_launch_count() - n0
+    # second pass with per-kernel-family events (86 event records per step would otherwise sit inside a 6 ms step)
+    ctx.profile_enable(True); ctx.profile_read()
+    for _ in range(steps):
+        ctx.time_step(dt)
     fam_ms, fam_n = ctx.profile_read()
     ctx.profile_enable(False)
     peak, peak_src = measured_peak()
@@ -231,7 +235,6 @@ def bench_bomex(args, steps, warmup, with_cpu=True):
     for _ in range(max(warmup, 3)):
         ctx.time_step(dt)
     ctx.synchronize()
-    ctx.profile_enable(True); ctx.profile_read()
     n0 = ctx.kernel_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
@@ -241,6 +244,10 @@ def bench_bomex(args, steps, warmup, with_cpu=True):
     e1.record(ext_stream)
     ctx.synchronize(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
+    launches = ctx.kernel_launch_count() - n0
+    ctx.profile_enable(True); ctx.profile_read()          # second pass: per-kernel-family events kept out of the timed region
+    for _ in range(steps):
+        ctx.time_step(dt)
     fam_ms, fam_n = ctx.profile_read()
     ctx.profile_enable(False)
     peak, peak_src = measured_peak()
@@ -256,7 +263,7 @@ def bench_bomex(args, steps, warmup, with_cpu=True):
                      "kernel": "stage_kernel<FORCED, saturation adjustment>", "kernel_ms": stage_ms, "peak_source": peak_src,
                      "bytes_per_cell": STAGE_BYTES_PER_CELL},
         "breakdown_ms_per_step": {n: round(fam_ms[f] / steps, 4) for f, n in enumerate(["stage_tendency_rk", "poisson_forward", "thomas", "poisson_inverse", "projection_halo_means"])},
-        "gpu_launches": int(ctx.kernel_launch_count() - n0),
+        "gpu_launches": int(launches),
         "checks": {"max_abs_divergence": ctx.max_abs_divergence(), "max_cloud_liquid": float(m.field("qˡ").max())},
     }
     if not with_cpu:
