@@ -13,6 +13,7 @@ from .model import (B200, DragFluxBoundaryCondition, FluxBoundaryCondition, Forc
 
 from .compressible import (CompressibleAtmosphereModel, CompressibleContext, CompressibleDynamics, ConstantSubstepSize, MonolithicFirstStage,
                            NoDivergenceDamping, ProportionalSubsteps, SplitExplicitTimeDiscretization, ThermalDivergenceDamping,
+                           UpperSponge, LinearRamp, CubicRamp, Sin2Ramp,
                            bzc_config, compressible_library)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -20,6 +20,7 @@ from .abi import BreezeError, bz_config
 BZC_REFERENCE_NONE, BZC_REFERENCE_EXNER = 0, 1
 BZC_NO_DIVERGENCE_DAMPING, BZC_THERMAL_DIVERGENCE_DAMPING = 0, 1
 BZC_PROPORTIONAL_SUBSTEPS, BZC_CONSTANT_SUBSTEP_SIZE, BZC_MONOLITHIC_FIRST_STAGE = 0, 1, 2
+BZC_SPONGE_NONE, BZC_SPONGE_LINEAR_RAMP, BZC_SPONGE_CUBIC_RAMP, BZC_SPONGE_SIN2_RAMP = 0, 1, 2, 3
 
 FIELD_IDS = {
     "ρ": 0, "ρᵈ": 0, "ρu": 1, "ρv": 2, "ρw": 3, "ρθ": 4, "u": 5, "v": 6, "w": 7, "θ": 8, "T": 9, "p": 10,
@@ -39,7 +40,8 @@ class bzc_config(C.Structure):
         ("acoustic_cfl", C.c_double), ("forward_weight", C.c_double), ("damping_coefficient", C.c_double),
         ("damping_length_scale", C.c_double), ("thermodynamic_tendency_factor", C.c_double),
         ("vertical_momentum_tendency_factor", C.c_double),
-        ("reserved", C.c_int32 * 8),
+        ("sponge", C.c_int32), ("reserved1", C.c_int32), ("sponge_damping_rate", C.c_double), ("sponge_depth", C.c_double),
+        ("reserved", C.c_int32 * 2),
     ]
 
 
@@ -235,6 +237,33 @@ class ThermalDivergenceDamping:
 
 
 @dataclass
+class LinearRamp:
+    pass
+
+
+@dataclass
+class CubicRamp:
+    pass
+
+
+@dataclass
+class Sin2Ramp:
+    pass
+
+
+@dataclass
+class UpperSponge:
+    """UpperSponge(damping_rate = 0.2, depth = 5e3, ramp = CubicRamp()) (time_discretizations.jl:440-520)."""
+    damping_rate: float = 0.2
+    depth: float = 5e3
+    ramp: object = _dc_field(default_factory=CubicRamp)
+
+    def __post_init__(self):
+        if not isinstance(self.ramp, (LinearRamp, CubicRamp, Sin2Ramp)):
+            raise ValueError("`ramp` must be an `<:AbstractRamp` (e.g. `CubicRamp()`, `Sin2Ramp()`, `LinearRamp()`)")
+
+
+@dataclass
 class ProportionalSubsteps:
     pass
 
@@ -251,7 +280,7 @@ class MonolithicFirstStage:
 
 @dataclass
 class SplitExplicitTimeDiscretization:
-    """time_discretizations.jl:540-588 (sponge and open boundaries are not on the path)."""
+    """time_discretizations.jl:540-588 (open boundaries are not on the path)."""
     substeps: Optional[int] = None
     acoustic_cfl: float = 0.5
     forward_weight: float = 0.65
@@ -265,8 +294,8 @@ class SplitExplicitTimeDiscretization:
     def __post_init__(self):
         if not isinstance(self.damping, (NoDivergenceDamping, ThermalDivergenceDamping)):
             raise ValueError("`damping` must be an `AcousticDampingStrategy`")
-        if self.sponge is not None:
-            raise NotImplementedError("UpperSponge is not on the path")
+        if self.sponge is not None and not isinstance(self.sponge, UpperSponge):
+            raise ValueError("`sponge` must be `nothing` or an `UpperSponge`")
         if not self.acoustic_cfl > 0:
             raise ValueError(f"`acoustic_cfl` must be positive (got {self.acoustic_cfl})")
 
@@ -332,6 +361,9 @@ class CompressibleAtmosphereModel:
             cfg.damp_vertical = int(td.damping.damp_vertical)
         else:
             cfg.damping = BZC_NO_DIVERGENCE_DAMPING
+        if td.sponge is not None:
+            cfg.sponge = {LinearRamp: 1, CubicRamp: 2, Sin2Ramp: 3}[type(td.sponge.ramp)]
+            cfg.sponge_damping_rate, cfg.sponge_depth = td.sponge.damping_rate, td.sponge.depth
         cfg.substep_distribution = {ProportionalSubsteps: 0, ConstantSubstepSize: 1, MonolithicFirstStage: 2}[type(td.substep_distribution)]
         self.context = CompressibleContext(lib, cfg)
         if callable(θr):

@@ -268,6 +268,7 @@ struct CColumnArgs {
     double *rho_s, *rth_s, *rth_old, *tfac;    // predictors, stashed (ρθ)′, Thomas factors
     double *avg_u, *avg_v, *avg_w;
     const double *Grho, *Grth, *Gs_rw, *thL, *CL;
+    const double* sponge;                      // UpperSponge: rate · ramp at the Nz + 1 z-faces, or nullptr (sponge = nothing)
     double dtau, dtm, dts, dm, ds, g, fth, fw;
     // first substep of a stage: ρ′, (ρθ)′, (ρw)′ are the rewind U⁰ - U_stage formed on the fly and the ⟨ρ𝐮′⟩ accumulators start from
     // zero (_zero_stage_workspaces!, _initialize_stage_perturbations!, _initialize_perturbation_with_rewind!); null otherwise
@@ -359,10 +360,12 @@ __global__ void __launch_bounds__(128) c_acoustic_column(Layout L, CColumnArgs A
             double Gb = A.g * (A.dts * ((rp_0 + rp_m) / 2) + A.dtm * ((rs_0 + rs_m) / 2));
             double d2 = ((w_p - w_0) * rdz - (w_0 - w_m) * rdz) * rdz;
             double Gd = -A.ds * d2;
-            double rhs = w_0 + A.dtau * A.fw * cur.Gs - Gp - Gb - Gd;
+            const double sp = A.sponge ? A.sponge[k] : 0.0;        // level-uniform: one broadcast load
+            double rhs = w_0 + A.dtau * A.fw * cur.Gs - Gp - Gb - Gd - fabs(A.dts) * sp * w_0;
             // get_coefficient(::AcousticTridiagLower / Diagonal / Upper) for row k
             double al = -dtm2 * C_m * thf_m * rdzc * rdzf + dtm2 * A.g * rdzc / 2 - A.dm * rdzc * rdzf;
-            double b = 1.0 + (dtm2 * thf_0 * (C_0 * rdzc + C_m * rdzc) * rdzf + dtm2 * A.g * (rdzc - rdzc) / 2 + A.dm * (rdzc + rdzc) * rdzf);
+            double b = 1.0 + (dtm2 * thf_0 * (C_0 * rdzc + C_m * rdzc) * rdzf + dtm2 * A.g * (rdzc - rdzc) / 2 + A.dm * (rdzc + rdzc) * rdzf
+                              + fabs(A.dtm) * sp);
             cu = -dtm2 * C_0 * thf_p * rdzc * rdzf - dtm2 * A.g * rdzc / 2 - A.dm * rdzc * rdzf;
             t = cu_prev / beta;
             beta = b - al * t;

@@ -14,7 +14,7 @@ struct bzc_ctx {
     CEos eos;
     int has_ref = 0;
     std::vector<double> h_p, h_rho, h_pi, h_theta;     // ExnerReferenceState columns (host, Nz)
-    double* d_cols = nullptr;                          // p_r | rho_r on the device
+    double* d_cols = nullptr;                          // p_r | rho_r | sponge rate·ramp at the Nz + 1 faces, on the device
     size_t fsize = 0;                                  // doubles per field: plane * (Nz + 1)
     double* arena = nullptr;
     double *U[5] = {}, *U0[5] = {}, *G[5] = {}, *P[5] = {};          // prognostics, step-start copy, slow tendencies, perturbations
@@ -231,6 +231,7 @@ static int c_substep_loop(bzc_ctx* c, double dt, double beta) {
     K.rho_s = c->rho_s; K.rth_s = c->rth_s; K.rth_old = c->rth_old; K.tfac = c->tfac;
     K.avg_u = c->avg[0]; K.avg_v = c->avg[1]; K.avg_w = c->avg[2];
     K.Grho = c->G[CF_RHO]; K.Grth = c->G[CF_RTH]; K.Gs_rw = c->Gs_rw; K.thL = c->thL; K.CL = c->CL;
+    K.sponge = c->cfg.sponge != BZC_SPONGE_NONE ? c->d_cols + 2 * L.Nz : nullptr;
     K.dtau = dtau; K.dtm = dtm; K.dts = dts; K.dm = dm; K.ds = ds; K.g = c->eos.g;
     K.fth = c->cfg.thermodynamic_tendency_factor; K.fw = c->cfg.vertical_momentum_tendency_factor;
     const int cb = L.nx >= 128 ? 128 : (L.nx >= 64 ? 64 : 32);
@@ -305,6 +306,7 @@ void bzc_default_config(bzc_config* c) {
     c->substep_distribution = BZC_PROPORTIONAL_SUBSTEPS;
     c->acoustic_cfl = 0.5; c->forward_weight = 0.65; c->damping_coefficient = 0.1; c->damping_length_scale = 0.0;
     c->thermodynamic_tendency_factor = 1.0; c->vertical_momentum_tendency_factor = 1.0;
+    c->sponge = BZC_SPONGE_NONE; c->sponge_damping_rate = 0.2; c->sponge_depth = 5e3;
 }
 
 const char* bzc_last_error(const bzc_ctx* c) { return c ? c->err : gc_err; }
@@ -332,6 +334,8 @@ int bzc_create(const bzc_config* cfg, bzc_ctx** out) {
     if ((fx && b->Nx != 1) || (fy && b->Ny != 1)) FAIL(BZ_ERR_INVALID, "a Flat dimension must have size 1");
     if ((!fx && b->Nx < 4) || (!fy && b->Ny < 4) || b->Nz < 4) FAIL(BZ_ERR_INVALID, "at least 4 cells per non-Flat dimension");
     if (!(cfg->acoustic_cfl > 0)) FAIL(BZ_ERR_INVALID, "`acoustic_cfl` must be positive");
+    if (cfg->sponge < BZC_SPONGE_NONE || cfg->sponge > BZC_SPONGE_SIN2_RAMP) FAIL(BZ_ERR_INVALID, "unknown sponge ramp %d", cfg->sponge);
+    if (cfg->sponge != BZC_SPONGE_NONE && !(cfg->sponge_depth > 0)) FAIL(BZ_ERR_INVALID, "`sponge_depth` must be positive");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) FAIL(BZ_ERR_CUDA, "no CUDA device: libbreeze_b200 has no CPU fallback");
     if (b->device < 0 || b->device >= ndev) FAIL(BZ_ERR_INVALID, "device ordinal %d out of range (%d devices)", b->device, ndev);
@@ -380,7 +384,21 @@ int bzc_create(const bzc_config* cfg, bzc_ctx** out) {
         c->rqv = take(); c->rqv0 = take(); c->Grqv = take(); c->qv = take(); c->rho_tot = take();
     }
     TRYCUDA(cudaMalloc((void**)&c->dense, (size_t)L.nx * L.Ny * (L.Nz + 1) * sizeof(double)));
-    TRYCUDA(cudaMalloc((void**)&c->d_cols, (size_t)2 * L.Nz * sizeof(double)));
+    TRYCUDA(cudaMalloc((void**)&c->d_cols, (size_t)(3 * L.Nz + 1) * sizeof(double)));
+    if (cfg->sponge != BZC_SPONGE_NONE) {               // sponge_term_diag / sponge_rhs profile (acoustic_substepping.jl:591-603)
+        std::vector<double> sp(L.Nz + 1);
+        const double Lz = b->z1 - b->z0;
+        for (int k = 0; k <= L.Nz; ++k) {
+            double sf = ((b->z0 + k * L.dz) - (Lz - cfg->sponge_depth)) / cfg->sponge_depth;
+            sf = sf < 0 ? 0 : (sf > 1 ? 1 : sf);
+            double ramp = sf;
+            if (cfg->sponge == BZC_SPONGE_CUBIC_RAMP) ramp = sf * sf * (3 - 2 * sf);
+            else if (cfg->sponge == BZC_SPONGE_SIN2_RAMP) { double sn = sin(M_PI / 2 * sf); ramp = sn * sn; }
+            sp[k] = cfg->sponge_damping_rate * ramp;
+        }
+        TRYCUDA(cudaMemcpyAsync(c->d_cols + 2 * L.Nz, sp.data(), sp.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        TRYCUDA(cudaStreamSynchronize(c->stream));
+    }
     c->bytes += (int64_t)((size_t)L.nx * L.Ny * (L.Nz + 1) + 2 * L.Nz) * 8;
     c->h_p.assign(L.Nz, b->surface_pressure); c->h_rho.assign(L.Nz, 0.0); c->h_pi.assign(L.Nz, 0.0);
     c->h_theta.assign(L.Nz, b->potential_temperature);

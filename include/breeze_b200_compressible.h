@@ -7,7 +7,7 @@
  *   acoustic_rk3_substep_loop!                                  src/CompressibleEquations/acoustic_substepping.jl:1404-1590
  * for dry or vapour-laden air (microphysics = nothing: the moisture density ρqᵛ is transported by the acoustic-mean velocities, enters
  * the mixture EOS, the linearized PGF coefficient γᵐRᵐ and — through the total density — the buoyancy), WENO(order=5),
- * LiquidIcePotentialTemperature formulation, no closure, no sponge, (Periodic | Flat, Periodic | Flat, Bounded) uniform grids.
+ * LiquidIcePotentialTemperature formulation, no closure, optional UpperSponge, (Periodic | Flat, Periodic | Flat, Bounded) uniform grids.
  *
  * Same conventions as breeze_b200.h (plain pointers, HOST arrays interior-only with x fastest, 0 / negative return
  * codes, bzc_last_error for text). The CPU oracle exports the same ABI with prefix orcc_.
@@ -25,6 +25,8 @@ extern "C" {
 enum { BZC_REFERENCE_NONE = 0, BZC_REFERENCE_EXNER = 1 };
 /* damping strategy (src/CompressibleEquations/time_discretizations.jl:134-247) */
 enum { BZC_NO_DIVERGENCE_DAMPING = 0, BZC_THERMAL_DIVERGENCE_DAMPING = 1 };
+/* UpperSponge ramp shapes (time_discretizations.jl:397-437): ramp(z, Lz, depth) with s = clamp((z - (Lz - depth))/depth, 0, 1) */
+enum { BZC_SPONGE_NONE = 0, BZC_SPONGE_LINEAR_RAMP = 1, BZC_SPONGE_CUBIC_RAMP = 2, BZC_SPONGE_SIN2_RAMP = 3 };
 /* substep distribution (acoustic_substepping.jl:476-508) */
 enum { BZC_PROPORTIONAL_SUBSTEPS = 0, BZC_CONSTANT_SUBSTEP_SIZE = 1, BZC_MONOLITHIC_FIRST_STAGE = 2 };
 
@@ -60,7 +62,13 @@ typedef struct bzc_config {
     double  damping_length_scale;                   /* 0 = `nothing`: mesh-local min(Δx, Δy) */
     double  thermodynamic_tendency_factor;          /* 1 */
     double  vertical_momentum_tendency_factor;      /* 1 */
-    int32_t reserved[8];
+    /* UpperSponge(damping_rate, depth, ramp) (time_discretizations.jl:440-520): implicit Rayleigh damping of (ρw)′ below the lid, folded
+     * into the column tridiagonal (acoustic_substepping.jl:584-603): |δτᵐ⁺| rate ramp(z) on the diagonal, |δτˢ⁻| rate ramp(z) (ρw)′ on the rhs */
+    int32_t sponge;                                 /* BZC_SPONGE_*; default NONE (`sponge = nothing`) */
+    int32_t reserved1;
+    double  sponge_damping_rate;                    /* 0.2 (1/s) */
+    double  sponge_depth;                           /* 5e3 (m)   */
+    int32_t reserved[2];
 } bzc_config;
 
 typedef struct bzc_ctx bzc_ctx;

@@ -96,6 +96,7 @@ void orcc_default_config(bzc_config* c) {
     c->damping_length_scale = 0.0;
     c->thermodynamic_tendency_factor = 1.0;
     c->vertical_momentum_tendency_factor = 1.0;
+    c->sponge = BZC_SPONGE_NONE; c->sponge_damping_rate = 0.2; c->sponge_depth = 5e3;
 }
 
 static double* new_field(orcc_ctx* c) { return (double*)calloc(c->n_padded, sizeof(double)); }
@@ -467,6 +468,27 @@ static inline double interp_bz(const orcc_ctx* c, const double* f, size_t n, int
     return (fp + fm) / 2;
 }
 
+/* UpperSponge: rate · ramp(z_face, Lz, depth) at z-face k (acoustic_substepping.jl:591-603, time_discretizations.jl:397-437);
+ * the ramp receives grid.Lz as the sponge top */
+static inline double sponge_rate_at_face(const orcc_ctx* c, int k) {
+    if (c->cfg.sponge == BZC_SPONGE_NONE) return 0.0;
+    double z = c->cfg.base.z0 + k * c->dz, Lz = c->cfg.base.z1 - c->cfg.base.z0, depth = c->cfg.sponge_depth;
+    double sfrac = (z - (Lz - depth)) / depth;
+    sfrac = sfrac < 0 ? 0 : (sfrac > 1 ? 1 : sfrac);
+    double ramp = sfrac;
+    if (c->cfg.sponge == BZC_SPONGE_CUBIC_RAMP) ramp = sfrac * sfrac * (3 - 2 * sfrac);
+    else if (c->cfg.sponge == BZC_SPONGE_SIN2_RAMP) { double sn = sin(M_PI / 2 * sfrac); ramp = sn * sn; }
+    return c->cfg.sponge_damping_rate * ramp;
+}
+double orcc_test_sponge_term_diag(const bzc_config* cfg, int k_ref, double dtm) {
+    orcc_ctx c; memset(&c, 0, sizeof(c)); c.cfg = *cfg; c.dz = (cfg->base.z1 - cfg->base.z0) / cfg->base.Nz;
+    return fabs(dtm) * sponge_rate_at_face(&c, k_ref - 1);
+}
+double orcc_test_sponge_rhs(const bzc_config* cfg, int k_ref, double dts, double rho_w_old) {
+    orcc_ctx c; memset(&c, 0, sizeof(c)); c.cfg = *cfg; c.dz = (cfg->base.z1 - cfg->base.z0) / cfg->base.Nz;
+    return fabs(dts) * sponge_rate_at_face(&c, k_ref - 1) * rho_w_old;
+}
+
 /* get_coefficient for the three diagonal tags (:605-659); row = z-face k (0-based). */
 static inline double tri_lower_for_row(const orcc_ctx* c, size_t n, int k, double dtm, double g, double dm) {
     /* reference: get_coefficient(k_ref - 1, ::AcousticTridiagLower) with kᶠ = k_ref */
@@ -485,7 +507,7 @@ static inline double tri_diag(const orcc_ctx* c, size_t n, int k, double dtm, do
     double pgf = (dtm * dtm) * th * (Cp * rdzp + Cm * rdzm) * rdzf;
     double buoy = (dtm * dtm) * g * (rdzp - rdzm) / 2;
     double damp = dm * (rdzp + rdzm) * rdzf;
-    double sponge = 0.0;
+    double sponge = fabs(dtm) * sponge_rate_at_face(c, k);
     return 1 + (pgf + buoy + damp + sponge) * (k > 0);
 }
 static inline double tri_upper(const orcc_ctx* c, size_t n, int k, double dtm, double g, double dm) {
@@ -555,7 +577,7 @@ static void build_vertical_rhs(orcc_ctx* c, double dtau, double dtm, double dts,
         double Gb = g * (dts * r_o + dtm * r_s);
         double d2 = ((c->rw_p[n + SZ] - c->rw_p[n]) * rdz - (c->rw_p[n] - c->rw_p[n - SZ]) * rdz) * rdz;
         double Gd = -ds * d2;
-        double Gsp = 0.0;
+        double Gsp = fabs(dts) * sponge_rate_at_face(c, k) * c->rw_p[n];
         double rhs = c->rw_p[n] + dtau * fw * c->Gs_rw[n] - Gp - Gb - Gd - Gsp;
         c->rhs[n] = ((k != 0) & (k != Nz)) ? rhs : 0.0;
     }

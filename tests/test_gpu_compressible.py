@@ -111,7 +111,8 @@ def test_slow_tendencies_match_oracle(oracle_arch, size, flat_y, reference):
 
 @pytest.mark.parametrize("size,flat_y", [((32, 16, 24), False), ((64, 40), True)])
 @pytest.mark.parametrize("td", [dict(substeps=6), dict(substeps=4, forward_weight=0.55, damping="none"),
-                                dict(substeps=6, damping="vertical"), dict(substeps=3, apply_first_substep_pressure_gradient=True)])
+                                dict(substeps=6, damping="vertical"), dict(substeps=3, apply_first_substep_pressure_gradient=True),
+                                dict(substeps=6, sponge="cubic")])
 @pytest.mark.parametrize("beta", [1.0 / 3.0, 1.0])
 def test_acoustic_substep_loop_matches_oracle(oracle_arch, size, flat_y, td, beta):
     import breeze_b200 as bz
@@ -122,6 +123,8 @@ def test_acoustic_substep_loop_matches_oracle(oracle_arch, size, flat_y, td, bet
         td["damping"] = bz.NoDivergenceDamping()
     elif d == "vertical":
         td["damping"] = bz.ThermalDivergenceDamping(coefficient=0.12, damp_vertical=True)
+    if td.get("sponge") == "cubic":
+        td["sponge"] = bz.UpperSponge(damping_rate=0.25, depth=4000.0)
     gpu, cpu = _pair(oracle_arch, size, flat_y, seed=2, noise=0.2, **td)
     oracle_lib.set_beta_form(1)
     try:

@@ -264,3 +264,55 @@ def test_vapour_mass_is_conserved_and_moves_with_the_flow():
     assert abs(m.field("ρ").sum() - D0) / D0 < 1e-13
     assert np.abs(m.field("ρqᵛ") - q_start).max() > 1e-6                     # u = 2 m/s carries the x-modulated vapour
     assert np.isfinite(m.field("w")).all() and m.field("qᵛ").min() > 0
+
+
+# ---- UpperSponge --------------------------------------------------------------------------------------------------------------
+def test_upper_sponge_coefficients():
+    """test/acoustic_substepping_components.jl:476-499: LinearRamp, rate 0.2, depth 2000 on z ∈ [0, 8000], Nz = 8."""
+    from breeze_b200 import compressible
+    lib = load_oracle_library()
+    cfg = compressible.bzc_config()
+    lib.dll.orcc_default_config(C.byref(cfg))
+    cfg.base.Nx = cfg.base.Ny = cfg.base.Nz = 8
+    cfg.base.z0, cfg.base.z1 = 0.0, 8000.0
+    cfg.sponge, cfg.sponge_damping_rate, cfg.sponge_depth = compressible.BZC_SPONGE_LINEAR_RAMP, 0.2, 2000.0
+    diag, rhs = lib.dll.orcc_test_sponge_term_diag, lib.dll.orcc_test_sponge_rhs
+    diag.restype = rhs.restype = C.c_double
+    diag.argtypes = [C.POINTER(compressible.bzc_config), C.c_int, C.c_double]
+    rhs.argtypes = [C.POINTER(compressible.bzc_config), C.c_int, C.c_double, C.c_double]
+    dtm, dts = 3.0, 2.0
+    assert diag(C.byref(cfg), 1, dtm) == 0
+    assert diag(C.byref(cfg), 9, dtm) == pytest.approx(dtm * 0.2)
+    assert rhs(C.byref(cfg), 9, dts, 4.0) == pytest.approx(dts * 0.2 * 4.0)
+    assert diag(C.byref(cfg), 8, dtm) == pytest.approx(dtm * 0.2 * 0.5)          # half-way up the ramp
+    cfg.sponge = compressible.BZC_SPONGE_NONE
+    assert diag(C.byref(cfg), 9, dtm) == 0 and rhs(C.byref(cfg), 9, dts, 4.0) == 0
+    cfg.sponge = compressible.BZC_SPONGE_CUBIC_RAMP
+    assert diag(C.byref(cfg), 8, dtm) == pytest.approx(dtm * 0.2 * (0.25 * (3 - 1.0)))
+    cfg.sponge = compressible.BZC_SPONGE_SIN2_RAMP
+    assert diag(C.byref(cfg), 8, dtm) == pytest.approx(dtm * 0.2 * np.sin(np.pi / 4) ** 2)
+
+
+def test_upper_sponge_damps_the_vertical_momentum_perturbation_below_the_lid():
+    """The sponge is a Rayleigh term on the acoustic PERTURBATION (ρw)′ = ρw − ρwᴸ (acoustic_substepping.jl:584-590): within the layer it
+    shrinks the change of ρw over a step; below the layer the solution is untouched to first order."""
+    def run(sponge):
+        grid = bz.RectilinearGrid(CPUOracle(), size=(16, 16, 16), x=(-5e3, 5e3), y=(-5e3, 5e3), z=(0, 10e3))
+        td = bz.SplitExplicitTimeDiscretization(substeps=6, sponge=sponge)
+        m = bz.AtmosphereModel(grid, dynamics=bz.CompressibleDynamics(td, reference_potential_temperature=300.0))
+        _, rho, _ = m.reference_profiles()
+        m.set(ρ=np.broadcast_to(rho[:, None, None], m.context.shape(0)).copy(), θ=300.0,
+              w=lambda x, y, z: 0.5 * np.sin(np.pi * z / 10e3) * np.cos(2 * np.pi * x / 10e3) + 0 * y)
+        start = m.field("ρw").copy()
+        m.time_step(3.0)
+        return m.field("ρw") - start
+    free, damped = run(None), run(bz.UpperSponge(damping_rate=0.3, depth=4000.0, ramp=bz.Sin2Ramp()))
+    low = slice(2, 6)
+    for k in (12, 13, 14, 15):                                    # the ramp grows towards the lid: 3 … 12 % less change per step
+        assert np.abs(damped[k]).max() < 0.98 * np.abs(free[k]).max(), k
+    assert np.abs(damped[15]).max() < 0.92 * np.abs(free[15]).max()
+    assert np.abs(damped[low] - free[low]).max() < 0.05 * np.abs(free[low]).max()
+    with pytest.raises(ValueError):
+        bz.SplitExplicitTimeDiscretization(sponge="strong")
+    with pytest.raises(ValueError):
+        bz.UpperSponge(ramp="cubic")
