@@ -16,6 +16,7 @@ from breeze_b200 import abi
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+CASE = sys.argv[3] if len(sys.argv) > 3 else "bubble"      # "bomex": forcings, flux BCs, saturation adjustment, horizontal means across slabs
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
@@ -29,6 +30,11 @@ P2P = os.environ.get("BZ_P2P", "1") == "1"
 
 
 def build(arch):
+    if CASE == "bomex":
+        m = bz.cases.bomex_model(arch, size=(N, N // 2, 24), extent=100.0 * N, seed=11)
+        if P2P:                            # set! ran through the NCCL exchange; the steps below use peer loads
+            bz.enable_peer_memory(m)
+        return m
     grid = bz.RectilinearGrid(arch, size=(N, N // 2, N // 2), x=(-10e3, 10e3), y=(-5e3, 5e3), z=(0, 10e3))
     m = bz.AtmosphereModel(grid, dynamics=bz.AnelasticDynamics(bz.ReferenceState(grid, potential_temperature=300)))
     if P2P:

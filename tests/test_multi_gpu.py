@@ -24,3 +24,14 @@ def test_slabs_match_single_gpu(world, p2p):
            "--master-port", str(29600 + 10 * world + p2p), os.path.join(ROOT, "scripts", "multi_gpu_check.py"), "64", "3"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, BZ_P2P=str(p2p)))
     assert "MULTI_GPU_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("p2p", [1, 0])
+def test_bomex_slabs_match_single_gpu(p2p):
+    """BOMEX-type physics on 2 slabs: the subsidence forcing's horizontal means are all-reduced across ranks every stage."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(29650 + p2p), os.path.join(ROOT, "scripts", "multi_gpu_check.py"), "64", "3", "bomex"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, BZ_P2P=str(p2p)))
+    assert "MULTI_GPU_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
