@@ -138,7 +138,7 @@ static int make_tensor_maps(bz_ctx* c, int box_w, int box_h) {
 static int upload_columns(bz_ctx* c) {
     const int Nz = c->L.Nz;
     const bz_config& g = c->cfg;
-    std::vector<double> h((size_t)8 * (Nz + 1), 0.0);
+    std::vector<double> h((size_t)8 * (Nz + 1) + (size_t)LEV_REC * Nz, 0.0);
     double* rho = &h[0]; double* rho_inv = rho + (Nz + 1); double* rho_f = rho_inv + (Nz + 1); double* rho_f_inv = rho_f + (Nz + 1);
     double* p = rho_f_inv + (Nz + 1); double* T = p + (Nz + 1); double* ex = T + (Nz + 1); double* lg = ex + (Nz + 1);
     for (int k = 0; k < Nz; ++k) {
@@ -150,11 +150,26 @@ static int upload_columns(bz_ctx* c) {
     for (int k = 1; k < Nz; ++k) rho_f[k] = 0.5 * (rho[k] + rho[k - 1]);
     rho_f[0] = rho[0]; rho_f[Nz] = rho[Nz - 1];          // wall faces: only ever multiply w = 0
     for (int k = 0; k <= Nz; ++k) rho_f_inv[k] = 1.0 / rho_f[k];
+    double* lev = lg + (Nz + 1);                           // per-level records of the stage kernel (common.cuh: LEV_REC)
+    for (int k = 0; k < Nz; ++k) {
+        double* r = lev + (size_t)LEV_REC * k;
+        for (int m = 0; m < 4; ++m) {
+            int kc = k - 2 + m, kf = k - 1 + m;
+            r[m] = (kc >= 0 && kc < Nz) ? rho[kc] : 0.0;
+            r[4 + m] = (kf >= 0 && kf <= Nz) ? rho_f[kf] : 0.0;
+        }
+        r[8] = ex[k]; r[9] = T[k];
+        r[10] = (k + 3 < Nz) ? rho_inv[k + 3] : 0.0; r[11] = (k + 3 < Nz) ? rho_f_inv[k + 3] : 0.0;
+        int kn = k + 1 < Nz ? k + 1 : Nz - 1;
+        r[12] = ex[kn]; r[13] = T[kn];
+        r[14] = (k + 4 < Nz) ? rho_inv[k + 4] : 0.0; r[15] = (k + 4 < Nz) ? rho_f_inv[k + 4] : 0.0;
+    }
     CUDA_TRY(c, cudaMemcpyAsync(c->col_store, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     double* d = c->col_store;
     c->col.rho = d; c->col.rho_inv = d + (Nz + 1); c->col.rho_f = d + 2 * (Nz + 1); c->col.rho_f_inv = d + 3 * (Nz + 1);
     c->col.p = d + 4 * (Nz + 1); c->col.T = d + 5 * (Nz + 1); c->col.exner_dry = d + 6 * (Nz + 1); c->col.log_p_pst = d + 7 * (Nz + 1);
+    c->col.lev = d + 8 * (Nz + 1);
     return BZ_OK;
 }
 
@@ -596,7 +611,7 @@ int bz_create(const bz_config* cfg, bz_ctx** out) {
     }
     TRY(dev_alloc(c, &c->dense, (size_t)L.nx * L.Ny * (L.Nz + 1)));
     TRY(dev_alloc(c, &c->scalar, 8));
-    TRY(dev_alloc(c, &c->col_store, (size_t)8 * (L.Nz + 1)));
+    TRY(dev_alloc(c, &c->col_store, (size_t)8 * (L.Nz + 1) + (size_t)LEV_REC * L.Nz));
     default_reference_state(c);
     TRY(upload_columns(c));
     TRY(setup_poisson(c));

@@ -45,7 +45,15 @@ struct Columns {
     const double* T;         // Tᵣ
     const double* exner_dry; // (pᵣ/pˢᵗ)^(Rᵈ/cᵖᵈ)
     const double* log_p_pst; // log(pᵣ/pˢᵗ)
+    const double* lev;       // per-level records of the stage kernel: LEV_REC doubles for each k (layout: upload_columns in api.cu)
 };
+
+// One record per level k with every column value the stage kernel's level k consumes, so that a level is one 128-byte
+// relay through shared memory instead of fourteen bounds-checked loads rolled through registers:
+//   0-3  ρᵣ at centres k-2 .. k+1        4-7  ℑzρᵣ at z-faces k-1 .. k+2      (0 outside the column)
+//   8,9  Exner (dry), Tᵣ at k            10,11  1/ρᵣ, 1/ℑzρᵣ of plane k+3 (0 outside)      12,13  Exner, Tᵣ at min(k+1, Nz-1)
+//   14,15  1/ρᵣ, 1/ℑzρᵣ of plane k+4 (the plane staged at level k under BZ_SPLIT_BARRIER)
+#define LEV_REC 16
 
 struct Thermo {
     double Rd, Rv, cpd, cpv, cl, ci, g, Ll, Li, pst;

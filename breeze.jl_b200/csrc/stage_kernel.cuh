@@ -139,6 +139,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "WAIT_DONE:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y, int z) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -156,7 +159,9 @@ struct StageShared {
     double ring[RING][NPROG][PLANE];
     double fx[2][NPROG][TY][TX + 1];                  // double-buffered by level parity: one CTA barrier per level
     double fy[2][NPROG][HAS_Y ? TY + 1 : 1][TX];
+    alignas(16) double lev[4][LEV_REC];               // per-level column records (common.cuh), relayed one level ahead
     uint64_t bar[RING];
+    uint64_t lbar;                                    // BZ_SPLIT_BARRIER: the level barrier as an mbarrier (arrive early, wait late)
 };
 
 // Biased reconstruction from six consecutive values with the buffer R known at compile time on the fast path.
@@ -232,12 +237,42 @@ __global__ void __launch_bounds__(2 * TX * TY, 1) stage_kernel(const __grid_cons
             tma_load_3d(S.ring[kk & (RING - 1)][f], &P.tmap[f], bar, i0 - xs, HAS_Y ? (j0 + L.HY - 3) : 0, kk);
     };
     auto convert_plane = [&](int kk, double sc_c, double sc_f) {   // raw prognostics → velocities / specific values, in place
-        double* dst = S.ring[kk & (RING - 1)][0];                      // the five (padded) field slices of a slot are contiguous
-        for (int e = tid; e < NPROG * PL; e += NT) dst[e] *= (e >= 2 * PL && e < 3 * PL) ? sc_f : sc_c;
+        // the five (padded, 128-byte aligned) field slices of a slot are contiguous: 16-byte accesses, a fixed trip count, and the
+        // ρw slice (pairs PL .. 3 PL / 2) picked out by comparisons that fold away in the iterations that cannot contain it
+        double2* dst = reinterpret_cast<double2*>(S.ring[kk & (RING - 1)][0]);
+        constexpr int NPAIR = NPROG * PL / 2;
+#pragma unroll
+        for (int it = 0; it < (NPAIR + NT - 1) / NT; ++it) {
+            const int p = tid + it * NT;
+            if ((it + 1) * NT <= NPAIR || p < NPAIR) {
+                const bool maybe_f = (it * NT < 3 * PL / 2) && ((it + 1) * NT > PL);
+                const double sc = (maybe_f && p >= PL && p < 3 * PL / 2) ? sc_f : sc_c;
+                double2 v = dst[p];
+                v.x *= sc; v.y *= sc;
+                dst[p] = v;
+            }
+        }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes before a later TMA refill of the slot
     };
 
     uint32_t phase_bits = 0;                     // one parity bit per ring slot
+#ifdef BZ_SPLIT_BARRIER
+    // Split level barrier: a thread ARRIVES once its x/y fluxes of level k are in shared memory and its share of plane k+4 is
+    // converted, evaluates the z fluxes (which read planes that were complete one level earlier), and only then WAITS for the
+    // other warps before it reads their x/y fluxes — the arrival skew between warps is hidden behind the z-flux work.
+    // Planes therefore run one level further ahead than with the plain barrier: used k-2 .. k+3, converted k+4, in flight k+5.
+    constexpr int AHEAD = 4;
+    uint32_t lpar = 0;
+    {
+        if (tid == 0) {
+            for (int s = 0; s < RING; ++s) mbar_init(&S.bar[s], 1);
+            mbar_init(&S.lbar, NT);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    }
+#else
+    constexpr int AHEAD = 3;
     if (P.use_tma) {
         if (tid == 0) {
             for (int s = 0; s < RING; ++s) mbar_init(&S.bar[s], 1);
@@ -245,6 +280,7 @@ __global__ void __launch_bounds__(2 * TX * TY, 1) stage_kernel(const __grid_cons
         }
         __syncthreads();
     }
+#endif
     auto wait_plane_tma = [&](int kk) {
         int s = kk & (RING - 1);
         mbar_wait(&S.bar[s], (phase_bits >> s) & 1u);
@@ -252,14 +288,15 @@ __global__ void __launch_bounds__(2 * TX * TY, 1) stage_kernel(const __grid_cons
     };
 
     const int kstart = (kb > 0) ? kb - 1 : 0;    // a chunk that starts above the ground first rebuilds the carried z fluxes
-    // prologue: planes kstart-2 .. kstart+2 (the loop brings in kstart+3)
+    // prologue: planes kstart-2 .. kstart+AHEAD-1 (the loop brings in kstart+AHEAD; every plane issued is also waited for)
     if (P.use_tma) {
-        if (tid == 0) for (int kk = kstart - 2; kk <= kstart + 3; ++kk) issue_plane_tma(kk);
-        for (int kk = kstart - 2; kk <= kstart + 2; ++kk) { wait_plane_tma(kk); convert_plane(kk, scale_of(0, kk), scale_of(2, kk)); }
+        if (tid == 0) for (int kk = kstart - 2; kk <= kstart + AHEAD; ++kk) if (kk < kstart + AHEAD || AHEAD == 3 || kstart + 1 < ke) issue_plane_tma(kk);
+        for (int kk = kstart - 2; kk < kstart + AHEAD; ++kk) { wait_plane_tma(kk); convert_plane(kk, scale_of(0, kk), scale_of(2, kk)); }
     } else {
-        for (int kk = kstart - 2; kk <= kstart + 2; ++kk) load_plane_direct(kk);
+        for (int kk = kstart - 2; kk < kstart + AHEAD; ++kk) load_plane_direct(kk);
     }
-    __syncthreads();                             // prologue planes are converted and visible
+    if (tid < LEV_REC) S.lev[kstart & 3][tid] = P.col.lev[(long long)kstart * LEV_REC + tid];
+    __syncthreads();                             // prologue planes are converted and visible, and the first level's record
 
     // carried from the level below: z-type fluxes through the bottom face (role 0: ρu, ρv; role 1: ρw, θ, q), buoyancy below
     double zb0 = 0.0, zb1 = 0.0, zb2 = 0.0, b_below = 0.0;
@@ -270,28 +307,26 @@ __global__ void __launch_bounds__(2 * TX * TY, 1) stage_kernel(const __grid_cons
     const bool in_x = i < L.nx;
     const int f_first = role == 0 ? 0 : 2, f_count = role == 0 ? 2 : 3;   // fields this thread assembles and stores
 
-    // reference density at centres k-2..k+1 and z-faces k-1..k+2, rolled along the march (0 outside the column: those
-    // entries only ever multiply zero planes or are ignored by the reduced-order interpolation)
-    auto rho_c = [&](int kk) -> double { return (kk >= 0 && kk < Nz) ? P.col.rho[kk] : 0.0; };
-    auto rho_fc = [&](int kk) -> double { return (kk >= 0 && kk <= Nz) ? P.col.rho_f[kk] : 0.0; };
-    double r_m2 = rho_c(kstart - 3), r_m1 = rho_c(kstart - 2), r_0 = rho_c(kstart - 1), r_p1 = rho_c(kstart);
-    double f_m1 = rho_fc(kstart - 2), f_0 = rho_fc(kstart - 1), f_p1 = rho_fc(kstart), f_p2 = rho_fc(kstart + 1);
-    // per-level column values are fetched one level ahead of their use so that their (L2) latency never stalls a level
-    double nx_rc = rho_c(kstart + 1), nx_rf = rho_fc(kstart + 2);                       // become r_p1 / f_p2 of level kstart
-    double nx_sc = scale_of(0, kstart + 3), nx_sf = scale_of(2, kstart + 3);            // conversion scales of plane kstart+3
-    double nx_ex = P.col.exner_dry[kstart], nx_Tr = P.col.T[kstart];                    // buoyancy inputs of level kstart
+    // Column values of a level (reference density at centres k-2..k+1 and z-faces k-1..k+2, Exner / Tᵣ, conversion scales of plane
+    // k+3; 0 outside the column: those entries only ever multiply zero planes or are ignored by the reduced-order interpolation)
+    // come as one record per level (Columns::lev). The last half-warp of the least loaded warp fetches the next level's record
+    // at the top of a level and stores it to shared memory just before the level's barrier; four buffers, so the values of
+    // level k stay readable through both flux phases while the record of level k+1 lands.
+    long long n = lidx(L, i, j, kstart);         // own point, advanced by one plane per level
+    const bool relay_lane = tid >= NT - LEV_REC;
 
     for (int k = kstart; k < ke; ++k) {
-        r_m2 = r_m1; r_m1 = r_0; r_0 = r_p1; r_p1 = nx_rc;
-        f_m1 = f_0; f_0 = f_p1; f_p1 = f_p2; f_p2 = nx_rf;
-        const double rho_k = r_0, rho_ft = f_p1;                       // ρ at this centre, ℑz ρ at the top face k+1
-        const double ex_k = nx_ex, Tr_k = nx_Tr, sc_now = nx_sc, sf_now = nx_sf;
-        nx_rc = rho_c(k + 2); nx_rf = rho_fc(k + 3);
-        nx_sc = scale_of(0, k + 4); nx_sf = scale_of(2, k + 4);
-        { int kn = min(k + 1, Nz - 1); nx_ex = P.col.exner_dry[kn]; nx_Tr = P.col.T[kn]; }
+        const double2* const rec = reinterpret_cast<const double2*>(S.lev[k & 3]);
+        const bool relay = relay_lane && (k + 1 < ke);
+        double rec_next = 0.0;
+        if (relay) rec_next = P.col.lev[(long long)(k + 1) * LEV_REC + (tid - (NT - LEV_REC))];
+        const double2 rc01 = rec[0], rc23 = rec[1];
+        const double r_m2 = rc01.x, r_m1 = rc01.y, rho_k = rc23.x, r_p1 = rc23.y;   // ρ at centres k-2, k-1, k (this level), k+1
+        // filled in after the level's barrier (only the z-flux phase reads them)
+        double f_m1 = 0.0, f_0 = 0.0, rho_ft = 0.0, f_p2 = 0.0;                      // ℑz ρ at faces k-1, k, k+1 (the top face), k+2
+        double ex_k = 0.0, Tr_k = 0.0, nx_ex = 0.0, nx_Tr = 0.0;                      // buoyancy inputs of level k and of level k+1
 
         // own-point values for the RK update: issued now, consumed after the flux phase
-        const long long n = lidx(L, i, j, k);
         const bool do_store = (k >= kb) && own_cell;
         double Uc[3] = {0.0, 0.0, 0.0}, U0c[3] = {0.0, 0.0, 0.0};
         if (do_store && P.mode == 0) {
@@ -479,12 +514,29 @@ __global__ void __launch_bounds__(2 * TX * TY, 1) stage_kernel(const __grid_cons
         using PH0 = std::integral_constant<int, 0>; using PH1 = std::integral_constant<int, 1>;
         // x/y fluxes of level k need the planes k-2 .. k+1 only …
         if (full) level(std::true_type{}, PH0{}); else level(std::false_type{}, PH0{});
+        if (relay) S.lev[(k + 1) & 3][tid - (NT - LEV_REC)] = rec_next;
+#ifdef BZ_SPLIT_BARRIER
+        // plane k+4 (first read by the z stencils of level k+1): its TMA was issued a whole level ago
+        if (k + 1 < ke) {
+            if (P.use_tma) { wait_plane_tma(k + 4); const double2 sc = rec[7]; convert_plane(k + 4, sc.x, sc.y); }
+            else load_plane_direct(k + 4);
+        }
+        mbar_arrive(&S.lbar);                                          // fx / fy of this level, plane k+4 and the next record are written
+        { const double2 a = rec[2], b = rec[3], c = rec[4], d = rec[6];
+          f_m1 = a.x; f_0 = a.y; rho_ft = b.x; f_p2 = b.y; ex_k = c.x; Tr_k = c.y; nx_ex = d.x; nx_Tr = d.y; }
+        if (full) level(std::true_type{}, PH1{}); else level(std::false_type{}, PH1{});
+        mbar_wait(&S.lbar, lpar); lpar ^= 1u;                          // every warp has arrived: their fx / fy are visible, plane k-3 is dead
+        if (P.use_tma && tid == NT - 32 && k + 2 < ke) issue_plane_tma(k + 5);   // slot of plane k-3; the least loaded warp issues
+#else
         // … so plane k+3 (needed by the z stencils) is staged behind them: its TMA had a whole level to land
-        if (P.use_tma) { wait_plane_tma(k + 3); convert_plane(k + 3, sc_now, sf_now); }
+        if (P.use_tma) { wait_plane_tma(k + 3); const double2 sc = rec[5]; convert_plane(k + 3, sc.x, sc.y); }
         else load_plane_direct(k + 3);
-        __syncthreads();                                               // the level's only CTA barrier: plane k+3 and fx / fy are complete
+        __syncthreads();                                               // the level's only CTA barrier: plane k+3, fx / fy and the next record are complete
+        { const double2 a = rec[2], b = rec[3], c = rec[4], d = rec[6];
+          f_m1 = a.x; f_0 = a.y; rho_ft = b.x; f_p2 = b.y; ex_k = c.x; Tr_k = c.y; nx_ex = d.x; nx_Tr = d.y; }
         if (P.use_tma && tid == NT - 32 && k + 1 < ke) issue_plane_tma(k + 4);   // slot of plane k-4; the least loaded warp issues
         if (full) level(std::true_type{}, PH1{}); else level(std::false_type{}, PH1{});
+#endif
 
         // ---- tendencies, RK update, store -----------------------------------------------------------------------
         if (do_store) {
@@ -531,6 +583,7 @@ __global__ void __launch_bounds__(2 * TX * TY, 1) stage_kernel(const __grid_cons
             }
         }
         zb0 = zt0; zb1 = zt1; zb2 = zt2; b_below = b_here; b_carry = b_above;
+        n += L.plane;
         // fx / fy are double-buffered by level parity: the next level writes the other buffer, and the barrier after that
         // orders it against this level's readers
     }

@@ -26,7 +26,7 @@ def model(size, **kw):
 
 
 def main():
-    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    args = [a for a in sys.argv[1:] if a.endswith(".so")]
     size = int(sys.argv[sys.argv.index("--size") + 1]) if "--size" in sys.argv else 512
     steps = int(sys.argv[sys.argv.index("--steps") + 1]) if "--steps" in sys.argv else 5
     ref_fields = None
