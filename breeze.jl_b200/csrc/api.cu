@@ -262,6 +262,7 @@ static int setup_poisson(bz_ctx* c) {
     // launch shapes: each thread owns 8 points of a line
     if (!L.flat_y) {
         int lines = 2048 / g.Ny; if (lines < 1) lines = 1;
+        if (const char* e = getenv("BZ_FFT_LINES_Y")) { int v = atoi(e); if (v >= 1 && v * g.Ny / 8 <= 1024) lines = v; }   // tuning sweeps only
         int half = (L.nx + 1) / 2; if (lines > half) lines = half;
         while (lines & (lines - 1)) lines &= lines - 1;       // power of two (the kernels shift instead of dividing)
         c->lines_y = lines;
@@ -273,6 +274,7 @@ static int setup_poisson(bz_ctx* c) {
     }
     if (!L.flat_x) {
         int lines = 1024 / g.Nx; if (lines < 1) lines = 1;
+        if (const char* e = getenv("BZ_FFT_LINES_X")) { int v = atoi(e); if (v >= 1 && v * g.Nx / 8 <= 1024) lines = v; }   // tuning sweeps only
         long long nl = (long long)G.Nz * G.nky_loc; if (nl < 1) nl = 1;
         if (lines > nl) lines = (int)nl;
         while (lines & (lines - 1)) lines &= lines - 1;

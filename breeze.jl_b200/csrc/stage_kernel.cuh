@@ -25,6 +25,9 @@
 #include <type_traits>
 
 #define RING 8
+#ifndef BZ_PLAIN_BARRIER
+#define BZ_SPLIT_BARRIER 1     // default: split level barrier (arrive after the x/y fluxes, wait before the tendency assembly)
+#endif
 
 struct StageParams {
     CUtensorMap tmap[NPROG];          // 64-byte aligned; only used when use_tma

@@ -10,7 +10,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O
 echo "pytest rc=$?" >> $OUT/${TAG}_pytest.log
 tail -3 $OUT/${TAG}_pytest.log
 if ls breeze.jl_b200/csrc/variants/*.so >/dev/null 2>&1; then
-  timeout 300 python scripts/variant_bench.py breeze.jl_b200/csrc/variants/base.so $(ls breeze.jl_b200/csrc/variants/*.so | grep -v base.so) --steps 5 > $OUT/${TAG}_variants.log 2>&1
+  timeout 300 python scripts/variant_bench.py $(ls breeze.jl_b200/csrc/variants/*.so) --steps 5 > $OUT/${TAG}_variants.log 2>&1
   cat $OUT/${TAG}_variants.log | tail -5
 fi
 ( time timeout 480 python bench.py ) > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
