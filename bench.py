@@ -27,6 +27,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the ONE JSON line; NCCL's version / debug lines go to stderr
 
 STAGE_BYTES_PER_CELL = (88.0 + 128.0 + 128.0) / 3.0      # average over the three stage-kernel launches of a step
 METRIC = "Mcell-updates/s"
