@@ -282,7 +282,10 @@ class AtmosphereModel:
 
     def _profile(self, value, face=False):
         z = self.grid.znodes(face=face)
-        return np.array([value(zz) for zz in z], dtype=np.float64) if callable(value) else np.asarray(value, dtype=np.float64)
+        if callable(value):
+            return np.array([value(zz) for zz in z], dtype=np.float64)
+        a = np.asarray(value, dtype=np.float64)
+        return np.full(len(z), float(a)) if a.ndim == 0 else a          # a constant (SubsidenceForcing(wˢ::Number), subsidence_forcing.jl)
 
     def _install_forcing(self):
         """forcing = (; u = (subsidence, geostrophic.u), θ = subsidence, qᵉ = (subsidence, Forcing(drying)), e = Forcing(cooling))
