@@ -148,6 +148,28 @@ def test_reference_state_closed_forms(oracle_arch):
     assert np.max(np.abs(np.diff(p) / grid.Δz + g * 0.5 * (rho[1:] + rho[:-1]))) < 2e-3
 
 
+def test_reference_state_respects_standard_pressure(oracle_arch):
+    """test/reference_states.jl:275-293 ("Closed-form hydrostatic pressure respects standard pressure") and :73-81 (surface density):
+    with p₀ = 101325 ≠ pˢᵗ = 1e5 the surface temperature is T₀ = θ₀ (p₀/pˢᵗ)^κ, and pᵣ(z) = p₀ (1 - g z/(cᵖᵈ T₀))^(cᵖᵈ/Rᵈ) — not the
+    same expression with θ₀ in place of T₀ (the reference asserts both, rtol sqrt(eps) and "not within 1e-4")."""
+    Rd, cp, g = 8.314462618 / 0.02897, 1005.0, 9.81
+    p0, pst, th0 = 101325.0, 1e5, 288.0
+    grid = bz.RectilinearGrid(oracle_arch, size=(8, 8, 22), x=(0, 100), y=(0, 100), z=(0, 22e3))
+    ref = bz.ReferenceState(grid, surface_pressure=p0, potential_temperature=th0, standard_pressure=pst)
+    rho, p, T = bz.AtmosphereModel(grid, dynamics=bz.AnelasticDynamics(ref)).reference_profiles()
+    z = grid.znodes()
+    T0 = th0 * (p0 / pst) ** (Rd / cp)
+    assert np.allclose(p, p0 * (1 - g * z / (cp * T0)) ** (cp / Rd), rtol=np.sqrt(np.finfo(float).eps))
+    wrong = p0 * (1 - g * z / (cp * th0)) ** (cp / Rd)
+    sel = z >= 1000.0
+    assert np.all(np.abs(p[sel] - wrong[sel]) > 1e-4 * np.abs(wrong[sel]))
+    # surface density close to p₀ / (Rᵈ θ₀) (rtol 0.01 in the reference, which evaluates it at z = 0; the lowest centre is 500 m up)
+    grid2 = bz.RectilinearGrid(oracle_arch, size=(8, 8, 16), x=(0, 100), y=(0, 100), z=(0, 160.0))
+    ref2 = bz.ReferenceState(grid2, surface_pressure=101325.0, potential_temperature=300.0)
+    rho2, _, _ = bz.AtmosphereModel(grid2, dynamics=bz.AnelasticDynamics(ref2)).reference_profiles()
+    assert rho2[0] == pytest.approx(101325.0 / (Rd * 300.0), rel=0.01)
+
+
 def test_theta_temperature_relation(oracle_arch):
     """T = Π θ with Π = (pᵣ/pˢᵗ)^(Rᵐ/cᵖᵐ) (dynamic_states.jl:31-58), dry and with vapour."""
     m = make_bubble_model(oracle_arch, (8, 8, 16))
