@@ -28,6 +28,9 @@
 #ifndef BZ_PLAIN_BARRIER
 #define BZ_SPLIT_BARRIER 1     // default: split level barrier (arrive after the x/y fluxes, wait before the tendency assembly)
 #endif
+#if defined(BZ_BALANCED_STORES) && !defined(BZ_SPLIT_BARRIER)
+#error "BZ_BALANCED_STORES evaluates a z flux before the level barrier: it needs the split barrier's plane schedule"
+#endif
 
 struct StageParams {
     CUtensorMap tmap[NPROG];          // 64-byte aligned; only used when use_tma
@@ -165,6 +168,9 @@ struct StageShared {
     alignas(16) double lev[4][LEV_REC];               // per-level column records (common.cuh), relayed one level ahead
     uint64_t bar[RING];
     uint64_t lbar;                                    // BZ_SPLIT_BARRIER: the level barrier as an mbarrier (arrive early, wait late)
+#ifdef BZ_BALANCED_STORES
+    double fz[2][TY][TX];                             // z-flux difference of ρq, handed from role 1 to role 0 (which stores ρq)
+#endif
 };
 
 // Biased reconstruction from six consecutive values with the buffer R known at compile time on the fast path.
@@ -308,7 +314,15 @@ __global__ void __launch_bounds__(2 * TX * TY, 1) stage_kernel(const __grid_cons
     const double rdx = L.rdx, rdy = L.rdy, rdz = L.rdz;
     const bool own_cell = (j < L.Ny);
     const bool in_x = i < L.nx;
+#ifdef BZ_BALANCED_STORES
+    // role 0 assembles and stores ρu, ρv and ρq (whose z-flux difference role 1 hands over through shared memory), role 1 ρw and ρθ:
+    // 8 reconstructions + 3 stores against 8 reconstructions (one of them a tile-edge flux) + buoyancy + 2 stores per level
+    const int f_count = role == 0 ? 3 : 2;
+    auto field_of = [&](int a) -> int { return role == 0 ? (a < 2 ? a : 4) : 2 + a; };
+#else
     const int f_first = role == 0 ? 0 : 2, f_count = role == 0 ? 2 : 3;   // fields this thread assembles and stores
+    auto field_of = [&](int a) -> int { return f_first + a; };
+#endif
 
     // Column values of a level (reference density at centres k-2..k+1 and z-faces k-1..k+2, Exner / Tᵣ, conversion scales of plane
     // k+3; 0 outside the column: those entries only ever multiply zero planes or are ignored by the reduced-order interpolation)
@@ -327,6 +341,9 @@ __global__ void __launch_bounds__(2 * TX * TY, 1) stage_kernel(const __grid_cons
         const double r_m2 = rc01.x, r_m1 = rc01.y, rho_k = rc23.x, r_p1 = rc23.y;   // ρ at centres k-2, k-1, k (this level), k+1
         // filled in after the level's barrier (only the z-flux phase reads them)
         double f_m1 = 0.0, f_0 = 0.0, rho_ft = 0.0, f_p2 = 0.0;                      // ℑz ρ at faces k-1, k, k+1 (the top face), k+2
+#ifdef BZ_BALANCED_STORES
+        rho_ft = rec[3].x;                                                            // the ρq z flux is evaluated with the x/y fluxes
+#endif
         double ex_k = 0.0, Tr_k = 0.0, nx_ex = 0.0, nx_Tr = 0.0;                      // buoyancy inputs of level k and of level k+1
 
         // own-point values for the RK update: issued now, consumed after the flux phase
@@ -335,7 +352,7 @@ __global__ void __launch_bounds__(2 * TX * TY, 1) stage_kernel(const __grid_cons
         if (do_store && P.mode == 0) {
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
-                int f = f_first + a;
+                int f = field_of(a);
                 if (a < f_count && (in_x || (f == 0 && i < P.nx_u))) {
                     Uc[a] = P.U[f][n];
                     if (P.alpha != 1.0) U0c[a] = P.U0[f][n];
@@ -469,6 +486,9 @@ __global__ void __launch_bounds__(2 * TX * TY, 1) stage_kernel(const __grid_cons
                         }
                     }
                 } else {
+#ifdef BZ_BALANCED_STORES
+                    zt2 = z_flux(K4{}); S.fz[k & 1][ty][tx] = zt2 - zb2;      // ρq is stored by role 0
+#endif
                     if (!FLAT_X) {
                         FX[2][ty][tx] = x_flux(K2{}, Lk, 0); FX[4][ty][tx] = x_flux(K4{}, Lk, 0);
                         if (BALANCED) {
@@ -500,7 +520,11 @@ __global__ void __launch_bounds__(2 * TX * TY, 1) stage_kernel(const __grid_cons
             } else {
                 if (role == 0) { zt0 = z_flux(K0{}); zt1 = z_flux(K1{}); }
                 else {
+#ifdef BZ_BALANCED_STORES
+                    zt0 = z_flux(K2{}); zt1 = z_flux(K3{});
+#else
                     zt0 = z_flux(K2{}); zt1 = z_flux(K3{}); zt2 = z_flux(K4{});
+#endif
                     if (MICRO == BZ_THERMO_STATIC_ENERGY) {
                         // the ρe tendency needs the buoyancy at k-1, k, k+1 (static_energy_tendency.jl:60-63): evaluate it one level ahead
                         b_here = (k == kstart) ? buoyancy_center<MICRO>(P.th, P.col, k, rho_k, ex_k, Tr_k, Lk[3 * PL], Lk[4 * PL]) : b_carry;
@@ -546,13 +570,18 @@ __global__ void __launch_bounds__(2 * TX * TY, 1) stage_kernel(const __grid_cons
             double zt[3] = {zt0, zt1, zt2}, zb[3] = {zb0, zb1, zb2};
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
-                const int f = f_first + a;
+                const int f = field_of(a);
                 if (a >= f_count) break;
                 if (!(in_x || (f == 0 && i < P.nx_u))) continue;
                 double g = 0.0;
                 if (!FLAT_X) g += (S.fx[k & 1][f][ty][tx + 1] - S.fx[k & 1][f][ty][tx]) * rdx;
                 if (HAS_Y) g += (S.fy[k & 1][f][ty + 1][tx] - S.fy[k & 1][f][ty][tx]) * rdy;
+#ifdef BZ_BALANCED_STORES
+                const double dzf = (role == 0 && a == 2) ? S.fz[k & 1][ty][tx] : zt[a] - zb[a];
+                g = -(g + dzf * rdz);
+#else
                 g = -(g + (zt[a] - zb[a]) * rdz);
+#endif
                 if (f == 2) g = (k >= 1) ? g + 0.5 * (b_here + b_below) : 0.0;
                 if (MICRO == BZ_THERMO_STATIC_ENERGY && f == 3)      // - ℑzᵃᵃᶜ(w ℑzᵃᵃᶠ(ρb)); w = 0 on both walls (zero plane above the top)
                     g -= 0.5 * (Lk[2 * PL] * (0.5 * (b_here + b_below)) + Lt[2 * PL] * (0.5 * (b_above + b_here)));
