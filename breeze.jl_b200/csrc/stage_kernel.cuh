@@ -28,6 +28,9 @@
 #ifndef BZ_PLAIN_BARRIER
 #define BZ_SPLIT_BARRIER 1     // default: split level barrier (arrive after the x/y fluxes, wait before the tendency assembly)
 #endif
+#if defined(BZ_SPLIT_BARRIER) && !defined(BZ_ROLE1_STORES_Q)
+#define BZ_BALANCED_STORES 1   // default: role 0 stores ρq (role 1 hands over its z-flux difference), evening out the two warp roles
+#endif
 #if defined(BZ_BALANCED_STORES) && !defined(BZ_SPLIT_BARRIER)
 #error "BZ_BALANCED_STORES evaluates a z flux before the level barrier: it needs the split barrier's plane schedule"
 #endif
