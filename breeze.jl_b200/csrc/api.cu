@@ -416,11 +416,12 @@ static int update_column_forcing(bz_ctx* c, int set_index) {
 template <int TX, int TY, bool HAS_Y, bool FLAT_X, int MICRO, bool FORCED>
 static int launch_stage_t(bz_ctx* c, const StageParams& P, int nz_chunks) {
     using SM = StageShared<TX, TY, HAS_Y>;
-    static bool configured = false;
+    static bool configured[64] = {false};            // function attributes are per device: one flag per device ordinal
     auto kern = stage_kernel<TX, TY, HAS_Y, FLAT_X, MICRO, FORCED>;
-    if (!configured) {
+    const int dev = c->cfg.device;
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
         CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SM)));
-        configured = true;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     dim3 grid((P.nx_u + TX - 1) / TX, (c->L.Ny + TY - 1) / TY, nz_chunks);
     kern<<<grid, 2 * TX * TY, sizeof(SM), c->stream>>>(P);
