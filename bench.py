@@ -93,12 +93,23 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def run_oracle(size, steps, warmup, dt):
-    """Time the CPU oracle on `size`^3 cells of the same bubble, all host threads. Returns (Mcell/s, cores, seconds/step)."""
+def run_oracle(size, steps, warmup, dt, threads=None):
+    """Time the CPU oracle on `size`^3 cells of the same bubble, all host threads (or `threads`). Returns (Mcell/s, cores, seconds/step)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import breeze_b200 as bz
     import oracle_lib
     lib = oracle_lib.load_oracle_library()
+    all_threads = lib.dll.orc_num_threads()
+    if threads is not None:
+        lib.dll.orc_set_num_threads(int(threads))
+    try:
+        return _run_oracle(bz, oracle_lib, lib, size, steps, warmup, dt)
+    finally:
+        if threads is not None:
+            lib.dll.orc_set_num_threads(all_threads)
+
+
+def _run_oracle(bz, oracle_lib, lib, size, steps, warmup, dt):
     cores = lib.dll.orc_num_threads()
     grid = bz.RectilinearGrid(oracle_lib.CPUOracle(), size=(size, size, size), x=(-10e3, 10e3), y=(-10e3, 10e3), z=(0, 10e3))
     m = bz.AtmosphereModel(grid, dynamics=bz.AnelasticDynamics(bz.ReferenceState(grid, potential_temperature=300)), advection=bz.WENO(order=5))
@@ -464,6 +475,9 @@ def main():
         v, cores, sps = run_oracle(cs, 3, 1, args.dt)
         cpu = {"value": v, "unit": "Mcell-updates/s", "cores": cores, "kind": "port",
                "sample": f"{cs}^3 cells of the same bubble, 3 steps after 1 warm-up, {sps:.2f} s/step (CPU restatement of the reference algorithm)"}
+        c1 = min(128, cs)
+        v1, _, sps1 = run_oracle(c1, 1, 1, args.dt, threads=1)      # at one thread and at all cores
+        cpu["single_thread"] = {"value": v1, "unit": "Mcell-updates/s", "cores": 1, "sample": f"{c1}^3 cells, 1 step after 1 warm-up, {sps1:.2f} s/step"}
 
     if rank == 0:
         out = {
