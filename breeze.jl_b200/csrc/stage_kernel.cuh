@@ -18,7 +18,12 @@
 // the extra row of y-faces at the tile's high edges are spread one flux kind per warp), the bottom z flux is carried
 // in registers from the previous level. So every face flux is evaluated once.
 // Planes are staged either by TMA (cp.async.bulk.tensor, one 3-D box per field and level, mbarrier
-// completion, prefetched one level ahead) or by plain coalesced loads (selected at run time; bit-identical).
+// completion) or by plain coalesced loads (selected at run time; bit-identical).
+// Level schedule (default build): planes k-2 .. k+3 are in use, plane k+4 is converted and plane k+5 is in flight — the 8 ring
+// slots. The level's CTA barrier is split: a thread ARRIVES after its x/y fluxes and its share of plane k+4, evaluates the
+// z fluxes / buoyancy, and WAITS only before the tendency assembly reads the other threads' x/y fluxes. The per-level column
+// values (reference density, Exner, conversion scales) come as one 128-byte record relayed through shared memory.
+// -DBZ_PLAIN_BARRIER / -DBZ_ROLE1_STORES_Q / -DBZ_EDGE_UNBALANCED rebuild the earlier variants (profiles/r1j_stage_variants.txt).
 #pragma once
 #include "common.cuh"
 #include "weno.cuh"
@@ -201,6 +206,7 @@ __global__ void __launch_bounds__(2 * TX * TY, 1) stage_kernel(const __grid_cons
     // Two threads per cell column ("roles", warp-uniform): the FP64 pipe needs ~4 warps per scheduler to stay busy and the
     // plane ring leaves room for one CTA per SM, so the 15 flux kinds of a cell are split between two warp sets that share
     // the ring:   role 0: ρu, ρv (all directions) + the x/y fluxes of θ;   role 1: ρw, the z flux of θ, ρq, buoyancy.
+    // Tendency assembly and stores: role 0 → ρu, ρv, ρq;  role 1 → ρw, ρθ (BZ_BALANCED_STORES).
     const Layout& L = P.L;
     const int tid = threadIdx.x;
     const int role = tid / NCELL, ctid = tid % NCELL;
