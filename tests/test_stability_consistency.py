@@ -119,6 +119,9 @@ def test_oracle_tiny_bubble_split_explicit_matches_anelastic_scale(oracle_arch):
     ws, wa, zs, za = _check_tiny_bubble(oracle_arch)
     # the two responses are in fact much closer than the reference's wiring thresholds; keep a tighter regression band
     assert abs(zs - za) <= 600.0 and 0.2 < ws / wa < 5.0
+    # frozen oracle values of this case (regression guard for the oracle itself; generated by this very test on the oracle of round 1)
+    assert (ws, wa) == pytest.approx((0.11671592213357988, 0.049573037547965534), rel=1e-9)
+    assert (zs, za) == pytest.approx((3004.8913660376206, 3430.053537683285), rel=1e-9)
 
 
 def test_oracle_balanced_state_stays_quiet(oracle_arch):
