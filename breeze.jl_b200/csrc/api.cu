@@ -55,6 +55,7 @@ struct bz_ctx {
     double* fstore = nullptr;            // ws[Nz+1] | ug | vg | q_tend | e_tend | sums[4Nz] | fcol[4Nz]
     double *d_ws = nullptr, *d_ug = nullptr, *d_vg = nullptr, *d_qt = nullptr, *d_et = nullptr, *d_sums = nullptr, *d_fcol = nullptr;
     int lines_x = 1, lines_y = 1;
+    int fft_wide_y = 0, fft_x_minb = 3;   // fft_wide_y: 0 default (256, 3); 1: (512, 2) wide tiles; 2: (256, 4) 64-register build  // tuning experiments (BZ_FFT_LINES_Y > 256 threads per CTA; BZ_FFT_X_MINB = 4: 64-register build of fft_x)
     cudaStream_t stream = nullptr;
     Comm comm;
     int use_tma = 0, z_chunks = 1;
@@ -262,11 +263,24 @@ static int setup_poisson(bz_ctx* c) {
     // launch shapes: each thread owns 8 points of a line
     if (!L.flat_y) {
         int lines = 2048 / g.Ny; if (lines < 1) lines = 1;
-        if (const char* e = getenv("BZ_FFT_LINES_Y")) { int v = atoi(e); if (v >= 1 && v * g.Ny / 8 <= 1024) lines = v; }   // tuning sweeps only
+        if (const char* e = getenv("BZ_FFT_LINES_Y")) { int v = atoi(e); if (v >= 1 && v * g.Ny / 8 <= 512) lines = v; }   // tuning sweeps only
         int half = (L.nx + 1) / 2; if (lines > half) lines = half;
         while (lines & (lines - 1)) lines &= lines - 1;       // power of two (the kernels shift instead of dividing)
         c->lines_y = lines;
+        c->fft_wide_y = (lines * g.Ny / 8 > 256);
+        if (!c->fft_wide_y) { const char* e = getenv("BZ_FFT_Y_MINB"); if (e && atoi(e) == 4) c->fft_wide_y = 2; }          // tuning sweeps only
         size_t sm = fft_smem_bytes(g.Ny, lines);
+        if (c->fft_wide_y == 1) {
+            FFT_DISPATCH(g.Ny, {
+                CUDA_TRY(c, cudaFuncSetAttribute(poisson_forward_y<FN, 512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+                CUDA_TRY(c, cudaFuncSetAttribute(poisson_inverse_y<FN, 512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            })
+        } else if (c->fft_wide_y == 2) {
+            FFT_DISPATCH(g.Ny, {
+                CUDA_TRY(c, cudaFuncSetAttribute(poisson_forward_y<FN, 256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+                CUDA_TRY(c, cudaFuncSetAttribute(poisson_inverse_y<FN, 256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            })
+        } else
         FFT_DISPATCH(g.Ny, {
             CUDA_TRY(c, cudaFuncSetAttribute(poisson_forward_y<FN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
             CUDA_TRY(c, cudaFuncSetAttribute(poisson_inverse_y<FN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
@@ -274,13 +288,15 @@ static int setup_poisson(bz_ctx* c) {
     }
     if (!L.flat_x) {
         int lines = 1024 / g.Nx; if (lines < 1) lines = 1;
-        if (const char* e = getenv("BZ_FFT_LINES_X")) { int v = atoi(e); if (v >= 1 && v * g.Nx / 8 <= 1024) lines = v; }   // tuning sweeps only
+        if (const char* e = getenv("BZ_FFT_LINES_X")) { int v = atoi(e); if (v >= 1 && v * g.Nx / 8 <= 256) lines = v; }   // tuning sweeps only
+        if (const char* e = getenv("BZ_FFT_X_MINB")) { if (atoi(e) == 4) c->fft_x_minb = 4; }                               // tuning sweeps only
         long long nl = (long long)G.Nz * G.nky_loc; if (nl < 1) nl = 1;
         if (lines > nl) lines = (int)nl;
         while (lines & (lines - 1)) lines &= lines - 1;
         c->lines_x = lines;
         size_t sm = fft_smem_bytes(g.Nx, lines);
-        FFT_DISPATCH(g.Nx, { CUDA_TRY(c, cudaFuncSetAttribute(fft_x_kernel<FN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); })
+        if (c->fft_x_minb == 4) { FFT_DISPATCH(g.Nx, { CUDA_TRY(c, cudaFuncSetAttribute(fft_x_kernel<FN, 256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); }) }
+        else FFT_DISPATCH(g.Nx, { CUDA_TRY(c, cudaFuncSetAttribute(fft_x_kernel<FN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); })
     }
     return setup_thomas(c);
 }
@@ -297,7 +313,9 @@ static int poisson_solve(bz_ctx* c, double dt) {
             int lines = c->lines_y;
             dim3 grid((L.nx + 2 * lines - 1) / (2 * lines), L.Nz);
             size_t sm = fft_smem_bytes(G.Ny, lines);
-            FFT_DISPATCH(G.Ny, (poisson_forward_y<FN><<<grid, lines * G.Ny / 8, sm, c->stream>>>(L, G, U[0], U[1], U[2], dz_over_dt, c->W, c->tw_y, lines)));
+            if (c->fft_wide_y == 1) { FFT_DISPATCH(G.Ny, (poisson_forward_y<FN, 512, 2><<<grid, lines * G.Ny / 8, sm, c->stream>>>(L, G, U[0], U[1], U[2], dz_over_dt, c->W, c->tw_y, lines))); }
+            else if (c->fft_wide_y == 2) { FFT_DISPATCH(G.Ny, (poisson_forward_y<FN, 256, 4><<<grid, lines * G.Ny / 8, sm, c->stream>>>(L, G, U[0], U[1], U[2], dz_over_dt, c->W, c->tw_y, lines))); }
+            else FFT_DISPATCH(G.Ny, (poisson_forward_y<FN><<<grid, lines * G.Ny / 8, sm, c->stream>>>(L, G, U[0], U[1], U[2], dz_over_dt, c->W, c->tw_y, lines)));
         } else {
             dim3 grid((L.nx + 127) / 128, L.Nz);
             poisson_pack_flat_y<<<grid, 128, 0, c->stream>>>(L, G, U[0], U[1], U[2], dz_over_dt, c->W);
@@ -317,7 +335,8 @@ static int poisson_solve(bz_ctx* c, double dt) {
         ProfScope ps(c, 1);
         int lines = c->lines_x;
         size_t sm = fft_smem_bytes(G.Nx, lines);
-        FFT_DISPATCH(G.Nx, (fft_x_kernel<FN><<<(unsigned)((n_lines + lines - 1) / lines), lines * G.Nx / 8, sm, c->stream>>>(G, c->W2, n_lines, c->tw_x, lines, 0, peers, pull ? 1 : 0)));
+        if (c->fft_x_minb == 4) { FFT_DISPATCH(G.Nx, (fft_x_kernel<FN, 256, 4><<<(unsigned)((n_lines + lines - 1) / lines), lines * G.Nx / 8, sm, c->stream>>>(G, c->W2, n_lines, c->tw_x, lines, 0, peers, pull ? 1 : 0))); }
+        else FFT_DISPATCH(G.Nx, (fft_x_kernel<FN><<<(unsigned)((n_lines + lines - 1) / lines), lines * G.Nx / 8, sm, c->stream>>>(G, c->W2, n_lines, c->tw_x, lines, 0, peers, pull ? 1 : 0)));
         c->launches++;
     }
     if (G.nky_loc > 0) {
@@ -331,7 +350,8 @@ static int poisson_solve(bz_ctx* c, double dt) {
         ProfScope ps(c, 3);
         int lines = c->lines_x;
         size_t sm = fft_smem_bytes(G.Nx, lines);
-        FFT_DISPATCH(G.Nx, (fft_x_kernel<FN><<<(unsigned)((n_lines + lines - 1) / lines), lines * G.Nx / 8, sm, c->stream>>>(G, c->W2, n_lines, c->tw_x, lines, 1, peers, 0)));
+        if (c->fft_x_minb == 4) { FFT_DISPATCH(G.Nx, (fft_x_kernel<FN, 256, 4><<<(unsigned)((n_lines + lines - 1) / lines), lines * G.Nx / 8, sm, c->stream>>>(G, c->W2, n_lines, c->tw_x, lines, 1, peers, 0))); }
+        else FFT_DISPATCH(G.Nx, (fft_x_kernel<FN><<<(unsigned)((n_lines + lines - 1) / lines), lines * G.Nx / 8, sm, c->stream>>>(G, c->W2, n_lines, c->tw_x, lines, 1, peers, 0)));
         c->launches++;
     }
     if (c->comm.n_ranks > 1) {
@@ -346,7 +366,9 @@ static int poisson_solve(bz_ctx* c, double dt) {
             int lines = c->lines_y;
             dim3 grid((L.nx + 2 * lines - 1) / (2 * lines), L.Nz);
             size_t sm = fft_smem_bytes(G.Ny, lines);
-            FFT_DISPATCH(G.Ny, (poisson_inverse_y<FN><<<grid, lines * G.Ny / 8, sm, c->stream>>>(L, G, c->W, c->phi, c->tw_y, lines, scale, peers, pull ? 1 : 0)));
+            if (c->fft_wide_y == 1) { FFT_DISPATCH(G.Ny, (poisson_inverse_y<FN, 512, 2><<<grid, lines * G.Ny / 8, sm, c->stream>>>(L, G, c->W, c->phi, c->tw_y, lines, scale, peers, pull ? 1 : 0))); }
+            else if (c->fft_wide_y == 2) { FFT_DISPATCH(G.Ny, (poisson_inverse_y<FN, 256, 4><<<grid, lines * G.Ny / 8, sm, c->stream>>>(L, G, c->W, c->phi, c->tw_y, lines, scale, peers, pull ? 1 : 0))); }
+            else FFT_DISPATCH(G.Ny, (poisson_inverse_y<FN><<<grid, lines * G.Ny / 8, sm, c->stream>>>(L, G, c->W, c->phi, c->tw_y, lines, scale, peers, pull ? 1 : 0)));
         } else {
             dim3 grid((L.nx + 127) / 128, L.Nz);
             poisson_unpack_flat_y<<<grid, 128, 0, c->stream>>>(L, G, c->W, c->phi, scale);

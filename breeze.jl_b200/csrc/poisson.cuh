@@ -170,9 +170,11 @@ __device__ __forceinline__ double source_term(const Layout& L, const double* __r
 }
 
 // ---- pass 1: source term + real-to-complex FFT along y ----------------------------------------------------------
-// grid (ceil(nx / (2*lines)), Nz); block lines*Ny/8 <= 256 threads; smem 2*lines*line_pitch(Ny) doubles.
-template <int N>
-__global__ void __launch_bounds__(256, 3) poisson_forward_y(Layout L, PoissonGeom G, const double* __restrict__ ru, const double* __restrict__ rv,
+// grid (ceil(nx / (2*lines)), Nz); block lines*Ny/8 <= MAXT threads; smem 2*lines*line_pitch(Ny) doubles.
+// MAXT / MINB: launch bounds. The default (256, 3) is the tuned configuration; (512, 2) exists for the wide-tile experiment
+// (8 lines per CTA = 128-byte rows of the momentum fields; BZ_FFT_LINES_Y).
+template <int N, int MAXT = 256, int MINB = 3>
+__global__ void __launch_bounds__(MAXT, MINB) poisson_forward_y(Layout L, PoissonGeom G, const double* __restrict__ ru, const double* __restrict__ rv,
                                   const double* __restrict__ rw, double dz_over_dt, double2* __restrict__ W,
                                   const double2* __restrict__ tw_y, int lines) {
     extern __shared__ double sm[];
@@ -224,8 +226,8 @@ __global__ void poisson_pack_flat_y(Layout L, PoissonGeom G, const double* __res
 }
 
 // ---- pass 5: complex-to-real inverse FFT along y → φ (padded field interior) -------------------------------------
-template <int N>
-__global__ void __launch_bounds__(256, 3) poisson_inverse_y(Layout L, PoissonGeom G, const double2* __restrict__ W, double* __restrict__ phi,
+template <int N, int MAXT = 256, int MINB = 3>
+__global__ void __launch_bounds__(MAXT, MINB) poisson_inverse_y(Layout L, PoissonGeom G, const double2* __restrict__ W, double* __restrict__ phi,
                                   const double2* __restrict__ tw_y, int lines, double scale, PeerBases peers, int pull) {
     extern __shared__ double sm[];
     constexpr int LP = ((N + (N >> 4) + 15) & ~15) + 4;
@@ -292,8 +294,8 @@ __global__ void poisson_unpack_flat_y(Layout L, PoissonGeom G, const double2* __
 
 // ---- passes 2 / 4: complex FFT along x, in place; one line = Nx contiguous complex numbers ----------------------
 // grid ceil(n_lines / lines); block lines*Nx/8 <= 256 threads; smem 2*lines*line_pitch(Nx) doubles.
-template <int N>
-__global__ void __launch_bounds__(256, 3) fft_x_kernel(PoissonGeom G, double2* __restrict__ W, long long n_lines, const double2* __restrict__ tw_x, int lines, int inverse,
+template <int N, int MAXT = 256, int MINB = 3>
+__global__ void __launch_bounds__(MAXT, MINB) fft_x_kernel(PoissonGeom G, double2* __restrict__ W, long long n_lines, const double2* __restrict__ tw_x, int lines, int inverse,
                                                        PeerBases peers, int pull) {
     extern __shared__ double sm[];
     constexpr int LP = ((N + (N >> 4) + 15) & ~15) + 4;
