@@ -332,8 +332,8 @@ class CompressibleAtmosphereModel:
         self.grid, self.architecture, self.dynamics = grid, grid.architecture, dynamics
         self.thermodynamic_constants = thermodynamic_constants or ThermodynamicConstants()
         self.advection = advection or WENO(order=5)
-        if self.advection.order != 5:
-            raise NotImplementedError("only WENO(order=5) is on the hot path")
+        if self.advection.order not in (5, 7, 9):
+            raise NotImplementedError("WENO(order = 5) is on the hot path; orders 7 and 9 exist in the CPU oracle only (the CUDA library rejects them)")
         lib = compressible_library(self.architecture.library())
         cfg = bzc_config()
         lib.default_config(C.byref(cfg))
@@ -348,6 +348,7 @@ class CompressibleAtmosphereModel:
         for name in ThermodynamicConstants.__dataclass_fields__:
             setattr(b, name, getattr(self.thermodynamic_constants, name))
         b.device = getattr(self.architecture, "device", 0)
+        b.advection_order = self.advection.order
         cfg.reference_state = BZC_REFERENCE_NONE if dynamics.reference_state is None else BZC_REFERENCE_EXNER
         cfg.substeps = int(td.substeps or 0)
         cfg.acoustic_cfl, cfg.forward_weight = td.acoustic_cfl, td.forward_weight

@@ -244,8 +244,8 @@ class AtmosphereModel:
         ref = dynamics.reference_state
         self.thermodynamic_constants = thermodynamic_constants or ref.constants
         self.advection = advection or WENO(order=5)
-        if self.advection.order != 5:
-            raise NotImplementedError("only WENO(order=5) is on the hot path")
+        if self.advection.order not in (5, 7, 9):
+            raise NotImplementedError("WENO(order = 5) is on the hot path; orders 7 and 9 exist in the CPU oracle only (the CUDA library rejects them)")
         self.microphysics = microphysics
 
         lib = self.architecture.library()

@@ -38,7 +38,7 @@
 #endif
 #include "../include/breeze_b200.h"
 
-#define HALO 4            /* any halo >= 3 gives identical results; the reference default is 3 */
+#define HALO 6            /* any halo >= buffer + 1 gives identical results (WENO5: 3 + 1, WENO9: 5 + 1); the reference default is 3 */
 #define NPROG 5
 
 typedef double complex cplx;
@@ -52,6 +52,7 @@ typedef struct orc_ctx {
     bz_config cfg;
     int Nx, Ny, Nz;       /* local == global (the oracle is single-process) */
     int Hx, Hy, Hz;
+    int B, Bs;               /* buffers of the biased (WENO) and the symmetric (Centered) reconstructions: (order + 1) / 2 and B - 1 */
     int Px, Py, Pz;       /* padded sizes; Pz covers Nz+1 faces */
     size_t n_padded;
     double dx, dy, dz;    /* Flat dimension: spacing 1, as in Oceananigans */
@@ -413,14 +414,14 @@ static inline double tracer_flux_x(const orc_ctx* c, const double* cfield, int i
     size_t n = IDX(c, i, j, k);
     double ut = c->u[n];
     double rho = c->rho_r[k + c->Hz];
-    double cR = biased_interp(cfield + n, 1, 3, ut > 0);
+    double cR = biased_interp(cfield + n, 1, c->B, ut > 0);
     return (0.5 * (rho + rho)) * (c->dy * c->dz * ut * cR);
 }
 static inline double tracer_flux_y(const orc_ctx* c, const double* cfield, int i, int j, int k) {
     size_t n = IDX(c, i, j, k);
     double vt = c->v[n];
     double rho = c->rho_r[k + c->Hz];
-    double cR = biased_interp(cfield + n, c->Px, 3, vt > 0);
+    double cR = biased_interp(cfield + n, c->Px, c->B, vt > 0);
     return (0.5 * (rho + rho)) * (c->dx * c->dz * vt * cR);
 }
 static inline double tracer_flux_z(const orc_ctx* c, const double* cfield, int i, int j, int k) {
@@ -428,7 +429,7 @@ static inline double tracer_flux_z(const orc_ctx* c, const double* cfield, int i
     size_t n = IDX(c, i, j, k);
     double wt = c->w[n];
     double rho_f = 0.5 * (c->rho_r[k + c->Hz] + c->rho_r[k - 1 + c->Hz]);
-    double cR = biased_interp(cfield + n, (ptrdiff_t)c->Px * c->Py, red_face(k, c->Nz, 3), wt > 0);
+    double cR = biased_interp(cfield + n, (ptrdiff_t)c->Px * c->Py, red_face(k, c->Nz, c->B), wt > 0);
     return rho_f * (c->dx * c->dy * wt * cR);
 }
 
@@ -452,50 +453,50 @@ static inline double div_rhoUc(const orc_ctx* c, const double* cfield, int i, in
 
 static inline double flux_Uu(const orc_ctx* c, int i, int j, int k) {        /* at centre i */
     size_t n1 = IDX(c, i + 1, j, k);
-    double ut = c->dy * c->dz * symmetric_interp(c->U[BZ_RHO_U] + n1, SX, 2);
-    return ut * biased_interp(c->u + n1, SX, 3, ut > 0);
+    double ut = c->dy * c->dz * symmetric_interp(c->U[BZ_RHO_U] + n1, SX, c->Bs);
+    return ut * biased_interp(c->u + n1, SX, c->B, ut > 0);
 }
 static inline double flux_Vu(const orc_ctx* c, int i, int j, int k) {        /* at (face i, face j) */
     size_t n = IDX(c, i, j, k);
-    double vt = c->dx * c->dz * SYM_X(c->U[BZ_RHO_V] + n, 2);
-    return vt * biased_interp(c->u + n, SY, 3, vt > 0);
+    double vt = c->dx * c->dz * SYM_X(c->U[BZ_RHO_V] + n, c->Bs);
+    return vt * biased_interp(c->u + n, SY, c->B, vt > 0);
 }
 static inline double flux_Wu(const orc_ctx* c, int i, int j, int k) {        /* at (face i, z-face k) */
     if (k == 0 || k == c->Nz) return 0.0;
     size_t n = IDX(c, i, j, k);
-    double wt = c->dx * c->dy * SYM_X(c->U[BZ_RHO_W] + n, 2);
-    return wt * biased_interp(c->u + n, SZ, red_face(k, c->Nz, 3), wt > 0);
+    double wt = c->dx * c->dy * SYM_X(c->U[BZ_RHO_W] + n, c->Bs);
+    return wt * biased_interp(c->u + n, SZ, red_face(k, c->Nz, c->B), wt > 0);
 }
 static inline double flux_Uv(const orc_ctx* c, int i, int j, int k) {        /* at (face i, face j) */
     size_t n = IDX(c, i, j, k);
-    double ut = c->dy * c->dz * SYM_Y(c->U[BZ_RHO_U] + n, 2);
-    return ut * biased_interp(c->v + n, SX, 3, ut > 0);
+    double ut = c->dy * c->dz * SYM_Y(c->U[BZ_RHO_U] + n, c->Bs);
+    return ut * biased_interp(c->v + n, SX, c->B, ut > 0);
 }
 static inline double flux_Vv(const orc_ctx* c, int i, int j, int k) {        /* at centre j */
     size_t n1 = IDX(c, i, j + 1, k);
-    double vt = c->dx * c->dz * symmetric_interp(c->U[BZ_RHO_V] + n1, SY, 2);
-    return vt * biased_interp(c->v + n1, SY, 3, vt > 0);
+    double vt = c->dx * c->dz * symmetric_interp(c->U[BZ_RHO_V] + n1, SY, c->Bs);
+    return vt * biased_interp(c->v + n1, SY, c->B, vt > 0);
 }
 static inline double flux_Wv(const orc_ctx* c, int i, int j, int k) {        /* at (face j, z-face k) */
     if (k == 0 || k == c->Nz) return 0.0;
     size_t n = IDX(c, i, j, k);
-    double wt = c->dx * c->dy * SYM_Y(c->U[BZ_RHO_W] + n, 2);
-    return wt * biased_interp(c->v + n, SZ, red_face(k, c->Nz, 3), wt > 0);
+    double wt = c->dx * c->dy * SYM_Y(c->U[BZ_RHO_W] + n, c->Bs);
+    return wt * biased_interp(c->v + n, SZ, red_face(k, c->Nz, c->B), wt > 0);
 }
 static inline double flux_Uw(const orc_ctx* c, int i, int j, int k) {        /* at (face i, z-face k), 1 <= k <= Nz-1 */
     size_t n = IDX(c, i, j, k);
-    double ut = c->dy * c->dz * symmetric_interp(c->U[BZ_RHO_U] + n, SZ, red_face(k, c->Nz, 2));
-    return ut * biased_interp(c->w + n, SX, 3, ut > 0);
+    double ut = c->dy * c->dz * symmetric_interp(c->U[BZ_RHO_U] + n, SZ, red_face(k, c->Nz, c->Bs));
+    return ut * biased_interp(c->w + n, SX, c->B, ut > 0);
 }
 static inline double flux_Vw(const orc_ctx* c, int i, int j, int k) {
     size_t n = IDX(c, i, j, k);
-    double vt = c->dx * c->dz * symmetric_interp(c->U[BZ_RHO_V] + n, SZ, red_face(k, c->Nz, 2));
-    return vt * biased_interp(c->w + n, SY, 3, vt > 0);
+    double vt = c->dx * c->dz * symmetric_interp(c->U[BZ_RHO_V] + n, SZ, red_face(k, c->Nz, c->Bs));
+    return vt * biased_interp(c->w + n, SY, c->B, vt > 0);
 }
 static inline double flux_Ww(const orc_ctx* c, int i, int j, int k) {        /* at centre k, 0 <= k <= Nz-1 */
     size_t n1 = IDX(c, i, j, k + 1);
-    double wt = c->dx * c->dy * symmetric_interp(c->U[BZ_RHO_W] + n1, SZ, red_center(k, c->Nz, 2));
-    return wt * biased_interp(c->w + n1, SZ, red_center(k, c->Nz, 3), wt > 0);
+    double wt = c->dx * c->dy * symmetric_interp(c->U[BZ_RHO_W] + n1, SZ, red_center(k, c->Nz, c->Bs));
+    return wt * biased_interp(c->w + n1, SZ, red_center(k, c->Nz, c->B), wt > 0);
 }
 
 /* compute_forcing!(::SubsidenceForcing): horizontal averages of the specific fields (subsidence_forcing.jl:137-141) */
@@ -868,7 +869,8 @@ int orc_create(const bz_config* cfg, orc_ctx** out) {
     if (!cfg || !out) return BZ_ERR_INVALID;
     if (cfg->abi_version != BZ_ABI_VERSION) { set_err(NULL, "abi_version mismatch"); return BZ_ERR_INVALID; }
     if (cfg->Nx < 1 || cfg->Ny < 1 || cfg->Nz < 1) { set_err(NULL, "grid size must be positive"); return BZ_ERR_INVALID; }
-    if (cfg->advection_order != 5) { set_err(NULL, "only WENO(order=5) is on the path"); return BZ_ERR_UNSUPPORTED; }
+    /* the oracle also restates WENO(order = 7 / 9) (not yet on the CUDA path, which rejects it) */
+    if (cfg->advection_order != 5 && cfg->advection_order != 7 && cfg->advection_order != 9) { set_err(NULL, "WENO(order = 5, 7 or 9)"); return BZ_ERR_UNSUPPORTED; }
     if (cfg->formulation == BZ_FORMULATION_STATIC_ENERGY && cfg->microphysics != BZ_MICROPHYSICS_NONE) {
         set_err(NULL, "StaticEnergyFormulation is on the path without microphysics only"); return BZ_ERR_UNSUPPORTED; }
     if ((cfg->topology_x == BZ_FLAT && cfg->Nx != 1) || (cfg->topology_y == BZ_FLAT && cfg->Ny != 1)) {
@@ -880,6 +882,7 @@ int orc_create(const bz_config* cfg, orc_ctx** out) {
     c->Hx = cfg->topology_x == BZ_FLAT ? 0 : HALO;
     c->Hy = cfg->topology_y == BZ_FLAT ? 0 : HALO;
     c->Hz = HALO;
+    c->B = (cfg->advection_order + 1) / 2; c->Bs = c->B - 1;
     c->Px = c->Nx + 2 * c->Hx; c->Py = c->Ny + 2 * c->Hy; c->Pz = c->Nz + 1 + 2 * c->Hz;
     c->n_padded = (size_t)c->Px * c->Py * c->Pz;
     c->dx = cfg->topology_x == BZ_FLAT ? 1.0 : (cfg->x1 - cfg->x0) / cfg->Nx;
@@ -1108,3 +1111,11 @@ void orc_set_num_threads(int n) {
 /* Stand-alone reconstructions exported for unit tests of the GPU device functions */
 double orc_weno5_biased(const double* s) { return weno5_biased(s[0], s[1], s[2], s[3], s[4]); }
 double orc_weno3_biased(const double* s) { return weno3_biased(s[0], s[1], s[2]); }
+/* order = 5, 7, 9: left-biased value at the face between w[R-1] and w[R] from the window w[0 .. 2R-2], R = (order + 1) / 2 */
+double orc_weno_biased_window(const double* w, int order) {
+    int R = (order + 1) / 2;
+    if (R == 3) return weno5_biased(w[0], w[1], w[2], w[3], w[4]);
+    return weno_hi_window(w, R);
+}
+/* Centered(order) value at the face between a[order/2 - 1] and a[order/2] from the window a[0 .. order-1] */
+double orc_centered_window(const double* a, int order) { return symmetric_interp(a + order / 2, 1, order / 2); }

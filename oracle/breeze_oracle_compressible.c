@@ -34,13 +34,14 @@
 #include "../include/breeze_b200_compressible.h"
 #include "oracle_weno.h"
 
-#define HALO 4
+#define HALO 6   /* buffer + 1 of the widest scheme (WENO9: 5 + 1); results do not depend on it */
 enum { C_RHO = 0, C_RU = 1, C_RV = 2, C_RW = 3, C_RTH = 4, NPROGC = 5 };
 enum { LOC_CENTER = 0, LOC_ZFACE = 1 };
 
 typedef struct orcc_ctx {
     bzc_config cfg;
     int Nx, Ny, Nz, Hx, Hy, Hz, Px, Py, Pz;
+    int B, Bs;                     /* buffers of the biased (WENO) and symmetric (Centered) reconstructions: (order + 1) / 2, B - 1 */
     size_t n_padded;
     int flat_x, flat_y;
     double dx, dy, dz;
@@ -272,70 +273,70 @@ static void refresh_linearization_basic_state(orcc_ctx* c) {
 
 static inline double flux_Uu(const orcc_ctx* c, int i, int j, int k) {
     size_t n1 = IDX(c, i + 1, j, k);
-    double ut = c->dy * c->dz * symmetric_interp(c->U[C_RU] + n1, SX, 2);
-    return ut * biased_interp(c->u + n1, SX, 3, ut > 0);
+    double ut = c->dy * c->dz * symmetric_interp(c->U[C_RU] + n1, SX, c->Bs);
+    return ut * biased_interp(c->u + n1, SX, c->B, ut > 0);
 }
 static inline double flux_Vu(const orcc_ctx* c, int i, int j, int k) {
     size_t n = IDX(c, i, j, k);
-    double vt = c->dx * c->dz * SYM_X(c->U[C_RV] + n, 2);
-    return vt * biased_interp(c->u + n, SY, 3, vt > 0);
+    double vt = c->dx * c->dz * SYM_X(c->U[C_RV] + n, c->Bs);
+    return vt * biased_interp(c->u + n, SY, c->B, vt > 0);
 }
 static inline double flux_Wu(const orcc_ctx* c, int i, int j, int k) {
     if (k == 0 || k == c->Nz) return 0.0;
     size_t n = IDX(c, i, j, k);
-    double wt = c->dx * c->dy * SYM_X(c->U[C_RW] + n, 2);
-    return wt * biased_interp(c->u + n, SZ, red_face(k, c->Nz, 3), wt > 0);
+    double wt = c->dx * c->dy * SYM_X(c->U[C_RW] + n, c->Bs);
+    return wt * biased_interp(c->u + n, SZ, red_face(k, c->Nz, c->B), wt > 0);
 }
 static inline double flux_Uv(const orcc_ctx* c, int i, int j, int k) {
     size_t n = IDX(c, i, j, k);
-    double ut = c->dy * c->dz * SYM_Y(c->U[C_RU] + n, 2);
-    return ut * biased_interp(c->v + n, SX, 3, ut > 0);
+    double ut = c->dy * c->dz * SYM_Y(c->U[C_RU] + n, c->Bs);
+    return ut * biased_interp(c->v + n, SX, c->B, ut > 0);
 }
 static inline double flux_Vv(const orcc_ctx* c, int i, int j, int k) {
     size_t n1 = IDX(c, i, j + 1, k);
-    double vt = c->dx * c->dz * symmetric_interp(c->U[C_RV] + n1, SY, 2);
-    return vt * biased_interp(c->v + n1, SY, 3, vt > 0);
+    double vt = c->dx * c->dz * symmetric_interp(c->U[C_RV] + n1, SY, c->Bs);
+    return vt * biased_interp(c->v + n1, SY, c->B, vt > 0);
 }
 static inline double flux_Wv(const orcc_ctx* c, int i, int j, int k) {
     if (k == 0 || k == c->Nz) return 0.0;
     size_t n = IDX(c, i, j, k);
-    double wt = c->dx * c->dy * SYM_Y(c->U[C_RW] + n, 2);
-    return wt * biased_interp(c->v + n, SZ, red_face(k, c->Nz, 3), wt > 0);
+    double wt = c->dx * c->dy * SYM_Y(c->U[C_RW] + n, c->Bs);
+    return wt * biased_interp(c->v + n, SZ, red_face(k, c->Nz, c->B), wt > 0);
 }
 static inline double flux_Uw(const orcc_ctx* c, int i, int j, int k) {
     size_t n = IDX(c, i, j, k);
-    double ut = c->dy * c->dz * symmetric_interp(c->U[C_RU] + n, SZ, red_face(k, c->Nz, 2));
-    return ut * biased_interp(c->w + n, SX, 3, ut > 0);
+    double ut = c->dy * c->dz * symmetric_interp(c->U[C_RU] + n, SZ, red_face(k, c->Nz, c->Bs));
+    return ut * biased_interp(c->w + n, SX, c->B, ut > 0);
 }
 static inline double flux_Vw(const orcc_ctx* c, int i, int j, int k) {
     size_t n = IDX(c, i, j, k);
-    double vt = c->dx * c->dz * symmetric_interp(c->U[C_RV] + n, SZ, red_face(k, c->Nz, 2));
-    return vt * biased_interp(c->w + n, SY, 3, vt > 0);
+    double vt = c->dx * c->dz * symmetric_interp(c->U[C_RV] + n, SZ, red_face(k, c->Nz, c->Bs));
+    return vt * biased_interp(c->w + n, SY, c->B, vt > 0);
 }
 static inline double flux_Ww(const orcc_ctx* c, int i, int j, int k) {
     size_t n1 = IDX(c, i, j, k + 1);
-    double wt = c->dx * c->dy * symmetric_interp(c->U[C_RW] + n1, SZ, red_center(k, c->Nz, 2));
-    return wt * biased_interp(c->w + n1, SZ, red_center(k, c->Nz, 3), wt > 0);
+    double wt = c->dx * c->dy * symmetric_interp(c->U[C_RW] + n1, SZ, red_center(k, c->Nz, c->Bs));
+    return wt * biased_interp(c->w + n1, SZ, red_center(k, c->Nz, c->B), wt > 0);
 }
 /* tracer_mass_flux_{x,y,z} with the 3-D coupling density ρᵈ */
 static inline double tracer_flux_x(const orcc_ctx* c, const double* f, int i, int j, int k) {
     size_t n = IDX(c, i, j, k);
     const double* rho = c->U[C_RHO];
     double ut = c->u[n];
-    return ((rho[n] + rho[n - SX]) / 2) * (c->dy * c->dz * ut * biased_interp(f + n, SX, 3, ut > 0));
+    return ((rho[n] + rho[n - SX]) / 2) * (c->dy * c->dz * ut * biased_interp(f + n, SX, c->B, ut > 0));
 }
 static inline double tracer_flux_y(const orcc_ctx* c, const double* f, int i, int j, int k) {
     size_t n = IDX(c, i, j, k);
     const double* rho = c->U[C_RHO];
     double vt = c->v[n];
-    return ((rho[n] + rho[n - SY]) / 2) * (c->dx * c->dz * vt * biased_interp(f + n, SY, 3, vt > 0));
+    return ((rho[n] + rho[n - SY]) / 2) * (c->dx * c->dz * vt * biased_interp(f + n, SY, c->B, vt > 0));
 }
 static inline double tracer_flux_z(const orcc_ctx* c, const double* f, int i, int j, int k) {
     if (k == 0 || k == c->Nz) return 0.0;
     size_t n = IDX(c, i, j, k);
     const double* rho = c->U[C_RHO];
     double wt = c->w[n];
-    return ((rho[n] + rho[n - SZ]) / 2) * (c->dx * c->dy * wt * biased_interp(f + n, SZ, red_face(k, c->Nz, 3), wt > 0));
+    return ((rho[n] + rho[n - SZ]) / 2) * (c->dx * c->dy * wt * biased_interp(f + n, SZ, red_face(k, c->Nz, c->B), wt > 0));
 }
 
 static void compute_slow_tendencies(orcc_ctx* c) {
@@ -391,20 +392,20 @@ static void compute_moisture_tendency(orcc_ctx* c) {
         double fx = 0.0, fy = 0.0, fz;
         if (!c->flat_x) {
             double ue = c->avg_u[n + SX], uw = c->avg_u[n];
-            double Fe = ((rho[n + SX] + rho[n]) / 2) * (Ax * ue * biased_interp(q + n + SX, SX, 3, ue > 0));
-            double Fw = ((rho[n] + rho[n - SX]) / 2) * (Ax * uw * biased_interp(q + n, SX, 3, uw > 0));
+            double Fe = ((rho[n + SX] + rho[n]) / 2) * (Ax * ue * biased_interp(q + n + SX, SX, c->B, ue > 0));
+            double Fw = ((rho[n] + rho[n - SX]) / 2) * (Ax * uw * biased_interp(q + n, SX, c->B, uw > 0));
             fx = Fe - Fw;
         }
         if (!c->flat_y) {
             double vn = c->avg_v[n + SY], vs = c->avg_v[n];
-            double Fn = ((rho[n + SY] + rho[n]) / 2) * (Ay * vn * biased_interp(q + n + SY, SY, 3, vn > 0));
-            double Fs = ((rho[n] + rho[n - SY]) / 2) * (Ay * vs * biased_interp(q + n, SY, 3, vs > 0));
+            double Fn = ((rho[n + SY] + rho[n]) / 2) * (Ay * vn * biased_interp(q + n + SY, SY, c->B, vn > 0));
+            double Fs = ((rho[n] + rho[n - SY]) / 2) * (Ay * vs * biased_interp(q + n, SY, c->B, vs > 0));
             fy = Fn - Fs;
         }
         {
             double Ft = 0.0, Fb = 0.0;
-            if (k + 1 < c->Nz) { double wt = c->avg_w[n + SZ]; Ft = ((rho[n + SZ] + rho[n]) / 2) * (Az * wt * biased_interp(q + n + SZ, SZ, red_face(k + 1, c->Nz, 3), wt > 0)); }
-            if (k > 0) { double wb = c->avg_w[n]; Fb = ((rho[n] + rho[n - SZ]) / 2) * (Az * wb * biased_interp(q + n, SZ, red_face(k, c->Nz, 3), wb > 0)); }
+            if (k + 1 < c->Nz) { double wt = c->avg_w[n + SZ]; Ft = ((rho[n + SZ] + rho[n]) / 2) * (Az * wt * biased_interp(q + n + SZ, SZ, red_face(k + 1, c->Nz, c->B), wt > 0)); }
+            if (k > 0) { double wb = c->avg_w[n]; Fb = ((rho[n] + rho[n - SZ]) / 2) * (Az * wb * biased_interp(q + n, SZ, red_face(k, c->Nz, c->B), wb > 0)); }
             fz = Ft - Fb;
         }
         c->Grqv[n] = -((1 / V) * (fx + fy + fz));
@@ -796,13 +797,15 @@ int orcc_create(const bzc_config* cfg, orcc_ctx** out) {
     const bz_config* b = &cfg->base;
     if (b->abi_version != BZ_ABI_VERSION) { set_err(NULL, "ABI version mismatch"); return BZ_ERR_INVALID; }
     if (b->microphysics != BZ_MICROPHYSICS_NONE || b->n_ranks > 1) { set_err(NULL, "compressible path: dry air, one rank"); return BZ_ERR_UNSUPPORTED; }
-    if (b->advection_order != 5) { set_err(NULL, "only WENO(order=5)"); return BZ_ERR_UNSUPPORTED; }
+    /* the oracle also restates WENO(order = 7 / 9) (the CUDA path rejects them) */
+    if (b->advection_order != 5 && b->advection_order != 7 && b->advection_order != 9) { set_err(NULL, "WENO(order = 5, 7 or 9)"); return BZ_ERR_UNSUPPORTED; }
     if (b->Nz < 4) { set_err(NULL, "Nz >= 4 required"); return BZ_ERR_INVALID; }
     orcc_ctx* c = (orcc_ctx*)calloc(1, sizeof(orcc_ctx));
     c->cfg = *cfg;
     c->flat_x = b->topology_x == BZ_FLAT; c->flat_y = b->topology_y == BZ_FLAT;
     c->Nx = c->flat_x ? 1 : b->Nx; c->Ny = c->flat_y ? 1 : b->Ny; c->Nz = b->Nz;
     c->Hx = c->flat_x ? 0 : HALO; c->Hy = c->flat_y ? 0 : HALO; c->Hz = HALO;
+    c->B = (b->advection_order + 1) / 2; c->Bs = c->B - 1;
     c->Px = c->Nx + 2 * c->Hx; c->Py = c->Ny + 2 * c->Hy; c->Pz = c->Nz + 1 + 2 * c->Hz;
     c->n_padded = (size_t)c->Px * c->Py * c->Pz;
     c->dx = c->flat_x ? 1.0 : (b->x1 - b->x0) / c->Nx;

@@ -45,6 +45,10 @@ def load_oracle_library() -> abi.Library:
         d.orc_weno5_biased.argtypes = [C.POINTER(C.c_double)]
         d.orc_weno3_biased.restype = C.c_double
         d.orc_weno3_biased.argtypes = [C.POINTER(C.c_double)]
+        d.orc_weno_biased_window.restype = C.c_double
+        d.orc_weno_biased_window.argtypes = [C.POINTER(C.c_double), C.c_int]
+        d.orc_centered_window.restype = C.c_double
+        d.orc_centered_window.argtypes = [C.POINTER(C.c_double), C.c_int]
         d.orc_num_threads.restype = C.c_int
         d.orc_set_beta_form.argtypes = [C.c_int]
         d.orc_set_num_threads.argtypes = [C.c_int]

@@ -58,9 +58,58 @@ static inline double weno3_biased(double m2, double m1, double p0) {
     return (a0 * q0 + a1 * q1) / (a0 + a1);
 }
 
+/* ---- WENO(order = 7 / 9) (buffers 4, 5): SURVEY §8f rank 4 (the reference's shipped examples use WENO(order = 9)) ------------------
+ * Candidates, optimal weights and smoothness forms are DERIVED from their definitions in exact arithmetic
+ * (scripts/derive_weno_coefficients.py → oracle_weno_tables.h; the same derivation reproduces the order-5 constants above).
+ * Recalled from upstream Oceananigans, not verifiable here (PARITY UNPINNED like the rest of this header):
+ *   - the WENO-Z global indicator  tau_7 = |b0 + 3 b1 - 3 b2 - b3|,  tau_9 = |b0 + 2 b1 - 6 b2 + 2 b3 + b4|  (Castro et al. 2011);
+ *   - the scaling of the stored forms: 240 x JS / 1000 (order 7) and 5040 x JS / 100000 (order 9) — it only matters relative to eps;
+ *   - exponent 2 and eps = 1e-8 as for order 5. */
+#include "oracle_weno_tables.h"
+#define WENO7_BSCALE 0.24
+#define WENO9_BSCALE 0.0504
+
+/* w[0 .. 2R-2]: the window of the biased reconstruction, upwind cell at w[R-1], downwind side at w[R .. 2R-2]. */
+static inline double weno_hi_window(const double* w, int R) {
+    const double* C = (R == 4) ? &WENO7_C[0][0] : &WENO9_C[0][0];
+    const double* D = (R == 4) ? WENO7_D : WENO9_D;
+    const double* B = (R == 4) ? &WENO7_B[0][0][0] : &WENO9_B[0][0][0];
+    const double bscale = (R == 4) ? WENO7_BSCALE : WENO9_BSCALE;
+    static const double G4[4] = {1, 3, -3, -1}, G5[5] = {1, 2, -6, 2, 1};
+    const double* G = (R == 4) ? G4 : G5;
+    double p[5], beta[5], tau = 0;
+    for (int st = 0; st < R; ++st) {
+        const double* v = w + (R - 1 - st);            /* stencil st covers w[R-1-st .. 2R-2-st] */
+        double q = 0, b = 0;
+        for (int a = 0; a < R; ++a) {
+            q += C[st * R + a] * v[a];
+            double row = 0;
+            for (int c = a; c < R; ++c) row += B[(st * R + a) * R + c] * v[c];
+            b += v[a] * row;
+        }
+        p[st] = q; beta[st] = bscale * b;
+        tau += G[st] * beta[st];
+    }
+    tau = fabs(tau);
+    double num = 0, den = 0;
+    for (int st = 0; st < R; ++st) {
+        double rr = tau / (beta[st] + WENO_EPS);
+        double al = D[st] * (1 + rr * rr);
+        num += al * p[st]; den += al;
+    }
+    return num / den;
+}
+
+static inline double weno_hi_biased(const double* psi, ptrdiff_t s, int R, int left) {
+    double w[9];
+    for (int j = 0; j < 2 * R - 1; ++j) w[j] = left ? psi[(j - R) * s] : psi[(R - 1 - j) * s];
+    return weno_hi_window(w, R);
+}
+
 /* Biased interpolation of psi (stride s) to "face" i, i.e. between psi[i-1] and psi[i]; R = buffer in use
- * (3: WENO5, 2: WENO3, 1: first-order upwind); left != 0 selects the left (upwind = i-1) bias. */
+ * (5: WENO9, 4: WENO7, 3: WENO5, 2: WENO3, 1: first-order upwind); left != 0 selects the left (upwind = i-1) bias. */
 static inline double biased_interp(const double* psi, ptrdiff_t s, int R, int left) {
+    if (R >= 4) return weno_hi_biased(psi, s, R > 5 ? 5 : R, left);
     if (left) {
         if (R >= 3) return weno5_biased(psi[-3 * s], psi[-2 * s], psi[-s], psi[0], psi[s]);
         if (R == 2) return weno3_biased(psi[-2 * s], psi[-s], psi[0]);
@@ -72,8 +121,11 @@ static inline double biased_interp(const double* psi, ptrdiff_t s, int R, int le
     }
 }
 
-/* Centered(order = 4) symmetric interpolation to "face" i (between a[i-1], a[i]); R = 2: 4th order, 1: 2nd. */
+/* Centered(order = 2R) symmetric interpolation to "face" i (between a[i-1], a[i]); R = 4: 8th, 3: 6th, 2: 4th order, 1: 2nd.
+ * (WENO(order = n) advects with Centered(order = n - 1), recalled from upstream: buffer R_sym = R_weno - 1.) */
 static inline double symmetric_interp(const double* a, ptrdiff_t s, int R) {
+    if (R >= 4) { double v = 0; for (int j = 0; j < 4; ++j) v += CENTERED8_C[3 - j] * (a[(-1 - j) * s] + a[j * s]); return v; }
+    if (R == 3) { double v = 0; for (int j = 0; j < 3; ++j) v += CENTERED6_C[2 - j] * (a[(-1 - j) * s] + a[j * s]); return v; }
     if (R >= 2) return (7 * (a[-s] + a[0]) - (a[-2 * s] + a[s])) / 12;
     return 0.5 * (a[-s] + a[0]);
 }

@@ -117,7 +117,7 @@ def test_grid_and_model_argument_validation(oracle_arch):
         bz.RectilinearGrid(oracle_arch, size=(8, 8), x=(0, 1), y=(0, 1), z=(0, 1))
     grid = bz.RectilinearGrid(oracle_arch, size=(8, 8, 8), x=(0, 1), y=(0, 1), z=(0, 1))
     with pytest.raises(NotImplementedError):
-        bz.AtmosphereModel(grid, advection=bz.WENO(order=9))
+        bz.AtmosphereModel(grid, advection=bz.WENO(order=11))
     model = bz.AtmosphereModel(grid)
     with pytest.raises(ValueError):
         model.set(banana=1.0)
