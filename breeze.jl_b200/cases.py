@@ -45,8 +45,9 @@ def bomex_dTdt(z):
     return _pw(z, [0, 1500, 2500, 3000], [-2.0 / 86400, -2.0 / 86400, 0.0, 0.0])
 
 
-def bomex_model(arch, size=(64, 64, 75), extent=6400.0, seed=938):
-    """examples/bomex.jl:42-243 with WENO(order=5): grid, reference state, forcings, flux BCs, perturbed initial condition."""
+def bomex_model(arch, size=(64, 64, 75), extent=6400.0, seed=938, order=5):
+    """examples/bomex.jl:42-243: grid, reference state, forcings, flux BCs, perturbed initial condition. The example runs
+    WENO(order=9); the CUDA path carries order 5 (the default here), the CPU oracle also 7 and 9."""
     import breeze_b200 as bz
     grid = bz.RectilinearGrid(arch, size=size, x=(0, extent), y=(0, extent), z=(0, 3000.0))
     constants = bz.ThermodynamicConstants()
@@ -60,7 +61,7 @@ def bomex_model(arch, size=(64, 64, 75), extent=6400.0, seed=938):
                "e": bz.Forcing(lambda z: constants.dry_air_heat_capacity * bomex_dTdt(z))}
     drag = bz.DragFluxBoundaryCondition(rho0, 0.28)
     bcs = {"ρθ": bz.FluxBoundaryCondition(rho0 * 8e-3), "ρqᵉ": bz.FluxBoundaryCondition(rho0 * 5.2e-5), "ρu": drag, "ρv": drag}
-    model = bz.AtmosphereModel(grid, dynamics=bz.AnelasticDynamics(ref), advection=bz.WENO(order=5),
+    model = bz.AtmosphereModel(grid, dynamics=bz.AnelasticDynamics(ref), advection=bz.WENO(order=order),
                                microphysics=bz.SaturationAdjustment(), coriolis=bz.FPlane(f=3.76e-5), forcing=forcing,
                                boundary_conditions=bcs)
     rng = np.random.default_rng(seed)                            # the example seeds Julia's RNG (:26); not reproducible bit-wise
