@@ -38,7 +38,7 @@
 #endif
 #include "../include/breeze_b200.h"
 
-#define HALO 6            /* any halo >= buffer + 1 gives identical results (WENO5: 3 + 1, WENO9: 5 + 1); the reference default is 3 */
+#define HALO(order) (((order) + 1) / 2 + 1)   /* buffer + 1: 4 for WENO5 (any larger halo gives identical results; the reference default is 3), 6 for WENO9 */
 #define NPROG 5
 
 typedef double complex cplx;
@@ -879,9 +879,9 @@ int orc_create(const bz_config* cfg, orc_ctx** out) {
     if (!c) return BZ_ERR_NOMEM;
     c->cfg = *cfg;
     c->Nx = cfg->Nx; c->Ny = cfg->Ny; c->Nz = cfg->Nz;
-    c->Hx = cfg->topology_x == BZ_FLAT ? 0 : HALO;
-    c->Hy = cfg->topology_y == BZ_FLAT ? 0 : HALO;
-    c->Hz = HALO;
+    c->Hx = cfg->topology_x == BZ_FLAT ? 0 : HALO(cfg->advection_order);
+    c->Hy = cfg->topology_y == BZ_FLAT ? 0 : HALO(cfg->advection_order);
+    c->Hz = HALO(cfg->advection_order);
     c->B = (cfg->advection_order + 1) / 2; c->Bs = c->B - 1;
     c->Px = c->Nx + 2 * c->Hx; c->Py = c->Ny + 2 * c->Hy; c->Pz = c->Nz + 1 + 2 * c->Hz;
     c->n_padded = (size_t)c->Px * c->Py * c->Pz;

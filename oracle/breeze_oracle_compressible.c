@@ -34,7 +34,7 @@
 #include "../include/breeze_b200_compressible.h"
 #include "oracle_weno.h"
 
-#define HALO 6   /* buffer + 1 of the widest scheme (WENO9: 5 + 1); results do not depend on it */
+#define HALO(order) (((order) + 1) / 2 + 1)   /* buffer + 1: 4 for WENO5, 6 for WENO9; results do not depend on a larger halo */
 enum { C_RHO = 0, C_RU = 1, C_RV = 2, C_RW = 3, C_RTH = 4, NPROGC = 5 };
 enum { LOC_CENTER = 0, LOC_ZFACE = 1 };
 
@@ -804,7 +804,7 @@ int orcc_create(const bzc_config* cfg, orcc_ctx** out) {
     c->cfg = *cfg;
     c->flat_x = b->topology_x == BZ_FLAT; c->flat_y = b->topology_y == BZ_FLAT;
     c->Nx = c->flat_x ? 1 : b->Nx; c->Ny = c->flat_y ? 1 : b->Ny; c->Nz = b->Nz;
-    c->Hx = c->flat_x ? 0 : HALO; c->Hy = c->flat_y ? 0 : HALO; c->Hz = HALO;
+    c->Hx = c->flat_x ? 0 : HALO(b->advection_order); c->Hy = c->flat_y ? 0 : HALO(b->advection_order); c->Hz = HALO(b->advection_order);
     c->B = (b->advection_order + 1) / 2; c->Bs = c->B - 1;
     c->Px = c->Nx + 2 * c->Hx; c->Py = c->Ny + 2 * c->Hy; c->Pz = c->Nz + 1 + 2 * c->Hz;
     c->n_padded = (size_t)c->Px * c->Py * c->Pz;

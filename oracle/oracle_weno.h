@@ -100,7 +100,8 @@ static inline double weno_hi_window(const double* w, int R) {
     return num / den;
 }
 
-static inline double weno_hi_biased(const double* psi, ptrdiff_t s, int R, int left) {
+/* kept out of line so that the order-5 call sites (the CPU baseline that bench.py times) stay as small as they were */
+static __attribute__((noinline)) double weno_hi_biased(const double* psi, ptrdiff_t s, int R, int left) {
     double w[9];
     for (int j = 0; j < 2 * R - 1; ++j) w[j] = left ? psi[(j - R) * s] : psi[(R - 1 - j) * s];
     return weno_hi_window(w, R);
@@ -109,7 +110,7 @@ static inline double weno_hi_biased(const double* psi, ptrdiff_t s, int R, int l
 /* Biased interpolation of psi (stride s) to "face" i, i.e. between psi[i-1] and psi[i]; R = buffer in use
  * (5: WENO9, 4: WENO7, 3: WENO5, 2: WENO3, 1: first-order upwind); left != 0 selects the left (upwind = i-1) bias. */
 static inline double biased_interp(const double* psi, ptrdiff_t s, int R, int left) {
-    if (R >= 4) return weno_hi_biased(psi, s, R > 5 ? 5 : R, left);
+    if (__builtin_expect(R >= 4, 0)) return weno_hi_biased(psi, s, R > 5 ? 5 : R, left);
     if (left) {
         if (R >= 3) return weno5_biased(psi[-3 * s], psi[-2 * s], psi[-s], psi[0], psi[s]);
         if (R == 2) return weno3_biased(psi[-2 * s], psi[-s], psi[0]);
@@ -121,11 +122,17 @@ static inline double biased_interp(const double* psi, ptrdiff_t s, int R, int le
     }
 }
 
+static __attribute__((noinline)) double centered_hi(const double* a, ptrdiff_t s, int R) {
+    double v = 0;
+    if (R >= 4) { for (int j = 0; j < 4; ++j) v += CENTERED8_C[3 - j] * (a[(-1 - j) * s] + a[j * s]); return v; }
+    for (int j = 0; j < 3; ++j) v += CENTERED6_C[2 - j] * (a[(-1 - j) * s] + a[j * s]);
+    return v;
+}
+
 /* Centered(order = 2R) symmetric interpolation to "face" i (between a[i-1], a[i]); R = 4: 8th, 3: 6th, 2: 4th order, 1: 2nd.
  * (WENO(order = n) advects with Centered(order = n - 1), recalled from upstream: buffer R_sym = R_weno - 1.) */
 static inline double symmetric_interp(const double* a, ptrdiff_t s, int R) {
-    if (R >= 4) { double v = 0; for (int j = 0; j < 4; ++j) v += CENTERED8_C[3 - j] * (a[(-1 - j) * s] + a[j * s]); return v; }
-    if (R == 3) { double v = 0; for (int j = 0; j < 3; ++j) v += CENTERED6_C[2 - j] * (a[(-1 - j) * s] + a[j * s]); return v; }
+    if (__builtin_expect(R >= 3, 0)) return centered_hi(a, s, R);
     if (R >= 2) return (7 * (a[-s] + a[0]) - (a[-2 * s] + a[s])) / 12;
     return 0.5 * (a[-s] + a[0]);
 }
