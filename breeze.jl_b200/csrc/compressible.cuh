@@ -104,12 +104,19 @@ struct CSlowArgs {
 
 // biased reconstruction at the "face" between f[n - s] and f[n]; in x / y the ghost cells make R = 3 always valid,
 // in z the buffer R shrinks next to the walls (weno.cuh red_face / red_center) and only in-range levels are read
+// BUF: the scheme's buffer (3: WENO5, the path of record; 4 / 5: WENO7 / WENO9, experimental); R <= BUF: buffer in use at this point
+template <int BUF = 3>
 __device__ __forceinline__ double c_biased(const double* __restrict__ f, long long n, long long s, int R, bool left) {
+    if constexpr (BUF >= 5) { if (R >= 5) return weno_hi_mem<5>(f, n, s, left); }
+    if constexpr (BUF >= 4) { if (R == 4) return weno_hi_mem<4>(f, n, s, left); }
     if (R >= 3) return biased6c<3>(f[n - 3 * s], f[n - 2 * s], f[n - s], f[n], f[n + s], f[n + 2 * s], left);
     if (R == 2) return left ? weno3z(f[n - 2 * s], f[n - s], f[n]) : weno3z(f[n + s], f[n], f[n - s]);
     return left ? f[n - s] : f[n];
 }
+template <int BUF = 3>
 __device__ __forceinline__ double c_sym(const double* __restrict__ a, long long n, long long s, int R) {
+    if constexpr (BUF >= 5) { if (R >= 4) return centered_hi_mem<4>(a, n, s); }
+    if constexpr (BUF >= 4) { if (R == 3) return centered_hi_mem<3>(a, n, s); }
     if (R >= 2) return ((7.0 / 12.0) * (a[n - s] + a[n])) - ((1.0 / 12.0) * (a[n - 2 * s] + a[n + s]));
     return 0.5 * (a[n - s] + a[n]);
 }
@@ -125,7 +132,9 @@ __device__ __forceinline__ double c_sym(const double* __restrict__ a, long long 
 #ifndef CS_MINB
 #define CS_MINB 4             // 64 registers per thread: 4 CTAs of 256 threads per SM (A/B: 2 → 697 us, 3 → 570 us, 4 → 494 us at 256x256x64)
 #endif
-__global__ void __launch_bounds__(32 * CS_TY, CS_MINB) c_slow_tendencies(Layout L, CSlowArgs A, double g, int k_chunk) {
+template <int BUF = 3>
+__global__ void __launch_bounds__(32 * CS_TY, BUF == 3 ? CS_MINB : 1) c_slow_tendencies(Layout L, CSlowArgs A, double g, int k_chunk) {
+    constexpr int BS = BUF - 1;                           // buffer of the symmetric (advecting) interpolation: Centered(order - 1)
     __shared__ double sfy[2][4][CS_TY + 1][32];          // double-buffered by level parity: one CTA barrier per level
     const int lane = threadIdx.x, ty = threadIdx.y;
     const int i = blockIdx.x * CS_TX + lane, j = blockIdx.y * CS_TY + ty;
@@ -140,21 +149,21 @@ __global__ void __launch_bounds__(32 * CS_TY, CS_MINB) c_slow_tendencies(Layout 
     const bool top_ok = (ty < 4) && (j_top <= L.Ny) && (lane < CS_TX) && (i < L.nx);
     const double Ax = L.dy * L.dz, Ay = L.dx * L.dz, Az = L.dx * L.dy, Vinv = 1.0 / (L.dx * L.dy * L.dz);
     // advecting mass fluxes: centred-4 interpolation of the area-weighted momentum; advected velocity: WENO5-Z
-    auto symx = [&](const double* a, long long m) { return fx_ ? a[m] : c_sym(a, m, SX, 2); };
-    auto symy = [&](const double* a, long long m) { return fy_ ? a[m] : c_sym(a, m, SY, 2); };
-    auto Fuu = [&](long long m1) { double t = Ax * c_sym(A.ru, m1, SX, 2); return t * c_biased(A.u, m1, SX, 3, t > 0); };          // centre i (m1 = i + 1)
-    auto Fvu = [&](long long m) { double t = Ay * symx(A.rv, m); return t * c_biased(A.u, m, SY, 3, t > 0); };                      // (face i, face j)
-    auto Fwu = [&](long long m, int kk) { if (kk == 0 || kk == Nz) return 0.0; double t = Az * symx(A.rw, m); return t * c_biased(A.u, m, SZ, red_face(kk, Nz, 3), t > 0); };
-    auto Fuv = [&](long long m) { double t = Ax * symy(A.ru, m); return t * c_biased(A.v, m, SX, 3, t > 0); };
-    auto Fvv = [&](long long m1) { double t = Ay * c_sym(A.rv, m1, SY, 2); return t * c_biased(A.v, m1, SY, 3, t > 0); };
-    auto Fwv = [&](long long m, int kk) { if (kk == 0 || kk == Nz) return 0.0; double t = Az * symy(A.rw, m); return t * c_biased(A.v, m, SZ, red_face(kk, Nz, 3), t > 0); };
-    auto Fuw = [&](long long m, int kk) { if (kk == 0) return 0.0; double t = Ax * c_sym(A.ru, m, SZ, red_face(kk, Nz, 2)); return t * c_biased(A.w, m, SX, 3, t > 0); };
-    auto Fvw = [&](long long m, int kk) { if (kk == 0) return 0.0; double t = Ay * c_sym(A.rv, m, SZ, red_face(kk, Nz, 2)); return t * c_biased(A.w, m, SY, 3, t > 0); };
-    auto Fww = [&](long long m1, int kc) { double t = Az * c_sym(A.rw, m1, SZ, red_center(kc, Nz, 2)); return t * c_biased(A.w, m1, SZ, red_center(kc, Nz, 3), t > 0); };
-    auto Tx = [&](long long m) { double t = A.u[m]; return ((A.rho[m] + A.rho[m - SX]) / 2) * (Ax * t * c_biased(A.theta, m, SX, 3, t > 0)); };
-    auto Ty = [&](long long m) { double t = A.v[m]; return ((A.rho[m] + A.rho[m - SY]) / 2) * (Ay * t * c_biased(A.theta, m, SY, 3, t > 0)); };
+    auto symx = [&](const double* a, long long m) { return fx_ ? a[m] : c_sym<BUF>(a, m, SX, BS); };
+    auto symy = [&](const double* a, long long m) { return fy_ ? a[m] : c_sym<BUF>(a, m, SY, BS); };
+    auto Fuu = [&](long long m1) { double t = Ax * c_sym<BUF>(A.ru, m1, SX, BS); return t * c_biased<BUF>(A.u, m1, SX, BUF, t > 0); };          // centre i (m1 = i + 1)
+    auto Fvu = [&](long long m) { double t = Ay * symx(A.rv, m); return t * c_biased<BUF>(A.u, m, SY, BUF, t > 0); };                      // (face i, face j)
+    auto Fwu = [&](long long m, int kk) { if (kk == 0 || kk == Nz) return 0.0; double t = Az * symx(A.rw, m); return t * c_biased<BUF>(A.u, m, SZ, red_face(kk, Nz, BUF), t > 0); };
+    auto Fuv = [&](long long m) { double t = Ax * symy(A.ru, m); return t * c_biased<BUF>(A.v, m, SX, BUF, t > 0); };
+    auto Fvv = [&](long long m1) { double t = Ay * c_sym<BUF>(A.rv, m1, SY, BS); return t * c_biased<BUF>(A.v, m1, SY, BUF, t > 0); };
+    auto Fwv = [&](long long m, int kk) { if (kk == 0 || kk == Nz) return 0.0; double t = Az * symy(A.rw, m); return t * c_biased<BUF>(A.v, m, SZ, red_face(kk, Nz, BUF), t > 0); };
+    auto Fuw = [&](long long m, int kk) { if (kk == 0) return 0.0; double t = Ax * c_sym<BUF>(A.ru, m, SZ, red_face(kk, Nz, BS)); return t * c_biased<BUF>(A.w, m, SX, BUF, t > 0); };
+    auto Fvw = [&](long long m, int kk) { if (kk == 0) return 0.0; double t = Ay * c_sym<BUF>(A.rv, m, SZ, red_face(kk, Nz, BS)); return t * c_biased<BUF>(A.w, m, SY, BUF, t > 0); };
+    auto Fww = [&](long long m1, int kc) { double t = Az * c_sym<BUF>(A.rw, m1, SZ, red_center(kc, Nz, BS)); return t * c_biased<BUF>(A.w, m1, SZ, red_center(kc, Nz, BUF), t > 0); };
+    auto Tx = [&](long long m) { double t = A.u[m]; return ((A.rho[m] + A.rho[m - SX]) / 2) * (Ax * t * c_biased<BUF>(A.theta, m, SX, BUF, t > 0)); };
+    auto Ty = [&](long long m) { double t = A.v[m]; return ((A.rho[m] + A.rho[m - SY]) / 2) * (Ay * t * c_biased<BUF>(A.theta, m, SY, BUF, t > 0)); };
     auto Tz = [&](long long m, int kk) { if (kk == 0 || kk == Nz) return 0.0; double t = A.w[m];
-                                         return ((A.rho[m] + A.rho[m - SZ]) / 2) * (Az * t * c_biased(A.theta, m, SZ, red_face(kk, Nz, 3), t > 0)); };
+                                         return ((A.rho[m] + A.rho[m - SZ]) / 2) * (Az * t * c_biased<BUF>(A.theta, m, SZ, red_face(kk, Nz, BUF), t > 0)); };
     const long long n0 = lidx(L, min(i, L.nx), min(j, L.Ny), 0);
     const long long n0_top = lidx(L, min(i, L.nx), min(j_top, L.Ny), 0);
     // z-type fluxes through the bottom face of the chunk's first level (Fww: at centre kb - 1)
@@ -475,6 +484,7 @@ __global__ void c_recover(Layout L, CFields5 U, CConst5 P, double* __restrict__ 
 
 // compute_scalar_tendency! for the moisture density (update_atmosphere_model_state.jl:343, dynamics_kernel_functions.jl:132-159):
 // Gⁿ.ρqᵛ = -div_ρUc(ρ_total, ⟨𝐮⟩, qᵛ) with the acoustic-mean transport velocities. ρ_total, qᵛ, ⟨𝐮⟩ need valid ghost cells.
+template <int BUF = 3>
 __global__ void __launch_bounds__(128) c_moisture_tendency(Layout L, const double* __restrict__ rho, const double* __restrict__ q,
                                                            const double* __restrict__ au, const double* __restrict__ av,
                                                            const double* __restrict__ aw, double* __restrict__ G) {
@@ -483,10 +493,10 @@ __global__ void __launch_bounds__(128) c_moisture_tendency(Layout L, const doubl
     const long long n = lidx(L, i, j, k), SX = 1, SY = L.PX, SZ = L.plane;
     const int Nz = L.Nz;
     const double Ax = L.dy * L.dz, Ay = L.dx * L.dz, Az = L.dx * L.dy, Vinv = 1.0 / (L.dx * L.dy * L.dz);
-    auto Fx = [&](long long m) { double t = au[m]; return ((rho[m] + rho[m - SX]) / 2) * (Ax * t * c_biased(q, m, SX, 3, t > 0)); };
-    auto Fy = [&](long long m) { double t = av[m]; return ((rho[m] + rho[m - SY]) / 2) * (Ay * t * c_biased(q, m, SY, 3, t > 0)); };
+    auto Fx = [&](long long m) { double t = au[m]; return ((rho[m] + rho[m - SX]) / 2) * (Ax * t * c_biased<BUF>(q, m, SX, BUF, t > 0)); };
+    auto Fy = [&](long long m) { double t = av[m]; return ((rho[m] + rho[m - SY]) / 2) * (Ay * t * c_biased<BUF>(q, m, SY, BUF, t > 0)); };
     auto Fz = [&](long long m, int kk) { if (kk == 0 || kk == Nz) return 0.0; double t = aw[m];
-                                         return ((rho[m] + rho[m - SZ]) / 2) * (Az * t * c_biased(q, m, SZ, red_face(kk, Nz, 3), t > 0)); };
+                                         return ((rho[m] + rho[m - SZ]) / 2) * (Az * t * c_biased<BUF>(q, m, SZ, red_face(kk, Nz, BUF), t > 0)); };
     double fx = L.flat_x ? 0.0 : Fx(n + SX) - Fx(n);
     double fy = L.flat_y ? 0.0 : Fy(n + SY) - Fy(n);
     double fz = Fz(n + SZ, k + 1) - Fz(n, k);

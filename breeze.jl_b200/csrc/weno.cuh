@@ -98,6 +98,60 @@ __device__ __forceinline__ double sym4(double v0, double v1, double v2, double v
     return 0.5 * (v1 + v2);
 }
 
+// ---- WENO(order = 7 / 9)-Z and Centered(6 / 8): EXPERIMENTAL ---------------------------------------------
+// Table-driven restatement of oracle/oracle_weno.h (weno_hi_window / centered_hi) for the kernels that read their stencils from
+// global memory (compressible.cuh). Written for correctness first: ≈ 200 FP64 per order-9 reconstruction; no kernel instantiates
+// these unless the experimental switch of bzc_create is set, and they have not run on a GPU yet.
+#include "weno_tables.cuh"
+// w[0 .. 2R-2]: window of the biased reconstruction, upwind cell at w[R-1] (mirror the window for the right bias).
+template <int R>
+__device__ __forceinline__ double weno_hi(const double (&w)[2 * R - 1]) {
+    using T = WenoTab<R>;
+    double p[R], beta[R], tau = 0.0;
+#pragma unroll
+    for (int st = 0; st < R; ++st) {
+        double q = 0.0, b = 0.0;
+#pragma unroll
+        for (int a = 0; a < R; ++a) {
+            const double va = w[R - 1 - st + a];
+            q = fma(T::C(st, a), va, q);
+            double row = 0.0;
+#pragma unroll
+            for (int c = a; c < R; ++c) row = fma(T::B(st, a, c), w[R - 1 - st + c], row);
+            b = fma(va, row, b);
+        }
+        p[st] = q;
+        beta[st] = T::BS() * b;
+        tau = fma(T::G(st), beta[st], tau);
+    }
+    tau = fabs(tau);
+    double num = 0.0, den = 0.0;
+#pragma unroll
+    for (int st = 0; st < R; ++st) {
+        const double rr = tau / (beta[st] + WENO_EPS);
+        const double al = T::D(st) * fma(rr, rr, 1.0);
+        num = fma(al, p[st], num);
+        den += al;
+    }
+    return num / den;
+}
+// biased value at the face between f[n - s] and f[n] from a field in memory (stride s), buffer R = 4 or 5
+template <int R>
+__device__ __forceinline__ double weno_hi_mem(const double* __restrict__ f, long long n, long long s, bool left) {
+    double w[2 * R - 1];
+#pragma unroll
+    for (int j = 0; j < 2 * R - 1; ++j) w[j] = left ? f[n + (j - R) * s] : f[n + (R - 1 - j) * s];
+    return weno_hi<R>(w);
+}
+// Centered(order = 2R) value at the face between a[n - s] and a[n], R = 3 or 4
+template <int R>
+__device__ __forceinline__ double centered_hi_mem(const double* __restrict__ a, long long n, long long s) {
+    double v = 0.0;
+#pragma unroll
+    for (int j = 0; j < R; ++j) v = fma(R == 4 ? CENTERED8_C[j] : CENTERED6_C[j], a[n - (1 + j) * s] + a[n + j * s], v);
+    return v;
+}
+
 // Order reduction next to the Bounded z walls: z-face k (0..Nz) from centres, and centre k (0..Nz-1) from z-faces.
 __device__ __forceinline__ int red_face(int k, int Nz, int B) { return max(1, min(B, min(k, Nz - k))); }
 __device__ __forceinline__ int red_center(int k, int Nz, int B) { return max(1, min(B, min(k + 1, Nz - k))); }

@@ -135,6 +135,8 @@ def main():
             print(f" Centered({2 * m}):", [str(x) for x in centered(m)])
         assert centered(2) == [F(-1, 12), F(7, 12), F(7, 12), F(-1, 12)]
         return
+    if "--cuda" in sys.argv:
+        return write_cuda_tables()
     out = ["/* oracle_weno_tables.h — GENERATED by scripts/derive_weno_coefficients.py --header (exact rational derivation from the",
            " * definitions; do not edit). Finite-volume WENO of buffer r = 4 (order 7) and r = 5 (order 9), uniform grid, left-biased at the",
            " * face between psi[-1] and psi[0]: stencil s covers psi[-1 - s + a], a = 0 .. r-1. TEST INFRASTRUCTURE (CPU oracle). */",
@@ -157,6 +159,48 @@ def main():
     out.append("#endif")
     import os
     path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "oracle_weno_tables.h")
+    open(path, "w").write("\n".join(out) + "\n")
+    print("wrote", path)
+
+
+def write_cuda_tables():
+    """breeze.jl_b200/csrc/weno_tables.cuh: the same tables as device constants for the high-order reconstructions of weno.cuh."""
+    import os
+    out = ["// weno_tables.cuh — GENERATED by scripts/derive_weno_coefficients.py --header --cuda (exact rational derivation; do not edit).",
+           "// Finite-volume WENO of buffer R = 4 (order 7) and R = 5 (order 9): candidates C, optimal weights D, smoothness forms B",
+           "// (upper-triangular, unscaled Jiang-Shu / Balsara-Shu definition), WENO-Z global-indicator combination G, and the scale BS the",
+           "// stored forms carry upstream (oracle/oracle_weno.h documents what is derived and what is recalled).",
+           "#pragma once"]
+    G = {4: [1, 3, -3, -1], 5: [1, 2, -6, 2, 1]}
+    BS = {4: "0.24", 5: "0.0504"}
+    for r in (4, 5):
+        n = f"WENO{2 * r - 1}"
+        c, d, B = derive(r)
+        out.append(f"static __device__ const double {n}_G[{r}] = {{" + ", ".join(f"{g}.0" for g in G[r]) + "};")
+        out.append(f"static __device__ const double {n}_D[{r}] = {{" + ", ".join(fmt(x) for x in d) + "};")
+        out.append(f"static __device__ const double {n}_C[{r}][{r}] = {{")
+        for row in c:
+            out.append("    {" + ", ".join(fmt(x) for x in row) + "},")
+        out.append("};")
+        out.append(f"static __device__ const double {n}_B[{r}][{r}][{r}] = {{")
+        for Bs in B:
+            out.append("    {" + ", ".join("{" + ", ".join(fmt(x) for x in row) + "}" for row in Bs) + "},")
+        out.append("};")
+    out.append("template <int R> struct WenoTab;")
+    for r in (4, 5):
+        n = f"WENO{2 * r - 1}"
+        out.append(f"template <> struct WenoTab<{r}> {{")
+        out.append(f"    static __device__ __forceinline__ double BS() {{ return {BS[r]}; }}")
+        out.append(f"    static __device__ __forceinline__ double G(int s) {{ return {n}_G[s]; }}")
+        out.append(f"    static __device__ __forceinline__ double D(int s) {{ return {n}_D[s]; }}")
+        out.append(f"    static __device__ __forceinline__ double C(int s, int a) {{ return {n}_C[s][a]; }}")
+        out.append(f"    static __device__ __forceinline__ double B(int s, int a, int c) {{ return {n}_B[s][a][c]; }}")
+        out.append("};")
+    for m in (3, 4):
+        cc = centered(m)
+        out.append(f"// Centered(order = {2 * m}) at the face between a[-1] and a[0]: coefficient of (a[-1-j] + a[j]), j = 0 .. {m - 1}")
+        out.append(f"static __device__ const double CENTERED{2 * m}_C[{m}] = {{" + ", ".join(fmt(cc[m + j]) for j in range(m)) + "};")
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "breeze.jl_b200", "csrc", "weno_tables.cuh")
     open(path, "w").write("\n".join(out) + "\n")
     print("wrote", path)
 
