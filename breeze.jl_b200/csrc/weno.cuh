@@ -108,17 +108,21 @@ template <int R>
 __device__ __forceinline__ double weno_hi(const double (&w)[2 * R - 1]) {
     using T = WenoTab<R>;
     double p[R], beta[R], tau = 0.0;
+    double dw[2 * R - 2];                                  // first differences of the window, shared by the R stencils
+#pragma unroll
+    for (int j = 0; j < 2 * R - 2; ++j) dw[j] = w[j + 1] - w[j];
 #pragma unroll
     for (int st = 0; st < R; ++st) {
         double q = 0.0, b = 0.0;
 #pragma unroll
-        for (int a = 0; a < R; ++a) {
-            const double va = w[R - 1 - st + a];
-            q = fma(T::C(st, a), va, q);
+        for (int a = 0; a < R; ++a) q = fma(T::C(st, a), w[R - 1 - st + a], q);
+        // smoothness indicator as a quadratic form in the FIRST DIFFERENCES of the stencil (the oracle's beta form 1): no |psi|^2 cancellation
+#pragma unroll
+        for (int a = 0; a < R - 1; ++a) {
             double row = 0.0;
 #pragma unroll
-            for (int c = a; c < R; ++c) row = fma(T::B(st, a, c), w[R - 1 - st + c], row);
-            b = fma(va, row, b);
+            for (int c = a; c < R - 1; ++c) row = fma(T::M(st, a, c), dw[R - 1 - st + c], row);
+            b = fma(dw[R - 1 - st + a], row, b);
         }
         p[st] = q;
         beta[st] = T::BS() * b;

@@ -74,6 +74,7 @@ static inline double weno_hi_window(const double* w, int R) {
     const double* C = (R == 4) ? &WENO7_C[0][0] : &WENO9_C[0][0];
     const double* D = (R == 4) ? WENO7_D : WENO9_D;
     const double* B = (R == 4) ? &WENO7_B[0][0][0] : &WENO9_B[0][0][0];
+    const double* M = (R == 4) ? &WENO7_M[0][0][0] : &WENO9_M[0][0][0];   /* the same forms in the stencil's first differences */
     const double bscale = (R == 4) ? WENO7_BSCALE : WENO9_BSCALE;
     static const double G4[4] = {1, 3, -3, -1}, G5[5] = {1, 2, -6, 2, 1};
     const double* G = (R == 4) ? G4 : G5;
@@ -81,11 +82,21 @@ static inline double weno_hi_window(const double* w, int R) {
     for (int st = 0; st < R; ++st) {
         const double* v = w + (R - 1 - st);            /* stencil st covers w[R-1-st .. 2R-2-st] */
         double q = 0, b = 0;
-        for (int a = 0; a < R; ++a) {
-            q += C[st * R + a] * v[a];
-            double row = 0;
-            for (int c = a; c < R; ++c) row += B[(st * R + a) * R + c] * v[c];
-            b += v[a] * row;
+        for (int a = 0; a < R; ++a) q += C[st * R + a] * v[a];
+        if (g_beta_form == 0) {                        /* quadratic forms in the stencil VALUES (how the reference stores them) */
+            for (int a = 0; a < R; ++a) {
+                double row = 0;
+                for (int c = a; c < R; ++c) row += B[(st * R + a) * R + c] * v[c];
+                b += v[a] * row;
+            }
+        } else {                                       /* algebraically identical, in the first differences: no |psi|^2 cancellation; the CUDA form */
+            double d[4];
+            for (int a = 0; a < R - 1; ++a) d[a] = v[a + 1] - v[a];
+            for (int a = 0; a < R - 1; ++a) {
+                double row = 0;
+                for (int c = a; c < R - 1; ++c) row += M[(st * (R - 1) + a) * (R - 1) + c] * d[c];
+                b += d[a] * row;
+            }
         }
         p[st] = q; beta[st] = bscale * b;
         tau += G[st] * beta[st];

@@ -92,6 +92,21 @@ def derive(r):
     return c, d, B
 
 
+def difference_forms(B):
+    """The same smoothness indicators as quadratic forms in the FIRST DIFFERENCES d_a = psi_{a+1} - psi_a of the stencil
+    (beta of a constant vanishes, so beta depends on the differences only): beta = sum_{a<=b} M[a][b] d_a d_b.
+    Free of the cancellation of the value forms (|psi|^2 eps -> |d psi|^2 eps): what the CUDA kernels evaluate."""
+    out = []
+    for Bs in B:
+        r = len(Bs)
+        sym = [[(Bs[min(a, b)][max(a, b)] / (1 if a == b else 2)) for b in range(r)] for a in range(r)]
+        assert all(sum(row) == 0 for row in sym)                      # B * 1 = 0
+        # psi_j = psi_0 + sum_{a<j} d_a  ->  L[j][a] = 1 if a < j
+        M = [[sum(sym[i][j] * (1 if a < i else 0) * (1 if b < j else 0) for i in range(r) for j in range(r)) for b in range(r - 1)] for a in range(r - 1)]
+        out.append([[M[a][b] * (1 if a == b else 2) if b >= a else F(0) for b in range(r - 1)] for a in range(r - 1)])
+    return out
+
+
 def centered(m):
     """Centered(order = 2m) finite-volume reconstruction at the face between cells -1 and 0 from cells -m .. m-1."""
     cells = list(range(-m, m))
@@ -131,6 +146,18 @@ def main():
         flat = [[3 * Bs[0][0], 3 * Bs[0][1], 3 * Bs[0][2], 3 * Bs[1][1], 3 * Bs[1][2], 3 * Bs[2][2]] for Bs in B]
         assert flat == [[10, -31, 11, 25, -19, 4], [4, -13, 5, 13, -13, 4], [4, -19, 11, 25, -31, 10]], flat
         print("r = 3 reproduces the oracle's WENO5 constants (forms = 3 x Jiang-Shu)")
+        import random
+        random.seed(1)
+        for r in (3, 4, 5):
+            _, _, B = derive(r)
+            M = difference_forms(B)
+            v = [F(random.randint(-50, 50), random.randint(1, 9)) for _ in range(r)]
+            d1 = [v[a + 1] - v[a] for a in range(r - 1)]
+            for st in range(r):
+                bv = sum(B[st][a][b] * v[a] * v[b] for a in range(r) for b in range(a, r))
+                bd = sum(M[st][a][b] * d1[a] * d1[b] for a in range(r - 1) for b in range(a, r - 1))
+                assert bv == bd, (r, st)
+        print("difference forms == value forms (exact, random rational data)")
         for m in range(1, 5):
             print(f" Centered({2 * m}):", [str(x) for x in centered(m)])
         assert centered(2) == [F(-1, 12), F(7, 12), F(7, 12), F(-1, 12)]
@@ -153,6 +180,12 @@ def main():
         for Bs in B:
             out.append("    {" + ", ".join("{" + ", ".join(fmt(x) for x in row) + "}" for row in Bs) + "},")
         out.append("};")
+        M = difference_forms(B)
+        out.append(f"/* the same forms in the first differences d_a = psi_(a+1) - psi_a of the stencil: beta_s = sum_(a<=b) M[s][a][b] d_a d_b */")
+        out.append(f"static const double WENO{2 * r - 1}_M[{r}][{r - 1}][{r - 1}] = {{")
+        for Ms in M:
+            out.append("    {" + ", ".join("{" + ", ".join(fmt(x) for x in row) + "}" for row in Ms) + "},")
+        out.append("};")
     for m in (3, 4):
         out.append(f"/* Centered(order = {2 * m}) reconstruction at the face between a[-1] and a[0] from a[-{m}] .. a[{m - 1}] */")
         out.append(f"static const double CENTERED{2 * m}_C[{2 * m}] = {{" + ", ".join(fmt(x) for x in centered(m)) + "};")
@@ -167,8 +200,8 @@ def write_cuda_tables():
     """breeze.jl_b200/csrc/weno_tables.cuh: the same tables as device constants for the high-order reconstructions of weno.cuh."""
     import os
     out = ["// weno_tables.cuh — GENERATED by scripts/derive_weno_coefficients.py --header --cuda (exact rational derivation; do not edit).",
-           "// Finite-volume WENO of buffer R = 4 (order 7) and R = 5 (order 9): candidates C, optimal weights D, smoothness forms B",
-           "// (upper-triangular, unscaled Jiang-Shu / Balsara-Shu definition), WENO-Z global-indicator combination G, and the scale BS the",
+           "// Finite-volume WENO of buffer R = 4 (order 7) and R = 5 (order 9): candidates C, optimal weights D, smoothness forms M",
+           "// (upper-triangular, in the first differences of the stencil; unscaled Jiang-Shu / Balsara-Shu definition), WENO-Z global-indicator combination G, and the scale BS the",
            "// stored forms carry upstream (oracle/oracle_weno.h documents what is derived and what is recalled).",
            "#pragma once"]
     G = {4: [1, 3, -3, -1], 5: [1, 2, -6, 2, 1]}
@@ -182,9 +215,10 @@ def write_cuda_tables():
         for row in c:
             out.append("    {" + ", ".join(fmt(x) for x in row) + "},")
         out.append("};")
-        out.append(f"static __device__ const double {n}_B[{r}][{r}][{r}] = {{")
-        for Bs in B:
-            out.append("    {" + ", ".join("{" + ", ".join(fmt(x) for x in row) + "}" for row in Bs) + "},")
+        out.append(f"// smoothness forms in the first differences of the stencil (difference_forms() of the script)")
+        out.append(f"static __device__ const double {n}_M[{r}][{r - 1}][{r - 1}] = {{")
+        for Ms in difference_forms(B):
+            out.append("    {" + ", ".join("{" + ", ".join(fmt(x) for x in row) + "}" for row in Ms) + "},")
         out.append("};")
     out.append("template <int R> struct WenoTab;")
     for r in (4, 5):
@@ -194,7 +228,7 @@ def write_cuda_tables():
         out.append(f"    static __device__ __forceinline__ double G(int s) {{ return {n}_G[s]; }}")
         out.append(f"    static __device__ __forceinline__ double D(int s) {{ return {n}_D[s]; }}")
         out.append(f"    static __device__ __forceinline__ double C(int s, int a) {{ return {n}_C[s][a]; }}")
-        out.append(f"    static __device__ __forceinline__ double B(int s, int a, int c) {{ return {n}_B[s][a][c]; }}")
+        out.append(f"    static __device__ __forceinline__ double M(int s, int a, int c) {{ return {n}_M[s][a][c]; }}")
         out.append("};")
     for m in (3, 4):
         cc = centered(m)

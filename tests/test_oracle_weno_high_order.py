@@ -111,6 +111,35 @@ def test_essentially_non_oscillatory_at_a_step(orc, order):
     assert abs(v - 1.0) < 1e-3                               # the upwind side of the jump wins
 
 
+@pytest.mark.parametrize("order", [7, 9])
+def test_beta_forms_agree_to_cancellation_noise(orc, order):
+    """Value-form (how the reference stores the indicators) and difference-form (what the CUDA kernels evaluate) indicators are the
+    same polynomials; on θ-like data (≈ 300 with small variations) they differ by the value form's cancellation noise only."""
+    from oracle_lib import set_beta_form
+    rng = np.random.default_rng(order)
+    R = (order + 1) // 2
+    worst = 0.0
+    try:
+        for _ in range(200):
+            w = 300.0 + rng.standard_normal(2 * R - 1) * rng.choice([1e-3, 1e-1, 1.0])
+            set_beta_form(0)
+            a = orc.orc_weno_biased_window(_dp(w), order)
+            set_beta_form(1)
+            b = orc.orc_weno_biased_window(_dp(w), order)
+            worst = max(worst, abs(a - b) / abs(a))
+    finally:
+        set_beta_form(0)
+    assert worst < 1e-7
+    # and they are exactly the same on data without a large mean
+    w = rng.standard_normal(2 * R - 1)
+    set_beta_form(0)
+    a = orc.orc_weno_biased_window(_dp(w), order)
+    set_beta_form(1)
+    b = orc.orc_weno_biased_window(_dp(w), order)
+    set_beta_form(0)
+    assert a == pytest.approx(b, rel=1e-12)
+
+
 @pytest.mark.parametrize("order", [4, 6, 8])
 def test_centered_reconstruction_is_exact_to_its_order(orc, order):
     rng = np.random.default_rng(order)
