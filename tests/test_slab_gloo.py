@@ -70,6 +70,11 @@ def _worker(rank, world, port, q):
         recvb[rank] = torch.from_numpy(back[rank])
         Wy_back = slab.unpack_backward([r.numpy() for r in recvb])
         assert np.allclose(np.fft.irfft(Wy_back, n=Ny, axis=1), mine, rtol=1e-12, atol=1e-12)
+        # (5) horizontal means of the subsidence forcing (column_sums + all-reduce across slabs, compute_forcing! of
+        #     src/Forcings/subsidence_forcing.jl:137-141): per-level sums over my slab, summed over ranks == global sums
+        sums = torch.from_numpy(mine.sum(axis=(1, 2)).copy())
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+        assert np.allclose(sums.numpy() / (Nx * Ny), full.mean(axis=(1, 2)), rtol=1e-13, atol=1e-15)
         q.put((rank, "ok"))
     except Exception as e:  # noqa: BLE001
         q.put((rank, repr(e)))
