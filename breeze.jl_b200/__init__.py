@@ -8,7 +8,7 @@ from . import cases
 from .abi import BreezeError, Context, Library, bz_config, bz_forcing, load_cuda_library, cuda_library_path, FIELD_IDS
 from .model import (B200, DragFluxBoundaryCondition, FluxBoundaryCondition, Forcing, FPlane, GeostrophicForcing, SubsidenceForcing,
                     geostrophic_forcings, AnelasticDynamics, AtmosphereModel, Bounded, Flat, Periodic, RectilinearGrid, ReferenceState,
-                    SaturationAdjustment, Simulation, ThermodynamicConstants, TimeStepWizard, WENO,
+                    SaturationAdjustment, Simulation, ThermodynamicConstants, TimeStepWizard, NaNChecker, WENO,
                     conjure_time_step_wizard_, enable_peer_memory, many_time_steps_, run_, set_, time_step_)
 
 from .compressible import (CompressibleAtmosphereModel, CompressibleContext, CompressibleDynamics, ConstantSubstepSize, MonolithicFirstStage,

@@ -91,6 +91,8 @@ ABI_SYMBOLS = {
     "get_clock": (C.c_int, [_vp, _dp, C.POINTER(C.c_int64)]),
     "cell_advection_timescale": (C.c_int, [_vp, _dp]),
     "max_abs_divergence": (C.c_int, [_vp, _dp]),
+    "state_is_finite": (C.c_int, [_vp, C.POINTER(C.c_int)]),
+    "get_slice": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _dp]),
     "synchronize": (C.c_int, [_vp]),
 }
 # CUDA-library-only symbols (instrumentation); the oracle does not export them
@@ -267,6 +269,20 @@ class Context:
         d = C.c_double()
         self._check(self.lib.max_abs_divergence(self.handle, C.byref(d)), "max_abs_divergence")
         return d.value
+
+    def state_is_finite(self) -> bool:
+        ok = C.c_int()
+        self._check(self.lib.state_is_finite(self.handle, C.byref(ok)), "state_is_finite")
+        return bool(ok.value)
+
+    def get_slice(self, name_or_id, axis: str, index: int):
+        """One 2-D slice of interior(field): axis "x" → (Nz[+1], Ny), "y" → (Nz[+1], Nx), "z" → (Ny, Nx)."""
+        fid = FIELD_IDS[name_or_id] if isinstance(name_or_id, str) else int(name_or_id)
+        nz, ny, nx = self.shape(fid)
+        ax = {"x": 0, "y": 1, "z": 2}[axis]
+        out = np.empty({0: (nz, ny), 1: (nz, nx), 2: (ny, nx)}[ax])
+        self._check(self.lib.get_slice(self.handle, fid, ax, int(index), _as_dp(out)), "get_slice")
+        return out
 
     # --- instrumentation (CUDA library only) -----------------------------------------------------
     def profile_enable(self, on=True):

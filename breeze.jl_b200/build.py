@@ -1,4 +1,5 @@
 """In-tree build of csrc/libbreeze_b200.so for sm_100a (nvcc cross-compiles without a GPU)."""
+import glob
 import os
 import subprocess
 import sys
@@ -7,19 +8,23 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(CSRC, "libbreeze_b200.so")
 SOURCES = ["api.cu"]
-HEADERS = ["common.cuh", "weno.cuh", "stage_kernel.cuh", "poisson.cuh", "aux_kernels.cuh", "comm.cuh", "compressible.cuh",
-           "compressible_api.cuh", os.path.join("..", "..", "include", "breeze_b200.h"),
-           os.path.join("..", "..", "include", "breeze_b200_compressible.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
-         "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--use_fast_math=false" if False else "-Xcompiler", "-O2"]
+         "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-Xcompiler", "-O2"]
+
+
+def dependencies():
+    """Every file the library is compiled from: the sources, all headers under csrc/ (incl. generated tables) and include/."""
+    inc = os.path.join(HERE, "..", "include")
+    return ([os.path.join(CSRC, s) for s in SOURCES] + sorted(glob.glob(os.path.join(CSRC, "*.cuh")))
+            + sorted(glob.glob(os.path.join(inc, "*.h"))) + [os.path.abspath(__file__)])
 
 
 def needs_build():
     if not os.path.exists(OUT):
         return True
     t = os.path.getmtime(OUT)
-    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+    return any(os.path.getmtime(f) > t for f in dependencies())
 
 
 def build(force=False, verbose=False):

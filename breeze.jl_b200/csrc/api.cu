@@ -38,7 +38,9 @@ struct bz_ctx {
     size_t arena_bytes = 0, off_W = 0, off_W2 = 0;      // byte offsets of W / W2 inside the arena (fields: (s*5+f)*L.n, φ: 15*L.n doubles)
     double* G[NPROG] = {};               // tendencies, allocated on first bz_compute_tendencies
     double* dense = nullptr;             // nx*Ny*(Nz+1) staging buffer for host transfers
-    double* scalar = nullptr;            // device scalar for reductions
+    double* scalar = nullptr;            // device scalars for reductions
+    double* slice_buf = nullptr;         // bz_get_slice staging (grown on demand)
+    size_t slice_cap = 0;
     // Poisson solver
     PoissonGeom PG;
     double2* W = nullptr;
@@ -66,6 +68,7 @@ struct bz_ctx {
     // profiling
     int prof_on = 0;
     std::vector<cudaEvent_t> prof_ev;    // pairs
+    std::vector<cudaEvent_t> prof_pool;  // recycled events: no cudaEventCreate inside the step once the pool is warm
     std::vector<int> prof_fam;
     double prof_ms[NFAM] = {};
     int64_t prof_n[NFAM] = {};
@@ -92,15 +95,24 @@ static int dev_alloc(bz_ctx* c, T** p, size_t count) {
     return BZ_OK;
 }
 
+// Per-kernel-family timing. Events come from a pool that bz_profile_read refills, so a profiled step creates events only
+// the first time; at most PROF_MAX_SCOPES scopes are kept between two reads (later ones are not recorded).
+#define PROF_MAX_SCOPES 16384
+static cudaEvent_t prof_event(bz_ctx* c) {
+    cudaEvent_t e = nullptr;
+    if (!c->prof_pool.empty()) { e = c->prof_pool.back(); c->prof_pool.pop_back(); }
+    else cudaEventCreate(&e);
+    return e;
+}
 struct ProfScope {
-    bz_ctx* c; int fam; cudaEvent_t a = nullptr, b = nullptr;
-    ProfScope(bz_ctx* c_, int fam_) : c(c_), fam(fam_) {
-        if (!c->prof_on) return;
-        cudaEventCreate(&a); cudaEventCreate(&b);
+    bz_ctx* c; int fam; cudaEvent_t a = nullptr, b = nullptr; bool on;
+    ProfScope(bz_ctx* c_, int fam_) : c(c_), fam(fam_), on(c_->prof_on && c_->prof_fam.size() < PROF_MAX_SCOPES) {
+        if (!on) return;
+        a = prof_event(c); b = prof_event(c);
         cudaEventRecord(a, c->stream);
     }
     ~ProfScope() {
-        if (!c->prof_on) return;
+        if (!on) return;
         cudaEventRecord(b, c->stream);
         c->prof_ev.push_back(a); c->prof_ev.push_back(b); c->prof_fam.push_back(fam);
     }
@@ -197,6 +209,7 @@ static void default_reference_state(bz_ctx* c) {
 // ---------------------------------------------------------------------------------------------------------------
 static int setup_thomas(bz_ctx* c) {
     const PoissonGeom& G = c->PG;
+    if (G.nky_loc == 0) return BZ_OK;                  // a rank that owns no ky modes (Flat y on rank > 0, or Ny/2 + 1 < n_ranks)
     dim3 grid((G.Nx + 127) / 128, G.nky_loc);
     thomas_setup<<<grid, 128, 0, c->stream>>>(G, c->col.rho, c->col.rho_f, c->L.dz, c->lam_x, c->lam_y, c->inv_beta, c->tfac);
     c->launches++;
@@ -550,10 +563,11 @@ void bz_destroy(bz_ctx* c) {
     comm_destroy(c->comm);
     cudaFree(c->arena);
     for (int f = 0; f < NPROG; ++f) cudaFree(c->G[f]);
-    cudaFree(c->dense); cudaFree(c->scalar); cudaFree(c->col_store);
+    cudaFree(c->dense); cudaFree(c->scalar); cudaFree(c->slice_buf); cudaFree(c->col_store);
     cudaFree(c->tw_x); cudaFree(c->tw_y); cudaFree(c->lam_x); cudaFree(c->lam_y);
     cudaFree(c->inv_beta); cudaFree(c->tfac); cudaFree(c->ky_base); cudaFree(c->ky_kstride); cudaFree(c->ky_owner); cudaFree(c->ky_base2); cudaFree(c->fstore);
     for (auto e : c->prof_ev) cudaEventDestroy(e);
+    for (auto e : c->prof_pool) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -849,6 +863,75 @@ int bz_get_field(bz_ctx* c, int f, double* out) {
     return download_dense(c, out, nz_out);
 }
 
+// fills c->dense with interior(field) (nz_out levels) on the stream; no host copy
+static int field_to_dense(bz_ctx* c, int f, int* nz_out_p) {
+    const Layout& L = c->L;
+    int nz_out = (f == BZ_RHO_W || f == BZ_W) ? L.Nz + 1 : L.Nz;
+    dim3 grid((L.nx + 127) / 128, L.Ny, nz_out);
+    if (f >= 0 && f < NPROG) extract_interior<<<grid, 128, 0, c->stream>>>(L, c->set[c->cur][f], c->dense, nz_out);
+    else if (f == BZ_PHI) extract_interior<<<grid, 128, 0, c->stream>>>(L, c->phi, c->dense, nz_out);
+    else if (f >= BZ_U && f <= BZ_QL) {
+        FieldSet U; U.n = NPROG;
+        for (int a = 0; a < NPROG; ++a) U.f[a] = c->set[c->cur][a];
+        if (c->cfg.formulation == BZ_FORMULATION_STATIC_ENERGY) diagnose_field<BZ_THERMO_STATIC_ENERGY><<<grid, 128, 0, c->stream>>>(L, c->col, c->th, U, f, c->dense, nz_out);
+        else if (c->cfg.microphysics == BZ_MICROPHYSICS_NONE) diagnose_field<0><<<grid, 128, 0, c->stream>>>(L, c->col, c->th, U, f, c->dense, nz_out);
+        else diagnose_field<1><<<grid, 128, 0, c->stream>>>(L, c->col, c->th, U, f, c->dense, nz_out);
+    } else return BZ_ERR_INVALID;
+    c->launches++;
+    CUDA_TRY(c, cudaGetLastError());
+    *nz_out_p = nz_out;
+    return BZ_OK;
+}
+
+int bz_get_slice(bz_ctx* c, int f, int axis, int index, double* out) {
+    if (!c || !out || axis < 0 || axis > 2) return BZ_ERR_INVALID;
+    cudaSetDevice(c->cfg.device);
+    const Layout& L = c->L;
+    int nz_out = 0;
+    int rc = field_to_dense(c, f, &nz_out);
+    if (rc) return rc;
+    const int lim = axis == 0 ? L.nx : (axis == 1 ? L.Ny : nz_out);
+    if (index < 0 || index >= lim) { bz_set_error(c, "slice index %d out of range [0, %d)", index, lim); return BZ_ERR_INVALID; }
+    const size_t n = (size_t)(axis == 0 ? L.Ny : L.nx) * (axis == 2 ? L.Ny : nz_out);
+    if (!c->slice_buf || c->slice_cap < n) {
+        cudaFree(c->slice_buf); c->slice_buf = nullptr; c->slice_cap = 0;
+        CUDA_TRY(c, cudaMalloc((void**)&c->slice_buf, n * sizeof(double)));
+        c->slice_cap = n;
+    }
+    slice_kernel<<<(int)((n + 255) / 256), 256, 0, c->stream>>>(L.nx, L.Ny, nz_out, c->dense, c->slice_buf, axis, index);
+    c->launches++;
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaMemcpyAsync(out, c->slice_buf, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return BZ_OK;
+}
+
+int bz_state_is_finite(bz_ctx* c, int* finite) {
+    if (!c || !finite) return BZ_ERR_INVALID;
+    cudaSetDevice(c->cfg.device);
+    const Layout& L = c->L;
+    int* flag = reinterpret_cast<int*>(c->scalar + 1);
+    CUDA_TRY(c, cudaMemsetAsync(flag, 0, sizeof(int), c->stream));
+    FieldSet U; U.n = NPROG;
+    for (int a = 0; a < NPROG; ++a) U.f[a] = c->set[c->cur][a];
+    long long total = (long long)L.nx * L.Ny * L.Nz;
+    int blocks = (int)((total + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
+    nonfinite_kernel<<<blocks, 256, 0, c->stream>>>(L, U, flag);
+    c->launches++;
+    CUDA_TRY(c, cudaGetLastError());
+    int bad = 0;
+    CUDA_TRY(c, cudaMemcpyAsync(&bad, flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (c->comm.n_ranks > 1) {
+        double v = bad ? 1.0 : 0.0;
+        int rc = comm_allreduce_max(c->comm, &v, c->scalar, c->stream);
+        if (rc) { bz_set_error(c, "allreduce: %s", c->comm.err); return rc; }
+        bad = v > 0.0;
+    }
+    *finite = bad ? 0 : 1;
+    return BZ_OK;
+}
+
 int bz_get_state(bz_ctx* c, double* ru, double* rv, double* rw, double* rth, double* rq) {
     double* dst[NPROG] = {ru, rv, rw, rth, rq};
     for (int f = 0; f < NPROG; ++f)
@@ -915,7 +998,7 @@ int bz_profile_read(bz_ctx* c, double* ms, int64_t* n) {
         float t = 0.f;
         cudaEventElapsedTime(&t, c->prof_ev[2 * e], c->prof_ev[2 * e + 1]);
         c->prof_ms[c->prof_fam[e]] += t; c->prof_n[c->prof_fam[e]] += 1;
-        cudaEventDestroy(c->prof_ev[2 * e]); cudaEventDestroy(c->prof_ev[2 * e + 1]);
+        c->prof_pool.push_back(c->prof_ev[2 * e]); c->prof_pool.push_back(c->prof_ev[2 * e + 1]);
     }
     c->prof_ev.clear(); c->prof_fam.clear();
     for (int f = 0; f < NFAM; ++f) { if (ms) ms[f] = c->prof_ms[f]; if (n) n[f] = c->prof_n[f]; c->prof_ms[f] = 0; c->prof_n[f] = 0; }

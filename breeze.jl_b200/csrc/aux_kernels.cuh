@@ -118,6 +118,31 @@ __global__ void reduce_max_kernel(Layout L, Columns col, const double* __restric
     if ((threadIdx.x & 31) == 0) atomic_max_nonneg(out, m);
 }
 
+// NaNChecker: flag[0] = 1 if any interior value of the F.n fields is NaN or Inf
+__global__ void nonfinite_kernel(Layout L, FieldSet F, int* __restrict__ flag) {
+    const long long total = (long long)L.nx * L.Ny * L.Nz;
+    bool bad = false;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        int i = (int)(e % L.nx), j = (int)((e / L.nx) % L.Ny), k = (int)(e / ((long long)L.nx * L.Ny));
+        long long n = lidx(L, i, j, k);
+        for (int f = 0; f < F.n; ++f) {
+            // exponent bits all ones <=> NaN or Inf (integer test: no FP64 pipe)
+            bad |= ((__double2hiint(F.f[f][n]) & 0x7ff00000) == 0x7ff00000);
+        }
+    }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+
+// dense 2-D slice <- dense 3-D interior array (nx x Ny x nz_out, x fastest); axis 0: x = index, 1: y = index, 2: z = index
+__global__ void slice_kernel(int nx, int Ny, int nz_out, const double* __restrict__ src, double* __restrict__ dst, int axis, int index) {
+    const int n0 = axis == 0 ? Ny : nx, n1 = axis == 2 ? Ny : nz_out;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n0 * n1; e += gridDim.x * blockDim.x) {
+        const int a = e % n0, b = e / n0;
+        const int i = axis == 0 ? index : a, j = axis == 0 ? a : (axis == 1 ? index : b), k = axis == 2 ? index : b;
+        dst[e] = src[((size_t)k * Ny + j) * nx + i];
+    }
+}
+
 // x-face packing for the slab halo exchange: `w` columns starting at interior index i_src of nf fields -> contiguous buffer
 __global__ void pack_x_faces(Layout L, FieldSet F, int i_src, int w, double* __restrict__ buf) {
     const long long per_field = (long long)w * L.Ny * L.Nz;

@@ -32,6 +32,7 @@ struct bzc_ctx {
     int64_t iteration = 0, launches = 0, bytes = 0;
     int prof_on = 0;
     std::vector<cudaEvent_t> prof_ev;
+    std::vector<cudaEvent_t> prof_pool;  // recycled events (see ProfScope in api.cu)
     std::vector<int> prof_fam;
     double prof_ms[C_NFAM] = {};
     int64_t prof_n[C_NFAM] = {};
@@ -55,14 +56,19 @@ static void bzc_set_error(bzc_ctx* c, const char* fmt, ...) {
     } while (0)
 
 struct CProfScope {
-    bzc_ctx* c; int fam; cudaEvent_t a = nullptr, b = nullptr;
-    CProfScope(bzc_ctx* c_, int fam_) : c(c_), fam(fam_) {
-        if (!c->prof_on) return;
-        cudaEventCreate(&a); cudaEventCreate(&b);
+    bzc_ctx* c; int fam; cudaEvent_t a = nullptr, b = nullptr; bool on;
+    static cudaEvent_t take(bzc_ctx* c) {
+        cudaEvent_t e = nullptr;
+        if (!c->prof_pool.empty()) { e = c->prof_pool.back(); c->prof_pool.pop_back(); } else cudaEventCreate(&e);
+        return e;
+    }
+    CProfScope(bzc_ctx* c_, int fam_) : c(c_), fam(fam_), on(c_->prof_on && c_->prof_fam.size() < PROF_MAX_SCOPES) {
+        if (!on) return;
+        a = take(c); b = take(c);
         cudaEventRecord(a, c->stream);
     }
     ~CProfScope() {
-        if (!c->prof_on) return;
+        if (!on) return;
         cudaEventRecord(b, c->stream);
         c->prof_ev.push_back(a); c->prof_ev.push_back(b); c->prof_fam.push_back(fam);
     }
@@ -323,6 +329,7 @@ void bzc_destroy(bzc_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->arena); cudaFree(c->dense); cudaFree(c->d_cols);
     for (auto e : c->prof_ev) cudaEventDestroy(e);
+    for (auto e : c->prof_pool) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -627,7 +634,7 @@ int bzc_profile_read(bzc_ctx* c, double* ms, int64_t* n) {
         float t = 0.f;
         cudaEventElapsedTime(&t, c->prof_ev[2 * e], c->prof_ev[2 * e + 1]);
         c->prof_ms[c->prof_fam[e]] += t; c->prof_n[c->prof_fam[e]] += 1;
-        cudaEventDestroy(c->prof_ev[2 * e]); cudaEventDestroy(c->prof_ev[2 * e + 1]);
+        c->prof_pool.push_back(c->prof_ev[2 * e]); c->prof_pool.push_back(c->prof_ev[2 * e + 1]);
     }
     c->prof_ev.clear(); c->prof_fam.clear();
     for (int f = 0; f < C_NFAM; ++f) { if (ms) ms[f] = c->prof_ms[f]; if (n) n[f] = c->prof_n[f]; c->prof_ms[f] = 0; c->prof_n[f] = 0; }

@@ -409,6 +409,11 @@ class AtmosphereModel:
         """interior(field) as a numpy array shaped (Nz[+1], Ny, Nx): x fastest, as in Julia memory."""
         return self.context.get_field(name)
 
+    def slice(self, name, **at):
+        """view(field, :, j, :) etc. for slice output: model.slice("θ", y=64) → (Nz, Nx); indices are 0-based, x is rank-local."""
+        (axis, index), = at.items()
+        return self.context.get_slice(name, axis, index)
+
     @property
     def clock(self):
         t, it = self.context.clock()
@@ -477,14 +482,37 @@ def conjure_time_step_wizard_(simulation: Simulation, cfl=0.7, interval=10, **kw
     simulation.add_callback(TimeStepWizard(cfl=cfl, **kw), interval)
 
 
-def run_(simulation: Simulation):
-    """run!(simulation): the loop around time_step! (callbacks, wizard, NaN check)."""
+class NaNChecker:
+    """Oceananigans NaNChecker as installed by default_nan_checker(::AtmosphereModel) (atmosphere_model.jl:561-572): every
+    `interval` iterations a device-side reduction over the prognostic fields; stops the simulation on a NaN."""
+
+    def __init__(self, erroring=False):
+        self.erroring = erroring
+
+    def __call__(self, sim):
+        if not sim.model.context.state_is_finite():
+            t, it = sim.model.context.clock()
+            msg = f"time = {t}, iteration = {it}: NaN found in field ρu. Stopping simulation."
+            if self.erroring:
+                raise FloatingPointError(msg)
+            print(msg)
+            sim.running = False
+
+
+def run_(simulation: Simulation, nan_check_interval: int = 100):
+    """run!(simulation): the loop around time_step! (callbacks, wizard, NaN checker every 100 iterations as in Oceananigans)."""
     m = simulation.model
+    simulation.running = True
+    checker = NaNChecker()
     t, it = m.context.clock()
-    while t < simulation.stop_time and it < simulation.stop_iteration:
+    while simulation.running and t < simulation.stop_time and it < simulation.stop_iteration:
         for f, interval in simulation.callbacks:
             if it % interval == 0:
                 f(simulation)
+        if nan_check_interval and it % nan_check_interval == 0:
+            checker(simulation)
+            if not simulation.running:
+                break
         Δt = min(simulation.Δt, simulation.stop_time - t)
         m.time_step(Δt)
         t, it = m.context.clock()

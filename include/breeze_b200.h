@@ -181,6 +181,16 @@ int bz_get_clock(bz_ctx* ctx, double* time, int64_t* iteration);
  * 1/(|u|/Δx+|v|/Δy+|w|/Δz); what TimeStepWizard(cfl) multiplies. Global over ranks. */
 int bz_cell_advection_timescale(bz_ctx* ctx, double* tau);
 
+/* NaNChecker of `run!` (OceananigansDiagnostics.default_nan_checker(::AtmosphereModel), src/AtmosphereModels/atmosphere_model.jl:561-572):
+ * *finite = 0 if any prognostic value is NaN or Inf (the reference checks the first prognostic field, ρu; a NaN spreads to the
+ * others within one step, and the device reduction over all five costs the same launch). Global over ranks; synchronises. */
+int bz_state_is_finite(bz_ctx* ctx, int* finite);
+
+/* One 2-D slice of interior(field) → HOST without moving the whole field (what the examples' slice output writers save):
+ * axis 0: x = index → Ny*Nz[+1] values (y fastest); axis 1: y = index → Nx*Nz[+1] (x fastest); axis 2: z = index → Nx*Ny (x fastest).
+ * `index` is rank-local along x. Same field selectors as bz_get_field. */
+int bz_get_slice(bz_ctx* ctx, int field, int axis, int index, double* host_out);
+
 /* Discrete max |div(ρu)| over cells (the quantity test/anelastic_pressure_solver_nonhydrostatic.jl:40-46 bounds). */
 int bz_max_abs_divergence(bz_ctx* ctx, double* out);
 

@@ -1091,6 +1091,34 @@ int orc_max_abs_divergence(orc_ctx* c, double* out) {
     return BZ_OK;
 }
 
+/* NaNChecker on the first prognostic field and the others (atmosphere_model.jl:561-572) */
+int orc_state_is_finite(orc_ctx* c, int* finite) {
+    int ok = 1;
+    for (int f = 0; f < NPROG; ++f)
+        for (int k = 0; k < c->Nz; ++k) for (int j = 0; j < c->Ny; ++j) for (int i = 0; i < c->Nx; ++i)
+            if (!isfinite(c->U[f][IDX(c, i, j, k)])) ok = 0;
+    *finite = ok;
+    return BZ_OK;
+}
+
+int orc_get_slice(orc_ctx* c, int field, int axis, int index, double* out) {
+    if (axis < 0 || axis > 2) return BZ_ERR_INVALID;
+    const int nzl = (field == BZ_RHO_W || field == BZ_W) ? c->Nz + 1 : c->Nz;
+    double* full = (double*)malloc(sizeof(double) * (size_t)c->Nx * c->Ny * nzl);
+    int rc = orc_get_field(c, field, full);
+    if (rc == BZ_OK) {
+        const int n0 = axis == 0 ? c->Ny : c->Nx, n1 = axis == 2 ? c->Ny : nzl;
+        const int lim = axis == 0 ? c->Nx : (axis == 1 ? c->Ny : nzl);
+        if (index < 0 || index >= lim) rc = BZ_ERR_INVALID;
+        else for (int b = 0; b < n1; ++b) for (int a = 0; a < n0; ++a) {
+            int i = axis == 0 ? index : a, j = axis == 0 ? a : (axis == 1 ? index : b), k = axis == 2 ? index : b;
+            out[(size_t)b * n0 + a] = full[((size_t)k * c->Ny + j) * c->Nx + i];
+        }
+    }
+    free(full);
+    return rc;
+}
+
 int orc_synchronize(orc_ctx* c) { (void)c; return BZ_OK; }
 
 int orc_num_threads(void) {

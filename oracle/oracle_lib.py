@@ -18,8 +18,9 @@ LIB_PATH = os.path.join(_HERE, "liboracle.so")
 
 def build(force=False):
     inc = os.path.join(os.path.dirname(_HERE), "include")
-    deps = [os.path.join(_HERE, f) for f in ("breeze_oracle.c", "breeze_oracle_compressible.c", "oracle_weno.h", "Makefile")]
-    deps += [os.path.join(inc, f) for f in ("breeze_b200.h", "breeze_b200_compressible.h")]
+    import glob
+    deps = glob.glob(os.path.join(_HERE, "*.c")) + glob.glob(os.path.join(_HERE, "*.h")) + [os.path.join(_HERE, "Makefile")]
+    deps += glob.glob(os.path.join(inc, "*.h"))
     if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(d) for d in deps):
         return LIB_PATH
     subprocess.check_call(["make", "-C", _HERE, "-s"])

@@ -146,3 +146,29 @@ def test_time_step_wizard(oracle_arch):
     bz.conjure_time_step_wizard_(sim, cfl=0.5, interval=1)
     bz.run_(sim)
     assert sim.Δt == pytest.approx(1.1)                              # max_change limits the growth towards cfl·τ = 5
+
+
+def test_nan_checker_and_slices(oracle_arch):
+    """NaNChecker of run! (atmosphere_model.jl:561-572) and 2-D slice output, host logic + oracle side of the ABI."""
+    grid = bz.RectilinearGrid(oracle_arch, size=(8, 6, 5), x=(0, 800.0), y=(0, 600.0), z=(0, 500.0))
+    model = bz.AtmosphereModel(grid)
+    rng = np.random.default_rng(0)
+    model.set(u=rng.standard_normal((5, 6, 8)), θ=288 + rng.standard_normal((5, 6, 8)))
+    full, w = model.field("θ"), model.field("ρw")
+    assert np.array_equal(model.slice("θ", x=3), full[:, :, 3])
+    assert np.array_equal(model.slice("θ", y=2), full[:, 2, :])
+    assert np.array_equal(model.slice("θ", z=4), full[4])
+    assert np.array_equal(model.slice("ρw", y=5), w[:, 5, :]) and model.slice("ρw", y=5).shape == (6, 8)
+    with pytest.raises(bz.BreezeError):
+        model.slice("θ", z=5)
+    assert model.context.state_is_finite()
+    sim = bz.Simulation(model, Δt=0.1, stop_iteration=3)
+    bz.run_(sim, nan_check_interval=1)
+    assert model.clock["iteration"] == 3
+    bad = model.field("ρu")
+    bad[1, 2, 3] = np.nan
+    model.context.set_state(rho_u=bad, enforce_mass_conservation=False)
+    assert not model.context.state_is_finite()
+    sim = bz.Simulation(model, Δt=0.1, stop_iteration=10)
+    bz.run_(sim, nan_check_interval=1)
+    assert model.clock["iteration"] == 3                              # the checker stopped the run before another step

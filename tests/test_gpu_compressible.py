@@ -6,7 +6,10 @@ difference-form / single-reciprocal WENO5-Z of weno.cuh):
   * update_state! diagnostics (u, v, w, θ, T, p) and the linearization (Πᴸ, θᴸ)          : 1e-13 relative to the max-norm
   * one slow-tendency evaluation vs the oracle with the same (difference-form) indicators : 1e-11
   * one acoustic substep loop (perturbation fields, recovered state)                      : 1e-10
-  * N = 5 WS-RK3 steps of a moving warm bubble                                            : 1e-9
+  * N = 5 WS-RK3 steps of a moving warm bubble, oracle in the REFERENCE (quadratic) form  : 1e-8
+Multi-step comparisons always run against the oracle's default form (the reference's quadratic-form smoothness indicators);
+the kernel-matching difference form is only switched on for single slow-tendency evaluations (1e-11) and the single substep loop
+that follows one.
 """
 import numpy as np
 import pytest
@@ -18,7 +21,7 @@ pytestmark = pytest.mark.gpu
 TOL_DIAG = 1e-13
 TOL_TENDENCY = 1e-11
 TOL_LOOP = 1e-10
-TOL_STEPS = 1e-9
+TOL_STEPS = 1e-8
 PROGNOSTIC = ["ρ", "ρu", "ρv", "ρw", "ρθ"]
 RD = 8.314462618 / 0.02897
 
@@ -142,13 +145,9 @@ def test_acoustic_substep_loop_matches_oracle(oracle_arch, size, flat_y, td, bet
 def test_bubble_steps_match_oracle(oracle_arch, size, flat_y, dt):
     import oracle_lib
     gpu, cpu = _pair(oracle_arch, size, flat_y, seed=5, noise=0.0)
-    oracle_lib.set_beta_form(1)
-    try:
-        for m in (gpu, cpu):
-            for _ in range(5):
-                m.time_step(dt)
-    finally:
-        oracle_lib.set_beta_form(0)
+    for m in (gpu, cpu):
+        for _ in range(5):
+            m.time_step(dt)
     assert gpu.clock == cpu.clock
     for name in PROGNOSTIC + ["u", "w", "θ", "p"]:
         assert rel_err(gpu.field(name), cpu.field(name)) < TOL_STEPS, name
@@ -204,6 +203,28 @@ def test_mass_conservation_and_walls_on_gpu(oracle_arch):
     assert abs(gpu.field("ρ").sum() - M0) / M0 <= 1e-12
     rw = gpu.field("ρw")
     assert np.abs(rw[-1]).max() == 0 and np.abs(rw[0]).max() == 0
+
+
+def test_config4_full_size_one_step_vs_oracle(oracle_arch):
+    """BASELINE config 4 at its own size: the supercell-shaped 256 x 256 x 64 grid (168 km x 168 km x 20 km), split-explicit WS-RK3 with
+    6 acoustic substeps, one step of dt = 6 s against the oracle in the reference form (≈ 5 s of host work)."""
+    import breeze_b200 as bz
+
+    def model(arch):
+        grid = bz.RectilinearGrid(arch, size=(256, 256, 64), x=(0, 168e3), y=(0, 168e3), z=(0, 20e3))
+        m = bz.AtmosphereModel(grid, dynamics=bz.CompressibleDynamics(bz.SplitExplicitTimeDiscretization(substeps=6), reference_potential_temperature=300.0))
+        _, rho, _ = m.reference_profiles()
+        m.set(ρ=np.broadcast_to(rho[:, None, None], m.context.shape(0)).copy(),
+              θ=lambda x, y, z: 300.0 + 3.0 * np.exp(-((x - 84e3) ** 2 + (y - 84e3) ** 2) / 10e3 ** 2 - (z - 1500.0) ** 2 / 1500.0 ** 2),
+              u=10.0, v=5.0)
+        return m
+
+    gpu, cpu = model(bz.B200()), model(oracle_arch)
+    for m in (gpu, cpu):
+        m.time_step(6.0)
+    for name in PROGNOSTIC + ["u", "w", "θ", "p"]:
+        assert rel_err(gpu.field(name), cpu.field(name)) < TOL_STEPS, name
+    assert np.abs(gpu.field("w")).max() > 1e-3
 
 
 def test_config4_shape_runs_and_counts_launches():
@@ -276,14 +297,9 @@ def test_moist_bubble_steps_match_oracle(oracle_arch, size, flat_y, dt):
     import oracle_lib
     gpu, cpu = _moist_pair(oracle_arch, size, flat_y, seed=6, noise=0.0)
     M0 = gpu.field("ρqᵛ").sum()
-    oracle_lib.set_beta_form(1)
-    try:
-        for m in (gpu, cpu):
-            m.context.set_state()
-            for _ in range(5):
-                m.time_step(dt)
-    finally:
-        oracle_lib.set_beta_form(0)
+    for m in (gpu, cpu):
+        for _ in range(5):
+            m.time_step(dt)
     for name in PROGNOSTIC + ["ρqᵛ", "qᵛ", "u", "w", "θ", "p", "⟨w⟩"]:
         assert rel_err(gpu.field(name), cpu.field(name)) < TOL_STEPS, name
     assert abs(gpu.field("ρqᵛ").sum() - M0) / M0 < 1e-13          # flux form: vapour mass conserved on the CUDA path

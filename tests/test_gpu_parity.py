@@ -11,11 +11,16 @@ FFT butterfly order), so agreement is to round-off amplified by the WENO weights
     noise against β + ε ≈ 1e-8…1e-5: the reference's own CPU-vs-GPU runs differ by this much
     (docs/src/reproducibility.md). The oracle's two forms differ from each other by the same 1e-9…1e-8.
   * N = 10 full SSP-RK3 steps of the bubble       : 1e-8 relative to the field's max-norm
+Every MULTI-STEP comparison runs against the oracle in its default form, i.e. the reference's quadratic-form smoothness
+indicators; the kernel-matching difference form (set_beta_form(1)) is used for single tendency evaluations at 1e-11 only.
+States seeded with grid-scale random noise (BOMEX) put every WENO stencil in its most weight-sensitive regime, where the two
+algebraically identical indicator forms differ by the quadratic form's cancellation noise (≈ |ψ|² eps against β + ε): those
+comparisons state their own, looser tolerance (TOL_STEPS_NOISY), measured on a B200 (profiles/r2_parity_errors.txt).
 """
 import numpy as np
 import pytest
 
-from conftest import bubble_theta, make_bubble_model, rel_err
+from conftest import bubble_theta, make_bubble_model, rel_err, report
 
 pytestmark = pytest.mark.gpu
 
@@ -23,6 +28,7 @@ TOL_HOOK = 1e-9
 TOL_SAME_FORM = 1e-11
 TOL_REFERENCE_FORM = 1e-7
 TOL_STEPS = 1e-8
+TOL_STEPS_NOISY = 2e-7       # five steps from a state with grid-scale random noise, reference-form oracle (measured ≈ 1e-8; see above)
 PROGNOSTIC = ["ρu", "ρv", "ρw", "ρθ", "ρq"]
 
 
@@ -198,22 +204,19 @@ def test_bomex_forcings_match_oracle(oracle_arch):
         oracle_lib.set_beta_form(0)
     for name in PROGNOSTIC:
         assert rel_err(gpu.context.get_tendency(name), cpu.context.get_tendency(name)) < TOL_SAME_FORM, name
-    # Five steps. The initial state carries grid-scale random noise, where the WENO weights amplify the difference between
-    # the reference's quadratic-form and the kernels' difference-form smoothness indicators (≈ 4e-10 on ρθ, which buoyancy
-    # feeds into the small ρv, ρw); so the oracle steps in the kernels' form here, and momentum components are compared
-    # on the common momentum scale.
-    oracle_lib.set_beta_form(1)
-    try:
-        for _ in range(5):
-            gpu.time_step(2.0)
-            cpu.time_step(2.0)
-    finally:
-        oracle_lib.set_beta_form(0)
+    # Five steps against the oracle in the REFERENCE form (default). The initial state carries grid-scale random noise, where the
+    # WENO weights amplify the quadratic-form indicators' cancellation noise; momentum components are compared on the common
+    # momentum scale (ρv, ρw are small and fed by buoyancy).
+    for _ in range(5):
+        gpu.time_step(2.0)
+        cpu.time_step(2.0)
     mom_scale = max(np.abs(cpu.field(n)).max() for n in ("ρu", "ρv", "ρw"))
     for name in ("ρu", "ρv", "ρw"):
-        assert np.abs(gpu.field(name) - cpu.field(name)).max() < 1e-9 * mom_scale, name
+        err = np.abs(gpu.field(name) - cpu.field(name)).max() / mom_scale
+        report(err, name)
+        assert err < TOL_STEPS_NOISY, (name, err)
     for name in ("ρθ", "ρq", "T", "qˡ"):
-        assert rel_err(gpu.field(name), cpu.field(name)) < 1e-9, name
+        assert rel_err(gpu.field(name), cpu.field(name)) < TOL_STEPS_NOISY, name
 
 
 # ---- BASELINE configurations at (or near) their full sizes ------------------------------------------------------------
@@ -245,6 +248,70 @@ def test_config1_bubble_3d_128_vs_oracle(oracle_arch):
         cpu.time_step(0.5)
     for name in PROGNOSTIC + ["w", "θ"]:
         assert rel_err(gpu.field(name), cpu.field(name)) < TOL_STEPS, name
+
+
+def test_config3_bomex_full_size_with_cloud_vs_oracle(oracle_arch):
+    """BASELINE config 3 at its own size: BOMEX 128 x 128 x 75 (moist θ_li, warm-phase saturation adjustment, subsidence + geostrophic +
+    Coriolis + prescribed drying / cooling, surface flux BCs), two steps from a state WITH CLOUD (seeded moist thermals: the secant branch
+    of the saturation adjustment runs), against the oracle in the reference form."""
+    import breeze_b200 as bz
+    gpu = bz.cases.bomex_model(bz.B200(), size=(128, 128, 75), extent=12800.0, cloud=True)
+    cpu = bz.cases.bomex_model(oracle_arch, size=(128, 128, 75), extent=12800.0, cloud=True)
+    assert (cpu.field("qˡ") > 0).mean() > 0.01, "the state must contain cloud"
+    for _ in range(2):
+        gpu.time_step(1.0)
+        cpu.time_step(1.0)
+    assert (cpu.field("qˡ") > 0).mean() > 0.01
+    mom_scale = max(np.abs(cpu.field(n)).max() for n in ("ρu", "ρv", "ρw"))
+    for name in ("ρu", "ρv", "ρw"):
+        err = np.abs(gpu.field(name) - cpu.field(name)).max() / mom_scale
+        report(err, name)
+        assert err < TOL_STEPS_NOISY, (name, err)
+    for name in ("ρθ", "ρq", "T", "qᵛ", "qˡ"):
+        assert rel_err(gpu.field(name), cpu.field(name)) < TOL_STEPS_NOISY, name
+
+
+def test_config1_bubble_3d_256_vs_oracle(oracle_arch):
+    """BASELINE config 1 at its own size (256³, 3-D dry bubble, anelastic WENO5, FP64 match vs the CPU run): two steps against the oracle
+    (≈ 20 s of host work on 16 cores). bench.py repeats this comparison over four steps in every N = 1 run (checks.parity_256)."""
+    import breeze_b200 as bz
+    gpu = make_bubble_model(bz.B200(), (256, 256, 256))
+    cpu = make_bubble_model(oracle_arch, (256, 256, 256))
+    for m in (gpu, cpu):
+        m.set(θ=bubble_theta())
+    for _ in range(2):
+        gpu.time_step(0.5)
+        cpu.time_step(0.5)
+    for name in PROGNOSTIC + ["w", "θ"]:
+        assert rel_err(gpu.field(name), cpu.field(name)) < TOL_STEPS, name
+
+
+def test_cell_advection_timescale_and_finite_check_match_oracle(oracle_arch):
+    """cell_advection_timescale (src/AtmosphereModels/cell_advection_timescale.jl:46-65) and the NaN checker's reduction
+    (atmosphere_model.jl:561-572) on the device against the oracle / numpy."""
+    gpu, cpu = _pair(oracle_arch, (32, 16, 24))
+    tg, tc = gpu.context.cell_advection_timescale(), cpu.context.cell_advection_timescale()
+    report(abs(tg - tc) / tc, "tau")
+    assert abs(tg - tc) < 1e-12 * tc
+    for _ in range(3):
+        gpu.time_step(1.0)
+        cpu.time_step(1.0)
+    tg, tc = gpu.context.cell_advection_timescale(), cpu.context.cell_advection_timescale()
+    assert abs(tg - tc) < 1e-9 * tc
+    assert gpu.context.state_is_finite()
+    bad = gpu.field("ρθ")
+    bad[3, 2, 1] = np.nan
+    gpu.context.set_state(rho_theta=bad, enforce_mass_conservation=False)
+    assert not gpu.context.state_is_finite()
+
+
+def test_slices_match_full_fields(oracle_arch):
+    gpu, _ = _pair(oracle_arch, (32, 16, 24), moist=True)
+    for name in ("θ", "ρw", "T", "φ"):
+        full = gpu.field(name)
+        assert np.array_equal(gpu.slice(name, x=5), full[:, :, 5]), name
+        assert np.array_equal(gpu.slice(name, y=7), full[:, 7, :]), name
+        assert np.array_equal(gpu.slice(name, z=3), full[3]), name
 
 
 @pytest.mark.parametrize("N", [256, 512])
