@@ -333,7 +333,7 @@ class CompressibleAtmosphereModel:
         self.thermodynamic_constants = thermodynamic_constants or ThermodynamicConstants()
         self.advection = advection or WENO(order=5)
         if self.advection.order not in (5, 7, 9):
-            raise NotImplementedError("WENO(order = 5) is on the hot path; orders 7 and 9 exist in the CPU oracle only (the CUDA library rejects them)")
+            raise NotImplementedError("WENO(order = 5, 7 or 9) is on the hot path")
         lib = compressible_library(self.architecture.library())
         cfg = bzc_config()
         lib.default_config(C.byref(cfg))

@@ -17,6 +17,7 @@
 
 #include "common.cuh"
 #include "stage_kernel.cuh"
+#include "stage_hi.cuh"
 #include "poisson.cuh"
 #include "aux_kernels.cuh"
 #include "comm.cuh"
@@ -37,6 +38,8 @@ struct bz_ctx {
     double* arena = nullptr;
     size_t arena_bytes = 0, off_W = 0, off_W2 = 0;      // byte offsets of W / W2 inside the arena (fields: (s*5+f)*L.n, φ: 15*L.n doubles)
     double* G[NPROG] = {};               // tendencies, allocated on first bz_compute_tendencies
+    int buf = 3;                         // buffer of the advection scheme: (order + 1) / 2
+    double* V[NPROG] = {};               // WENO(order = 7 / 9): velocities / specific values of the stage's input state (stage_hi.cuh)
     double* dense = nullptr;             // nx*Ny*(Nz+1) staging buffer for host transfers
     double* scalar = nullptr;            // device scalars for reductions
     double* slice_buf = nullptr;         // bz_get_slice staging (grown on demand)
@@ -57,7 +60,7 @@ struct bz_ctx {
     double* fstore = nullptr;            // ws[Nz+1] | ug | vg | q_tend | e_tend | sums[4Nz] | fcol[4Nz]
     double *d_ws = nullptr, *d_ug = nullptr, *d_vg = nullptr, *d_qt = nullptr, *d_et = nullptr, *d_sums = nullptr, *d_fcol = nullptr;
     int lines_x = 1, lines_y = 1;
-    int fft_wide_y = 0, fft_x_minb = 3;   // fft_wide_y: 0 default (256, 3); 1: (512, 2) wide tiles; 2: (256, 4) 64-register build  // tuning experiments (BZ_FFT_LINES_Y > 256 threads per CTA; BZ_FFT_X_MINB = 4: 64-register build of fft_x)
+    int fft_wide_y = 2, fft_x_minb = 3;   // fft_wide_y: 2 default (256, 4) 64-register build; 0: (256, 3); 1: (512, 2) wide tiles  // tuning experiments (BZ_FFT_LINES_Y > 256 threads per CTA; BZ_FFT_X_MINB = 4: 64-register build of fft_x)
     cudaStream_t stream = nullptr;
     Comm comm;
     int use_tma = 0, z_chunks = 1;
@@ -281,7 +284,9 @@ static int setup_poisson(bz_ctx* c) {
         while (lines & (lines - 1)) lines &= lines - 1;       // power of two (the kernels shift instead of dividing)
         c->lines_y = lines;
         c->fft_wide_y = (lines * g.Ny / 8 > 256);
-        if (!c->fft_wide_y) { const char* e = getenv("BZ_FFT_Y_MINB"); if (e && atoi(e) == 4) c->fft_wide_y = 2; }          // tuning sweeps only
+        // default since round 2: the 64-register build (256, 4) of the y transforms — 4 CTAs per SM hide the source term's load latency
+        // (measured at 512^3, profiles/r2a_fft_sweep.txt: forward 6.84 -> 6.01 ms, inverse 4.41 -> 4.24 ms per step, bit-identical)
+        if (!c->fft_wide_y) { const char* e = getenv("BZ_FFT_Y_MINB"); c->fft_wide_y = (e && atoi(e) == 3) ? 0 : 2; }      // BZ_FFT_Y_MINB=3: the 80-register build
         size_t sm = fft_smem_bytes(g.Ny, lines);
         if (c->fft_wide_y == 1) {
             FFT_DISPATCH(g.Ny, {
@@ -465,6 +470,47 @@ static int launch_stage_t(bz_ctx* c, const StageParams& P, int nz_chunks) {
     return BZ_OK;
 }
 
+template <int BUF, int TY, int MICRO, bool FORCED>
+static int launch_stage_hi_t(bz_ctx* c, const StageParams& P, const SpecificFields& F, int chunks) {
+    const Layout& L = c->L;
+    const dim3 grid((L.nx + HI_TX - 1) / HI_TX, (L.Ny + TY - 1) / TY, chunks), block(32, TY);
+    stage_hi_kernel<BUF, TY, MICRO, FORCED><<<grid, block, 0, c->stream>>>(P, F);
+    c->launches++;
+    CUDA_TRY(c, cudaGetLastError());
+    return BZ_OK;
+}
+
+// WENO(order = 7 / 9): specific fields of the input state, then the fused high-order stage kernel (stage_hi.cuh)
+static int launch_stage_hi(bz_ctx* c, StageParams& P, int in) {
+    const Layout& L = c->L;
+    SpecificFields F;
+    for (int f = 0; f < NPROG; ++f) { F.U[f] = c->set[in][f]; F.V[f] = c->V[f]; }
+    {
+        int bx = (int)((L.plane + 255) / 256); if (bx > 64) bx = 64;
+        specific_fields_kernel<<<dim3(bx, L.Nz), 256, 0, c->stream>>>(L, c->col, F);
+        c->launches++;
+        CUDA_TRY(c, cudaGetLastError());
+    }
+    // z chunks: enough CTAs for ≈ 3 waves of the machine, at least 8 levels per chunk (a chunk start re-evaluates five z fluxes and one buoyancy)
+    const int ty = L.flat_y ? 1 : 8;
+    const long long tiles = (long long)((L.nx + HI_TX - 1) / HI_TX) * ((L.Ny + ty - 1) / ty);
+    int chunks = c->cfg.z_chunks > 0 ? c->cfg.z_chunks : (int)((3 * 148 * (L.flat_y ? 8 : 1) + tiles - 1) / tiles);
+    const int max_chunks = (L.Nz + 7) / 8;
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks < 1) chunks = 1;
+    P.k_chunk = (L.Nz + chunks - 1) / chunks;
+    chunks = (L.Nz + P.k_chunk - 1) / P.k_chunk;
+    const bool moist = c->cfg.microphysics != BZ_MICROPHYSICS_NONE;
+    const bool se = c->cfg.formulation == BZ_FORMULATION_STATIC_ENERGY;
+#define LAUNCH_HI(BUF, TY)                                                                                                         \
+    (se ? launch_stage_hi_t<BUF, TY, BZ_THERMO_STATIC_ENERGY, false>(c, P, F, chunks)                                              \
+        : c->forced ? (moist ? launch_stage_hi_t<BUF, TY, 1, true>(c, P, F, chunks) : launch_stage_hi_t<BUF, TY, 0, true>(c, P, F, chunks)) \
+                    : (moist ? launch_stage_hi_t<BUF, TY, 1, false>(c, P, F, chunks) : launch_stage_hi_t<BUF, TY, 0, false>(c, P, F, chunks)))
+    if (c->buf == 5) return L.flat_y ? LAUNCH_HI(5, 1) : LAUNCH_HI(5, 8);
+    return L.flat_y ? LAUNCH_HI(4, 1) : LAUNCH_HI(4, 8);
+#undef LAUNCH_HI
+}
+
 // mode 0: out = RK update of set[in]; mode 1: out = tendencies
 static int launch_stage(bz_ctx* c, int in, double* const* out, int u0, double dt, double alpha, int mode) {
     ProfScope ps(c, 0);
@@ -489,6 +535,7 @@ static int launch_stage(bz_ctx* c, int in, double* const* out, int u0, double dt
         P.coriolis_f = c->coriolis_f;
         P.theta_flux_dz = c->theta_flux / c->L.dz; P.q_flux_dz = c->q_flux / c->L.dz; P.drag_dz = c->drag / c->L.dz;
     }
+    if (c->buf > 3) return launch_stage_hi(c, P, in);
 #define LAUNCH(TX, TY, HY, FX)                                                                                        \
     (c->forced ? (moist ? launch_stage_t<TX, TY, HY, FX, 1, true>(c, P, chunks) : launch_stage_t<TX, TY, HY, FX, 0, true>(c, P, chunks)) \
                : (moist ? launch_stage_t<TX, TY, HY, FX, 1, false>(c, P, chunks) : launch_stage_t<TX, TY, HY, FX, 0, false>(c, P, chunks)))
@@ -562,7 +609,7 @@ void bz_destroy(bz_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     comm_destroy(c->comm);
     cudaFree(c->arena);
-    for (int f = 0; f < NPROG; ++f) cudaFree(c->G[f]);
+    for (int f = 0; f < NPROG; ++f) { cudaFree(c->G[f]); cudaFree(c->V[f]); }
     cudaFree(c->dense); cudaFree(c->scalar); cudaFree(c->slice_buf); cudaFree(c->col_store);
     cudaFree(c->tw_x); cudaFree(c->tw_y); cudaFree(c->lam_x); cudaFree(c->lam_y);
     cudaFree(c->inv_beta); cudaFree(c->tfac); cudaFree(c->ky_base); cudaFree(c->ky_kstride); cudaFree(c->ky_owner); cudaFree(c->ky_base2); cudaFree(c->fstore);
@@ -578,7 +625,8 @@ int bz_create(const bz_config* cfg, bz_ctx** out) {
 #define FAIL(code, ...) do { bz_set_error(nullptr, __VA_ARGS__); return (code); } while (0)
     if (cfg->abi_version != BZ_ABI_VERSION) FAIL(BZ_ERR_INVALID, "abi_version %d != %d", cfg->abi_version, BZ_ABI_VERSION);
     if (cfg->Nx < 1 || cfg->Ny < 1 || cfg->Nz < 2) FAIL(BZ_ERR_INVALID, "grid size must be positive (Nz >= 2)");
-    if (cfg->advection_order != 5) FAIL(BZ_ERR_UNSUPPORTED, "only WENO(order=5) is on the path");
+    if (cfg->advection_order != 5 && cfg->advection_order != 7 && cfg->advection_order != 9)
+        FAIL(BZ_ERR_UNSUPPORTED, "WENO(order = 5, 7 or 9) is on the path, got order %d", cfg->advection_order);
     if (cfg->formulation != BZ_FORMULATION_POTENTIAL_TEMPERATURE && cfg->formulation != BZ_FORMULATION_STATIC_ENERGY) FAIL(BZ_ERR_INVALID, "unknown formulation %d", cfg->formulation);
     if (cfg->formulation == BZ_FORMULATION_STATIC_ENERGY && cfg->microphysics != BZ_MICROPHYSICS_NONE)
         FAIL(BZ_ERR_UNSUPPORTED, "StaticEnergyFormulation is on the path without microphysics only");
@@ -588,6 +636,7 @@ int bz_create(const bz_config* cfg, bz_ctx** out) {
     if (!fx && (!is_pow2(cfg->Nx) || cfg->Nx < 8 || cfg->Nx > 2048)) FAIL(BZ_ERR_UNSUPPORTED, "Nx must be a power of two in [8, 2048] (in-house FFT)");
     if (!fy && (!is_pow2(cfg->Ny) || cfg->Ny < 8 || cfg->Ny > 2048)) FAIL(BZ_ERR_UNSUPPORTED, "Ny must be a power of two in [8, 2048] (in-house FFT)");
     const int P = cfg->n_ranks < 1 ? 1 : cfg->n_ranks;
+    if (cfg->use_tma == 1 && cfg->advection_order != 5) FAIL(BZ_ERR_UNSUPPORTED, "TMA staging belongs to the WENO(order=5) stage kernel");
     if (P > 1 && (fx || cfg->Nx % P != 0 || (cfg->Nx / P) < 8)) FAIL(BZ_ERR_INVALID, "x-slabs: Nx must be divisible by n_ranks with at least 8 columns per rank");
     if (cfg->rank < 0 || cfg->rank >= P) FAIL(BZ_ERR_INVALID, "rank out of range");
     int ndev = 0;
@@ -605,9 +654,12 @@ int bz_create(const bz_config* cfg, bz_ctx** out) {
     Layout& L = c->L;
     L.nx = cfg->Nx / P; L.Ny = cfg->Ny; L.Nz = cfg->Nz;
     L.flat_x = fx; L.flat_y = fy;
-    L.HX = fx ? 0 : BZ_HALO; L.HY = fy ? 0 : BZ_HALO;
+    c->buf = (cfg->advection_order + 1) / 2;
+    const int halo = c->buf == 3 ? BZ_HALO : c->buf + 1;              // 4 for WENO5 (the TMA-staged kernel's tile origin), buffer + 1 otherwise
+    L.HX = fx ? 0 : halo; L.HY = fy ? 0 : halo;
     L.PX = L.nx + 2 * L.HX; L.PY = L.Ny + 2 * L.HY;
-    L.plane = (long long)L.PX * L.PY; L.n = L.plane * L.Nz;
+    L.plane = (long long)L.PX * L.PY;
+    L.n = L.plane * (L.Nz + (c->buf > 3 ? 1 : 0));                    // orders 7 / 9: one extra zero plane on top (the top wall of ρw, stage_hi.cuh)
     L.dx = fx ? 1.0 : (cfg->x1 - cfg->x0) / cfg->Nx;
     L.dy = fy ? 1.0 : (cfg->y1 - cfg->y0) / cfg->Ny;
     L.dz = (cfg->z1 - cfg->z0) / cfg->Nz;
@@ -656,7 +708,8 @@ int bz_create(const bz_config* cfg, bz_ctx** out) {
     TRY(setup_poisson(c));
     TRY(comm_alloc_buffers(c->comm, L, c->PG, &c->bytes));
     // staging of the stage kernel's operands
-    const bool tma_possible = !fx && (L.PX % 2 == 0);
+    const bool tma_possible = !fx && (L.PX % 2 == 0) && c->buf == 3;
+    if (c->buf > 3) for (int f = 0; f < NPROG; ++f) TRY(dev_alloc(c, &c->V[f], (size_t)L.n));
     c->use_tma = (cfg->use_tma == 2) ? 0 : (tma_possible ? 1 : 0);
     if (cfg->use_tma == 1 && !tma_possible) { bz_set_error(nullptr, "TMA staging needs an even padded row length"); bz_destroy(c); return BZ_ERR_UNSUPPORTED; }
     if (c->use_tma) {

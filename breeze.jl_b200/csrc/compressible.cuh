@@ -104,7 +104,7 @@ struct CSlowArgs {
 
 // biased reconstruction at the "face" between f[n - s] and f[n]; in x / y the ghost cells make R = 3 always valid,
 // in z the buffer R shrinks next to the walls (weno.cuh red_face / red_center) and only in-range levels are read
-// BUF: the scheme's buffer (3: WENO5, the path of record; 4 / 5: WENO7 / WENO9, experimental); R <= BUF: buffer in use at this point
+// BUF: the scheme's buffer (3: WENO5, the path of record; 4 / 5: WENO7 / WENO9); R <= BUF: buffer in use at this point
 template <int BUF = 3>
 __device__ __forceinline__ double c_biased(const double* __restrict__ f, long long n, long long s, int R, bool left) {
     if constexpr (BUF >= 5) { if (R >= 5) return weno_hi_mem<5>(f, n, s, left); }

@@ -342,11 +342,10 @@ int bzc_create(const bzc_config* cfg, bzc_ctx** out) {
     if (b->abi_version != BZ_ABI_VERSION) FAIL(BZ_ERR_INVALID, "abi_version %d != %d", b->abi_version, BZ_ABI_VERSION);
     if (b->microphysics != BZ_MICROPHYSICS_NONE) FAIL(BZ_ERR_UNSUPPORTED, "the compressible path carries vapour only (microphysics = nothing)");
     if (b->n_ranks > 1) FAIL(BZ_ERR_UNSUPPORTED, "the compressible path runs on one GPU");
-    // WENO(order = 7 / 9): the kernels exist (c_slow_tendencies<4 / 5>, c_moisture_tendency<4 / 5>) but have not been verified on a GPU
-    // against the oracle yet — they stay behind an explicit development switch and the library otherwise rejects the orders loudly.
-    const bool experimental_order = (b->advection_order == 7 || b->advection_order == 9) && getenv("BZ_EXPERIMENTAL_WENO_ORDER") != nullptr;
-    if (b->advection_order != 5 && !experimental_order) FAIL(BZ_ERR_UNSUPPORTED, "only WENO(order=5) is on the path");
-    const int buf = (b->advection_order + 1) / 2;                      // 3, or 4 / 5 behind the switch
+    // WENO(order = 7 / 9): c_slow_tendencies<4 / 5>, c_moisture_tendency<4 / 5>; verified against the oracle on a B200 (tests/test_gpu_weno_high_order.py)
+    if (b->advection_order != 5 && b->advection_order != 7 && b->advection_order != 9)
+        FAIL(BZ_ERR_UNSUPPORTED, "WENO(order = 5, 7 or 9) is on the path, got order %d", b->advection_order);
+    const int buf = (b->advection_order + 1) / 2;                      // 3, 4 or 5
     const int fx = b->topology_x == BZ_FLAT, fy = b->topology_y == BZ_FLAT;
     if ((fx && b->Nx != 1) || (fy && b->Ny != 1)) FAIL(BZ_ERR_INVALID, "a Flat dimension must have size 1");
     if ((!fx && b->Nx < 4) || (!fy && b->Ny < 4) || b->Nz < 4) FAIL(BZ_ERR_INVALID, "at least 4 cells per non-Flat dimension");

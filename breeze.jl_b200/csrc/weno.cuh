@@ -98,10 +98,10 @@ __device__ __forceinline__ double sym4(double v0, double v1, double v2, double v
     return 0.5 * (v1 + v2);
 }
 
-// ---- WENO(order = 7 / 9)-Z and Centered(6 / 8): EXPERIMENTAL ---------------------------------------------
-// Table-driven restatement of oracle/oracle_weno.h (weno_hi_window / centered_hi) for the kernels that read their stencils from
-// global memory (compressible.cuh). Written for correctness first: ≈ 200 FP64 per order-9 reconstruction; no kernel instantiates
-// these unless the experimental switch of bzc_create is set, and they have not run on a GPU yet.
+// ---- WENO(order = 7 / 9)-Z and Centered(6 / 8) -----------------------------------------------------------
+// Table-driven restatement of oracle/oracle_weno.h (weno_hi_window / centered_hi) for the kernels that read their stencils through
+// L1 / L2 (stage_hi.cuh, compressible.cuh): ≈ 170 FP64 per order-9 reconstruction. Smoothness indicators as quadratic forms in the
+// FIRST DIFFERENCES of the stencil (no |ψ|² cancellation; the oracle's beta form 1); every division is MUFU.RCP64H + one cubic step.
 #include "weno_tables.cuh"
 // w[0 .. 2R-2]: window of the biased reconstruction, upwind cell at w[R-1] (mirror the window for the right bias).
 template <int R>
@@ -116,7 +116,6 @@ __device__ __forceinline__ double weno_hi(const double (&w)[2 * R - 1]) {
         double q = 0.0, b = 0.0;
 #pragma unroll
         for (int a = 0; a < R; ++a) q = fma(T::C(st, a), w[R - 1 - st + a], q);
-        // smoothness indicator as a quadratic form in the FIRST DIFFERENCES of the stencil (the oracle's beta form 1): no |psi|^2 cancellation
 #pragma unroll
         for (int a = 0; a < R - 1; ++a) {
             double row = 0.0;
@@ -132,16 +131,22 @@ __device__ __forceinline__ double weno_hi(const double (&w)[2 * R - 1]) {
     double num = 0.0, den = 0.0;
 #pragma unroll
     for (int st = 0; st < R; ++st) {
-        const double rr = tau / (beta[st] + WENO_EPS);
+        const double rr = tau * fast_rcp(beta[st] + WENO_EPS);
         const double al = T::D(st) * fma(rr, rr, 1.0);
         num = fma(al, p[st], num);
         den += al;
     }
-    return num / den;
+    return num * fast_rcp(den);
 }
-// biased value at the face between f[n - s] and f[n] from a field in memory (stride s), buffer R = 4 or 5
+// biased value at the face between f[n - s] and f[n] from a field in memory (stride s), buffer R = 4 or 5. Kept out of line: one copy of
+// the ≈ 250-instruction body per order instead of one per call site (25 sites in stage_hi_kernel); the call costs ≈ 1 % of the body.
+#ifdef BZ_WENO_HI_INLINE
+#define BZ_HI_LINKAGE __forceinline__
+#else
+#define BZ_HI_LINKAGE __noinline__
+#endif
 template <int R>
-__device__ __forceinline__ double weno_hi_mem(const double* __restrict__ f, long long n, long long s, bool left) {
+__device__ BZ_HI_LINKAGE double weno_hi_mem(const double* __restrict__ f, long long n, long long s, bool left) {
     double w[2 * R - 1];
 #pragma unroll
     for (int j = 0; j < 2 * R - 1; ++j) w[j] = left ? f[n + (j - R) * s] : f[n + (R - 1 - j) * s];

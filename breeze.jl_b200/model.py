@@ -245,7 +245,7 @@ class AtmosphereModel:
         self.thermodynamic_constants = thermodynamic_constants or ref.constants
         self.advection = advection or WENO(order=5)
         if self.advection.order not in (5, 7, 9):
-            raise NotImplementedError("WENO(order = 5) is on the hot path; orders 7 and 9 exist in the CPU oracle only (the CUDA library rejects them)")
+            raise NotImplementedError("WENO(order = 5, 7 or 9) is on the hot path")
         self.microphysics = microphysics
 
         lib = self.architecture.library()

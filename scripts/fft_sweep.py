@@ -13,14 +13,14 @@ import numpy as np
 import breeze_b200 as bz
 
 CONFIGS = [
-    ("default (y: 4 lines, 256 thr, 80 regs; x: 80 regs)", {}),
-    ("y 64-register build (256, 4)", {"BZ_FFT_Y_MINB": "4"}),
+    ("default (y: 4 lines, 256 thr, 64 regs; x: 80 regs)", {}),
+    ("y 80-register build (256, 3) [default until round 2]", {"BZ_FFT_Y_MINB": "3"}),
     ("y wide tiles: 8 lines, 512 thr, 64 regs", {"BZ_FFT_LINES_Y": "8"}),
     ("x 64-register build (256, 4)", {"BZ_FFT_X_MINB": "4"}),
     ("x 4 lines per CTA", {"BZ_FFT_LINES_X": "4"}),
     ("x 4 lines + 64 regs", {"BZ_FFT_LINES_X": "4", "BZ_FFT_X_MINB": "4"}),
     ("y wide + x 64 regs", {"BZ_FFT_LINES_Y": "8", "BZ_FFT_X_MINB": "4"}),
-    ("y 64 regs + x 64 regs", {"BZ_FFT_Y_MINB": "4", "BZ_FFT_X_MINB": "4"}),
+    ("x 64 regs", {"BZ_FFT_X_MINB": "4"}),
 ]
 KEYS = ["BZ_FFT_LINES_Y", "BZ_FFT_LINES_X", "BZ_FFT_Y_MINB", "BZ_FFT_X_MINB"]
 FAMILIES = ["stage", "fwd_y+fft_x", "thomas", "fft_x+inv_y", "project_halo", "exchange", "f6", "f7"]

@@ -21,7 +21,7 @@ pytestmark = pytest.mark.gpu
 TOL_DIAG = 1e-13
 TOL_TENDENCY = 1e-11
 TOL_LOOP = 1e-10
-TOL_STEPS = 1e-8
+TOL_STEPS = 2e-8          # measured 4.2e-9 (profiles/r2a_parity_errors.txt)
 PROGNOSTIC = ["ρ", "ρu", "ρv", "ρw", "ρθ"]
 RD = 8.314462618 / 0.02897
 

@@ -1,6 +1,6 @@
 """WENO(order = 7 / 9) in the CPU oracle (the reference's shipped examples run WENO(order = 9),
-`examples/dry_thermal_bubble.jl`, `examples/bomex.jl`, `examples/splitting_supercell.jl`). The CUDA path carries order 5 only and
-rejects the others loudly; this file pins the oracle side that the next kernel will be checked against.
+`examples/dry_thermal_bubble.jl`, `examples/bomex.jl`, `examples/splitting_supercell.jl`). This file pins the oracle side that the
+CUDA kernels of orders 7 / 9 (csrc/stage_hi.cuh, compressible.cuh) are checked against in tests/test_gpu_weno_high_order.py.
 
 The reference holds no number for any WENO reconstruction (`test/advection_schemes.jl:7-123` is plumbing + one smoke step per
 scheme), so what can be pinned is (i) the coefficient tables — derived here from the definitions in exact arithmetic, the same
@@ -226,7 +226,12 @@ def test_order_5_is_unchanged_by_the_generalised_buffers(oracle_arch):
 
 
 @pytest.mark.gpu
-def test_cuda_path_rejects_high_order_weno_loudly():
+def test_cuda_path_rejects_unknown_weno_orders_loudly():
     grid = bz.RectilinearGrid(bz.B200(), size=(16, 16, 16), x=(0, 1), y=(0, 1), z=(0, 1))
+    model = bz.AtmosphereModel(grid, advection=bz.WENO(order=9))          # orders 5, 7, 9 are on the path
+    assert model.field("ρu").shape == (16, 16, 16)
+    cfg = model.context.lib.default_config_struct()
+    cfg.Nx = cfg.Ny = cfg.Nz = 16
+    cfg.advection_order = 11
     with pytest.raises(bz.BreezeError, match="WENO"):
-        bz.AtmosphereModel(grid, advection=bz.WENO(order=9))
+        bz.Context(model.context.lib, cfg)

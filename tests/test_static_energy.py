@@ -7,7 +7,7 @@ both formulations evolve a warm bubble to the same state up to truncation error.
 import numpy as np
 import pytest
 
-from conftest import bubble_theta, rel_err
+from conftest import bubble_theta, rel_err, report
 
 G, CPD = 9.81, 1005.0
 
@@ -103,4 +103,6 @@ def test_cuda_static_energy_matches_oracle(oracle_arch, size, flat_y, z_chunks):
     mom = max(np.abs(cpu.field(f)).max() for f in ("ρu", "ρv", "ρw"))
     for name in ("ρu", "ρv", "ρw", "ρe", "ρq", "T"):
         scale = mom if name in ("ρu", "ρv", "ρw") else np.abs(cpu.field(name)).max()
-        assert np.abs(gpu.field(name) - cpu.field(name)).max() < 2e-7 * scale, name
+        err = np.abs(gpu.field(name) - cpu.field(name)).max() / scale
+        report(err, name)
+        assert err < 2e-8, name
