@@ -97,6 +97,8 @@ ABI_SYMBOLS = {
 }
 # CUDA-library-only symbols (instrumentation); the oracle does not export them
 CUDA_ONLY_SYMBOLS = {
+    "set_state_async": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _dp, C.c_int]),
+    "get_state_async": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _dp]),
     "profile_enable": (C.c_int, [_vp, C.c_int]),
     "profile_read": (C.c_int, [_vp, _dp, C.POINTER(C.c_int64)]),
     "kernel_launch_count": (C.c_int64, [_vp]),
@@ -232,6 +234,13 @@ class Context:
             out = [np.empty(self.shape(f)) for f in range(5)]
         self._check(self.lib.get_state(self.handle, *[_as_dp(a) for a in out]), "get_state")
         return out
+
+    def set_state_async(self, arrays, enforce_mass_conservation=False):
+        """bz_set_state_async: `arrays` = five C-contiguous float64 arrays (or None) that stay alive until synchronize()."""
+        self._check(self.lib.set_state_async(self.handle, *[_as_dp(a) for a in arrays], int(enforce_mass_conservation)), "set_state_async")
+
+    def get_state_async(self, out):
+        self._check(self.lib.get_state_async(self.handle, *[_as_dp(a) for a in out]), "get_state_async")
 
     def get_tendency(self, name_or_id):
         fid = FIELD_IDS[name_or_id] if isinstance(name_or_id, str) else int(name_or_id)

@@ -62,6 +62,12 @@ struct bz_ctx {
     int lines_x = 1, lines_y = 1;
     int fft_wide_y = 2, fft_x_minb = 3;   // fft_wide_y: 2 default (256, 4) 64-register build; 0: (256, 3); 1: (512, 2) wide tiles  // tuning experiments (BZ_FFT_LINES_Y > 256 threads per CTA; BZ_FFT_X_MINB = 4: 64-register build of fft_x)
     cudaStream_t stream = nullptr;
+    // host <-> device marshalling: strided 3-D copies straight between the caller's dense arrays and the padded fields, in z chunks,
+    // on two copy streams (one per PCIe direction) so that a download and the upload that follows it run full duplex
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_main = nullptr, ev_in = nullptr;
+    std::vector<cudaEvent_t> ev_out;     // one per (field, chunk) of the last bz_get_state_async
+    const double* out_ptr[NPROG] = {};   // host destinations of the last bz_get_state_async (an upload from the same buffer waits chunk-wise)
     Comm comm;
     int use_tma = 0, z_chunks = 1;
     double time = 0.0;
@@ -607,6 +613,8 @@ void bz_destroy(bz_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->s_in) cudaStreamSynchronize(c->s_in);
+    if (c->s_out) cudaStreamSynchronize(c->s_out);
     comm_destroy(c->comm);
     cudaFree(c->arena);
     for (int f = 0; f < NPROG; ++f) { cudaFree(c->G[f]); cudaFree(c->V[f]); }
@@ -615,6 +623,11 @@ void bz_destroy(bz_ctx* c) {
     cudaFree(c->inv_beta); cudaFree(c->tfac); cudaFree(c->ky_base); cudaFree(c->ky_kstride); cudaFree(c->ky_owner); cudaFree(c->ky_base2); cudaFree(c->fstore);
     for (auto e : c->prof_ev) cudaEventDestroy(e);
     for (auto e : c->prof_pool) cudaEventDestroy(e);
+    for (auto e : c->ev_out) cudaEventDestroy(e);
+    if (c->ev_main) cudaEventDestroy(c->ev_main);
+    if (c->ev_in) cudaEventDestroy(c->ev_in);
+    if (c->s_in) cudaStreamDestroy(c->s_in);
+    if (c->s_out) cudaStreamDestroy(c->s_out);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -677,6 +690,10 @@ int bz_create(const bz_config* cfg, bz_ctx** out) {
 #define TRY(x) do { rc = (x); if (rc) { strncpy(g_err, c->err, 511); bz_destroy(c); return rc; } } while (0)
 #define TRYCUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { bz_set_error(nullptr, "%s: %s", #x, cudaGetErrorString(e_)); bz_destroy(c); return BZ_ERR_CUDA; } } while (0)
     TRYCUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    TRYCUDA(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+    TRYCUDA(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+    TRYCUDA(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
+    TRYCUDA(cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming));
     rc = comm_init(c->comm, cfg, c->stream);
     if (rc) { bz_set_error(nullptr, "comm_init: %s", c->comm.err); bz_destroy(c); return rc; }
     {
@@ -781,27 +798,66 @@ int bz_set_reference_state(bz_ctx* c, const double* rho, const double* p, const 
     return setup_thomas(c);
 }
 
-static int upload_field(bz_ctx* c, const double* host, double* dst, int zero_level0) {
+#define COPY_CHUNKS 8      // z chunks per field: the upload of a chunk can start as soon as the download of the same chunk has landed
+
+static void chunk_range(int nz, int ch, int* k0, int* k1) {
+    const int per = (nz + COPY_CHUNKS - 1) / COPY_CHUNKS;
+    *k0 = ch * per < nz ? ch * per : nz;
+    *k1 = (ch + 1) * per < nz ? (ch + 1) * per : nz;
+}
+
+// levels [k0, k1) of a dense host array (x fastest, nx x Ny per level) <-> the interior of a padded device field
+static cudaError_t copy_levels(const bz_ctx* c, double* dev_field, double* host, int k0, int k1, bool to_host, cudaStream_t s) {
     const Layout& L = c->L;
-    size_t n = (size_t)L.nx * L.Ny * L.Nz;             // a z-face field's top wall level is ignored (always 0)
-    CUDA_TRY(c, cudaMemcpyAsync(c->dense, host, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    dim3 grid((L.nx + 127) / 128, L.Ny, L.Nz);
-    scatter_interior<<<grid, 128, 0, c->stream>>>(L, c->dense, dst, zero_level0);
-    c->launches++;
-    CUDA_TRY(c, cudaGetLastError());
-    CUDA_TRY(c, cudaStreamSynchronize(c->stream));    // the caller's buffer and `dense` are free again
+    if (k1 <= k0) return cudaSuccess;
+    cudaMemcpy3DParms p;
+    memset(&p, 0, sizeof(p));
+    cudaPitchedPtr hp = make_cudaPitchedPtr(host + (size_t)k0 * L.nx * L.Ny, (size_t)L.nx * sizeof(double), (size_t)L.nx * sizeof(double), (size_t)L.Ny);
+    cudaPitchedPtr dp = make_cudaPitchedPtr(dev_field + (size_t)k0 * L.plane, (size_t)L.PX * sizeof(double), (size_t)L.PX * sizeof(double), (size_t)L.PY);
+    const cudaPos dpos = make_cudaPos((size_t)L.HX * sizeof(double), (size_t)L.HY, 0), hpos = make_cudaPos(0, 0, 0);
+    if (to_host) { p.srcPtr = dp; p.srcPos = dpos; p.dstPtr = hp; p.dstPos = hpos; p.kind = cudaMemcpyDeviceToHost; }
+    else { p.srcPtr = hp; p.srcPos = hpos; p.dstPtr = dp; p.dstPos = dpos; p.kind = cudaMemcpyHostToDevice; }
+    p.extent = make_cudaExtent((size_t)L.nx * sizeof(double), (size_t)L.Ny, (size_t)(k1 - k0));
+    return cudaMemcpy3DAsync(&p, s);
+}
+
+int bz_set_state_async(bz_ctx* c, const double* ru, const double* rv, const double* rw, const double* rth, const double* rq, int enforce) {
+    if (!c) return BZ_ERR_INVALID;
+    cudaSetDevice(c->cfg.device);
+    const Layout& L = c->L;
+    const double* src[NPROG] = {ru, rv, rw, rth, rq};
+    CUDA_TRY(c, cudaEventRecord(c->ev_main, c->stream));          // the fields are free once the work queued so far has completed
+    CUDA_TRY(c, cudaStreamWaitEvent(c->s_in, c->ev_main, 0));
+    for (int f = 0; f < NPROG; ++f) {
+        if (!src[f]) continue;
+        double* dst = c->set[c->cur][f];
+        // A pending bz_get_state_async gates this upload chunk by chunk: the download of the SAME field still reads the device chunk we
+        // are about to overwrite, and a download that targets the host buffer we read from must have landed first.
+        int dep = -1;
+        for (int g = 0; g < NPROG; ++g) if (c->out_ptr[g] && c->out_ptr[g] == src[f]) dep = g;
+        for (int ch = 0; ch < COPY_CHUNKS; ++ch) {
+            int k0, k1; chunk_range(L.Nz, ch, &k0, &k1);
+            if (c->out_ptr[f]) CUDA_TRY(c, cudaStreamWaitEvent(c->s_in, c->ev_out[f * COPY_CHUNKS + ch], 0));
+            if (dep >= 0 && dep != f) CUDA_TRY(c, cudaStreamWaitEvent(c->s_in, c->ev_out[dep * COPY_CHUNKS + ch], 0));
+            if (f == BZ_RHO_W && k0 == 0) {                        // the wall face k = 0 is not the caller's to set (always 0)
+                CUDA_TRY(c, cudaMemset2DAsync(dst + (size_t)L.HY * L.PX + L.HX, (size_t)L.PX * 8, 0, (size_t)L.nx * 8, (size_t)L.Ny, c->s_in));
+                k0 = 1;
+            }
+            CUDA_TRY(c, copy_levels(c, dst, const_cast<double*>(src[f]), k0, k1, false, c->s_in));
+        }
+    }
+    CUDA_TRY(c, cudaEventRecord(c->ev_in, c->s_in));
+    CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_in, 0));
+    int rc;
+    if ((rc = fill_halos(c, c->set[c->cur], NPROG, 4))) return rc;
+    if (enforce && (rc = pressure_correct(c, 1.0))) return rc;
     return BZ_OK;
 }
 
 int bz_set_state(bz_ctx* c, const double* ru, const double* rv, const double* rw, const double* rth, const double* rq, int enforce) {
-    if (!c) return BZ_ERR_INVALID;
-    cudaSetDevice(c->cfg.device);
-    const double* src[NPROG] = {ru, rv, rw, rth, rq};
-    int rc;
-    for (int f = 0; f < NPROG; ++f)
-        if (src[f] && (rc = upload_field(c, src[f], c->set[c->cur][f], f == BZ_RHO_W))) return rc;
-    if ((rc = fill_halos(c, c->set[c->cur], NPROG, 4))) return rc;
-    if (enforce && (rc = pressure_correct(c, 1.0))) return rc;
+    int rc = bz_set_state_async(c, ru, rv, rw, rth, rq, enforce);
+    if (rc) return rc;
+    CUDA_TRY(c, cudaStreamSynchronize(c->s_in));                   // the caller's buffers are free again
     return BZ_OK;
 }
 
@@ -985,10 +1041,35 @@ int bz_state_is_finite(bz_ctx* c, int* finite) {
     return BZ_OK;
 }
 
-int bz_get_state(bz_ctx* c, double* ru, double* rv, double* rw, double* rth, double* rq) {
+int bz_get_state_async(bz_ctx* c, double* ru, double* rv, double* rw, double* rth, double* rq) {
+    if (!c) return BZ_ERR_INVALID;
+    cudaSetDevice(c->cfg.device);
+    const Layout& L = c->L;
     double* dst[NPROG] = {ru, rv, rw, rth, rq};
-    for (int f = 0; f < NPROG; ++f)
-        if (dst[f]) { int rc = bz_get_field(c, f, dst[f]); if (rc) return rc; }
+    if (c->ev_out.empty()) {
+        c->ev_out.resize((size_t)NPROG * COPY_CHUNKS);
+        for (auto& e : c->ev_out) CUDA_TRY(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    CUDA_TRY(c, cudaEventRecord(c->ev_main, c->stream));
+    CUDA_TRY(c, cudaStreamWaitEvent(c->s_out, c->ev_main, 0));
+    for (int f = 0; f < NPROG; ++f) {
+        c->out_ptr[f] = dst[f];
+        if (!dst[f]) continue;
+        for (int ch = 0; ch < COPY_CHUNKS; ++ch) {
+            int k0, k1; chunk_range(L.Nz, ch, &k0, &k1);
+            CUDA_TRY(c, copy_levels(c, c->set[c->cur][f], dst[f], k0, k1, true, c->s_out));
+            CUDA_TRY(c, cudaEventRecord(c->ev_out[f * COPY_CHUNKS + ch], c->s_out));
+        }
+        if (f == BZ_RHO_W) memset(dst[f] + (size_t)L.Nz * L.nx * L.Ny, 0, (size_t)L.nx * L.Ny * sizeof(double));   // top wall face (not stored on the device)
+    }
+    return BZ_OK;
+}
+
+int bz_get_state(bz_ctx* c, double* ru, double* rv, double* rw, double* rth, double* rq) {
+    int rc = bz_get_state_async(c, ru, rv, rw, rth, rq);
+    if (rc) return rc;
+    CUDA_TRY(c, cudaStreamSynchronize(c->s_out));
+    for (int f = 0; f < NPROG; ++f) c->out_ptr[f] = nullptr;       // landed: nothing left to order against
     return BZ_OK;
 }
 
@@ -1034,6 +1115,9 @@ int bz_synchronize(bz_ctx* c) {
     if (!c) return BZ_ERR_INVALID;
     cudaSetDevice(c->cfg.device);
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->s_in));
+    CUDA_TRY(c, cudaStreamSynchronize(c->s_out));
+    for (int f = 0; f < NPROG; ++f) c->out_ptr[f] = nullptr;
     return BZ_OK;
 }
 

@@ -59,8 +59,11 @@ __global__ void specific_fields_kernel(Layout L, Columns col, SpecificFields F) 
     }
 }
 
+#ifndef BZ_HI_MINB
+#define BZ_HI_MINB 2     // 128 registers, 2 CTAs of 256 threads per SM: 9.45 -> 6.36 ms per launch at 256^3, order 9 (profiles/r2c_hi_order_variants.txt)
+#endif
 template <int BUF, int TY, int MICRO, bool FORCED>
-__global__ void __launch_bounds__(32 * TY, 1) stage_hi_kernel(const __grid_constant__ StageParams P, SpecificFields F) {
+__global__ void __launch_bounds__(32 * TY, TY >= 8 ? BZ_HI_MINB : 1) stage_hi_kernel(const __grid_constant__ StageParams P, SpecificFields F) {
     constexpr int BS = BUF - 1;                          // WENO(order) advects with Centered(order - 1)
     constexpr int NK = NPROG;
     __shared__ double sfy[2][NK][TY + 1][32];            // y-face fluxes, double-buffered by level parity: one CTA barrier per level

@@ -174,6 +174,15 @@ int bz_pressure_correct(bz_ctx* ctx, double dt);
 int bz_get_field(bz_ctx* ctx, int field, double* host_out);
 int bz_get_state(bz_ctx* ctx, double* rho_u, double* rho_v, double* rho_w, double* rho_theta, double* rho_q);
 
+/* Asynchronous forms of bz_set_state / bz_get_state for a caller that hands host buffers in and out every step: the copies are
+ * strided 3-D transfers between the dense host arrays and the padded device fields, cut in z chunks and queued on two copy streams
+ * (one per PCIe direction), so the download of step n and the upload of step n + 1 run full duplex; an upload from a buffer that a
+ * pending download is still filling is ordered behind it chunk by chunk. The host buffers must stay valid (and should be page-locked)
+ * until bz_synchronize; the synchronous forms above are these plus a wait. */
+int bz_set_state_async(bz_ctx* ctx, const double* rho_u, const double* rho_v, const double* rho_w,
+                       const double* rho_theta, const double* rho_q, int enforce_mass_conservation);
+int bz_get_state_async(bz_ctx* ctx, double* rho_u, double* rho_v, double* rho_w, double* rho_theta, double* rho_q);
+
 /* model.clock: time and iteration. */
 int bz_get_clock(bz_ctx* ctx, double* time, int64_t* iteration);
 
