@@ -60,10 +60,13 @@ struct bz_ctx {
     double* fstore = nullptr;            // ws[Nz+1] | ug | vg | q_tend | e_tend | sums[4Nz] | fcol[4Nz]
     double *d_ws = nullptr, *d_ug = nullptr, *d_vg = nullptr, *d_qt = nullptr, *d_et = nullptr, *d_sums = nullptr, *d_fcol = nullptr;
     int lines_x = 1, lines_y = 1;
-    int fft_wide_y = 2, fft_x_minb = 3;   // fft_wide_y: 2 default (256, 4) 64-register build; 0: (256, 3); 1: (512, 2) wide tiles  // tuning experiments (BZ_FFT_LINES_Y > 256 threads per CTA; BZ_FFT_X_MINB = 4: 64-register build of fft_x)
     cudaStream_t stream = nullptr;
     // host <-> device marshalling: strided 3-D copies straight between the caller's dense arrays and the padded fields, in z chunks,
     // on two copy streams (one per PCIe direction) so that a download and the upload that follows it run full duplex
+    cudaStream_t s2 = nullptr;           // second compute stream: x-halo exchanges overlapped with the Poisson solve / the interior projection (slabs)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int overlap = 1;                     // BZ_NO_OVERLAP=1: every exchange serialised on the main stream (A/B and debugging)
+    int scalars_in_flight = 0;           // the θ / q ghosts of set[cur] are being pulled on s2
     cudaStream_t s_in = nullptr, s_out = nullptr;
     cudaEvent_t ev_main = nullptr, ev_in = nullptr;
     std::vector<cudaEvent_t> ev_out;     // one per (field, chunk) of the last bz_get_state_async
@@ -128,6 +131,9 @@ struct ProfScope {
 };
 
 static int is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
+// line lengths of the in-house FFT: 2^m in [8, 2048] or 3 * 2^m in [24, 1536]
+static int fft_length_ok(int n) { return (is_pow2(n) && n >= 8 && n <= 2048) || (n % 3 == 0 && is_pow2(n / 3) && n >= 24 && n <= 1536); }
+static int fft_threads(int N, int lines) { return lines * N / fft_pt(N); }
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -283,44 +289,28 @@ static int setup_poisson(bz_ctx* c) {
     if ((rc = dev_alloc(c, &c->inv_beta, nW2 > 0 ? nW2 : 1))) return rc;
     if ((rc = dev_alloc(c, &c->tfac, nW2 > 0 ? nW2 : 1))) return rc;
     // launch shapes: each thread owns 8 points of a line
+    // launch shapes: each thread owns fft_pt(N) points of a line. The y transforms run as the 64-register build (256, 4) — 4 CTAs per SM
+    // hide the source term's load latency (round-2 sweep at 512^3, profiles/r2a_fft_sweep.txt: forward 6.84 -> 6.01 ms, inverse 4.41 -> 4.24 ms
+    // per step; 8-line / 512-thread tiles and a 64-register x transform measured no gain and were dropped).
     if (!L.flat_y) {
-        int lines = 2048 / g.Ny; if (lines < 1) lines = 1;
-        if (const char* e = getenv("BZ_FFT_LINES_Y")) { int v = atoi(e); if (v >= 1 && v * g.Ny / 8 <= 512) lines = v; }   // tuning sweeps only
+        int lines = 256 * fft_pt(g.Ny) / g.Ny; if (lines < 1) lines = 1;      // 256 threads per CTA
         int half = (L.nx + 1) / 2; if (lines > half) lines = half;
         while (lines & (lines - 1)) lines &= lines - 1;       // power of two (the kernels shift instead of dividing)
         c->lines_y = lines;
-        c->fft_wide_y = (lines * g.Ny / 8 > 256);
-        // default since round 2: the 64-register build (256, 4) of the y transforms — 4 CTAs per SM hide the source term's load latency
-        // (measured at 512^3, profiles/r2a_fft_sweep.txt: forward 6.84 -> 6.01 ms, inverse 4.41 -> 4.24 ms per step, bit-identical)
-        if (!c->fft_wide_y) { const char* e = getenv("BZ_FFT_Y_MINB"); c->fft_wide_y = (e && atoi(e) == 3) ? 0 : 2; }      // BZ_FFT_Y_MINB=3: the 80-register build
         size_t sm = fft_smem_bytes(g.Ny, lines);
-        if (c->fft_wide_y == 1) {
-            FFT_DISPATCH(g.Ny, {
-                CUDA_TRY(c, cudaFuncSetAttribute(poisson_forward_y<FN, 512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-                CUDA_TRY(c, cudaFuncSetAttribute(poisson_inverse_y<FN, 512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-            })
-        } else if (c->fft_wide_y == 2) {
-            FFT_DISPATCH(g.Ny, {
-                CUDA_TRY(c, cudaFuncSetAttribute(poisson_forward_y<FN, 256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-                CUDA_TRY(c, cudaFuncSetAttribute(poisson_inverse_y<FN, 256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-            })
-        } else
         FFT_DISPATCH(g.Ny, {
-            CUDA_TRY(c, cudaFuncSetAttribute(poisson_forward_y<FN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-            CUDA_TRY(c, cudaFuncSetAttribute(poisson_inverse_y<FN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            CUDA_TRY(c, cudaFuncSetAttribute(poisson_forward_y<FN, 256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            CUDA_TRY(c, cudaFuncSetAttribute(poisson_inverse_y<FN, 256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
         })
     }
     if (!L.flat_x) {
-        int lines = 1024 / g.Nx; if (lines < 1) lines = 1;
-        if (const char* e = getenv("BZ_FFT_LINES_X")) { int v = atoi(e); if (v >= 1 && v * g.Nx / 8 <= 256) lines = v; }   // tuning sweeps only
-        if (const char* e = getenv("BZ_FFT_X_MINB")) { if (atoi(e) == 4) c->fft_x_minb = 4; }                               // tuning sweeps only
+        int lines = 128 * fft_pt(g.Nx) / g.Nx; if (lines < 1) lines = 1;      // 128 threads per CTA
         long long nl = (long long)G.Nz * G.nky_loc; if (nl < 1) nl = 1;
         if (lines > nl) lines = (int)nl;
         while (lines & (lines - 1)) lines &= lines - 1;
         c->lines_x = lines;
         size_t sm = fft_smem_bytes(g.Nx, lines);
-        if (c->fft_x_minb == 4) { FFT_DISPATCH(g.Nx, { CUDA_TRY(c, cudaFuncSetAttribute(fft_x_kernel<FN, 256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); }) }
-        else FFT_DISPATCH(g.Nx, { CUDA_TRY(c, cudaFuncSetAttribute(fft_x_kernel<FN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); })
+        FFT_DISPATCH(g.Nx, { CUDA_TRY(c, cudaFuncSetAttribute(fft_x_kernel<FN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); })
     }
     return setup_thomas(c);
 }
@@ -337,9 +327,7 @@ static int poisson_solve(bz_ctx* c, double dt) {
             int lines = c->lines_y;
             dim3 grid((L.nx + 2 * lines - 1) / (2 * lines), L.Nz);
             size_t sm = fft_smem_bytes(G.Ny, lines);
-            if (c->fft_wide_y == 1) { FFT_DISPATCH(G.Ny, (poisson_forward_y<FN, 512, 2><<<grid, lines * G.Ny / 8, sm, c->stream>>>(L, G, U[0], U[1], U[2], dz_over_dt, c->W, c->tw_y, lines))); }
-            else if (c->fft_wide_y == 2) { FFT_DISPATCH(G.Ny, (poisson_forward_y<FN, 256, 4><<<grid, lines * G.Ny / 8, sm, c->stream>>>(L, G, U[0], U[1], U[2], dz_over_dt, c->W, c->tw_y, lines))); }
-            else FFT_DISPATCH(G.Ny, (poisson_forward_y<FN><<<grid, lines * G.Ny / 8, sm, c->stream>>>(L, G, U[0], U[1], U[2], dz_over_dt, c->W, c->tw_y, lines)));
+            FFT_DISPATCH(G.Ny, (poisson_forward_y<FN, 256, 4><<<grid, fft_threads(G.Ny, lines), sm, c->stream>>>(L, G, U[0], U[1], U[2], dz_over_dt, c->W, c->tw_y, lines)));
         } else {
             dim3 grid((L.nx + 127) / 128, L.Nz);
             poisson_pack_flat_y<<<grid, 128, 0, c->stream>>>(L, G, U[0], U[1], U[2], dz_over_dt, c->W);
@@ -359,14 +347,17 @@ static int poisson_solve(bz_ctx* c, double dt) {
         ProfScope ps(c, 1);
         int lines = c->lines_x;
         size_t sm = fft_smem_bytes(G.Nx, lines);
-        if (c->fft_x_minb == 4) { FFT_DISPATCH(G.Nx, (fft_x_kernel<FN, 256, 4><<<(unsigned)((n_lines + lines - 1) / lines), lines * G.Nx / 8, sm, c->stream>>>(G, c->W2, n_lines, c->tw_x, lines, 0, peers, pull ? 1 : 0))); }
-        else FFT_DISPATCH(G.Nx, (fft_x_kernel<FN><<<(unsigned)((n_lines + lines - 1) / lines), lines * G.Nx / 8, sm, c->stream>>>(G, c->W2, n_lines, c->tw_x, lines, 0, peers, pull ? 1 : 0)));
+        FFT_DISPATCH(G.Nx, (fft_x_kernel<FN><<<(unsigned)((n_lines + lines - 1) / lines), fft_threads(G.Nx, lines), sm, c->stream>>>(G, c->W2, n_lines, c->tw_x, lines, 0, peers, pull ? 1 : 0)));
         c->launches++;
     }
     if (G.nky_loc > 0) {
         ProfScope ps(c, 2);
-        dim3 grid((G.Nx + 127) / 128, G.nky_loc);
-        thomas_z<<<grid, 128, 0, c->stream>>>(G, c->W2, c->col.rho_f, L.dz, c->inv_beta, c->tfac);
+        // one thread per (kx, ky) column: on a rank that keeps few ky modes (8 slabs of 512^3: 4 x 33 blocks of 128) the blocks shrink
+        // until the grid covers the machine a few times over
+        int tb = 128;
+        while (tb > 32 && (long long)((G.Nx + tb - 1) / tb) * G.nky_loc < 4 * 148) tb >>= 1;
+        dim3 grid((G.Nx + tb - 1) / tb, G.nky_loc);
+        thomas_z<<<grid, tb, 0, c->stream>>>(G, c->W2, c->col.rho_f, L.dz, c->inv_beta, c->tfac);
         c->launches++;
         if (G.ky0 == 0) { remove_mean_mode<<<1, 256, 0, c->stream>>>(G, c->W2); c->launches++; }
     }
@@ -374,8 +365,7 @@ static int poisson_solve(bz_ctx* c, double dt) {
         ProfScope ps(c, 3);
         int lines = c->lines_x;
         size_t sm = fft_smem_bytes(G.Nx, lines);
-        if (c->fft_x_minb == 4) { FFT_DISPATCH(G.Nx, (fft_x_kernel<FN, 256, 4><<<(unsigned)((n_lines + lines - 1) / lines), lines * G.Nx / 8, sm, c->stream>>>(G, c->W2, n_lines, c->tw_x, lines, 1, peers, 0))); }
-        else FFT_DISPATCH(G.Nx, (fft_x_kernel<FN><<<(unsigned)((n_lines + lines - 1) / lines), lines * G.Nx / 8, sm, c->stream>>>(G, c->W2, n_lines, c->tw_x, lines, 1, peers, 0)));
+        FFT_DISPATCH(G.Nx, (fft_x_kernel<FN><<<(unsigned)((n_lines + lines - 1) / lines), fft_threads(G.Nx, lines), sm, c->stream>>>(G, c->W2, n_lines, c->tw_x, lines, 1, peers, 0)));
         c->launches++;
     }
     if (c->comm.n_ranks > 1) {
@@ -390,9 +380,7 @@ static int poisson_solve(bz_ctx* c, double dt) {
             int lines = c->lines_y;
             dim3 grid((L.nx + 2 * lines - 1) / (2 * lines), L.Nz);
             size_t sm = fft_smem_bytes(G.Ny, lines);
-            if (c->fft_wide_y == 1) { FFT_DISPATCH(G.Ny, (poisson_inverse_y<FN, 512, 2><<<grid, lines * G.Ny / 8, sm, c->stream>>>(L, G, c->W, c->phi, c->tw_y, lines, scale, peers, pull ? 1 : 0))); }
-            else if (c->fft_wide_y == 2) { FFT_DISPATCH(G.Ny, (poisson_inverse_y<FN, 256, 4><<<grid, lines * G.Ny / 8, sm, c->stream>>>(L, G, c->W, c->phi, c->tw_y, lines, scale, peers, pull ? 1 : 0))); }
-            else FFT_DISPATCH(G.Ny, (poisson_inverse_y<FN><<<grid, lines * G.Ny / 8, sm, c->stream>>>(L, G, c->W, c->phi, c->tw_y, lines, scale, peers, pull ? 1 : 0)));
+            FFT_DISPATCH(G.Ny, (poisson_inverse_y<FN, 256, 4><<<grid, fft_threads(G.Ny, lines), sm, c->stream>>>(L, G, c->W, c->phi, c->tw_y, lines, scale, peers, pull ? 1 : 0)));
         } else {
             dim3 grid((L.nx + 127) / 128, L.Nz);
             poisson_unpack_flat_y<<<grid, 128, 0, c->stream>>>(L, G, c->W, c->phi, scale);
@@ -415,7 +403,7 @@ static int fill_halos(bz_ctx* c, double* const* fields, int nf, int fam, bool ex
     int mode = 3;
     if (c->comm.n_ranks > 1) {
         if (exchange_x) {
-            int rc = c->comm.p2p ? comm_pull_x_halos(c->comm, L, F, 0, c->stream, &c->launches)
+            int rc = c->comm.p2p ? comm_pull_x_halos(c->comm, L, F, 0, c->stream, &c->launches, 0, nf == 1 ? 1 : 3)
                                  : comm_exchange_x_halos(c->comm, L, F, c->stream, &c->launches);
             if (rc) { bz_set_error(c, "halo exchange: %s", c->comm.err); return rc; }
         }
@@ -556,31 +544,101 @@ static int launch_stage(bz_ctx* c, int in, double* const* out, int u0, double dt
 #undef LAUNCH
 }
 
+static int y_halo_fill(bz_ctx* c, double* const* fields, int nf, cudaStream_t s) {
+    const Layout& L = c->L;
+    if (L.HY == 0) return BZ_OK;
+    FieldSet F; F.n = nf;
+    for (int f = 0; f < nf; ++f) F.f[f] = fields[f];
+    long long total = (long long)2 * L.HY * L.PX * L.Nz;
+    int blocks = (int)((total + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
+    halo_fill_periodic<<<blocks, 256, 0, s>>>(L, F, 2);
+    c->launches++;
+    CUDA_TRY(c, cudaGetLastError());
+    return BZ_OK;
+}
+
+// Slabs with peer memory: right after the stage kernel the x ghosts of ρθ and ρq of the new state can travel — the projection does not
+// touch them — so their exchange runs on the second stream underneath the whole Poisson solve. Joined in pressure_correct.
+static int start_scalar_exchange(bz_ctx* c) {
+    if (!(c->comm.n_ranks > 1 && c->comm.p2p && c->overlap)) return BZ_OK;
+    double** U = c->set[c->cur];
+    CUDA_TRY(c, cudaEventRecord(c->ev_fork, c->stream));
+    CUDA_TRY(c, cudaStreamWaitEvent(c->s2, c->ev_fork, 0));
+    FieldSet F; F.n = 2; F.f[0] = U[BZ_RHO_THETA]; F.f[1] = U[BZ_RHO_Q];
+    int rc = comm_pull_x_halos(c->comm, c->L, F, 0, c->s2, &c->launches, 1, 2);
+    if (rc) { bz_set_error(c, "halo exchange: %s", c->comm.err); return rc; }
+    c->scalars_in_flight = 1;
+    return BZ_OK;
+}
+
 // compute_pressure_correction! + make_pressure_correction! on set[cur], then refresh all ghosts
 static int pressure_correct(bz_ctx* c, double dt) {
     int rc;
     double** U = c->set[c->cur];
+    const Layout& L = c->L;
     if (c->comm.n_ranks == 1) { if ((rc = fill_halos(c, U, 2, 4))) return rc; }       // ρu, ρv ghosts for the divergence
     else {                                                                               // slabs: y ghosts of ρv are local; ρu at the first ghost face
         double* uv[1] = {U[1]};                                                          // comes from the right neighbour's first column
         if ((rc = fill_halos(c, uv, 1, 4, false))) return rc;
         ProfScope ps(c, 5);
-        if (c->comm.p2p) { FieldSet Fu; Fu.n = 1; Fu.f[0] = U[0]; rc = comm_pull_x_halos(c->comm, c->L, Fu, 1, c->stream, &c->launches); }
+        if (c->comm.p2p) { FieldSet Fu; Fu.n = 1; Fu.f[0] = U[0]; rc = comm_pull_x_halos(c->comm, c->L, Fu, 1, c->stream, &c->launches, 0, 0); }
         else rc = comm_exchange_u_face(c->comm, c->L, U[0], c->stream, &c->launches);
         if (rc) { bz_set_error(c, "face exchange: %s", c->comm.err); return rc; }
     }
     if ((rc = poisson_solve(c, dt))) return rc;
     double* ph[1] = {c->phi};
     if ((rc = fill_halos(c, ph, 1, 4))) return rc;
+    const bool split = c->comm.n_ranks > 1 && c->comm.p2p && c->overlap && !L.flat_x && L.nx >= 4 * L.HX;
+    if (!split) {
+        {
+            ProfScope ps(c, 4);
+            dim3 grid((L.nx + 127) / 128, L.Ny, L.Nz);
+            project_momentum<<<grid, 128, 0, c->stream>>>(L, c->col, U[0], U[1], U[2], c->phi, dt);
+            c->launches++;
+            CUDA_TRY(c, cudaGetLastError());
+        }
+        if (c->scalars_in_flight) {                            // the θ / q exchange of start_scalar_exchange joins here
+            CUDA_TRY(c, cudaEventRecord(c->ev_join, c->s2));
+            CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+            c->scalars_in_flight = 0;
+            if ((rc = fill_halos(c, U, 3, 4))) return rc;      // momentum: x exchange + y ghosts
+            return y_halo_fill(c, U + 3, 2, c->stream);        // θ, q: y ghosts (full padded width: after their x ghosts have landed)
+        }
+        return fill_halos(c, U, NPROG, 4);
+    }
+    // Slabs, overlapped: project the HX edge columns of either side first; while the second stream waits for the neighbours to have done
+    // the same and pulls their edge columns into our momentum ghosts, the main stream projects the interior columns.
+    ProfScope ps(c, 4);
     {
-        ProfScope ps(c, 4);
-        const Layout& L = c->L;
-        dim3 grid((L.nx + 127) / 128, L.Ny, L.Nz);
-        project_momentum<<<grid, 128, 0, c->stream>>>(L, c->col, U[0], U[1], U[2], c->phi, dt);
+        const int nc = 2 * L.HX;
+        dim3 grid((nc * L.Ny + 127) / 128, L.Nz);
+        project_momentum_columns<<<grid, 128, 0, c->stream>>>(L, c->col, U[0], U[1], U[2], c->phi, dt, 0, L.HX, L.nx - L.HX, L.HX);
         c->launches++;
         CUDA_TRY(c, cudaGetLastError());
     }
-    return fill_halos(c, U, NPROG, 4);
+    CUDA_TRY(c, cudaEventRecord(c->ev_fork, c->stream));
+    CUDA_TRY(c, cudaStreamWaitEvent(c->s2, c->ev_fork, 0));
+    {
+        FieldSet F; F.n = 3; F.f[0] = U[0]; F.f[1] = U[1]; F.f[2] = U[2];
+        rc = comm_pull_x_halos(c->comm, L, F, 0, c->s2, &c->launches, 1, 3);
+        if (rc) { bz_set_error(c, "halo exchange: %s", c->comm.err); return rc; }
+        if (!c->scalars_in_flight) {                            // bz_set_state / bz_pressure_correct: θ, q travel here as well
+            FieldSet S; S.n = 2; S.f[0] = U[3]; S.f[1] = U[4];
+            rc = comm_pull_x_halos(c->comm, L, S, 0, c->s2, &c->launches, 1, 2);
+            if (rc) { bz_set_error(c, "halo exchange: %s", c->comm.err); return rc; }
+        }
+        c->scalars_in_flight = 0;
+    }
+    CUDA_TRY(c, cudaEventRecord(c->ev_join, c->s2));
+    {
+        const int ni = L.nx - 2 * L.HX;
+        dim3 grid((ni * L.Ny + 127) / 128, L.Nz);
+        project_momentum_columns<<<grid, 128, 0, c->stream>>>(L, c->col, U[0], U[1], U[2], c->phi, dt, L.HX, ni, 0, 0);
+        c->launches++;
+        CUDA_TRY(c, cudaGetLastError());
+    }
+    CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+    return y_halo_fill(c, U, NPROG, c->stream);                 // y ghosts over the full padded width, corners included
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -613,6 +671,7 @@ void bz_destroy(bz_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->s2) cudaStreamSynchronize(c->s2);
     if (c->s_in) cudaStreamSynchronize(c->s_in);
     if (c->s_out) cudaStreamSynchronize(c->s_out);
     comm_destroy(c->comm);
@@ -626,6 +685,9 @@ void bz_destroy(bz_ctx* c) {
     for (auto e : c->ev_out) cudaEventDestroy(e);
     if (c->ev_main) cudaEventDestroy(c->ev_main);
     if (c->ev_in) cudaEventDestroy(c->ev_in);
+    if (c->s2) cudaStreamDestroy(c->s2);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->s_in) cudaStreamDestroy(c->s_in);
     if (c->s_out) cudaStreamDestroy(c->s_out);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -646,8 +708,8 @@ int bz_create(const bz_config* cfg, bz_ctx** out) {
     const int fx = cfg->topology_x == BZ_FLAT, fy = cfg->topology_y == BZ_FLAT;
     if ((fx && cfg->Nx != 1) || (fy && cfg->Ny != 1)) FAIL(BZ_ERR_INVALID, "a Flat dimension must have size 1");
     if (fx && !fy) FAIL(BZ_ERR_UNSUPPORTED, "(Flat, Periodic, Bounded) is not supported; use (Periodic, Flat, Bounded)");
-    if (!fx && (!is_pow2(cfg->Nx) || cfg->Nx < 8 || cfg->Nx > 2048)) FAIL(BZ_ERR_UNSUPPORTED, "Nx must be a power of two in [8, 2048] (in-house FFT)");
-    if (!fy && (!is_pow2(cfg->Ny) || cfg->Ny < 8 || cfg->Ny > 2048)) FAIL(BZ_ERR_UNSUPPORTED, "Ny must be a power of two in [8, 2048] (in-house FFT)");
+    if (!fx && !fft_length_ok(cfg->Nx)) FAIL(BZ_ERR_UNSUPPORTED, "Nx must be 2^m in [8, 2048] or 3 * 2^m in [24, 1536] (in-house FFT), got %d", cfg->Nx);
+    if (!fy && !fft_length_ok(cfg->Ny)) FAIL(BZ_ERR_UNSUPPORTED, "Ny must be 2^m in [8, 2048] or 3 * 2^m in [24, 1536] (in-house FFT), got %d", cfg->Ny);
     const int P = cfg->n_ranks < 1 ? 1 : cfg->n_ranks;
     if (cfg->use_tma == 1 && cfg->advection_order != 5) FAIL(BZ_ERR_UNSUPPORTED, "TMA staging belongs to the WENO(order=5) stage kernel");
     if (P > 1 && (fx || cfg->Nx % P != 0 || (cfg->Nx / P) < 8)) FAIL(BZ_ERR_INVALID, "x-slabs: Nx must be divisible by n_ranks with at least 8 columns per rank");
@@ -690,6 +752,10 @@ int bz_create(const bz_config* cfg, bz_ctx** out) {
 #define TRY(x) do { rc = (x); if (rc) { strncpy(g_err, c->err, 511); bz_destroy(c); return rc; } } while (0)
 #define TRYCUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { bz_set_error(nullptr, "%s: %s", #x, cudaGetErrorString(e_)); bz_destroy(c); return BZ_ERR_CUDA; } } while (0)
     TRYCUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    TRYCUDA(cudaStreamCreateWithFlags(&c->s2, cudaStreamNonBlocking));
+    TRYCUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    TRYCUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    if (const char* e = getenv("BZ_NO_OVERLAP")) c->overlap = atoi(e) ? 0 : 1;
     TRYCUDA(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
     TRYCUDA(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
     TRYCUDA(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
@@ -702,11 +768,22 @@ int bz_create(const bz_config* cfg, bz_ctx** out) {
         G.nky = fy ? 1 : cfg->Ny / 2 + 1;
         comm_split_ky(c->comm, G.nky, &G.ky0, &G.nky_loc);
         G.P = c->comm.n_ranks;
-        G.nx_shift = 0;
-        while ((1 << G.nx_shift) < L.nx) ++G.nx_shift;
+        G.nx = L.nx;
         const size_t nW = (size_t)L.nx * G.nky * G.Nz, nW2 = (size_t)G.Nx * G.nky_loc * G.Nz;
         const size_t field_bytes = (size_t)16 * L.n * sizeof(double);
-        c->off_W = (field_bytes + 255) & ~(size_t)255;
+        // one page of barrier flags (comm.cuh) right behind the fields: like off_W / off_W2 its offset must be the SAME on every rank
+        // (the peers address it through their own copy of these offsets; only the size of W2 differs between ranks)
+        c->comm.off_flags = (long long)((field_bytes + 255) & ~(size_t)255);
+        c->comm.off_pack = c->comm.off_flags + 4096;
+        {   // packed x faces (comm.cuh): regions for the ρu face (1 column, 1 field), φ (1 field), the scalars (2 fields), all five fields
+            const size_t col = (size_t)L.Ny * L.Nz, hx = (size_t)(L.HX > 0 ? L.HX : 1);
+            c->comm.pack_start[0] = 0;
+            c->comm.pack_start[1] = col;
+            c->comm.pack_start[2] = c->comm.pack_start[1] + 2 * hx * col;
+            c->comm.pack_start[3] = c->comm.pack_start[2] + 2 * 2 * hx * col;
+            c->comm.pack_bytes = (P > 1) ? ((c->comm.pack_start[3] + 2 * NPROG * hx * col) * sizeof(double) + 255) & ~(size_t)255 : 0;
+        }
+        c->off_W = (size_t)c->comm.off_pack + c->comm.pack_bytes;
         c->off_W2 = (c->off_W + nW * sizeof(double2) + 255) & ~(size_t)255;
         c->arena_bytes = (P > 1) ? c->off_W2 + (nW2 > 0 ? nW2 : 1) * sizeof(double2) : c->off_W2;
         TRYCUDA(cudaMalloc((void**)&c->arena, c->arena_bytes));
@@ -798,7 +875,14 @@ int bz_set_reference_state(bz_ctx* c, const double* rho, const double* p, const 
     return setup_thomas(c);
 }
 
-#define COPY_CHUNKS 8      // z chunks per field: the upload of a chunk can start as soon as the download of the same chunk has landed
+#define COPY_CHUNKS_MAX 32
+// z chunks per field: the upload of a chunk can start as soon as the download of the same chunk has landed (BZ_COPY_CHUNKS overrides: sweeps)
+static int copy_chunks() {
+    static int n = 0;
+    if (!n) { const char* e = getenv("BZ_COPY_CHUNKS"); n = e ? atoi(e) : 8; if (n < 1) n = 1; if (n > COPY_CHUNKS_MAX) n = COPY_CHUNKS_MAX; }
+    return n;
+}
+#define COPY_CHUNKS copy_chunks()
 
 static void chunk_range(int nz, int ch, int* k0, int* k1) {
     const int per = (nz + COPY_CHUNKS - 1) / COPY_CHUNKS;
@@ -904,6 +988,7 @@ int bz_time_step(bz_ctx* c, double dt) {
         while (nxt == in || nxt == u0) ++nxt;          // the free set
         if ((rc = launch_stage(c, in, c->set[nxt], u0, dt, alpha[s], 0))) return rc;
         c->cur = nxt;
+        if ((rc = start_scalar_exchange(c))) return rc;
         if ((rc = pressure_correct(c, alpha[s] * dt))) return rc;
     }
     c->time += dt;
@@ -1047,7 +1132,7 @@ int bz_get_state_async(bz_ctx* c, double* ru, double* rv, double* rw, double* rt
     const Layout& L = c->L;
     double* dst[NPROG] = {ru, rv, rw, rth, rq};
     if (c->ev_out.empty()) {
-        c->ev_out.resize((size_t)NPROG * COPY_CHUNKS);
+        c->ev_out.resize((size_t)NPROG * COPY_CHUNKS_MAX);
         for (auto& e : c->ev_out) CUDA_TRY(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
     CUDA_TRY(c, cudaEventRecord(c->ev_main, c->stream));
@@ -1118,6 +1203,11 @@ int bz_synchronize(bz_ctx* c) {
     CUDA_TRY(c, cudaStreamSynchronize(c->s_in));
     CUDA_TRY(c, cudaStreamSynchronize(c->s_out));
     for (int f = 0; f < NPROG; ++f) c->out_ptr[f] = nullptr;
+    if (c->comm.p2p) {                                              // a flag barrier that timed out (dead peer) left its mark
+        unsigned long long bad = 0;
+        CUDA_TRY(c, cudaMemcpy(&bad, c->comm.peer_base[c->comm.rank] + c->comm.off_flags + BZ_FLAG_TIMEOUT_SLOT * 8, 8, cudaMemcpyDeviceToHost));
+        if (bad) { bz_set_error(c, "a peer-memory barrier timed out: another rank stopped"); return BZ_ERR_STATE; }
+    }
     return BZ_OK;
 }
 

@@ -46,6 +46,23 @@ __global__ void project_momentum(Layout L, Columns col, double* __restrict__ ru,
     if (k >= 1) rw[n] -= col.rho_f[k] * dt * ((p - phi[n - L.plane]) * L.rdz);
 }
 
+// The same projection restricted to the x columns [ia, ia + na) and [ib, ib + nb): on a slab the edge columns are corrected first so
+// that their exchange with the neighbours overlaps the projection of the interior columns (second stream, api.cu pressure_correct).
+__global__ void project_momentum_columns(Layout L, Columns col, double* __restrict__ ru, double* __restrict__ rv, double* __restrict__ rw,
+                                         const double* __restrict__ phi, double dt, int ia, int na, int ib, int nb) {
+    const int nc = na + nb, k = blockIdx.y;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nc * L.Ny; e += gridDim.x * blockDim.x) {
+        const int c = e % nc, j = e / nc;
+        const int i = c < na ? ia + c : ib + (c - na);
+        long long n = lidx(L, i, j, k);
+        double p = phi[n];
+        double rc = col.rho[k];
+        if (!L.flat_x) ru[n] -= rc * dt * ((p - phi[n - 1]) * L.rdx);
+        if (!L.flat_y) rv[n] -= rc * dt * ((p - phi[n - L.PX]) * L.rdy);
+        if (k >= 1) rw[n] -= col.rho_f[k] * dt * ((p - phi[n - L.plane]) * L.rdz);
+    }
+}
+
 // dense interior (x fastest, nz_out levels) <- padded field; levels >= Nz are the top wall (0)
 __global__ void extract_interior(Layout L, const double* __restrict__ src, double* __restrict__ dst, int nz_out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, k = blockIdx.z;

@@ -10,6 +10,7 @@
 // one), so a single-GPU context has no NCCL dependency. One process per GPU; rank r's periodic neighbours are r±1.
 #pragma once
 #include <dlfcn.h>
+#include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
 #include "poisson.cuh"
@@ -42,6 +43,20 @@ struct Comm {
     // LOADS issued by the consuming kernels over NVLink, ordered by a tiny NCCL all-reduce used as a stream barrier.
     int p2p = 0;
     char* peer_base[8] = {};        // arena base of every rank in THIS process' address space (own arena at [rank])
+    // Flag barriers in peer memory: every arena ends with a page of 64-bit flags, flag[channel][source rank]. A rank ARRIVES by storing the
+    // channel's next epoch into its slot on every peer of the barrier (st.release.sys over NVLink) and WAITS until its own copy of every
+    // peer's slot has reached that epoch (ld.acquire.sys). One ~3 us kernel instead of a one-element ncclAllReduce; channels keep the
+    // barriers of the two streams apart. use_flags = 0 (BZ_NCCL_BARRIER=1) falls back to the NCCL all-reduce.
+    long long off_flags = 0;
+    unsigned long long epoch[8] = {};
+    int use_flags = 1;
+    // Packed x faces in peer memory: the owner gathers its edge columns into a contiguous region of its arena, the neighbours read that
+    // region with fully coalesced peer loads and scatter it into their ghost cells. (Reading the 32-byte column segments straight out of
+    // the neighbour's padded field was 3 x slower over NVLink at 8 slabs.) Four regions — ρu face, φ, scalars, all / momentum — so that
+    // two uses of one region are always separated by at least one full barrier. BZ_DIRECT_PULL=1 selects the old direct reads.
+    long long off_pack = 0;
+    size_t pack_start[4] = {}, pack_bytes = 0;
+    int packed_pull = 1;
     double* token = nullptr;
     char err[256] = {};
 };
@@ -183,10 +198,47 @@ static int comm_transpose_backward(Comm& cm, const double2* W2, double2* W, int 
     return comm_alltoall(cm, W2, W, nx, G, false, s);
 }
 
-// Stream barrier across ranks: when it completes on this rank's stream, every rank's earlier work on its stream is complete.
-static int comm_barrier(Comm& cm, cudaStream_t s) {
+#define BZ_FLAG_CHANNELS 8
+#define BZ_FLAG_TIMEOUT_SLOT (BZ_FLAG_CHANNELS * 8)      // set to 1 by a barrier that gave up waiting (a peer died): checked by bz_synchronize
+
+struct PeerFlagPtrs { unsigned long long* base[8]; };
+
+__global__ void peer_barrier_kernel(PeerFlagPtrs flags, int rank, int n_ranks, unsigned mask, int channel, unsigned long long epoch) {
+    const int p = threadIdx.x;
+    if (p >= n_ranks || p == rank || !((mask >> p) & 1u)) return;
+    __threadfence_system();                                           // everything this stream wrote before the barrier is visible to the peers first
+    unsigned long long* remote = flags.base[p] + channel * 8 + rank;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(remote), "l"(epoch) : "memory");
+    const unsigned long long* mine = flags.base[rank] + channel * 8 + p;
+    volatile unsigned long long* dead = flags.base[rank] + BZ_FLAG_TIMEOUT_SLOT;
+    if (*dead) return;                                                // an earlier barrier gave up: drain the queue, bz_synchronize reports it
+    const long long t0 = clock64();
+    unsigned long long seen;
+    do {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
+        if (seen >= epoch) return;
+        __nanosleep(100);
+    } while (clock64() - t0 < 10000000000LL);                         // ~5 s at 2 GHz: never hang the GPU on a dead peer
+    *dead = 1ull;
+}
+
+// Stream barrier across ranks (all of them, or the ranks in `mask`): when it completes on this rank's stream, every participating rank's
+// earlier work on the stream it issued ITS barrier on is complete. Masks must be symmetric and all ranks must issue the same barrier
+// sequence per channel.
+static int comm_barrier(Comm& cm, cudaStream_t s, int channel = 0, unsigned mask = 0xffu) {
+    if (cm.p2p && cm.use_flags) {
+        PeerFlagPtrs F;
+        for (int p = 0; p < 8; ++p) F.base[p] = cm.peer_base[p] ? reinterpret_cast<unsigned long long*>(cm.peer_base[p] + cm.off_flags) : nullptr;
+        peer_barrier_kernel<<<1, 32, 0, s>>>(F, cm.rank, cm.n_ranks, mask, channel, ++cm.epoch[channel]);
+        if (cudaGetLastError() != cudaSuccess) { snprintf(cm.err, 256, "peer barrier launch failed"); return BZ_ERR_CUDA; }
+        return BZ_OK;
+    }
     NCCL_TRY(cm, cm.api.AllReduce(cm.token, cm.token, 1, NCCL_FLOAT64, NCCL_MAX, cm.comm, s));
     return BZ_OK;
+}
+static unsigned comm_neighbour_mask(const Comm& cm) {
+    const int P = cm.n_ranks;
+    return (1u << ((cm.rank + P - 1) % P)) | (1u << ((cm.rank + 1) % P));
 }
 
 static int comm_ipc_export(void* arena, uint8_t* out64, char* err) {
@@ -212,6 +264,8 @@ static int comm_ipc_attach(Comm& cm, void* own_arena, const uint8_t* handles) {
         cm.peer_base[p] = (char*)ptr;
     }
     cm.p2p = 1;
+    if (const char* e = getenv("BZ_NCCL_BARRIER")) cm.use_flags = atoi(e) ? 0 : 1;
+    if (const char* e = getenv("BZ_DIRECT_PULL")) cm.packed_pull = atoi(e) ? 0 : 1;
     return BZ_OK;
 }
 
@@ -232,13 +286,50 @@ __global__ void halo_pull_x(Layout L, FieldSet F, const char* my_base, const cha
     }
 }
 
-static int comm_pull_x_halos(Comm& cm, const Layout& L, const FieldSet& F, int mode, cudaStream_t s, int64_t* launches) {
+// Packed variant, owner side: side 0 = my first w columns (the LEFT neighbour's right ghosts), side 1 = my last w columns (the RIGHT
+// neighbour's left ghosts); layout [side][field][k][j][c], c fastest. nsides = 1 packs side 0 only (mode 1).
+__global__ void pack_faces_both(Layout L, FieldSet F, int w, int nsides, double* __restrict__ buf) {
+    const long long per_field = (long long)w * L.Ny * L.Nz, per_side = per_field * F.n, total = per_side * nsides;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int side = (int)(e / per_side); const long long q = e - side * per_side;
+        const int f = (int)(q / per_field); const long long r = q - f * per_field;
+        const int c = (int)(r % w), j = (int)((r / w) % L.Ny), k = (int)(r / ((long long)w * L.Ny));
+        buf[e] = F.f[f][lidx(L, (side == 0 ? 0 : L.nx - w) + c, j, k)];
+    }
+}
+// consumer side: right ghosts from the right neighbour's side 0, left ghosts (nsides = 2) from the left neighbour's side 1
+__global__ void unpack_faces_both(Layout L, FieldSet F, int w, int nsides, const double* __restrict__ left_buf, const double* __restrict__ right_buf) {
+    const long long per_field = (long long)w * L.Ny * L.Nz, per_side = per_field * F.n, total = per_side * nsides;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int side = (int)(e / per_side); const long long q = e - side * per_side;
+        const int f = (int)(q / per_field); const long long r = q - f * per_field;
+        const int c = (int)(r % w), j = (int)((r / w) % L.Ny), k = (int)(r / ((long long)w * L.Ny));
+        // my right ghosts are the right neighbour's side 0; my left ghosts are the left neighbour's side 1
+        const double v = side == 0 ? __ldcv(right_buf + q) : __ldcv(left_buf + per_side + q);
+        F.f[f][lidx(L, (side == 0 ? L.nx : -w) + c, j, k)] = v;
+    }
+}
+
+// region: 0 ρu face, 1 φ, 2 scalars, 3 all five / momentum (Comm::pack_start)
+static int comm_pull_x_halos(Comm& cm, const Layout& L, const FieldSet& F, int mode, cudaStream_t s, int64_t* launches, int channel = 0, int region = 3) {
     const int P = cm.n_ranks, left = (cm.rank + P - 1) % P, right = (cm.rank + 1) % P;
-    int rc = comm_barrier(cm, s);
-    if (rc) return rc;
-    const long long total = (long long)F.n * (mode == 0 ? 2 * L.HX : 1) * L.Ny * L.Nz;
+    const int w = mode == 0 ? L.HX : 1, nsides = mode == 0 ? 2 : 1;
+    const long long total = (long long)F.n * nsides * w * L.Ny * L.Nz;
     const int blocks = (int)((total + 255) / 256) > 148 * 8 ? 148 * 8 : (int)((total + 255) / 256);
-    halo_pull_x<<<blocks, 256, 0, s>>>(L, F, cm.peer_base[cm.rank], cm.peer_base[left], cm.peer_base[right], mode);
+    if (cm.packed_pull) {
+        double* mine = reinterpret_cast<double*>(cm.peer_base[cm.rank] + cm.off_pack) + cm.pack_start[region];
+        pack_faces_both<<<blocks, 256, 0, s>>>(L, F, w, nsides, mine);
+        *launches += 1;
+    }
+    int rc = comm_barrier(cm, s, channel, comm_neighbour_mask(cm));   // only the two neighbours' fields are read
+    if (rc) return rc;
+    if (cm.packed_pull) {
+        const double* lbuf = reinterpret_cast<const double*>(cm.peer_base[left] + cm.off_pack) + cm.pack_start[region];
+        const double* rbuf = reinterpret_cast<const double*>(cm.peer_base[right] + cm.off_pack) + cm.pack_start[region];
+        unpack_faces_both<<<blocks, 256, 0, s>>>(L, F, w, nsides, lbuf, rbuf);
+    } else {
+        halo_pull_x<<<blocks, 256, 0, s>>>(L, F, cm.peer_base[cm.rank], cm.peer_base[left], cm.peer_base[right], mode);
+    }
     *launches += 1;
     return BZ_OK;
 }

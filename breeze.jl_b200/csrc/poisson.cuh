@@ -24,8 +24,8 @@ struct PoissonGeom {
     int nky;       // number of ky modes held after the y transform: Ny/2 + 1 (1 if Flat y)
     int nky_loc;   // ky modes on this rank in the transposed layout
     int ky0;       // first global ky of this rank in the transposed layout
-    int P;         // ranks (x-slabs); nx = Nx / P is a power of two
-    int nx_shift;  // log2(nx)
+    int P;         // ranks (x-slabs)
+    int nx;        // columns per rank, Nx / P
     const long long* ky_base;   // per ky: offset of (k = 0, ky, i = 0) in the peer-blocked W   (device, nky entries)
     const int* ky_kstride;      // per ky: level stride of its block = count_p * nx              (device, nky entries)
     // peer-memory path (CUDA IPC): the all-to-all transposes become peer loads inside the consuming FFT kernels
@@ -47,12 +47,12 @@ __host__ __device__ __forceinline__ void ky_block(int nky, int P, int p, int* st
     *start = p * base + (p < rem ? p : rem);
 }
 __device__ __forceinline__ size_t w_index(const PoissonGeom& G, int k, int ky, int i) {
-    if (G.P == 1) return (((size_t)k * G.nky + ky) << G.nx_shift) + i;
+    if (G.P == 1) return ((size_t)k * G.nky + ky) * G.nx + i;
     return (size_t)__ldg(&G.ky_base[ky]) + (size_t)k * __ldg(&G.ky_kstride[ky]) + i;
 }
 __device__ __forceinline__ size_t w2_index(const PoissonGeom& G, int k, int kyl, int kx) {
-    const int p = kx >> G.nx_shift, i = kx & ((1 << G.nx_shift) - 1);
-    return (((size_t)p * G.Nz + k) * G.nky_loc + kyl << G.nx_shift) + i;
+    const int p = kx / G.nx, i = kx - p * G.nx;
+    return (((size_t)p * G.Nz + k) * G.nky_loc + kyl) * G.nx + i;
 }
 
 // ---- register butterflies (forward: e^{-2πi/R}) ----------------------------------------------------------------
@@ -66,6 +66,13 @@ __device__ __forceinline__ void dft2(cpx& a, cpx& b) { cpx t = a - b; a = a + b;
 __device__ __forceinline__ void dft4(cpx& x0, cpx& x1, cpx& x2, cpx& x3) {
     cpx s02 = x0 + x2, d02 = x0 - x2, s13 = x1 + x3, d13 = mul_mi(x1 - x3);
     x0 = s02 + s13; x2 = s02 - s13; x1 = d02 + d13; x3 = d02 - d13;
+}
+__device__ __forceinline__ void dft3(cpx& x0, cpx& x1, cpx& x2) {          // forward: W3 = e^{-2πi/3} = -1/2 - i √3/2
+    const double c = -0.5, sn = 0.86602540378443864676;
+    cpx s = x1 + x2, d = x1 - x2;
+    cpx m = {x0.x + c * s.x, x0.y + c * s.y};
+    cpx r = {sn * d.y, -sn * d.x};                                        // -i sin(2π/3) (x1 - x2)
+    x0 = x0 + s; x1 = m + r; x2 = m - r;
 }
 __device__ __forceinline__ void dft8(cpx* v) {
     const double h = 0.70710678118654752440;
@@ -92,8 +99,13 @@ __host__ __device__ __forceinline__ int line_pitch(int N) { return ((N + (N >> 4
 __host__ __device__ __forceinline__ int imag_offset(int N, int lines) { int o = lines * line_pitch(N); return o + ((2 - o) & 15); }
 __host__ __device__ __forceinline__ size_t fft_smem_bytes(int N, int lines) { return (size_t)(imag_offset(N, lines) + lines * line_pitch(N)) * sizeof(double); }
 
+// Line lengths: N = 2^m (8 .. 2048) or N = 3 · 2^m (24 .. 1536; the reference benchmarks 768 x 768 x 256, Benchmarks.yml:41).
+// Points per thread: 8 for the powers of two (radix-8 / 4 / 2 passes), 12 for 3 · 2^m (radix-4 / 2 passes and one radix-3 pass last, so
+// that every earlier pass keeps a power-of-two Ns).
+__host__ __device__ constexpr int fft_pt(int N) { return (N % 3 == 0) ? 12 : 8; }
+
 // One Stockham pass of radix R over lines of compile-time length N held as re[l*LP + pidx(n)], im[l*LP + pidx(n)].
-// Each thread owns 8/R butterflies (8 complex values in registers): blockDim.x == lines * N / 8. N, R, Ns are
+// Each thread owns PT/R butterflies (PT complex values in registers): blockDim.x == lines * N / PT. N, R, Ns are
 // compile-time, so every index below folds to shifts and immediates (the run-time-N version spent 85 % of its
 // instructions on index arithmetic).
 // padded offset of a compile-time displacement D from an element whose padded index is already known: when D is a multiple
@@ -102,7 +114,8 @@ template <int D> __device__ __forceinline__ int pidx_plus(int n, int pn) { retur
 
 template <int N, int R, int Ns>
 __device__ __forceinline__ void stockham_pass(double* __restrict__ re, double* __restrict__ im, const double2* __restrict__ tw) {
-    constexpr int ITEMS = 8 / R, PER_LINE = N / 8, NR = N / R, LP = ((N + (N >> 4) + 15) & ~15) + 4, STEP = N / (Ns * R);
+    constexpr int PT = fft_pt(N), ITEMS = PT / R, PER_LINE = N / PT, NR = N / R, LP = ((N + (N >> 4) + 15) & ~15) + 4, STEP = N / (Ns * R);
+    static_assert(PT % R == 0 && N % (Ns * R) == 0 && (Ns & (Ns - 1)) == 0, "pass shape");
     const int l = threadIdx.x / PER_LINE, t = threadIdx.x % PER_LINE;
     double* lre = re + l * LP;
     double* lim = im + l * LP;
@@ -129,8 +142,9 @@ __device__ __forceinline__ void stockham_pass(double* __restrict__ re, double* _
                 v[it][r] = cmul(v[it][r], cpx{w.x, w.y});
             }
         }
-        if (R == 8) dft8(v[it]);
-        else if (R == 4) dft4(v[it][0], v[it][1], v[it][2], v[it][3]);
+        if constexpr (R == 8) dft8(v[it]);
+        else if constexpr (R == 4) dft4(v[it][0], v[it][1], v[it][2], v[it][3]);
+        else if constexpr (R == 3) dft3(v[it][0], v[it][1], v[it][2]);
         else dft2(v[it][0], v[it][1]);
         const int j0 = (j - k) * R + k;
         const int pj0 = pidx(j0);
@@ -143,17 +157,29 @@ __device__ __forceinline__ void stockham_pass(double* __restrict__ re, double* _
     __syncthreads();
 }
 
-// Forward DFT (e^{-2πi nk/N}) of every line in shared memory; N = 2^m, 8 <= N <= 2048. Callers conjugate for the inverse.
+// Forward DFT (e^{-2πi nk/N}) of every line in shared memory; N = 2^m (8 .. 2048) or 3 · 2^m (24 .. 1536). Callers conjugate for the inverse.
+template <int N, int Ns, int REM>     // REM = remaining power-of-two factor of a 3 · 2^m length: radix-4 passes, then one radix-2 if odd
+__device__ __forceinline__ void pow2_passes_r4(double* __restrict__ re, double* __restrict__ im, const double2* __restrict__ tw) {
+    if constexpr (REM >= 4) { stockham_pass<N, 4, Ns>(re, im, tw); pow2_passes_r4<N, Ns * 4, REM / 4>(re, im, tw); }
+    else if constexpr (REM == 2) stockham_pass<N, 2, Ns>(re, im, tw);
+}
 template <int N>
 __device__ __forceinline__ void fft_lines_smem(double* __restrict__ re, double* __restrict__ im, const double2* __restrict__ tw) {
-    constexpr int m = (N == 8) ? 3 : (N == 16) ? 4 : (N == 32) ? 5 : (N == 64) ? 6 : (N == 128) ? 7 : (N == 256) ? 8 : (N == 512) ? 9 : (N == 1024) ? 10 : 11;
-    static_assert((1 << m) == N, "N must be a power of two in [8, 2048]");
-    stockham_pass<N, 8, 1>(re, im, tw);
-    if (m >= 6) stockham_pass<N, 8, (m >= 6 ? 8 : 1)>(re, im, tw);
-    if (m >= 9) stockham_pass<N, 8, (m >= 9 ? 64 : 1)>(re, im, tw);
-    constexpr int done = (m / 3) * 3, Ns = 1 << done;
-    if (m % 3 == 2) stockham_pass<N, 4, (m % 3 == 2 ? Ns : 1)>(re, im, tw);
-    else if (m % 3 == 1) stockham_pass<N, 2, (m % 3 == 1 ? Ns : 1)>(re, im, tw);
+    if constexpr (N % 3 == 0) {
+        constexpr int M = N / 3;
+        static_assert((M & (M - 1)) == 0 && M >= 8 && M <= 512, "N must be 3 * 2^m, 24 <= N <= 1536");
+        pow2_passes_r4<N, 1, M>(re, im, tw);
+        stockham_pass<N, 3, M>(re, im, tw);
+    } else {
+        constexpr int m = (N == 8) ? 3 : (N == 16) ? 4 : (N == 32) ? 5 : (N == 64) ? 6 : (N == 128) ? 7 : (N == 256) ? 8 : (N == 512) ? 9 : (N == 1024) ? 10 : 11;
+        static_assert((1 << m) == N, "N must be a power of two in [8, 2048]");
+        stockham_pass<N, 8, 1>(re, im, tw);
+        if (m >= 6) stockham_pass<N, 8, (m >= 6 ? 8 : 1)>(re, im, tw);
+        if (m >= 9) stockham_pass<N, 8, (m >= 9 ? 64 : 1)>(re, im, tw);
+        constexpr int done = (m / 3) * 3, Ns = 1 << done;
+        if (m % 3 == 2) stockham_pass<N, 4, (m % 3 == 2 ? Ns : 1)>(re, im, tw);
+        else if (m % 3 == 1) stockham_pass<N, 2, (m % 3 == 1 ? Ns : 1)>(re, im, tw);
+    }
 }
 
 // ---- source term ------------------------------------------------------------------------------------------------
@@ -174,7 +200,7 @@ __device__ __forceinline__ double source_term(const Layout& L, const double* __r
 // MAXT / MINB: launch bounds. The default (256, 3) is the tuned configuration; (512, 2) exists for the wide-tile experiment
 // (8 lines per CTA = 128-byte rows of the momentum fields; BZ_FFT_LINES_Y).
 template <int N, int MAXT = 256, int MINB = 3>
-__global__ void __launch_bounds__(MAXT, MINB) poisson_forward_y(Layout L, PoissonGeom G, const double* __restrict__ ru, const double* __restrict__ rv,
+__global__ void __launch_bounds__(MAXT, (N % 3 == 0 && MINB > 2) ? 2 : MINB) poisson_forward_y(Layout L, PoissonGeom G, const double* __restrict__ ru, const double* __restrict__ rv,
                                   const double* __restrict__ rw, double dz_over_dt, double2* __restrict__ W,
                                   const double2* __restrict__ tw_y, int lines) {
     extern __shared__ double sm[];
@@ -185,20 +211,21 @@ __global__ void __launch_bounds__(MAXT, MINB) poisson_forward_y(Layout L, Poisso
     const int XB = 2 * lines;                        // lines is a power of two
     const int xb_shift = 31 - __clz(XB);
     const int ib = blockIdx.x * XB;
-    // blockDim.x == lines * N / 8 and XB == 2 * lines: every thread evaluates 16 source-term values, 8 at a time so that
+    // blockDim.x == lines * N / PT and XB == 2 * lines: every thread evaluates 2 PT source-term values, PT at a time so that
     // their loads are in flight together
+    constexpr int PT = fft_pt(N);
     for (int half = 0; half < 2; ++half) {
-        double v[8];
+        double v[PT];
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            int e = threadIdx.x + (half * 8 + it) * blockDim.x;
+        for (int it = 0; it < PT; ++it) {
+            int e = threadIdx.x + (half * PT + it) * blockDim.x;
             int c = e & (XB - 1), y = e >> xb_shift;
             int i = ib + c;
             v[it] = (i < L.nx) ? source_term(L, ru, rv, rw, i, y, k, dz_over_dt) : 0.0;
         }
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            int e = threadIdx.x + (half * 8 + it) * blockDim.x;
+        for (int it = 0; it < PT; ++it) {
+            int e = threadIdx.x + (half * PT + it) * blockDim.x;
             int c = e & (XB - 1), y = e >> xb_shift;
             ((c & 1) ? im : re)[(c >> 1) * LP + pidx(y)] = v[it];
         }
@@ -210,7 +237,7 @@ __global__ void __launch_bounds__(MAXT, MINB) poisson_forward_y(Layout L, Poisso
         int c = e & (XB - 1), ky = e >> xb_shift;
         int i = ib + c;
         if (i >= L.nx) continue;
-        int l = c >> 1, km = (N - ky) & (N - 1);
+        int l = c >> 1, km = ky ? N - ky : 0;
         double zr = re[l * LP + pidx(ky)], zi = im[l * LP + pidx(ky)];
         double yr = re[l * LP + pidx(km)], yi = im[l * LP + pidx(km)];
         double2 o = (c & 1) ? make_double2(0.5 * (zi + yi), -0.5 * (zr - yr)) : make_double2(0.5 * (zr + yr), 0.5 * (zi - yi));
@@ -227,7 +254,7 @@ __global__ void poisson_pack_flat_y(Layout L, PoissonGeom G, const double* __res
 
 // ---- pass 5: complex-to-real inverse FFT along y → φ (padded field interior) -------------------------------------
 template <int N, int MAXT = 256, int MINB = 3>
-__global__ void __launch_bounds__(MAXT, MINB) poisson_inverse_y(Layout L, PoissonGeom G, const double2* __restrict__ W, double* __restrict__ phi,
+__global__ void __launch_bounds__(MAXT, (N % 3 == 0 && MINB > 2) ? 2 : MINB) poisson_inverse_y(Layout L, PoissonGeom G, const double2* __restrict__ W, double* __restrict__ phi,
                                   const double2* __restrict__ tw_y, int lines, double scale, PeerBases peers, int pull) {
     extern __shared__ double sm[];
     constexpr int LP = ((N + (N >> 4) + 15) & ~15) + 4;
@@ -238,12 +265,13 @@ __global__ void __launch_bounds__(MAXT, MINB) poisson_inverse_y(Layout L, Poisso
     const int xb_shift = 31 - __clz(XB);
     const int ib = blockIdx.x * XB;
     // rebuild the packed spectrum Z = A + iB (Hermitian halves), conjugated for the inverse-by-forward trick
-    // (N/2 + 1) * lines <= 5 * blockDim.x elements; loads are batched ahead of their use
+    // (N/2 + 1) * lines <= (PT/2 + 1) * blockDim.x elements; loads are batched ahead of their use
     {
+        constexpr int NIT = fft_pt(N) / 2 + 1;
         const int total = G.nky * lines;
-        double2 A[5], B[5];
+        double2 A[NIT], B[NIT];
 #pragma unroll
-        for (int it = 0; it < 5; ++it) {
+        for (int it = 0; it < NIT; ++it) {
             int e = threadIdx.x + it * blockDim.x;
             A[it] = make_double2(0.0, 0.0); B[it] = make_double2(0.0, 0.0);
             if (e < total) {
@@ -261,7 +289,7 @@ __global__ void __launch_bounds__(MAXT, MINB) poisson_inverse_y(Layout L, Poisso
             }
         }
 #pragma unroll
-        for (int it = 0; it < 5; ++it) {
+        for (int it = 0; it < NIT; ++it) {
             int e = threadIdx.x + it * blockDim.x;
             if (e < total) {
                 int l = e & (lines - 1), ky = e >> (xb_shift - 1);
@@ -295,7 +323,7 @@ __global__ void poisson_unpack_flat_y(Layout L, PoissonGeom G, const double2* __
 // ---- passes 2 / 4: complex FFT along x, in place; one line = Nx contiguous complex numbers ----------------------
 // grid ceil(n_lines / lines); block lines*Nx/8 <= 256 threads; smem 2*lines*line_pitch(Nx) doubles.
 template <int N, int MAXT = 256, int MINB = 3>
-__global__ void __launch_bounds__(MAXT, MINB) fft_x_kernel(PoissonGeom G, double2* __restrict__ W, long long n_lines, const double2* __restrict__ tw_x, int lines, int inverse,
+__global__ void __launch_bounds__(MAXT, (N % 3 == 0 && MINB > 2) ? 2 : MINB) fft_x_kernel(PoissonGeom G, double2* __restrict__ W, long long n_lines, const double2* __restrict__ tw_x, int lines, int inverse,
                                                        PeerBases peers, int pull) {
     extern __shared__ double sm[];
     constexpr int LP = ((N + (N >> 4) + 15) & ~15) + 4;
@@ -304,41 +332,41 @@ __global__ void __launch_bounds__(MAXT, MINB) fft_x_kernel(PoissonGeom G, double
     const int l0 = blockIdx.x * lines;                  // first line of this CTA; line = k * nky_loc + ky_loc (fits an int)
     const double sgn = inverse ? -1.0 : 1.0;
     const int k0 = l0 / G.nky_loc, r0 = l0 - k0 * G.nky_loc;    // one division per CTA; lines advance (k, ky) incrementally
-    const int xmask = (1 << G.nx_shift) - 1;
+    constexpr int PT = fft_pt(N);
     auto w2_of = [&](int l, int x) -> size_t {          // offset of element x of the CTA's line l in the peer-blocked W2
         int ky = r0 + l, k = k0;
         while (ky >= G.nky_loc) { ky -= G.nky_loc; ++k; }
-        const int p = x >> G.nx_shift;
-        return ((((size_t)p * G.Nz + k) * G.nky_loc + ky) << G.nx_shift) + (x & xmask);
+        const int p = x / G.nx;
+        return (((size_t)p * G.Nz + k) * G.nky_loc + ky) * G.nx + (x - p * G.nx);
     };
-    // blockDim.x == lines * N / 8: every thread moves exactly 8 elements; all 8 loads are issued before the first use
-    double2 v[8];
+    // blockDim.x == lines * N / PT: every thread moves exactly PT elements; all PT loads are issued before the first use
+    double2 v[PT];
     const long long chunk = (n_lines - l0 < lines ? n_lines - l0 : lines) * (long long)N;   // valid elements of this CTA's lines
     if (G.P == 1) {                                     // one rank: the CTA's lines are ONE contiguous chunk of W
         const double2* __restrict__ src = W + (size_t)l0 * N;
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
+        for (int it = 0; it < PT; ++it) {
             const int e = threadIdx.x + it * blockDim.x;
             v[it] = (e < chunk) ? src[e] : make_double2(0.0, 0.0);
         }
     } else {
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
+    for (int it = 0; it < PT; ++it) {
         const int e = threadIdx.x + it * blockDim.x;
         const int l = e / N, x = e % N;
         if (l0 + l >= n_lines) v[it] = make_double2(0.0, 0.0);
         else if (pull) {   // x-slab spectrum read straight from the rank that owns these columns (replaces the forward all-to-all)
             int ky = r0 + l, k = k0;
             while (ky >= G.nky_loc) { ky -= G.nky_loc; ++k; }
-            const int p = x >> G.nx_shift;
+            const int p = x / G.nx;
             const double2* src = reinterpret_cast<const double2*>(peers.base[p] + G.off_W)
-                                 + (((long long)G.ky0 * G.Nz + (long long)k * G.nky_loc + ky) << G.nx_shift) + (x & xmask);
+                                 + ((long long)G.ky0 * G.Nz + (long long)k * G.nky_loc + ky) * G.nx + (x - p * G.nx);
             v[it] = __ldcv(src);
         } else v[it] = W[w2_of(l, x)];
     }
     }
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
+    for (int it = 0; it < PT; ++it) {
         const int e = threadIdx.x + it * blockDim.x;
         const int l = e / N, x = e % N;
         re[l * LP + pidx(x)] = v[it].x;
@@ -349,14 +377,14 @@ __global__ void __launch_bounds__(MAXT, MINB) fft_x_kernel(PoissonGeom G, double
     if (G.P == 1) {
         double2* __restrict__ dst = W + (size_t)l0 * N;
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
+        for (int it = 0; it < PT; ++it) {
             const int e = threadIdx.x + it * blockDim.x;
             const int l = e / N, x = e % N;
             if (e < chunk) dst[e] = make_double2(re[l * LP + pidx(x)], sgn * im[l * LP + pidx(x)]);
         }
     } else {
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
+    for (int it = 0; it < PT; ++it) {
         const int e = threadIdx.x + it * blockDim.x;
         const int l = e / N, x = e % N;
         if (l0 + l < n_lines) W[w2_of(l, x)] = make_double2(re[l * LP + pidx(x)], sgn * im[l * LP + pidx(x)]);
@@ -400,7 +428,7 @@ __global__ void thomas_z(PoissonGeom G, double2* __restrict__ W, const double* _
     if (kx >= G.Nx) return;
     const size_t stride = (size_t)G.nky_loc * G.Nx;                    // level stride of the factor arrays (plain layout)
     const size_t n0 = (size_t)ky * G.Nx + kx;
-    const size_t wstride = (size_t)G.nky_loc << G.nx_shift;            // level stride of W2 inside its peer block
+    const size_t wstride = (size_t)G.nky_loc * G.nx;                   // level stride of W2 inside its peer block
     const size_t w0 = w2_index(G, 0, ky, kx);
     const int Nz = G.Nz;
     const double rdz = 1.0 / dz;
@@ -444,7 +472,7 @@ __global__ void thomas_z(PoissonGeom G, double2* __restrict__ W, const double* _
 // φ .-= mean(φ): only the (kx, ky) = (0, 0) column carries the mean. One block.
 __global__ void remove_mean_mode(PoissonGeom G, double2* __restrict__ W) {
     __shared__ double sr[256], si[256];
-    const size_t stride = (size_t)G.nky_loc << G.nx_shift;             // (kx, ky) = (0, 0) lives in peer block 0
+    const size_t stride = (size_t)G.nky_loc * G.nx;                    // (kx, ky) = (0, 0) lives in peer block 0
     double ar = 0.0, ai = 0.0;
     for (int k = threadIdx.x; k < G.Nz; k += blockDim.x) { double2 v = W[k * stride]; ar += v.x; ai += v.y; }
     sr[threadIdx.x] = ar; si[threadIdx.x] = ai;
@@ -457,12 +485,16 @@ __global__ void remove_mean_mode(PoissonGeom G, double2* __restrict__ W) {
     for (int k = threadIdx.x; k < G.Nz; k += blockDim.x) { double2 v = W[k * stride]; W[k * stride] = make_double2(v.x - mr, v.y - mi); }
 }
 
-// Host-side dispatch on the (power-of-two) line length.
+// Host-side dispatch on the line length (2^m or 3 · 2^m).
 #define FFT_DISPATCH(n, CALL)                                                                                    \
     switch (n) {                                                                                                  \
         case 8: { constexpr int FN = 8; CALL; break; }       case 16: { constexpr int FN = 16; CALL; break; }     \
         case 32: { constexpr int FN = 32; CALL; break; }     case 64: { constexpr int FN = 64; CALL; break; }     \
         case 128: { constexpr int FN = 128; CALL; break; }   case 256: { constexpr int FN = 256; CALL; break; }   \
         case 512: { constexpr int FN = 512; CALL; break; }   case 1024: { constexpr int FN = 1024; CALL; break; } \
-        case 2048: { constexpr int FN = 2048; CALL; break; } default: break;                                      \
+        case 2048: { constexpr int FN = 2048; CALL; break; }                                                      \
+        case 24: { constexpr int FN = 24; CALL; break; }     case 48: { constexpr int FN = 48; CALL; break; }     \
+        case 96: { constexpr int FN = 96; CALL; break; }     case 192: { constexpr int FN = 192; CALL; break; }   \
+        case 384: { constexpr int FN = 384; CALL; break; }   case 768: { constexpr int FN = 768; CALL; break; }   \
+        case 1536: { constexpr int FN = 1536; CALL; break; } default: break;                                      \
     }

@@ -305,6 +305,38 @@ def test_cell_advection_timescale_and_finite_check_match_oracle(oracle_arch):
     assert not gpu.context.state_is_finite()
 
 
+@pytest.mark.parametrize("size,flat_y", [((24, 48, 16), False), ((96, 24, 12), False), ((192, 20), True), ((48, 64, 10), False)])
+def test_mixed_radix_grids_match_oracle(oracle_arch, size, flat_y):
+    """Horizontal sizes 3 · 2^m (the reference benchmarks 768 x 768 x 256, .github/workflows/Benchmarks.yml:41): the in-house FFT's
+    radix-3 pass, the projection and three full steps against the oracle (whose DFT is an independent mixed-radix implementation)."""
+    gpu, cpu = _pair(oracle_arch, size, flat_y, seed=5, moist=True)
+    for name in PROGNOSTIC + ["φ"]:
+        assert rel_err(gpu.field(name), cpu.field(name)) < TOL_HOOK, name
+    assert gpu.context.max_abs_divergence() < np.prod(size) * 2.3e-16 * 50
+    for _ in range(3):
+        gpu.time_step(1.0)
+        cpu.time_step(1.0)
+    for name in PROGNOSTIC:
+        assert rel_err(gpu.field(name), cpu.field(name)) < TOL_STEPS_NOISY, name
+
+
+def test_reference_benchmark_grid_768x768x256_properties():
+    """`768x768x256` of the reference's benchmark matrix (Benchmarks.yml:41) on the CUDA path: divergence-free momentum after every step,
+    conservation of ∫ρθ, and the x↔y symmetry of the centred bubble (ρv(k, j, i) = ρu(k, i, j)) through the radix-3 transforms."""
+    import breeze_b200 as bz
+    grid = bz.RectilinearGrid(bz.B200(), size=(768, 768, 256), x=(-10e3, 10e3), y=(-10e3, 10e3), z=(0, 10e3))
+    m = bz.AtmosphereModel(grid, dynamics=bz.AnelasticDynamics(bz.ReferenceState(grid, potential_temperature=300)), advection=bz.WENO(order=5))
+    m.set(θ=bubble_theta())
+    s0 = m.field("ρθ").sum()
+    for _ in range(2):
+        m.time_step(0.5)
+    assert m.context.max_abs_divergence() < 1e-11
+    ru, rv, rt = m.field("ρu"), m.field("ρv"), m.field("ρθ")
+    assert abs(rt.sum() - s0) < 1e-12 * abs(s0)
+    assert np.abs(rv - np.swapaxes(ru, 1, 2)).max() < 1e-10 * max(np.abs(ru).max(), 1e-30)
+    assert np.abs(m.field("w")).max() > 1e-4
+
+
 def test_slices_match_full_fields(oracle_arch):
     gpu, _ = _pair(oracle_arch, (32, 16, 24), moist=True)
     for name in ("θ", "ρw", "T", "φ"):

@@ -22,7 +22,7 @@ def test_slabs_match_single_gpu(world, p2p):
         pytest.skip(f"needs {world} GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(29600 + 10 * world + p2p), os.path.join(ROOT, "scripts", "multi_gpu_check.py"), "64", "3"]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, BZ_P2P=str(p2p)))
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=180, env=dict(os.environ, BZ_P2P=str(p2p)))
     assert "MULTI_GPU_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
 
 
@@ -33,5 +33,5 @@ def test_bomex_slabs_match_single_gpu(p2p):
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", str(29650 + p2p), os.path.join(ROOT, "scripts", "multi_gpu_check.py"), "64", "3", "bomex"]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, BZ_P2P=str(p2p)))
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=180, env=dict(os.environ, BZ_P2P=str(p2p)))
     assert "MULTI_GPU_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
