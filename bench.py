@@ -311,6 +311,69 @@ def bench_bomex(args, steps, warmup, with_cpu=True):
     return out
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# The shipped examples' scheme: WENO(order = 9) + StaticEnergyFormulation (examples/dry_thermal_bubble.jl:24), stage_hi_kernel
+# ---------------------------------------------------------------------------------------------------------------------
+HI_BYTES_PER_CELL = STAGE_BYTES_PER_CELL + 80.0 + (80.0 + 40.0 + 40.0) / 3.0   # + specific-field pass (5 reads, 5 writes) + its 5 re-reads as stencil operands
+
+
+def bench_shipped_bubble(args):
+    import torch
+    import breeze_b200 as bz
+    dev = int(os.environ.get("LOCAL_RANK", "0"))
+    out = {}
+    # (i) examples/dry_thermal_bubble.jl as shipped: 2-D 128 x 128 (Periodic, Flat, Bounded), WENO9, :StaticEnergy, Δθ = 10 K
+    grid = bz.RectilinearGrid(bz.B200(device=dev), size=(128, 128), x=(-10e3, 10e3), z=(0, 10e3), topology=(bz.Periodic, bz.Flat, bz.Bounded))
+    m = bz.AtmosphereModel(grid, dynamics=bz.AnelasticDynamics(bz.ReferenceState(grid, potential_temperature=300)), advection=bz.WENO(order=9),
+                           formulation="StaticEnergy")
+    m.set(θ=lambda x, z: 300.0 + 10.0 * np.maximum(0.0, 1.0 - np.sqrt(x ** 2 + (z - 3000.0) ** 2) / 2000.0))
+    ctx = m.context
+    for _ in range(5):
+        ctx.time_step(2.0)
+    ctx.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(200):
+        ctx.time_step(2.0)
+    ctx.synchronize()
+    ms2d = (time.perf_counter() - t0) / 200 * 1e3
+    out["as_shipped_2d_128x128"] = {"ms_per_step": ms2d, "value": 128 * 128 / (ms2d * 1e-3) / 1e6, "unit": "Mcell-updates/s", "steps": 200,
+                                    "note": "launch-bound: 16 384 cells; wall clock around 200 steps incl. launch overheads", "max_abs_w": float(np.abs(m.field("w")).max())}
+    del m, ctx
+    # (ii) the same scheme and formulation on the 3-D 256^3 bubble (BASELINE config 1's grid)
+    N = 256
+    m = bubble_model(bz.B200(device=dev), N, order=9, formulation="StaticEnergy")
+    ctx = m.context
+    ext_stream = torch.cuda.ExternalStream(ctx.stream())
+    for _ in range(3):
+        ctx.time_step(args.dt)
+    ctx.profile_enable(True)
+    for _ in range(5):
+        ctx.time_step(args.dt)
+    ctx.profile_read()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ctx.synchronize(); torch.cuda.synchronize()
+    e0.record(ext_stream)
+    for _ in range(5):
+        ctx.time_step(args.dt)
+    e1.record(ext_stream)
+    ctx.synchronize(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    fam_ms, fam_n = ctx.profile_read()
+    ctx.profile_enable(False)
+    peak, peak_src = measured_peak()
+    stage_ms = fam_ms[0] / max(1, fam_n[0])                  # specific-field pass + stage_hi_kernel per stage
+    achieved = HI_BYTES_PER_CELL * N ** 3 / (stage_ms * 1e-3) / 1e9
+    out["weno9_static_energy_3d_256"] = {
+        "value": N ** 3 / (ms * 1e-3) / 1e6, "unit": "Mcell-updates/s", "ms_per_step": ms, "steps": 5,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "kernel": "specific_fields_kernel + stage_hi_kernel<5> (fused WENO9 tendencies + RK update)", "kernel_ms": stage_ms,
+                     "bytes_per_cell": HI_BYTES_PER_CELL, "peak_source": peak_src,
+                     "note": "≈ 2700 FP64 instructions per cell: FP64-pipe bound (floor ≈ 2.4 ms per launch at 256^3), not HBM bound"},
+        "breakdown_ms_per_step": {n: round(fam_ms[f] / 5, 4) for f, n in enumerate(["stage_tendency_rk", "poisson_forward", "thomas", "poisson_inverse", "projection_halo"])},
+        "checks": {"max_abs_divergence": ctx.max_abs_divergence()}}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -470,13 +533,14 @@ def main():
     peak, peak_src = measured_peak()
     stage_ms = fam_ms[0] / max(1, fam_n[0])
     achieved = STAGE_BYTES_PER_CELL * cells_local / (stage_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_src = None, None
     tp = os.path.join(ROOT, "profiles", "stage_kernel_traffic.json")
     if os.path.exists(tp):
         try:
             t = json.load(open(tp))
             if t.get("size") == N and t.get("n_gpus") == world:
-                traffic = t.get("dram_bytes_per_launch")
+                traffic = t.get("dram_bytes_per_launch")                  # from the committed ncu capture named in the file (commit stamped there)
+                traffic_src = {k: t.get(k) for k in ("source", "commit", "launches_captured")}
         except Exception:
             pass
     families = ["stage_tendency_rk", "poisson_forward", "thomas", "poisson_inverse", "projection_halo", "exchange"]
@@ -586,7 +650,8 @@ def main():
                        "staging": "tma" if args.use_tma != 2 else "plain", "device_bytes": ctx.device_bytes()},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": "stage_kernel (fused WENO5 tendencies + RK update)", "kernel_ms": stage_ms, "peak_source": peak_src,
-                         "bytes_per_cell": STAGE_BYTES_PER_CELL},
+                         "bytes_per_cell": STAGE_BYTES_PER_CELL,
+                         "traffic_source": traffic_src},   # dram__bytes_read + write per launch from the committed ncu --set full capture of this kernel
             "breakdown_ms_per_step": breakdown,
             "e2e": {"value": e2e_value, "unit": "Mcell-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "api": "bz_set_state_async + bz_time_step + bz_get_state_async per step (pinned host buffers, all five prognostics both ways), bz_synchronize at the end"},
@@ -611,6 +676,10 @@ def main():
                 out["config3_bomex"]["workload"] = c3["config"]["workload"]
             except Exception as e:
                 out["config3_bomex"] = {"error": str(e)}
+            try:
+                out["shipped_scheme_weno9_static_energy"] = bench_shipped_bubble(args)
+            except Exception as e:
+                out["shipped_scheme_weno9_static_energy"] = {"error": str(e)}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -64,7 +64,10 @@ struct bz_ctx {
     // host <-> device marshalling: strided 3-D copies straight between the caller's dense arrays and the padded fields, in z chunks,
     // on two copy streams (one per PCIe direction) so that a download and the upload that follows it run full duplex
     cudaStream_t s2 = nullptr;           // second compute stream: x-halo exchanges overlapped with the Poisson solve / the interior projection (slabs)
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_chunk[8] = {};
+    int fft_z_chunks = 1;                // z chunks of the pipelined distributed transform (BZ_FFT_Z_CHUNKS). Measured at 2 slabs of 512^3
+                                         // (profiles/r2j_fft_z_chunks.txt): 1 -> 29.73, 2 -> 29.77, 4 -> 30.25, 8 -> 30.79 ms per step — the pulls
+                                         // already run at NVLink rate and do not overlap the next chunk's transform, so the default stays 1
     int overlap = 1;                     // BZ_NO_OVERLAP=1: every exchange serialised on the main stream (A/B and debugging)
     int scalars_in_flight = 0;           // the θ / q ghosts of set[cur] are being pulled on s2
     cudaStream_t s_in = nullptr, s_out = nullptr;
@@ -316,40 +319,72 @@ static int setup_poisson(bz_ctx* c) {
 }
 
 // compute_pressure_correction! (anelastic_time_stepping.jl:26-39): momentum ghosts must be valid on entry.
+// Slabs with peer memory: the two transposes of the distributed transform are peer loads inside fft_x (forward) and inverse_y
+// (backward). With BZ_FFT_Z_CHUNKS > 1 both are pipelined over z chunks across the two streams: while the high-priority second stream
+// waits for every rank to have finished chunk c and pulls it over NVLink, the main stream already transforms chunk c + 1 (an experiment
+// that measured no gain, see bz_ctx::fft_z_chunks).
+#define FFT_Z_CHUNKS_MAX 8
 static int poisson_solve(bz_ctx* c, double dt) {
     const Layout& L = c->L;
     const PoissonGeom& G = c->PG;
     double** U = c->set[c->cur];
     const double dz_over_dt = L.dz / dt;
-    {
-        ProfScope ps(c, 1);
-        if (!L.flat_y) {
-            int lines = c->lines_y;
-            dim3 grid((L.nx + 2 * lines - 1) / (2 * lines), L.Nz);
-            size_t sm = fft_smem_bytes(G.Ny, lines);
-            FFT_DISPATCH(G.Ny, (poisson_forward_y<FN, 256, 4><<<grid, fft_threads(G.Ny, lines), sm, c->stream>>>(L, G, U[0], U[1], U[2], dz_over_dt, c->W, c->tw_y, lines)));
-        } else {
-            dim3 grid((L.nx + 127) / 128, L.Nz);
-            poisson_pack_flat_y<<<grid, 128, 0, c->stream>>>(L, G, U[0], U[1], U[2], dz_over_dt, c->W);
-        }
-        c->launches++;
-    }
     const bool pull = c->comm.p2p && !L.flat_y;        // peer-memory path: the transposes are peer loads inside fft_x / inverse_y
     PeerBases peers;
     for (int p = 0; p < 8; ++p) peers.base[p] = c->comm.peer_base[p];
-    if (c->comm.n_ranks > 1) {
-        ProfScope ps(c, 5);
-        int rc = pull ? comm_barrier(c->comm, c->stream) : comm_transpose_forward(c->comm, c->W, c->W2, L.nx, G, c->stream, &c->launches);
-        if (rc) { bz_set_error(c, "transpose: %s", c->comm.err); return rc; }
-    }
     const long long n_lines = (long long)G.Nz * G.nky_loc;
-    if (!L.flat_x && n_lines > 0) {
-        ProfScope ps(c, 1);
+    const bool do_x = !L.flat_x;
+    int nch = 1;
+    if (pull && c->overlap && do_x) { nch = c->fft_z_chunks; if (nch > L.Nz / 8) nch = L.Nz / 8; if (nch < 1) nch = 1; }
+    const int kper = (L.Nz + nch - 1) / nch;
+    auto launch_fft_x = [&](int inverse, int do_pull, long long line0, long long line1, cudaStream_t s) {
+        if (!do_x || line1 <= line0) return;
         int lines = c->lines_x;
         size_t sm = fft_smem_bytes(G.Nx, lines);
-        FFT_DISPATCH(G.Nx, (fft_x_kernel<FN><<<(unsigned)((n_lines + lines - 1) / lines), fft_threads(G.Nx, lines), sm, c->stream>>>(G, c->W2, n_lines, c->tw_x, lines, 0, peers, pull ? 1 : 0)));
+        FFT_DISPATCH(G.Nx, (fft_x_kernel<FN><<<(unsigned)((line1 - line0 + lines - 1) / lines), fft_threads(G.Nx, lines), sm, s>>>(G, c->W2, line1, c->tw_x, lines, inverse, peers, do_pull, (int)line0)));
         c->launches++;
+    };
+    // ---- forward: source term + y transform (x-slab layout), transpose, x transform
+    if (nch == 1) {
+        {
+            ProfScope ps(c, 1);
+            if (!L.flat_y) {
+                int lines = c->lines_y;
+                dim3 grid((L.nx + 2 * lines - 1) / (2 * lines), L.Nz);
+                size_t sm = fft_smem_bytes(G.Ny, lines);
+                FFT_DISPATCH(G.Ny, (poisson_forward_y<FN, 256, 4><<<grid, fft_threads(G.Ny, lines), sm, c->stream>>>(L, G, U[0], U[1], U[2], dz_over_dt, c->W, c->tw_y, lines, 0)));
+            } else {
+                dim3 grid((L.nx + 127) / 128, L.Nz);
+                poisson_pack_flat_y<<<grid, 128, 0, c->stream>>>(L, G, U[0], U[1], U[2], dz_over_dt, c->W);
+            }
+            c->launches++;
+        }
+        if (c->comm.n_ranks > 1) {
+            ProfScope ps(c, 5);
+            int rc = pull ? comm_barrier(c->comm, c->stream) : comm_transpose_forward(c->comm, c->W, c->W2, L.nx, G, c->stream, &c->launches);
+            if (rc) { bz_set_error(c, "transpose: %s", c->comm.err); return rc; }
+        }
+        if (n_lines > 0) { ProfScope ps(c, 1); launch_fft_x(0, pull ? 1 : 0, 0, n_lines, c->stream); }
+    } else {
+        ProfScope ps(c, 1);
+        int lines = c->lines_y;
+        size_t sm = fft_smem_bytes(G.Ny, lines);
+        for (int ch = 0; ch < nch; ++ch) {
+            const int k0 = ch * kper, k1 = (k0 + kper < L.Nz) ? k0 + kper : L.Nz;
+            if (k1 <= k0) break;
+            dim3 grid((L.nx + 2 * lines - 1) / (2 * lines), k1 - k0);
+            FFT_DISPATCH(G.Ny, (poisson_forward_y<FN, 256, 4><<<grid, fft_threads(G.Ny, lines), sm, c->stream>>>(L, G, U[0], U[1], U[2], dz_over_dt, c->W, c->tw_y, lines, k0)));
+            c->launches++;
+            CUDA_TRY(c, cudaEventRecord(c->ev_chunk[ch], c->stream));
+            CUDA_TRY(c, cudaStreamWaitEvent(c->s2, c->ev_chunk[ch], 0));
+            int rc = comm_barrier(c->comm, c->s2, 1);                   // every rank has transformed chunk ch
+            if (rc) { bz_set_error(c, "transpose: %s", c->comm.err); return rc; }
+            launch_fft_x(0, 1, (long long)k0 * G.nky_loc, (long long)k1 * G.nky_loc, c->s2);
+        }
+        CUDA_TRY(c, cudaEventRecord(c->ev_join, c->s2));
+        CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
     }
+    // ---- z: batched Thomas in the transposed layout
     if (G.nky_loc > 0) {
         ProfScope ps(c, 2);
         // one thread per (kx, ky) column: on a rank that keeps few ky modes (8 slabs of 512^3: 4 x 33 blocks of 128) the blocks shrink
@@ -361,31 +396,44 @@ static int poisson_solve(bz_ctx* c, double dt) {
         c->launches++;
         if (G.ky0 == 0) { remove_mean_mode<<<1, 256, 0, c->stream>>>(G, c->W2); c->launches++; }
     }
-    if (!L.flat_x && n_lines > 0) {
+    // ---- inverse: x transform, transpose back, y transform → φ
+    const double scale = 1.0 / ((L.flat_x ? 1.0 : (double)G.Nx) * (L.flat_y ? 1.0 : (double)G.Ny));
+    if (nch == 1) {
+        if (n_lines > 0) { ProfScope ps(c, 3); launch_fft_x(1, 0, 0, n_lines, c->stream); }
+        if (c->comm.n_ranks > 1) {
+            ProfScope ps(c, 5);
+            int rc = pull ? comm_barrier(c->comm, c->stream) : comm_transpose_backward(c->comm, c->W2, c->W, L.nx, G, c->stream, &c->launches);
+            if (rc) { bz_set_error(c, "transpose: %s", c->comm.err); return rc; }
+        }
         ProfScope ps(c, 3);
-        int lines = c->lines_x;
-        size_t sm = fft_smem_bytes(G.Nx, lines);
-        FFT_DISPATCH(G.Nx, (fft_x_kernel<FN><<<(unsigned)((n_lines + lines - 1) / lines), fft_threads(G.Nx, lines), sm, c->stream>>>(G, c->W2, n_lines, c->tw_x, lines, 1, peers, 0)));
-        c->launches++;
-    }
-    if (c->comm.n_ranks > 1) {
-        ProfScope ps(c, 5);
-        int rc = pull ? comm_barrier(c->comm, c->stream) : comm_transpose_backward(c->comm, c->W2, c->W, L.nx, G, c->stream, &c->launches);
-        if (rc) { bz_set_error(c, "transpose: %s", c->comm.err); return rc; }
-    }
-    {
-        ProfScope ps(c, 3);
-        double scale = 1.0 / ((L.flat_x ? 1.0 : (double)G.Nx) * (L.flat_y ? 1.0 : (double)G.Ny));
         if (!L.flat_y) {
             int lines = c->lines_y;
             dim3 grid((L.nx + 2 * lines - 1) / (2 * lines), L.Nz);
             size_t sm = fft_smem_bytes(G.Ny, lines);
-            FFT_DISPATCH(G.Ny, (poisson_inverse_y<FN, 256, 4><<<grid, fft_threads(G.Ny, lines), sm, c->stream>>>(L, G, c->W, c->phi, c->tw_y, lines, scale, peers, pull ? 1 : 0)));
+            FFT_DISPATCH(G.Ny, (poisson_inverse_y<FN, 256, 4><<<grid, fft_threads(G.Ny, lines), sm, c->stream>>>(L, G, c->W, c->phi, c->tw_y, lines, scale, peers, pull ? 1 : 0, 0)));
         } else {
             dim3 grid((L.nx + 127) / 128, L.Nz);
             poisson_unpack_flat_y<<<grid, 128, 0, c->stream>>>(L, G, c->W, c->phi, scale);
         }
         c->launches++;
+    } else {
+        ProfScope ps(c, 3);
+        int lines = c->lines_y;
+        size_t sm = fft_smem_bytes(G.Ny, lines);
+        for (int ch = 0; ch < nch; ++ch) {
+            const int k0 = ch * kper, k1 = (k0 + kper < L.Nz) ? k0 + kper : L.Nz;
+            if (k1 <= k0) break;
+            launch_fft_x(1, 0, (long long)k0 * G.nky_loc, (long long)k1 * G.nky_loc, c->stream);
+            CUDA_TRY(c, cudaEventRecord(c->ev_chunk[ch], c->stream));
+            CUDA_TRY(c, cudaStreamWaitEvent(c->s2, c->ev_chunk[ch], 0));
+            int rc = comm_barrier(c->comm, c->s2, 1);                   // every rank has inverted its ky modes of chunk ch
+            if (rc) { bz_set_error(c, "transpose: %s", c->comm.err); return rc; }
+            dim3 grid((L.nx + 2 * lines - 1) / (2 * lines), k1 - k0);
+            FFT_DISPATCH(G.Ny, (poisson_inverse_y<FN, 256, 4><<<grid, fft_threads(G.Ny, lines), sm, c->s2>>>(L, G, c->W, c->phi, c->tw_y, lines, scale, peers, 1, k0)));
+            c->launches++;
+        }
+        CUDA_TRY(c, cudaEventRecord(c->ev_join, c->s2));
+        CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
     }
     CUDA_TRY(c, cudaGetLastError());
     return BZ_OK;
@@ -686,6 +734,7 @@ void bz_destroy(bz_ctx* c) {
     if (c->ev_main) cudaEventDestroy(c->ev_main);
     if (c->ev_in) cudaEventDestroy(c->ev_in);
     if (c->s2) cudaStreamDestroy(c->s2);
+    for (int e = 0; e < 8; ++e) if (c->ev_chunk[e]) cudaEventDestroy(c->ev_chunk[e]);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->s_in) cudaStreamDestroy(c->s_in);
@@ -752,7 +801,13 @@ int bz_create(const bz_config* cfg, bz_ctx** out) {
 #define TRY(x) do { rc = (x); if (rc) { strncpy(g_err, c->err, 511); bz_destroy(c); return rc; } } while (0)
 #define TRYCUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { bz_set_error(nullptr, "%s: %s", #x, cudaGetErrorString(e_)); bz_destroy(c); return BZ_ERR_CUDA; } } while (0)
     TRYCUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    TRYCUDA(cudaStreamCreateWithFlags(&c->s2, cudaStreamNonBlocking));
+    {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);                 // the exchange stream's CTAs go first whenever an SM has room
+        TRYCUDA(cudaStreamCreateWithPriority(&c->s2, cudaStreamNonBlocking, hi));
+    }
+    for (int e = 0; e < 8; ++e) TRYCUDA(cudaEventCreateWithFlags(&c->ev_chunk[e], cudaEventDisableTiming));
+    if (const char* e = getenv("BZ_FFT_Z_CHUNKS")) { int v = atoi(e); if (v >= 1 && v <= FFT_Z_CHUNKS_MAX) c->fft_z_chunks = v; }
     TRYCUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     TRYCUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     if (const char* e = getenv("BZ_NO_OVERLAP")) c->overlap = atoi(e) ? 0 : 1;

@@ -202,12 +202,12 @@ __device__ __forceinline__ double source_term(const Layout& L, const double* __r
 template <int N, int MAXT = 256, int MINB = 3>
 __global__ void __launch_bounds__(MAXT, (N % 3 == 0 && MINB > 2) ? 2 : MINB) poisson_forward_y(Layout L, PoissonGeom G, const double* __restrict__ ru, const double* __restrict__ rv,
                                   const double* __restrict__ rw, double dz_over_dt, double2* __restrict__ W,
-                                  const double2* __restrict__ tw_y, int lines) {
+                                  const double2* __restrict__ tw_y, int lines, int k_base) {
     extern __shared__ double sm[];
     constexpr int LP = ((N + (N >> 4) + 15) & ~15) + 4;
     double* re = sm;
     double* im = sm + imag_offset(N, lines);
-    const int k = blockIdx.y;
+    const int k = blockIdx.y + k_base;               // z chunks: the distributed transform is pipelined over levels (api.cu poisson_solve)
     const int XB = 2 * lines;                        // lines is a power of two
     const int xb_shift = 31 - __clz(XB);
     const int ib = blockIdx.x * XB;
@@ -255,12 +255,12 @@ __global__ void poisson_pack_flat_y(Layout L, PoissonGeom G, const double* __res
 // ---- pass 5: complex-to-real inverse FFT along y → φ (padded field interior) -------------------------------------
 template <int N, int MAXT = 256, int MINB = 3>
 __global__ void __launch_bounds__(MAXT, (N % 3 == 0 && MINB > 2) ? 2 : MINB) poisson_inverse_y(Layout L, PoissonGeom G, const double2* __restrict__ W, double* __restrict__ phi,
-                                  const double2* __restrict__ tw_y, int lines, double scale, PeerBases peers, int pull) {
+                                  const double2* __restrict__ tw_y, int lines, double scale, PeerBases peers, int pull, int k_base) {
     extern __shared__ double sm[];
     constexpr int LP = ((N + (N >> 4) + 15) & ~15) + 4;
     double* re = sm;
     double* im = sm + imag_offset(N, lines);
-    const int k = blockIdx.y;
+    const int k = blockIdx.y + k_base;
     const int XB = 2 * lines;                        // lines is a power of two
     const int xb_shift = 31 - __clz(XB);
     const int ib = blockIdx.x * XB;
@@ -324,12 +324,12 @@ __global__ void poisson_unpack_flat_y(Layout L, PoissonGeom G, const double2* __
 // grid ceil(n_lines / lines); block lines*Nx/8 <= 256 threads; smem 2*lines*line_pitch(Nx) doubles.
 template <int N, int MAXT = 256, int MINB = 3>
 __global__ void __launch_bounds__(MAXT, (N % 3 == 0 && MINB > 2) ? 2 : MINB) fft_x_kernel(PoissonGeom G, double2* __restrict__ W, long long n_lines, const double2* __restrict__ tw_x, int lines, int inverse,
-                                                       PeerBases peers, int pull) {
+                                                       PeerBases peers, int pull, int line_base) {
     extern __shared__ double sm[];
     constexpr int LP = ((N + (N >> 4) + 15) & ~15) + 4;
     double* re = sm;
     double* im = sm + imag_offset(N, lines);
-    const int l0 = blockIdx.x * lines;                  // first line of this CTA; line = k * nky_loc + ky_loc (fits an int)
+    const int l0 = line_base + blockIdx.x * lines;      // first line of this CTA; line = k * nky_loc + ky_loc (fits an int); lines [line_base, n_lines)
     const double sgn = inverse ? -1.0 : 1.0;
     const int k0 = l0 / G.nky_loc, r0 = l0 - k0 * G.nky_loc;    // one division per CTA; lines advance (k, ky) incrementally
     constexpr int PT = fft_pt(N);

@@ -25,6 +25,14 @@ PY
 }
 if [[ $LEGS == *bench* ]]; then run flags_overlap BZ_DUMMY=1; fi
 if [[ $LEGS == *ab* ]]; then
-  run flags_serial BZ_NO_OVERLAP=1
-  run nccl_serial BZ_NO_OVERLAP=1 BZ_NCCL_BARRIER=1
+  run direct_pull BZ_DIRECT_PULL=1
+  run packed_serial BZ_NO_OVERLAP=1
+fi
+if [[ $LEGS == *chunks* ]]; then
+  run zchunks1 BZ_FFT_Z_CHUNKS=1
+  run zchunks2 BZ_FFT_Z_CHUNKS=2
+  run zchunks8 BZ_FFT_Z_CHUNKS=8
+fi
+if [[ $LEGS == *r1style* ]]; then
+  run nccl_serial_direct BZ_NO_OVERLAP=1 BZ_NCCL_BARRIER=1 BZ_DIRECT_PULL=1
 fi
