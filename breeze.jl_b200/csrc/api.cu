@@ -624,24 +624,30 @@ static int pressure_correct(bz_ctx* c, double dt) {
     int rc;
     double** U = c->set[c->cur];
     const Layout& L = c->L;
-    if (c->comm.n_ranks == 1) { if ((rc = fill_halos(c, U, 2, 4))) return rc; }       // ρu, ρv ghosts for the divergence
-    else {                                                                               // slabs: y ghosts of ρv are local; ρu at the first ghost face
-        double* uv[1] = {U[1]};                                                          // comes from the right neighbour's first column
-        if ((rc = fill_halos(c, uv, 1, 4, false))) return rc;
+    // The divergence and the projection address the periodic images of ρu, ρv and φ directly (poisson.cuh source_term, project_momentum):
+    // on one GPU no ghost fill precedes them; across slabs only ρu at the first ghost face (the right neighbour's first column) and φ's
+    // first ghost column on the left travel.
+    if (c->comm.n_ranks > 1) {
         ProfScope ps(c, 5);
         if (c->comm.p2p) { FieldSet Fu; Fu.n = 1; Fu.f[0] = U[0]; rc = comm_pull_x_halos(c->comm, c->L, Fu, 1, c->stream, &c->launches, 0, 0); }
         else rc = comm_exchange_u_face(c->comm, c->L, U[0], c->stream, &c->launches);
         if (rc) { bz_set_error(c, "face exchange: %s", c->comm.err); return rc; }
     }
     if ((rc = poisson_solve(c, dt))) return rc;
-    double* ph[1] = {c->phi};
-    if ((rc = fill_halos(c, ph, 1, 4))) return rc;
+    if (c->comm.n_ranks > 1) {
+        ProfScope ps(c, 5);
+        FieldSet F; F.n = 1; F.f[0] = c->phi;
+        rc = c->comm.p2p ? comm_pull_x_halos(c->comm, L, F, 2, c->stream, &c->launches, 0, 1)      // φ at i = -1 only
+                         : comm_exchange_x_halos(c->comm, L, F, c->stream, &c->launches);
+        if (rc) { bz_set_error(c, "halo exchange: %s", c->comm.err); return rc; }
+    }
+    const int wrap_x = c->comm.n_ranks == 1;
     const bool split = c->comm.n_ranks > 1 && c->comm.p2p && c->overlap && !L.flat_x && L.nx >= 4 * L.HX;
     if (!split) {
         {
             ProfScope ps(c, 4);
             dim3 grid((L.nx + 127) / 128, L.Ny, L.Nz);
-            project_momentum<<<grid, 128, 0, c->stream>>>(L, c->col, U[0], U[1], U[2], c->phi, dt);
+            project_momentum<<<grid, 128, 0, c->stream>>>(L, c->col, U[0], U[1], U[2], c->phi, dt, wrap_x);
             c->launches++;
             CUDA_TRY(c, cudaGetLastError());
         }

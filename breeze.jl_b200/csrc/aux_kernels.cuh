@@ -34,15 +34,17 @@ __global__ void halo_fill_periodic(Layout L, FieldSet F, int mode) {
 }
 
 // _pressure_correct_momentum! (src/AnelasticEquations/anelastic_time_stepping.jl:45-54), in place.
+// wrap_x / the y wrap: the periodic images of φ are addressed directly, so φ needs no ghost fill on one GPU (across slabs, wrap_x = 0,
+// its first ghost column on the left is pulled from the neighbour).
 __global__ void project_momentum(Layout L, Columns col, double* __restrict__ ru, double* __restrict__ rv, double* __restrict__ rw,
-                                 const double* __restrict__ phi, double dt) {
+                                 const double* __restrict__ phi, double dt, int wrap_x) {
     int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, k = blockIdx.z;
     if (i >= L.nx) return;
     long long n = lidx(L, i, j, k);
     double p = phi[n];
     double rc = col.rho[k];
-    if (!L.flat_x) ru[n] -= rc * dt * ((p - phi[n - 1]) * L.rdx);
-    if (!L.flat_y) rv[n] -= rc * dt * ((p - phi[n - L.PX]) * L.rdy);
+    if (!L.flat_x) ru[n] -= rc * dt * ((p - phi[(wrap_x && i == 0) ? n - 1 + L.nx : n - 1]) * L.rdx);
+    if (!L.flat_y) rv[n] -= rc * dt * ((p - phi[j == 0 ? n - L.PX + (long long)L.Ny * L.PX : n - L.PX]) * L.rdy);
     if (k >= 1) rw[n] -= col.rho_f[k] * dt * ((p - phi[n - L.plane]) * L.rdz);
 }
 
@@ -58,7 +60,7 @@ __global__ void project_momentum_columns(Layout L, Columns col, double* __restri
         double p = phi[n];
         double rc = col.rho[k];
         if (!L.flat_x) ru[n] -= rc * dt * ((p - phi[n - 1]) * L.rdx);
-        if (!L.flat_y) rv[n] -= rc * dt * ((p - phi[n - L.PX]) * L.rdy);
+        if (!L.flat_y) rv[n] -= rc * dt * ((p - phi[j == 0 ? n - L.PX + (long long)L.Ny * L.PX : n - L.PX]) * L.rdy);
         if (k >= 1) rw[n] -= col.rho_f[k] * dt * ((p - phi[n - L.plane]) * L.rdz);
     }
 }

@@ -287,38 +287,41 @@ __global__ void halo_pull_x(Layout L, FieldSet F, const char* my_base, const cha
 }
 
 // Packed variant, owner side: side 0 = my first w columns (the LEFT neighbour's right ghosts), side 1 = my last w columns (the RIGHT
-// neighbour's left ghosts); layout [side][field][k][j][c], c fastest. nsides = 1 packs side 0 only (mode 1).
-__global__ void pack_faces_both(Layout L, FieldSet F, int w, int nsides, double* __restrict__ buf) {
+// neighbour's left ghosts); layout [side - side0][field][k][j][c], c fastest; sides side0 .. side0 + nsides - 1 are packed.
+__global__ void pack_faces_both(Layout L, FieldSet F, int w, int nsides, int side0, double* __restrict__ buf) {
     const long long per_field = (long long)w * L.Ny * L.Nz, per_side = per_field * F.n, total = per_side * nsides;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-        const int side = (int)(e / per_side); const long long q = e - side * per_side;
+        const int s = (int)(e / per_side); const long long q = e - s * per_side;
         const int f = (int)(q / per_field); const long long r = q - f * per_field;
         const int c = (int)(r % w), j = (int)((r / w) % L.Ny), k = (int)(r / ((long long)w * L.Ny));
-        buf[e] = F.f[f][lidx(L, (side == 0 ? 0 : L.nx - w) + c, j, k)];
+        buf[e] = F.f[f][lidx(L, (side0 + s == 0 ? 0 : L.nx - w) + c, j, k)];
     }
 }
-// consumer side: right ghosts from the right neighbour's side 0, left ghosts (nsides = 2) from the left neighbour's side 1
-__global__ void unpack_faces_both(Layout L, FieldSet F, int w, int nsides, const double* __restrict__ left_buf, const double* __restrict__ right_buf) {
+// consumer side: right ghosts from the right neighbour's side 0, left ghosts from the left neighbour's side 1
+__global__ void unpack_faces_both(Layout L, FieldSet F, int w, int nsides, int side0, const double* __restrict__ left_buf, const double* __restrict__ right_buf) {
     const long long per_field = (long long)w * L.Ny * L.Nz, per_side = per_field * F.n, total = per_side * nsides;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-        const int side = (int)(e / per_side); const long long q = e - side * per_side;
+        const int s = (int)(e / per_side); const long long q = e - s * per_side;
         const int f = (int)(q / per_field); const long long r = q - f * per_field;
         const int c = (int)(r % w), j = (int)((r / w) % L.Ny), k = (int)(r / ((long long)w * L.Ny));
-        // my right ghosts are the right neighbour's side 0; my left ghosts are the left neighbour's side 1
-        const double v = side == 0 ? __ldcv(right_buf + q) : __ldcv(left_buf + per_side + q);
+        const int side = side0 + s;
+        const double v = side == 0 ? __ldcv(right_buf + e) : __ldcv(left_buf + e);
         F.f[f][lidx(L, (side == 0 ? L.nx : -w) + c, j, k)] = v;
     }
 }
 
+// mode 0: HX ghost columns on both sides; mode 1: the first ghost column on the right only (ρu at i = nx for the divergence);
+// mode 2: the first ghost column on the left only (φ at i = -1 for the projection).
 // region: 0 ρu face, 1 φ, 2 scalars, 3 all five / momentum (Comm::pack_start)
 static int comm_pull_x_halos(Comm& cm, const Layout& L, const FieldSet& F, int mode, cudaStream_t s, int64_t* launches, int channel = 0, int region = 3) {
     const int P = cm.n_ranks, left = (cm.rank + P - 1) % P, right = (cm.rank + 1) % P;
-    const int w = mode == 0 ? L.HX : 1, nsides = mode == 0 ? 2 : 1;
+    if (!cm.packed_pull && mode == 2) mode = 0;                        // the direct reads know modes 0 and 1
+    const int w = mode == 0 ? L.HX : 1, nsides = mode == 0 ? 2 : 1, side0 = mode == 2 ? 1 : 0;
     const long long total = (long long)F.n * nsides * w * L.Ny * L.Nz;
     const int blocks = (int)((total + 255) / 256) > 148 * 8 ? 148 * 8 : (int)((total + 255) / 256);
     if (cm.packed_pull) {
         double* mine = reinterpret_cast<double*>(cm.peer_base[cm.rank] + cm.off_pack) + cm.pack_start[region];
-        pack_faces_both<<<blocks, 256, 0, s>>>(L, F, w, nsides, mine);
+        pack_faces_both<<<blocks, 256, 0, s>>>(L, F, w, nsides, side0, mine);
         *launches += 1;
     }
     int rc = comm_barrier(cm, s, channel, comm_neighbour_mask(cm));   // only the two neighbours' fields are read
@@ -326,7 +329,7 @@ static int comm_pull_x_halos(Comm& cm, const Layout& L, const FieldSet& F, int m
     if (cm.packed_pull) {
         const double* lbuf = reinterpret_cast<const double*>(cm.peer_base[left] + cm.off_pack) + cm.pack_start[region];
         const double* rbuf = reinterpret_cast<const double*>(cm.peer_base[right] + cm.off_pack) + cm.pack_start[region];
-        unpack_faces_both<<<blocks, 256, 0, s>>>(L, F, w, nsides, lbuf, rbuf);
+        unpack_faces_both<<<blocks, 256, 0, s>>>(L, F, w, nsides, side0, lbuf, rbuf);
     } else {
         halo_pull_x<<<blocks, 256, 0, s>>>(L, F, cm.peer_base[cm.rank], cm.peer_base[left], cm.peer_base[right], mode);
     }

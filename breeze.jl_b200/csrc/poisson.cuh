@@ -185,11 +185,13 @@ __device__ __forceinline__ void fft_lines_smem(double* __restrict__ re, double* 
 // ---- source term ------------------------------------------------------------------------------------------------
 // _compute_anelastic_source_term!: rhs = Δzᶜ · divᶜᶜᶜ(ρu, ρv, ρw) / Δt  (anelastic_pressure_solver.jl:99-105)
 __device__ __forceinline__ double source_term(const Layout& L, const double* __restrict__ ru, const double* __restrict__ rv,
-                                              const double* __restrict__ rw, int i, int j, int k, double dz_over_dt) {
+                                              const double* __restrict__ rw, int i, int j, int k, double dz_over_dt, int wrap_x) {
     long long n = lidx(L, i, j, k);
     double d = 0.0;
-    if (!L.flat_x) d += (ru[n + 1] - ru[n]) * L.rdx;
-    if (!L.flat_y) d += (rv[n + L.PX] - rv[n]) * L.rdy;
+    // the periodic images are addressed directly (no ghost fill of ρv needed; of ρu only across slabs, where wrap_x = 0 and the
+    // first ghost column holds the right neighbour's face)
+    if (!L.flat_x) d += (ru[(wrap_x && i + 1 == L.nx) ? n + 1 - L.nx : n + 1] - ru[n]) * L.rdx;
+    if (!L.flat_y) d += (rv[(j + 1 == L.Ny) ? n + L.PX - (long long)L.Ny * L.PX : n + L.PX] - rv[n]) * L.rdy;
     double wt = (k + 1 < L.Nz) ? rw[n + L.plane] : 0.0;
     d += (wt - rw[n]) * L.rdz;
     return d * dz_over_dt;
@@ -221,7 +223,7 @@ __global__ void __launch_bounds__(MAXT, (N % 3 == 0 && MINB > 2) ? 2 : MINB) poi
             int e = threadIdx.x + (half * PT + it) * blockDim.x;
             int c = e & (XB - 1), y = e >> xb_shift;
             int i = ib + c;
-            v[it] = (i < L.nx) ? source_term(L, ru, rv, rw, i, y, k, dz_over_dt) : 0.0;
+            v[it] = (i < L.nx) ? source_term(L, ru, rv, rw, i, y, k, dz_over_dt, G.P == 1) : 0.0;
         }
 #pragma unroll
         for (int it = 0; it < PT; ++it) {
@@ -249,7 +251,7 @@ __global__ void __launch_bounds__(MAXT, (N % 3 == 0 && MINB > 2) ? 2 : MINB) poi
 __global__ void poisson_pack_flat_y(Layout L, PoissonGeom G, const double* __restrict__ ru, const double* __restrict__ rv,
                                     const double* __restrict__ rw, double dz_over_dt, double2* __restrict__ W) {
     int i = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
-    if (i < L.nx) W[w_index(G, k, 0, i)] = make_double2(source_term(L, ru, rv, rw, i, 0, k, dz_over_dt), 0.0);
+    if (i < L.nx) W[w_index(G, k, 0, i)] = make_double2(source_term(L, ru, rv, rw, i, 0, k, dz_over_dt, G.P == 1), 0.0);
 }
 
 // ---- pass 5: complex-to-real inverse FFT along y → φ (padded field interior) -------------------------------------

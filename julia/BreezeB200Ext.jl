@@ -69,6 +69,8 @@ function B200Context(model)
     cfg = grid_config(model; surface_pressure = ref.surface_pressure, potential_temperature = ref.potential_temperature,
                       standard_pressure = ref.standard_pressure,
                       formulation = model.formulation isa Breeze.StaticEnergyFormulation ? 1 : 0)
+    # WENO(order = 5 | 7 | 9) (examples/dry_thermal_bubble.jl:24, examples/bomex.jl:204): 2 * buffer - 1 of the momentum scheme
+    cfg.advection_order = 2 * Oceananigans.Advection.required_halo_size_x(model.advection.momentum) - 1
     h = Ref{Ptr{Cvoid}}(C_NULL)
     rc = ccall((:bz_create, lib), Cint, (Ref{BzConfig}, Ref{Ptr{Cvoid}}), cfg, h)
     rc == 0 || error(unsafe_string(ccall((:bz_last_error, lib), Cstring, (Ptr{Cvoid},), C_NULL)))
@@ -98,6 +100,31 @@ function time_step!(model::B200AnelasticModel, Δt; callbacks = [])
     check(ccall((:bz_time_step, lib), Cint, (Ptr{Cvoid}, Cdouble), ctx.handle, Δt), ctx.handle)
     model.clock.time += Δt; model.clock.iteration += 1
     return nothing
+end
+
+# NaNChecker callback of run! (atmosphere_model.jl:561-572): a device-side reduction instead of copying ρu to the host
+function state_is_finite(model::B200AnelasticModel)
+    ctx = context(model); ok = Ref{Cint}(0)
+    check(ccall((:bz_state_is_finite, lib), Cint, (Ptr{Cvoid}, Ref{Cint}), ctx.handle, ok), ctx.handle)
+    return ok[] == 1
+end
+
+# one x-z / x-y / y-z slice for an output writer (axis 0: x = index, 1: y = index, 2: z = index; 0-based)
+function pull_slice(model::B200AnelasticModel, id::Integer, axis::Integer, index::Integer, dims)
+    a = Array{Float64}(undef, dims)
+    ctx = context(model)
+    check(ccall((:bz_get_slice, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Float64}), ctx.handle, id, axis, index, a), ctx.handle)
+    return a
+end
+
+# host-resident driver loop: buffers in and out every step without blocking (pinned arrays; bz_synchronize before touching them)
+function step_with_host_buffers!(model::B200AnelasticModel, Δt, inputs::NTuple{5,Array{Float64,3}}, outputs::NTuple{5,Array{Float64,3}})
+    ctx = context(model)
+    check(ccall((:bz_set_state_async, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint),
+                ctx.handle, inputs..., 0), ctx.handle)
+    check(ccall((:bz_time_step, lib), Cint, (Ptr{Cvoid}, Cdouble), ctx.handle, Δt), ctx.handle)
+    check(ccall((:bz_get_state_async, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                ctx.handle, outputs...), ctx.handle)
 end
 
 # pull a field back when an output writer / diagnostic needs it
