@@ -38,6 +38,7 @@ struct bz_ctx {
     double* arena = nullptr;
     size_t arena_bytes = 0, off_W = 0, off_W2 = 0;      // byte offsets of W / W2 inside the arena (fields: (s*5+f)*L.n, φ: 15*L.n doubles)
     double* G[NPROG] = {};               // tendencies, allocated on first bz_compute_tendencies
+    StepGraphCache graphs;               // captured time steps (common.cuh)
     int buf = 3;                         // buffer of the advection scheme: (order + 1) / 2
     double* V[NPROG] = {};               // WENO(order = 7 / 9): velocities / specific values of the stage's input state (stage_hi.cuh)
     double* dense = nullptr;             // nx*Ny*(Nz+1) staging buffer for host transfers
@@ -624,10 +625,12 @@ static int pressure_correct(bz_ctx* c, double dt) {
     int rc;
     double** U = c->set[c->cur];
     const Layout& L = c->L;
-    // The divergence and the projection address the periodic images of ρu, ρv and φ directly (poisson.cuh source_term, project_momentum):
-    // on one GPU no ghost fill precedes them; across slabs only ρu at the first ghost face (the right neighbour's first column) and φ's
-    // first ghost column on the left travel.
-    if (c->comm.n_ranks > 1) {
+    // The projection addresses the periodic images of φ directly (project_momentum): φ needs no ghost fill on one GPU, and across slabs
+    // only its first ghost column on the left travels. The divergence reads ghosts of ρu, ρv (see source_term for why).
+    if (c->comm.n_ranks == 1) { if ((rc = fill_halos(c, U, 2, 4))) return rc; }       // ρu, ρv ghosts for the divergence
+    else {                                                                               // slabs: y ghosts of ρv are local; ρu at the first ghost face
+        double* uv[1] = {U[1]};                                                          // comes from the right neighbour's first column
+        if ((rc = fill_halos(c, uv, 1, 4, false))) return rc;
         ProfScope ps(c, 5);
         if (c->comm.p2p) { FieldSet Fu; Fu.n = 1; Fu.f[0] = U[0]; rc = comm_pull_x_halos(c->comm, c->L, Fu, 1, c->stream, &c->launches, 0, 0); }
         else rc = comm_exchange_u_face(c->comm, c->L, U[0], c->stream, &c->launches);
@@ -728,6 +731,7 @@ void bz_destroy(bz_ctx* c) {
     if (c->s2) cudaStreamSynchronize(c->s2);
     if (c->s_in) cudaStreamSynchronize(c->s_in);
     if (c->s_out) cudaStreamSynchronize(c->s_out);
+    c->graphs.clear();
     comm_destroy(c->comm);
     cudaFree(c->arena);
     for (int f = 0; f < NPROG; ++f) { cudaFree(c->G[f]); cudaFree(c->V[f]); }
@@ -931,6 +935,7 @@ int bz_set_reference_state(bz_ctx* c, const double* rho, const double* p, const 
         if (p) c->h_p[k] = p[k];
         if (T) c->h_T[k] = T[k];
     }
+    c->graphs.clear();
     int rc = upload_columns(c);
     if (rc) return rc;
     return setup_thomas(c);
@@ -1009,6 +1014,7 @@ int bz_set_state(bz_ctx* c, const double* ru, const double* rv, const double* rw
 int bz_set_forcing(bz_ctx* c, const bz_forcing* F) {
     if (!c) return BZ_ERR_INVALID;
     cudaSetDevice(c->cfg.device);
+    c->graphs.clear();                                  // captured steps carry the old forcing arguments
     if (!F) { c->forced = 0; return BZ_OK; }
     if (c->cfg.formulation == BZ_FORMULATION_STATIC_ENERGY) { bz_set_error(c, "forcings are on the path for the potential-temperature formulation only"); return BZ_ERR_UNSUPPORTED; }
     const int Nz = c->L.Nz;
@@ -1037,9 +1043,7 @@ int bz_set_forcing(bz_ctx* c, const bz_forcing* F) {
     return BZ_OK;
 }
 
-int bz_time_step(bz_ctx* c, double dt) {
-    if (!c) return BZ_ERR_INVALID;
-    cudaSetDevice(c->cfg.device);
+static int time_step_body(bz_ctx* c, double dt) {
     const double alpha[3] = {1.0, 1.0 / 4.0, 2.0 / 3.0};
     const int u0 = c->cur;                             // store_initial_state! without a copy
     int rc;
@@ -1052,6 +1056,38 @@ int bz_time_step(bz_ctx* c, double dt) {
         if ((rc = start_scalar_exchange(c))) return rc;
         if ((rc = pressure_correct(c, alpha[s] * dt))) return rc;
     }
+    return BZ_OK;
+}
+
+int bz_time_step(bz_ctx* c, double dt) {
+    if (!c) return BZ_ERR_INVALID;
+    cudaSetDevice(c->cfg.device);
+    int rc;
+    // one GPU, no per-kernel events wanted: replay the step as a CUDA graph keyed by (which buffer set holds the state, dt)
+    if (c->graphs.on() && c->comm.n_ranks == 1 && !c->prof_on) {
+        StepGraphEntry* g = c->graphs.find(c->cur, dt);
+        if (g && g->exec) {
+            CUDA_TRY(c, cudaGraphLaunch(g->exec, c->stream));
+            c->cur = g->cur_after; c->launches += g->launches;
+        } else if (g && g->seen) {                      // second step with this key: capture it
+            const long long l0 = c->launches;
+            cudaGraph_t graph = nullptr;
+            CUDA_TRY(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
+            rc = time_step_body(c, dt);
+            cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (e != cudaSuccess || !graph) { bz_set_error(c, "graph capture of the time step failed: %s", cudaGetErrorString(e)); return BZ_ERR_CUDA; }
+            e = cudaGraphInstantiate(&g->exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (e != cudaSuccess) { g->exec = nullptr; bz_set_error(c, "cudaGraphInstantiate: %s", cudaGetErrorString(e)); return BZ_ERR_CUDA; }
+            g->cur_after = c->cur; g->launches = c->launches - l0;
+            CUDA_TRY(c, cudaGraphLaunch(g->exec, c->stream));      // the capture recorded the step without running it
+        } else {
+            if (!g) g = c->graphs.add(c->cur, dt);
+            g->seen = 1;
+            if ((rc = time_step_body(c, dt))) return rc;
+        }
+    } else if ((rc = time_step_body(c, dt))) return rc;
     c->time += dt;
     c->iteration += 1;
     return BZ_OK;

@@ -14,6 +14,7 @@
 #include <cuda.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include "../../include/breeze_b200.h"
 
 #define BZ_HALO 4
@@ -75,3 +76,24 @@ struct Thermo {
     } while (0)
 
 void bz_set_error(bz_ctx* ctx, const char* fmt, ...);
+
+// ---- CUDA-graph replay of a whole time step ---------------------------------------------------------------------------------------
+// A step is 27 (anelastic) to 43 (compressible) launches of pure stream work. On small grids (the shipped 2-D 128 x 128 bubble, BOMEX,
+// the README quick-start) the launch overhead on the host is the step time, so a step is captured once per (state-buffer rotation, dt)
+// and replayed as ONE graph launch. The first step with a key runs eagerly (function attributes, lazy allocations), the second is
+// captured, later ones replay. Anything that changes what the kernels' arguments mean (forcings, reference state, profiling) clears
+// the cache. BZ_GRAPHS=0 disables it.
+#include <vector>
+struct StepGraphEntry { int key; double dt; int seen; cudaGraphExec_t exec; int cur_after; long long launches; };
+struct StepGraphCache {
+    std::vector<StepGraphEntry> e;
+    int enabled = -1;
+    bool on() { if (enabled < 0) { const char* v = getenv("BZ_GRAPHS"); enabled = (v && atoi(v) == 0) ? 0 : 1; } return enabled == 1; }
+    StepGraphEntry* find(int key, double dt) { for (auto& x : e) if (x.key == key && x.dt == dt) return &x; return nullptr; }
+    StepGraphEntry* add(int key, double dt) {
+        if (e.size() >= 8) { if (e.front().exec) cudaGraphExecDestroy(e.front().exec); e.erase(e.begin()); }
+        e.push_back(StepGraphEntry{key, dt, 0, nullptr, 0, 0});
+        return &e.back();
+    }
+    void clear() { for (auto& x : e) if (x.exec) cudaGraphExecDestroy(x.exec); e.clear(); }
+};

@@ -33,6 +33,7 @@ struct bzc_ctx {
     int prof_on = 0;
     std::vector<cudaEvent_t> prof_ev;
     std::vector<cudaEvent_t> prof_pool;  // recycled events (see ProfScope in api.cu)
+    StepGraphCache graphs;               // captured time steps (common.cuh)
     std::vector<int> prof_fam;
     double prof_ms[C_NFAM] = {};
     int64_t prof_n[C_NFAM] = {};
@@ -327,6 +328,7 @@ void bzc_destroy(bzc_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->cfg.base.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    c->graphs.clear();
     cudaFree(c->arena); cudaFree(c->dense); cudaFree(c->d_cols);
     for (auto e : c->prof_ev) cudaEventDestroy(e);
     for (auto e : c->prof_pool) cudaEventDestroy(e);
@@ -438,6 +440,7 @@ int bzc_create(const bzc_config* cfg, bzc_ctx** out) {
 }
 
 int bzc_set_reference_potential_temperature(bzc_ctx* c, const double* theta_r) {
+    if (c) c->graphs.clear();
     if (!c || !theta_r) return BZ_ERR_INVALID;
     if (!c->has_ref) { bzc_set_error(c, "reference_state = nothing"); return BZ_ERR_STATE; }
     cudaSetDevice(c->cfg.base.device);
@@ -458,6 +461,7 @@ int bzc_get_reference_state(bzc_ctx* c, double* p, double* rho, double* pi) {
 }
 
 int bzc_set_state(bzc_ctx* c, const double* rho, const double* ru, const double* rv, const double* rw, const double* rth, const double* rqv) {
+    if (c) c->graphs.clear();                          // the moist path adds kernels to the step
     if (!c) return BZ_ERR_INVALID;
     cudaSetDevice(c->cfg.base.device);
     const Layout& L = c->L;
@@ -488,9 +492,36 @@ int bzc_set_state(bzc_ctx* c, const double* rho, const double* ru, const double*
     return rc;
 }
 
+// the same CUDA-graph replay as bz_time_step (common.cuh: StepGraphCache); the WS-RK3 step is 43 launches with a fixed substep schedule per dt
 int bzc_time_step(bzc_ctx* c, double dt) {
     if (!c) return BZ_ERR_INVALID;
     cudaSetDevice(c->cfg.base.device);
+    if (!(c->graphs.on() && !c->prof_on)) return c_time_step(c, dt);
+    StepGraphEntry* g = c->graphs.find(0, dt);
+    if (g && g->exec) {
+        CC_TRY(c, cudaGraphLaunch(g->exec, c->stream));
+        c->launches += g->launches; c->time += dt; c->iteration += 1;
+        return BZ_OK;
+    }
+    if (g && g->seen) {
+        const long long l0 = c->launches;
+        const double t0 = c->time; const int64_t it0 = c->iteration;
+        cudaGraph_t graph = nullptr;
+        CC_TRY(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
+        int rc = c_time_step(c, dt);
+        cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (e != cudaSuccess || !graph) { bzc_set_error(c, "graph capture of the time step failed: %s", cudaGetErrorString(e)); return BZ_ERR_CUDA; }
+        e = cudaGraphInstantiate(&g->exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) { g->exec = nullptr; bzc_set_error(c, "cudaGraphInstantiate: %s", cudaGetErrorString(e)); return BZ_ERR_CUDA; }
+        g->launches = c->launches - l0;
+        c->time = t0 + dt; c->iteration = it0 + 1;          // c_time_step advanced the clock while recording
+        CC_TRY(c, cudaGraphLaunch(g->exec, c->stream));
+        return BZ_OK;
+    }
+    if (!g) g = c->graphs.add(0, dt);
+    g->seen = 1;
     return c_time_step(c, dt);
 }
 

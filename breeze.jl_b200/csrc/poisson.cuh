@@ -112,8 +112,17 @@ __host__ __device__ constexpr int fft_pt(int N) { return (N % 3 == 0) ? 12 : 8; 
 // of 16 the padding term folds to a constant (pidx(n + D) = pidx(n) + D + D/16)
 template <int D> __device__ __forceinline__ int pidx_plus(int n, int pn) { return (D % 16 == 0) ? pn + D + D / 16 : pidx(n + D); }
 
-template <int N, int R, int Ns>
-__device__ __forceinline__ void stockham_pass(double* __restrict__ re, double* __restrict__ im, const double2* __restrict__ tw) {
+// IN: the pass takes its inputs from `ld(line, element)` (global memory) instead of shared memory; OUT: it hands its outputs to
+// `st(line, element, value)` instead of storing them to shared memory. The x transform uses both at its two ends: element j + r N/R of the
+// first pass and element j + r Ns of the last pass are contiguous across the threads of a line for every r, so the accesses coalesce and
+// the transform keeps two of its four shared-memory round trips and four of its eight barriers.
+struct NoLineIO {
+    __device__ __forceinline__ cpx operator()(int, int) const { return cpx{0.0, 0.0}; }
+    __device__ __forceinline__ void operator()(int, int, cpx) const {}
+};
+template <int N, int R, int Ns, bool IN = false, bool OUT = false, typename LD = NoLineIO, typename ST = NoLineIO>
+__device__ __forceinline__ void stockham_pass(double* __restrict__ re, double* __restrict__ im, const double2* __restrict__ tw,
+                                              const LD& ld = LD(), const ST& st = ST()) {
     constexpr int PT = fft_pt(N), ITEMS = PT / R, PER_LINE = N / PT, NR = N / R, LP = ((N + (N >> 4) + 15) & ~15) + 4, STEP = N / (Ns * R);
     static_assert(PT % R == 0 && N % (Ns * R) == 0 && (Ns & (Ns - 1)) == 0, "pass shape");
     const int l = threadIdx.x / PER_LINE, t = threadIdx.x % PER_LINE;
@@ -126,11 +135,14 @@ __device__ __forceinline__ void stockham_pass(double* __restrict__ re, double* _
         const int pj = pidx(j);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            const int o = (NR % 16 == 0) ? pj + r * (NR + NR / 16) : pidx(j + r * NR);
-            v[it][r] = {lre[o], lim[o]};
+            if constexpr (IN) v[it][r] = ld(l, j + r * NR);
+            else {
+                const int o = (NR % 16 == 0) ? pj + r * (NR + NR / 16) : pidx(j + r * NR);
+                v[it][r] = {lre[o], lim[o]};
+            }
         }
     }
-    __syncthreads();
+    if constexpr (!IN) __syncthreads();             // every thread has read its inputs before anybody overwrites them
 #pragma unroll
     for (int it = 0; it < ITEMS; ++it) {
         const int j = t + it * PER_LINE;
@@ -150,48 +162,55 @@ __device__ __forceinline__ void stockham_pass(double* __restrict__ re, double* _
         const int pj0 = pidx(j0);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            const int o = (Ns % 16 == 0) ? pj0 + r * (Ns + Ns / 16) : pidx(j0 + r * Ns);
-            lre[o] = v[it][r].x; lim[o] = v[it][r].y;
+            if constexpr (OUT) st(l, j0 + r * Ns, v[it][r]);
+            else {
+                const int o = (Ns % 16 == 0) ? pj0 + r * (Ns + Ns / 16) : pidx(j0 + r * Ns);
+                lre[o] = v[it][r].x; lim[o] = v[it][r].y;
+            }
         }
     }
-    __syncthreads();
+    if constexpr (!OUT) __syncthreads();
 }
 
-// Forward DFT (e^{-2πi nk/N}) of every line in shared memory; N = 2^m (8 .. 2048) or 3 · 2^m (24 .. 1536). Callers conjugate for the inverse.
-template <int N, int Ns, int REM>     // REM = remaining power-of-two factor of a 3 · 2^m length: radix-4 passes, then one radix-2 if odd
-__device__ __forceinline__ void pow2_passes_r4(double* __restrict__ re, double* __restrict__ im, const double2* __restrict__ tw) {
-    if constexpr (REM >= 4) { stockham_pass<N, 4, Ns>(re, im, tw); pow2_passes_r4<N, Ns * 4, REM / 4>(re, im, tw); }
-    else if constexpr (REM == 2) stockham_pass<N, 2, Ns>(re, im, tw);
+// Forward DFT (e^{-2πi nk/N}) of every line; N = 2^m (8 .. 2048) or 3 · 2^m (24 .. 1536). Callers conjugate for the inverse.
+// IO = false: the lines are in shared memory on entry and on exit (y transforms). IO = true: the first pass reads through `ld`, the last
+// pass writes through `st`, shared memory only carries the values between passes (x transform).
+template <int N, int Ns, int REM, bool IN, typename LD>     // REM = remaining power-of-two factor of a 3 · 2^m length: radix-4 passes, then one radix-2 if odd
+__device__ __forceinline__ void pow2_passes_r4(double* __restrict__ re, double* __restrict__ im, const double2* __restrict__ tw, const LD& ld) {
+    if constexpr (REM >= 4) { stockham_pass<N, 4, Ns, IN, false, LD>(re, im, tw, ld); pow2_passes_r4<N, Ns * 4, REM / 4, false, LD>(re, im, tw, ld); }
+    else if constexpr (REM == 2) stockham_pass<N, 2, Ns, IN, false, LD>(re, im, tw, ld);
 }
-template <int N>
-__device__ __forceinline__ void fft_lines_smem(double* __restrict__ re, double* __restrict__ im, const double2* __restrict__ tw) {
+template <int N, bool IO = false, typename LD = NoLineIO, typename ST = NoLineIO>
+__device__ __forceinline__ void fft_lines_smem(double* __restrict__ re, double* __restrict__ im, const double2* __restrict__ tw,
+                                               const LD& ld = LD(), const ST& st = ST()) {
     if constexpr (N % 3 == 0) {
         constexpr int M = N / 3;
         static_assert((M & (M - 1)) == 0 && M >= 8 && M <= 512, "N must be 3 * 2^m, 24 <= N <= 1536");
-        pow2_passes_r4<N, 1, M>(re, im, tw);
-        stockham_pass<N, 3, M>(re, im, tw);
+        pow2_passes_r4<N, 1, M, IO, LD>(re, im, tw, ld);
+        stockham_pass<N, 3, M, false, IO, LD, ST>(re, im, tw, ld, st);
     } else {
         constexpr int m = (N == 8) ? 3 : (N == 16) ? 4 : (N == 32) ? 5 : (N == 64) ? 6 : (N == 128) ? 7 : (N == 256) ? 8 : (N == 512) ? 9 : (N == 1024) ? 10 : 11;
         static_assert((1 << m) == N, "N must be a power of two in [8, 2048]");
-        stockham_pass<N, 8, 1>(re, im, tw);
-        if (m >= 6) stockham_pass<N, 8, (m >= 6 ? 8 : 1)>(re, im, tw);
-        if (m >= 9) stockham_pass<N, 8, (m >= 9 ? 64 : 1)>(re, im, tw);
-        constexpr int done = (m / 3) * 3, Ns = 1 << done;
-        if (m % 3 == 2) stockham_pass<N, 4, (m % 3 == 2 ? Ns : 1)>(re, im, tw);
-        else if (m % 3 == 1) stockham_pass<N, 2, (m % 3 == 1 ? Ns : 1)>(re, im, tw);
+        constexpr int n8 = m / 3, rem = m % 3;      // radix-8 passes, then one radix-4 / radix-2 pass for the remainder
+        stockham_pass<N, 8, 1, IO, IO && n8 == 1 && rem == 0, LD, ST>(re, im, tw, ld, st);
+        if constexpr (n8 >= 2) stockham_pass<N, 8, 8, false, IO && n8 == 2 && rem == 0, LD, ST>(re, im, tw, ld, st);
+        if constexpr (n8 >= 3) stockham_pass<N, 8, 64, false, IO && n8 == 3 && rem == 0, LD, ST>(re, im, tw, ld, st);
+        constexpr int Ns = 1 << (n8 * 3);
+        if constexpr (rem == 2) stockham_pass<N, 4, Ns, false, IO, LD, ST>(re, im, tw, ld, st);
+        else if constexpr (rem == 1) stockham_pass<N, 2, Ns, false, IO, LD, ST>(re, im, tw, ld, st);
     }
 }
 
 // ---- source term ------------------------------------------------------------------------------------------------
 // _compute_anelastic_source_term!: rhs = Δzᶜ · divᶜᶜᶜ(ρu, ρv, ρw) / Δt  (anelastic_pressure_solver.jl:99-105)
 __device__ __forceinline__ double source_term(const Layout& L, const double* __restrict__ ru, const double* __restrict__ rv,
-                                              const double* __restrict__ rw, int i, int j, int k, double dz_over_dt, int wrap_x) {
+                                              const double* __restrict__ rw, int i, int j, int k, double dz_over_dt) {
     long long n = lidx(L, i, j, k);
     double d = 0.0;
-    // the periodic images are addressed directly (no ghost fill of ρv needed; of ρu only across slabs, where wrap_x = 0 and the
-    // first ghost column holds the right neighbour's face)
-    if (!L.flat_x) d += (ru[(wrap_x && i + 1 == L.nx) ? n + 1 - L.nx : n + 1] - ru[n]) * L.rdx;
-    if (!L.flat_y) d += (rv[(j + 1 == L.Ny) ? n + L.PX - (long long)L.Ny * L.PX : n + L.PX] - rv[n]) * L.rdy;
+    // reads the first ghost column of ρu and the first ghost row of ρv (filled before the solve). Addressing the periodic images here
+    // instead was measured: the extra selects cost the 64-register y transform its loads in flight (1.35 -> 2.10 ms per launch at 512^3).
+    if (!L.flat_x) d += (ru[n + 1] - ru[n]) * L.rdx;
+    if (!L.flat_y) d += (rv[n + L.PX] - rv[n]) * L.rdy;
     double wt = (k + 1 < L.Nz) ? rw[n + L.plane] : 0.0;
     d += (wt - rw[n]) * L.rdz;
     return d * dz_over_dt;
@@ -223,7 +242,7 @@ __global__ void __launch_bounds__(MAXT, (N % 3 == 0 && MINB > 2) ? 2 : MINB) poi
             int e = threadIdx.x + (half * PT + it) * blockDim.x;
             int c = e & (XB - 1), y = e >> xb_shift;
             int i = ib + c;
-            v[it] = (i < L.nx) ? source_term(L, ru, rv, rw, i, y, k, dz_over_dt, G.P == 1) : 0.0;
+            v[it] = (i < L.nx) ? source_term(L, ru, rv, rw, i, y, k, dz_over_dt) : 0.0;
         }
 #pragma unroll
         for (int it = 0; it < PT; ++it) {
@@ -251,7 +270,7 @@ __global__ void __launch_bounds__(MAXT, (N % 3 == 0 && MINB > 2) ? 2 : MINB) poi
 __global__ void poisson_pack_flat_y(Layout L, PoissonGeom G, const double* __restrict__ ru, const double* __restrict__ rv,
                                     const double* __restrict__ rw, double dz_over_dt, double2* __restrict__ W) {
     int i = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
-    if (i < L.nx) W[w_index(G, k, 0, i)] = make_double2(source_term(L, ru, rv, rw, i, 0, k, dz_over_dt, G.P == 1), 0.0);
+    if (i < L.nx) W[w_index(G, k, 0, i)] = make_double2(source_term(L, ru, rv, rw, i, 0, k, dz_over_dt), 0.0);
 }
 
 // ---- pass 5: complex-to-real inverse FFT along y → φ (padded field interior) -------------------------------------
@@ -328,7 +347,6 @@ template <int N, int MAXT = 256, int MINB = 3>
 __global__ void __launch_bounds__(MAXT, (N % 3 == 0 && MINB > 2) ? 2 : MINB) fft_x_kernel(PoissonGeom G, double2* __restrict__ W, long long n_lines, const double2* __restrict__ tw_x, int lines, int inverse,
                                                        PeerBases peers, int pull, int line_base) {
     extern __shared__ double sm[];
-    constexpr int LP = ((N + (N >> 4) + 15) & ~15) + 4;
     double* re = sm;
     double* im = sm + imag_offset(N, lines);
     const int l0 = line_base + blockIdx.x * lines;      // first line of this CTA; line = k * nky_loc + ky_loc (fits an int); lines [line_base, n_lines)
@@ -341,57 +359,31 @@ __global__ void __launch_bounds__(MAXT, (N % 3 == 0 && MINB > 2) ? 2 : MINB) fft
         const int p = x / G.nx;
         return (((size_t)p * G.Nz + k) * G.nky_loc + ky) * G.nx + (x - p * G.nx);
     };
-    // blockDim.x == lines * N / PT: every thread moves exactly PT elements; all PT loads are issued before the first use
-    double2 v[PT];
-    const long long chunk = (n_lines - l0 < lines ? n_lines - l0 : lines) * (long long)N;   // valid elements of this CTA's lines
-    if (G.P == 1) {                                     // one rank: the CTA's lines are ONE contiguous chunk of W
-        const double2* __restrict__ src = W + (size_t)l0 * N;
-#pragma unroll
-        for (int it = 0; it < PT; ++it) {
-            const int e = threadIdx.x + it * blockDim.x;
-            v[it] = (e < chunk) ? src[e] : make_double2(0.0, 0.0);
-        }
-    } else {
-#pragma unroll
-    for (int it = 0; it < PT; ++it) {
-        const int e = threadIdx.x + it * blockDim.x;
-        const int l = e / N, x = e % N;
-        if (l0 + l >= n_lines) v[it] = make_double2(0.0, 0.0);
+    // The first pass reads its PT inputs per thread straight from global memory and the last pass writes its outputs straight back
+    // (coalesced: for every r the threads of a line touch contiguous elements); lines beyond n_lines read zeros and are not written.
+    const bool p1 = (G.P == 1);
+    const double2* __restrict__ src1 = W + (size_t)l0 * N;
+    double2* __restrict__ dst1 = W + (size_t)l0 * N;
+    auto ld = [&](int l, int x) -> cpx {
+        if (l0 + l >= n_lines) return cpx{0.0, 0.0};
+        double2 v;
+        if (p1) v = src1[l * N + x];                    // one rank: the CTA's lines are ONE contiguous chunk of W
         else if (pull) {   // x-slab spectrum read straight from the rank that owns these columns (replaces the forward all-to-all)
             int ky = r0 + l, k = k0;
             while (ky >= G.nky_loc) { ky -= G.nky_loc; ++k; }
             const int p = x / G.nx;
             const double2* src = reinterpret_cast<const double2*>(peers.base[p] + G.off_W)
                                  + ((long long)G.ky0 * G.Nz + (long long)k * G.nky_loc + ky) * G.nx + (x - p * G.nx);
-            v[it] = __ldcv(src);
-        } else v[it] = W[w2_of(l, x)];
-    }
-    }
-#pragma unroll
-    for (int it = 0; it < PT; ++it) {
-        const int e = threadIdx.x + it * blockDim.x;
-        const int l = e / N, x = e % N;
-        re[l * LP + pidx(x)] = v[it].x;
-        im[l * LP + pidx(x)] = sgn * v[it].y;
-    }
-    __syncthreads();
-    fft_lines_smem<N>(re, im, tw_x);
-    if (G.P == 1) {
-        double2* __restrict__ dst = W + (size_t)l0 * N;
-#pragma unroll
-        for (int it = 0; it < PT; ++it) {
-            const int e = threadIdx.x + it * blockDim.x;
-            const int l = e / N, x = e % N;
-            if (e < chunk) dst[e] = make_double2(re[l * LP + pidx(x)], sgn * im[l * LP + pidx(x)]);
-        }
-    } else {
-#pragma unroll
-    for (int it = 0; it < PT; ++it) {
-        const int e = threadIdx.x + it * blockDim.x;
-        const int l = e / N, x = e % N;
-        if (l0 + l < n_lines) W[w2_of(l, x)] = make_double2(re[l * LP + pidx(x)], sgn * im[l * LP + pidx(x)]);
-    }
-    }
+            v = __ldcv(src);
+        } else v = W[w2_of(l, x)];
+        return cpx{v.x, sgn * v.y};
+    };
+    auto st = [&](int l, int x, cpx v) {
+        if (l0 + l >= n_lines) return;
+        const double2 o = make_double2(v.x, sgn * v.y);
+        if (p1) dst1[l * N + x] = o; else W[w2_of(l, x)] = o;
+    };
+    fft_lines_smem<N, true>(re, im, tw_x, ld, st);
 }
 
 // ---- pass 3: batched Thomas in z -----------------------------------------------------------------------------------

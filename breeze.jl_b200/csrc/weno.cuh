@@ -41,29 +41,9 @@ __device__ __forceinline__ bool positive(double x) { return __double2hiint(x) >=
 //   β' = β / 0.75 = (13/3) s² + t²  (ε scaled alike: the weights only see the ratios τ/(β+ε));
 //   Σ ω_r q_r = q₁ + ω₀ (q₀ - q₁) + ω₂ (q₂ - q₁)  with  q₀ - q₁ = (s₁ - s₀)/6,  q₂ - q₁ = (s₂ - s₁)/3
 // (s_r are the second differences already formed for β), so only the central candidate polynomial is evaluated.
-#ifdef BZ_WENO_FP32_WEIGHTS
-// Declared-tolerance variant (the reference exposes the analogous `weight_computation` switch of its WENO scheme): the candidate
-// polynomials and their differences stay FP64, the nonlinear weights — smoothness indicators, τ, α_r and their normalisation — are
-// evaluated in FP32 on the FMA pipe (18 FP64 + 8 conversions + ≈ 30 FP32 instead of 47 FP64). The weights multiply second differences of
-// ψ, so their 2⁻²⁴ relative error enters the face value as ≈ 6e-8 |δ²ψ|.
-__device__ __forceinline__ double weno5z(double a, double b, double c, double d, double e) {
-    double s0 = fma(-2.0, d, c) + e, t0 = fma(3.0, c, fma(-4.0, d, e));
-    double s1 = fma(-2.0, c, b) + d, t1 = b - d;
-    double s2 = fma(-2.0, b, a) + c, t2 = fma(3.0, c, fma(-4.0, b, a));
-    const float K = 13.0f / 3.0f, EPSP = (float)(WENO_EPS / 0.75);
-    const float fs0 = (float)s0, ft0 = (float)t0, fs1 = (float)s1, ft1 = (float)t1, fs2 = (float)s2, ft2 = (float)t2;
-    const float b0 = fmaf(fs0 * K, fs0, fmaf(ft0, ft0, EPSP));
-    const float b1 = fmaf(fs1 * K, fs1, fmaf(ft1, ft1, EPSP));
-    const float b2 = fmaf(fs2 * K, fs2, fmaf(ft2, ft2, EPSP));
-    const float tau = b0 - b2;
-    const float r0 = tau * __frcp_rn(b0), r1 = tau * __frcp_rn(b1), r2 = tau * __frcp_rn(b2);
-    const float a0 = 0.3f * fmaf(r0, r0, 1.0f), a1 = 0.6f * fmaf(r1, r1, 1.0f), a2 = 0.1f * fmaf(r2, r2, 1.0f);
-    const float rs = __frcp_rn(a0 + a1 + a2);
-    const double w0 = (double)(a0 * rs * (1.0f / 6.0f)), w2 = (double)(a2 * rs * (1.0f / 3.0f));
-    double qc = fma(-1.0 / 6.0, b, fma(5.0 / 6.0, c, (1.0 / 3.0) * d));
-    return fma(w0, s1 - s0, fma(w2, s2 - s1, qc));       // q0 - q1 = (s1 - s0)/6, q2 - q1 = (s2 - s1)/3
-}
-#else
+// (An FP32-weights variant of this function — indicators, τ and α_r on the FMA pipe, polynomials in FP64 — was measured and rejected:
+// 17.45 against 11.28 ms per stage-kernel launch at 512^3, because an FP64 <-> FP32 conversion issues at 8.5 cycles per warp instruction on
+// this part; profiles/r2_stage_fp32_weights_variant.txt, commit b2d200f carries the source.)
 __device__ __forceinline__ double weno5z(double a, double b, double c, double d, double e) {
     const double K = 13.0 / 3.0, EPSP = WENO_EPS / 0.75;
     double s0 = fma(-2.0, d, c) + e, t0 = fma(3.0, c, fma(-4.0, d, e));   // stencil (c, d, e)
@@ -87,7 +67,6 @@ __device__ __forceinline__ double weno5z(double a, double b, double c, double d,
     double den = fma(3.0, w0, fma(6.0, w1, w2));
     return fma(num, fast_rcp(den), qc);
 }
-#endif
 
 // WENO3-Z: left-biased value at the face between b and c from a b | c.
 __device__ __forceinline__ double weno3z(double a, double b, double c) {
@@ -171,17 +150,23 @@ __device__ __forceinline__ double weno_hi(const double (&w)[2 * R - 1]) {
 #endif
 template <int R>
 __device__ BZ_HI_LINKAGE double weno_hi_mem(const double* __restrict__ f, long long n, long long s, bool left) {
+    // window w[j] = left ? f[n + (j - R) s] : f[n + (R - 1 - j) s]: ONE selected start pointer and a signed step, 2R - 1 loads — instead of
+    // 2R loads at both windows' addresses (a 64-bit multiply-add each) and 4R - 2 selecting moves
+    const double* p = f + n + (left ? -(long long)R * s : (long long)(R - 1) * s);
+    const long long step = left ? s : -s;
     double w[2 * R - 1];
 #pragma unroll
-    for (int j = 0; j < 2 * R - 1; ++j) w[j] = left ? f[n + (j - R) * s] : f[n + (R - 1 - j) * s];
+    for (int j = 0; j < 2 * R - 1; ++j) { w[j] = *p; p += step; }
     return weno_hi<R>(w);
 }
 // Centered(order = 2R) value at the face between a[n - s] and a[n], R = 3 or 4
 template <int R>
 __device__ __forceinline__ double centered_hi_mem(const double* __restrict__ a, long long n, long long s) {
+    const double* lo = a + n - s;
+    const double* hi = a + n;
     double v = 0.0;
 #pragma unroll
-    for (int j = 0; j < R; ++j) v = fma(R == 4 ? CENTERED8_C[j] : CENTERED6_C[j], a[n - (1 + j) * s] + a[n + j * s], v);
+    for (int j = 0; j < R; ++j) { v = fma(R == 4 ? CENTERED8_C[j] : CENTERED6_C[j], *lo + *hi, v); lo -= s; hi += s; }
     return v;
 }
 

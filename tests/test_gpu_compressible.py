@@ -227,6 +227,20 @@ def test_config4_full_size_one_step_vs_oracle(oracle_arch):
     assert np.abs(gpu.field("w")).max() > 1e-3
 
 
+def test_graph_replay_is_bit_identical_to_eager_steps(oracle_arch):
+    """bzc_time_step replays a captured CUDA graph from the third step with the same Δt on; with profiling enabled it launches eagerly."""
+    a, _ = _pair(oracle_arch, (32, 16, 24), seed=5, noise=0.0)
+    b, _ = _pair(oracle_arch, (32, 16, 24), seed=5, noise=0.0)
+    b.context.profile_enable(True)
+    for dt in (2.0, 2.0, 2.0, 2.0, 1.0, 2.0):
+        a.time_step(dt)
+        b.time_step(dt)
+    b.context.profile_read()
+    for name in PROGNOSTIC + ["u", "w", "p"]:
+        assert np.array_equal(a.field(name), b.field(name)), name
+    assert a.clock == b.clock
+
+
 def test_config4_shape_runs_and_counts_launches():
     """BASELINE config 4 shape (256 x 256 x 64, 6 substeps per full step): two launches per substep."""
     import breeze_b200 as bz
