@@ -70,64 +70,80 @@ class BreezeError(RuntimeError):
 _dp = C.POINTER(C.c_double)
 _vp = C.c_void_p
 
-# name -> (restype, argtypes); every symbol include/breeze_b200.h declares
-ABI_SYMBOLS = {
-    "default_config": (None, [C.POINTER(bz_config)]),
-    "abi_version": (C.c_int, []),
-    "create": (C.c_int, [C.POINTER(bz_config), C.POINTER(_vp)]),
-    "destroy": (None, [_vp]),
-    "last_error": (C.c_char_p, [_vp]),
-    "get_reference_state": (C.c_int, [_vp, _dp, _dp, _dp]),
-    "set_reference_state": (C.c_int, [_vp, _dp, _dp, _dp]),
-    "set_state": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _dp, C.c_int]),
-    "set_forcing": (C.c_int, [_vp, C.POINTER(bz_forcing)]),
-    "time_step": (C.c_int, [_vp, C.c_double]),
-    "time_steps": (C.c_int, [_vp, C.c_double, C.c_int]),
-    "compute_tendencies": (C.c_int, [_vp]),
-    "get_tendency": (C.c_int, [_vp, C.c_int, _dp]),
-    "pressure_correct": (C.c_int, [_vp, C.c_double]),
-    "get_field": (C.c_int, [_vp, C.c_int, _dp]),
-    "get_state": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _dp]),
-    "get_clock": (C.c_int, [_vp, _dp, C.POINTER(C.c_int64)]),
-    "cell_advection_timescale": (C.c_int, [_vp, _dp]),
-    "max_abs_divergence": (C.c_int, [_vp, _dp]),
-    "state_is_finite": (C.c_int, [_vp, C.POINTER(C.c_int)]),
-    "get_slice": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _dp]),
-    "synchronize": (C.c_int, [_vp]),
-}
-# CUDA-library-only symbols (instrumentation); the oracle does not export them
-CUDA_ONLY_SYMBOLS = {
-    "set_state_async": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _dp, C.c_int]),
-    "get_state_async": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _dp]),
-    "profile_enable": (C.c_int, [_vp, C.c_int]),
-    "profile_read": (C.c_int, [_vp, _dp, C.POINTER(C.c_int64)]),
-    "kernel_launch_count": (C.c_int64, [_vp]),
-    "stream": (_vp, [_vp]),
-    "device_bytes": (C.c_int64, [_vp]),
-    "nccl_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
-    "ipc_export": (C.c_int, [_vp, C.POINTER(C.c_uint8)]),
-    "ipc_attach": (C.c_int, [_vp, C.POINTER(C.c_uint8)]),
-}
+
+def abi_symbols(real=C.c_double):
+    """name -> (restype, argtypes) of every symbol include/breeze_b200.h declares. `real` is the library's field type: c_double for
+    libbreeze_b200.so (bz_) and the oracle (orc_), c_float for the Float32 build libbreeze_b200_f32.so (bzf_), whose entry points are the
+    same with every `double` array / scalar argument a `float` (the clock of bz_get_clock and the profiles of bz_forcing stay double)."""
+    rp = C.POINTER(real)
+    return {
+        "default_config": (None, [C.POINTER(bz_config)]),
+        "abi_version": (C.c_int, []),
+        "create": (C.c_int, [C.POINTER(bz_config), C.POINTER(_vp)]),
+        "destroy": (None, [_vp]),
+        "last_error": (C.c_char_p, [_vp]),
+        "get_reference_state": (C.c_int, [_vp, rp, rp, rp]),
+        "set_reference_state": (C.c_int, [_vp, rp, rp, rp]),
+        "set_state": (C.c_int, [_vp, rp, rp, rp, rp, rp, C.c_int]),
+        "set_forcing": (C.c_int, [_vp, C.POINTER(bz_forcing)]),
+        "time_step": (C.c_int, [_vp, real]),
+        "time_steps": (C.c_int, [_vp, real, C.c_int]),
+        "compute_tendencies": (C.c_int, [_vp]),
+        "get_tendency": (C.c_int, [_vp, C.c_int, rp]),
+        "pressure_correct": (C.c_int, [_vp, real]),
+        "get_field": (C.c_int, [_vp, C.c_int, rp]),
+        "get_state": (C.c_int, [_vp, rp, rp, rp, rp, rp]),
+        "get_clock": (C.c_int, [_vp, _dp, C.POINTER(C.c_int64)]),
+        "cell_advection_timescale": (C.c_int, [_vp, rp]),
+        "max_abs_divergence": (C.c_int, [_vp, rp]),
+        "state_is_finite": (C.c_int, [_vp, C.POINTER(C.c_int)]),
+        "get_slice": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, rp]),
+        "synchronize": (C.c_int, [_vp]),
+    }
+
+
+def cuda_only_symbols(real=C.c_double):
+    """CUDA-library-only symbols (instrumentation, asynchronous marshalling, multi-GPU bootstrap); the oracle does not export them."""
+    rp = C.POINTER(real)
+    return {
+        "set_state_async": (C.c_int, [_vp, rp, rp, rp, rp, rp, C.c_int]),
+        "get_state_async": (C.c_int, [_vp, rp, rp, rp, rp, rp]),
+        "profile_enable": (C.c_int, [_vp, C.c_int]),
+        "profile_read": (C.c_int, [_vp, rp, C.POINTER(C.c_int64)]),
+        "kernel_launch_count": (C.c_int64, [_vp]),
+        "stream": (_vp, [_vp]),
+        "device_bytes": (C.c_int64, [_vp]),
+        "nccl_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
+        "ipc_export": (C.c_int, [_vp, C.POINTER(C.c_uint8)]),
+        "ipc_attach": (C.c_int, [_vp, C.POINTER(C.c_uint8)]),
+    }
+
+
+ABI_SYMBOLS = abi_symbols()
+CUDA_ONLY_SYMBOLS = cuda_only_symbols()
 
 
 def _as_dp(a):
+    """pointer to a C-contiguous float64 or float32 array (ctypes checks it against the bound library's argument type)"""
     if a is None:
         return None
-    assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
-    return a.ctypes.data_as(_dp)
+    assert a.dtype in (np.float64, np.float32) and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.POINTER(C.c_double if a.dtype == np.float64 else C.c_float))
 
 
 class Library:
     """One loaded shared object exporting the ABI with a given prefix."""
 
-    def __init__(self, path: str, prefix: str, cuda: bool):
+    def __init__(self, path: str, prefix: str, cuda: bool, real=np.float64):
         if not os.path.exists(path):
             raise BreezeError(f"{path} is missing — build it first (python -c 'import __graft_entry__ as g; g.build()')")
         self.path, self.prefix, self.cuda = path, prefix, cuda
+        self.real = np.dtype(real).type                   # the library's field / host-array type
+        self.creal = C.c_double if self.real is np.float64 else C.c_float
         self.dll = C.CDLL(path, mode=C.RTLD_GLOBAL if not cuda else C.RTLD_LOCAL)
-        table = dict(ABI_SYMBOLS)
+        table = abi_symbols(self.creal)
         if cuda:
-            table.update(CUDA_ONLY_SYMBOLS)
+            table.update(cuda_only_symbols(self.creal))
         for name, (res, args) in table.items():
             fn = getattr(self.dll, prefix + name)      # AttributeError if the symbol is not exported
             fn.restype, fn.argtypes = res, args
@@ -146,6 +162,7 @@ class Context:
     def __init__(self, lib: Library, cfg: bz_config):
         self.lib = lib
         self.cfg = cfg
+        self.real = getattr(lib, "real", np.float64)
         self.handle = _vp()
         rc = lib.create(C.byref(cfg), C.byref(self.handle))
         if rc != 0:
@@ -176,12 +193,12 @@ class Context:
 
     # --- reference state -------------------------------------------------------------------------
     def reference_state(self):
-        rho, p, T = (np.empty(self.Nz) for _ in range(3))
+        rho, p, T = (np.empty(self.Nz, dtype=self.real) for _ in range(3))
         self._check(self.lib.get_reference_state(self.handle, _as_dp(rho), _as_dp(p), _as_dp(T)), "get_reference_state")
         return rho, p, T
 
     def set_reference_state(self, density=None, pressure=None, temperature=None):
-        arrs = [None if a is None else np.ascontiguousarray(a, dtype=np.float64) for a in (density, pressure, temperature)]
+        arrs = [None if a is None else np.ascontiguousarray(a, dtype=self.real) for a in (density, pressure, temperature)]
         self._check(self.lib.set_reference_state(self.handle, *[_as_dp(a) for a in arrs]), "set_reference_state")
 
     # --- state -----------------------------------------------------------------------------------
@@ -191,7 +208,7 @@ class Context:
             if a is None:
                 arrs.append(None)
                 continue
-            a = np.ascontiguousarray(a, dtype=np.float64)
+            a = np.ascontiguousarray(a, dtype=self.real)
             if a.shape != self.shape(fid):
                 raise BreezeError(f"field {fid}: expected shape {self.shape(fid)}, got {a.shape}")
             arrs.append(a)
@@ -225,13 +242,13 @@ class Context:
 
     def get_field(self, name_or_id):
         fid = FIELD_IDS[name_or_id] if isinstance(name_or_id, str) else int(name_or_id)
-        out = np.empty(self.shape(fid))
+        out = np.empty(self.shape(fid), dtype=self.real)
         self._check(self.lib.get_field(self.handle, fid, _as_dp(out)), "get_field")
         return out
 
     def get_state(self, out=None):
         if out is None:
-            out = [np.empty(self.shape(f)) for f in range(5)]
+            out = [np.empty(self.shape(f), dtype=self.real) for f in range(5)]
         self._check(self.lib.get_state(self.handle, *[_as_dp(a) for a in out]), "get_state")
         return out
 
@@ -244,7 +261,7 @@ class Context:
 
     def get_tendency(self, name_or_id):
         fid = FIELD_IDS[name_or_id] if isinstance(name_or_id, str) else int(name_or_id)
-        out = np.empty(self.shape(fid))
+        out = np.empty(self.shape(fid), dtype=self.real)
         self._check(self.lib.get_tendency(self.handle, fid, _as_dp(out)), "get_tendency")
         return out
 
@@ -270,12 +287,12 @@ class Context:
         return t.value, it.value
 
     def cell_advection_timescale(self):
-        tau = C.c_double()
+        tau = self.lib.creal() if hasattr(self.lib, "creal") else C.c_double()
         self._check(self.lib.cell_advection_timescale(self.handle, C.byref(tau)), "cell_advection_timescale")
         return tau.value
 
     def max_abs_divergence(self):
-        d = C.c_double()
+        d = self.lib.creal() if hasattr(self.lib, "creal") else C.c_double()
         self._check(self.lib.max_abs_divergence(self.handle, C.byref(d)), "max_abs_divergence")
         return d.value
 
@@ -289,7 +306,7 @@ class Context:
         fid = FIELD_IDS[name_or_id] if isinstance(name_or_id, str) else int(name_or_id)
         nz, ny, nx = self.shape(fid)
         ax = {"x": 0, "y": 1, "z": 2}[axis]
-        out = np.empty({0: (nz, ny), 1: (nz, nx), 2: (ny, nx)}[ax])
+        out = np.empty({0: (nz, ny), 1: (nz, nx), 2: (ny, nx)}[ax], dtype=self.real)
         self._check(self.lib.get_slice(self.handle, fid, ax, int(index), _as_dp(out)), "get_slice")
         return out
 
@@ -298,7 +315,7 @@ class Context:
         self._check(self.lib.profile_enable(self.handle, int(on)), "profile_enable")
 
     def profile_read(self):
-        ms = np.zeros(8)
+        ms = np.zeros(8, dtype=self.real)
         n = np.zeros(8, dtype=np.int64)
         self._check(self.lib.profile_read(self.handle, _as_dp(ms), n.ctypes.data_as(C.POINTER(C.c_int64))), "profile_read")
         return ms, n
@@ -348,3 +365,18 @@ def load_cuda_library() -> Library:
     if _CUDA_LIB is None:
         _CUDA_LIB = Library(cuda_library_path(), "bz_", cuda=True)
     return _CUDA_LIB
+
+
+_CUDA_LIB_F32 = None
+
+
+def cuda_library_path_f32() -> str:
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libbreeze_b200_f32.so")
+
+
+def load_cuda_library_f32() -> Library:
+    """The Float32 build of the anelastic path (prefix bzf_, float32 host arrays): B200(float_type="Float32")."""
+    global _CUDA_LIB_F32
+    if _CUDA_LIB_F32 is None:
+        _CUDA_LIB_F32 = Library(cuda_library_path_f32(), "bzf_", cuda=True, real=np.float32)
+    return _CUDA_LIB_F32

@@ -328,6 +328,8 @@ class CompressibleAtmosphereModel:
         from .model import Flat, ThermodynamicConstants, WENO
         if microphysics is not None:
             raise NotImplementedError("the compressible path carries vapour only (microphysics = nothing)")
+        if getattr(grid.architecture, "float_type", "Float64") != "Float64":
+            raise NotImplementedError("the Float32 library carries the anelastic path only; the compressible path is Float64")
         self._moist = False
         self.grid, self.architecture, self.dynamics = grid, grid.architecture, dynamics
         self.thermodynamic_constants = thermodynamic_constants or ThermodynamicConstants()

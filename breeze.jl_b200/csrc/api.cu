@@ -77,7 +77,7 @@ struct bz_ctx {
     const double* out_ptr[NPROG] = {};   // host destinations of the last bz_get_state_async (an upload from the same buffer waits chunk-wise)
     Comm comm;
     int use_tma = 0, z_chunks = 1;
-    double time = 0.0;
+    double time = 0.0;                   // BZ_KEEP_F64 (the clock stays double in the Float32 build)
     int64_t iteration = 0;
     int64_t launches = 0;
     int64_t bytes = 0;
@@ -151,7 +151,7 @@ static int make_tensor_maps(bz_ctx* c, int box_w, int box_h) {
     PFN_encodeTiled encode = (PFN_encodeTiled)fn;
     const Layout& L = c->L;
     cuuint64_t dims[3] = {(cuuint64_t)L.PX, (cuuint64_t)L.PY, (cuuint64_t)L.Nz};
-    cuuint64_t strides[2] = {(cuuint64_t)L.PX * 8, (cuuint64_t)L.plane * 8};
+    cuuint64_t strides[2] = {(cuuint64_t)L.PX * sizeof(double), (cuuint64_t)L.plane * sizeof(double)};
     cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     for (int s = 0; s < 3; ++s)
@@ -867,7 +867,7 @@ int bz_create(const bz_config* cfg, bz_ctx** out) {
     TRY(setup_poisson(c));
     TRY(comm_alloc_buffers(c->comm, L, c->PG, &c->bytes));
     // staging of the stage kernel's operands
-    const bool tma_possible = !fx && (L.PX % 2 == 0) && c->buf == 3;
+    const bool tma_possible = !fx && ((L.PX * sizeof(double)) % 16 == 0) && c->buf == 3;   // TMA: row pitch a multiple of 16 bytes
     if (c->buf > 3) for (int f = 0; f < NPROG; ++f) TRY(dev_alloc(c, &c->V[f], (size_t)L.n));
     c->use_tma = (cfg->use_tma == 2) ? 0 : (tma_possible ? 1 : 0);
     if (cfg->use_tma == 1 && !tma_possible) { bz_set_error(nullptr, "TMA staging needs an even padded row length"); bz_destroy(c); return BZ_ERR_UNSUPPORTED; }
@@ -884,10 +884,10 @@ int bz_create(const bz_config* cfg, bz_ctx** out) {
         {
             const long long tiles = (long long)gx * gy;
             const int max_ch = L.Nz / 16 > 1 ? L.Nz / 16 : 1;
-            double best = 1e300;
+            double best = -1.0;
             for (int ch = 1; ch <= max_ch; ++ch) {
                 double cost = (double)((tiles * ch + 147) / 148) * ((L.Nz + ch - 1) / ch + 5);
-                if (cost < best) { best = cost; best_ch = ch; }
+                if (best < 0.0 || cost < best) { best = cost; best_ch = ch; }
             }
         }
         c->z_chunks = cfg->z_chunks > 0 ? cfg->z_chunks : best_ch;
@@ -990,7 +990,7 @@ int bz_set_state_async(bz_ctx* c, const double* ru, const double* rv, const doub
             if (c->out_ptr[f]) CUDA_TRY(c, cudaStreamWaitEvent(c->s_in, c->ev_out[f * COPY_CHUNKS + ch], 0));
             if (dep >= 0 && dep != f) CUDA_TRY(c, cudaStreamWaitEvent(c->s_in, c->ev_out[dep * COPY_CHUNKS + ch], 0));
             if (f == BZ_RHO_W && k0 == 0) {                        // the wall face k = 0 is not the caller's to set (always 0)
-                CUDA_TRY(c, cudaMemset2DAsync(dst + (size_t)L.HY * L.PX + L.HX, (size_t)L.PX * 8, 0, (size_t)L.nx * 8, (size_t)L.Ny, c->s_in));
+                CUDA_TRY(c, cudaMemset2DAsync(dst + (size_t)L.HY * L.PX + L.HX, (size_t)L.PX * sizeof(double), 0, (size_t)L.nx * sizeof(double), (size_t)L.Ny, c->s_in));
                 k0 = 1;
             }
             CUDA_TRY(c, copy_levels(c, dst, const_cast<double*>(src[f]), k0, k1, false, c->s_in));
@@ -1024,8 +1024,8 @@ int bz_set_forcing(bz_ctx* c, const bz_forcing* F) {
     std::vector<double> h(total, 0.0);
     double* base = c->fstore;
     size_t off = 0;
-    auto put = [&](const double* src, size_t n, double** dev) {
-        if (src) { memcpy(&h[off], src, n * sizeof(double)); *dev = base + off; } else *dev = nullptr;
+    auto put = [&](const auto* src, size_t n, auto** dev) {      // the profiles of bz_forcing are double in both precisions
+        if (src) { for (size_t q = 0; q < n; ++q) h[off + q] = src[q]; *dev = base + off; } else *dev = nullptr;
         off += n;
     };
     put(F->subsidence_w, Nz + 1, &c->d_ws);
@@ -1064,7 +1064,7 @@ int bz_time_step(bz_ctx* c, double dt) {
     cudaSetDevice(c->cfg.device);
     int rc;
     // one GPU, no per-kernel events wanted: replay the step as a CUDA graph keyed by (which buffer set holds the state, dt)
-    if (c->graphs.on() && c->comm.n_ranks == 1 && !c->prof_on) {
+    if (c->graphs.on((long long)c->L.nx * c->L.Ny * c->L.Nz) && c->comm.n_ranks == 1 && !c->prof_on) {
         StepGraphEntry* g = c->graphs.find(c->cur, dt);
         if (g && g->exec) {
             CUDA_TRY(c, cudaGraphLaunch(g->exec, c->stream));
@@ -1255,7 +1255,7 @@ int bz_get_state(bz_ctx* c, double* ru, double* rv, double* rw, double* rth, dou
     return BZ_OK;
 }
 
-int bz_get_clock(bz_ctx* c, double* time, int64_t* iteration) {
+int bz_get_clock(bz_ctx* c, double* time, int64_t* iteration) {   // BZ_KEEP_F64
     if (!c) return BZ_ERR_INVALID;
     if (time) *time = c->time;
     if (iteration) *iteration = c->iteration;
@@ -1355,5 +1355,7 @@ int64_t bz_device_bytes(const bz_ctx* c) { return c ? c->bytes : 0; }
 
 }  // extern "C"
 
-// second hot-path family: compressible WS-RK3 with acoustic substepping (include/breeze_b200_compressible.h)
+// second hot-path family: compressible WS-RK3 with acoustic substepping (include/breeze_b200_compressible.h); FP64 library only
+#ifndef BZ_F32
 #include "compressible_api.cuh"
+#endif

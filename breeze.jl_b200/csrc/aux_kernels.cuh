@@ -106,9 +106,16 @@ __global__ void diagnose_field(Layout L, Columns col, Thermo th, FieldSet U, int
     dst[((size_t)k * L.Ny + j) * L.nx + i] = v;
 }
 
+#ifdef BZ_F32
+__device__ __forceinline__ void atomic_max_nonneg(float* addr, float v) { atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v)); }
+__device__ __forceinline__ bool is_nonfinite(float v) { return (__float_as_int(v) & 0x7f800000) == 0x7f800000; }
+#else
 __device__ __forceinline__ void atomic_max_nonneg(double* addr, double v) {
     atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
 }
+// exponent bits all ones <=> NaN or Inf (integer test: no FP64 pipe)
+__device__ __forceinline__ bool is_nonfinite(double v) { return (__double2hiint(v) & 0x7ff00000) == 0x7ff00000; }
+#endif
 
 // which = 0: max |div(ρu)|; which = 1: max (|u|/Δx + |v|/Δy + |w|/Δz)  (cell_advection_timescale.jl:46-65)
 __global__ void reduce_max_kernel(Layout L, Columns col, const double* __restrict__ ru, const double* __restrict__ rv,
@@ -145,8 +152,7 @@ __global__ void nonfinite_kernel(Layout L, FieldSet F, int* __restrict__ flag) {
         int i = (int)(e % L.nx), j = (int)((e / L.nx) % L.Ny), k = (int)(e / ((long long)L.nx * L.Ny));
         long long n = lidx(L, i, j, k);
         for (int f = 0; f < F.n; ++f) {
-            // exponent bits all ones <=> NaN or Inf (integer test: no FP64 pipe)
-            bad |= ((__double2hiint(F.f[f][n]) & 0x7ff00000) == 0x7ff00000);
+            bad |= is_nonfinite(F.f[f][n]);
         }
     }
     if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);

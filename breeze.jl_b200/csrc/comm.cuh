@@ -18,7 +18,7 @@
 
 typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId_t;
-enum { NCCL_FLOAT64 = 8, NCCL_SUM = 0, NCCL_MAX = 2 };      // ncclDataType_t / ncclRedOp_t values (nccl.h)
+enum { NCCL_FLOAT32 = 7, NCCL_FLOAT64 = 8, NCCL_SUM = 0, NCCL_MAX = 2 };      // ncclDataType_t / ncclRedOp_t values (nccl.h)  BZ_KEEP_F64
 
 struct NcclApi {
     void* lib = nullptr;
@@ -126,10 +126,10 @@ static void comm_destroy(Comm& cm) {
 static int comm_alloc_buffers(Comm& cm, const Layout& L, const PoissonGeom&, int64_t* bytes) {
     if (cm.n_ranks == 1) return BZ_OK;
     cm.halo_cap = (size_t)2 * (NPROG + 1) * L.HX * L.Ny * L.Nz;
-    if (cudaMalloc(&cm.halo_send, cm.halo_cap * 8) || cudaMalloc(&cm.halo_recv, cm.halo_cap * 8) || cudaMalloc(&cm.token, 64) || cudaMemset(cm.token, 0, 64)) {
+    if (cudaMalloc(&cm.halo_send, cm.halo_cap * sizeof(double)) || cudaMalloc(&cm.halo_recv, cm.halo_cap * sizeof(double)) || cudaMalloc(&cm.token, 64) || cudaMemset(cm.token, 0, 64)) {
         snprintf(cm.err, 256, "cudaMalloc of communication buffers failed"); return BZ_ERR_NOMEM;
     }
-    *bytes += (int64_t)(2 * cm.halo_cap * 8);
+    *bytes += (int64_t)(2 * cm.halo_cap * sizeof(double));
     return BZ_OK;
 }
 
@@ -343,9 +343,9 @@ static int comm_allreduce_sum_device(Comm& cm, double* dev, size_t n, cudaStream
 }
 
 static int comm_allreduce_max(Comm& cm, double* host_value, double* dev_scalar, cudaStream_t s) {
-    if (cudaMemcpyAsync(dev_scalar, host_value, 8, cudaMemcpyHostToDevice, s)) return BZ_ERR_CUDA;
+    if (cudaMemcpyAsync(dev_scalar, host_value, sizeof(double), cudaMemcpyHostToDevice, s)) return BZ_ERR_CUDA;
     NCCL_TRY(cm, cm.api.AllReduce(dev_scalar, dev_scalar, 1, NCCL_FLOAT64, NCCL_MAX, cm.comm, s));
-    if (cudaMemcpyAsync(host_value, dev_scalar, 8, cudaMemcpyDeviceToHost, s)) return BZ_ERR_CUDA;
+    if (cudaMemcpyAsync(host_value, dev_scalar, sizeof(double), cudaMemcpyDeviceToHost, s)) return BZ_ERR_CUDA;
     if (cudaStreamSynchronize(s)) return BZ_ERR_CUDA;
     return BZ_OK;
 }

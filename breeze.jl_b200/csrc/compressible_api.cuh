@@ -496,7 +496,7 @@ int bzc_set_state(bzc_ctx* c, const double* rho, const double* ru, const double*
 int bzc_time_step(bzc_ctx* c, double dt) {
     if (!c) return BZ_ERR_INVALID;
     cudaSetDevice(c->cfg.base.device);
-    if (!(c->graphs.on() && !c->prof_on)) return c_time_step(c, dt);
+    if (!(c->graphs.on((long long)c->L.nx * c->L.Ny * c->L.Nz) && !c->prof_on)) return c_time_step(c, dt);
     StepGraphEntry* g = c->graphs.find(0, dt);
     if (g && g->exec) {
         CC_TRY(c, cudaGraphLaunch(g->exec, c->stream));

@@ -409,7 +409,7 @@ __global__ void thomas_setup(PoissonGeom G, const double* __restrict__ rho, cons
         double t = 0.0;
         if (k > 0) { t = lo / beta; beta = D - lo * t; } else beta = D;
         tfac[n] = t;
-        inv_beta[n] = (fabs(beta) > 10.0 * 2.220446049250313e-16) ? 1.0 / beta : 0.0;
+        inv_beta[n] = (fabs(beta) > 10.0 * BZ_REAL_EPS) ? 1.0 / beta : 0.0;
     }
 }
 

@@ -199,7 +199,8 @@ struct StageShared {
     static constexpr int SW = TX + 8;                 // x: tile origin i0 - 4
     static constexpr int SH = HAS_Y ? TY + 6 : 1;     // y: tile origin j0 - 3
     static constexpr int YO = HAS_Y ? 3 : 0;
-    static constexpr int PLANE = (SW * SH + 15) & ~15;   // every field slice stays 128-byte aligned (TMA destination)
+    static constexpr int ALN = 128 / (int)sizeof(double);
+    static constexpr int PLANE = (SW * SH + ALN - 1) & ~(ALN - 1);   // every field slice stays 128-byte aligned (TMA destination)
     static_assert(!HAS_Y || (TY >= NPROG && TX == 32), "the extra y-face row is spread one flux kind per warp");
     double ring[RING][NPROG][PLANE];
     double fx[2][NPROG][TY][TX + 1];                  // double-buffered by level parity: one CTA barrier per level

@@ -15,6 +15,15 @@
 
 #define WENO_EPS 1e-8
 
+// (BZ_F32: the Float32 library is compiled from a retyped copy of these sources, breeze.jl_b200/make_f32.py; the few places where the
+// two precisions need different instructions — bit tests, the reciprocal, the range of the WENO weight products — sit under #ifdef BZ_F32.)
+#ifdef BZ_F32
+__device__ __forceinline__ float fast_rcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+#else
 __device__ __forceinline__ double fast_rcp(double x) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
@@ -31,10 +40,15 @@ __device__ __forceinline__ double fast_rcp(double x) {
 #endif
     return r;
 }
+#endif
 
 // sign test on the high word (integer pipe instead of DSETP on the FP64 pipe); differs from `x > 0` only for
 // x = ±0, where the flux it selects for is multiplied by that zero
+#ifdef BZ_F32
+__device__ __forceinline__ bool positive(float x) { return __float_as_int(x) >= 0; }
+#else
 __device__ __forceinline__ bool positive(double x) { return __double2hiint(x) >= 0; }
+#endif
 
 // Left-biased value at the face between c and d from the five cells a b c | d e (a = ψ[i-3] … e = ψ[i+1]).
 // Written with explicit fma() for the minimal FP64 instruction count (43 + one reciprocal):
@@ -44,6 +58,25 @@ __device__ __forceinline__ bool positive(double x) { return __double2hiint(x) >=
 // (An FP32-weights variant of this function — indicators, τ and α_r on the FMA pipe, polynomials in FP64 — was measured and rejected:
 // 17.45 against 11.28 ms per stage-kernel launch at 512^3, because an FP64 <-> FP32 conversion issues at 8.5 cycles per warp instruction on
 // this part; profiles/r2_stage_fp32_weights_variant.txt, commit b2d200f carries the source.)
+#ifdef BZ_F32
+// Float32: the product form below would underflow (b_r ≥ 1.3e-8 ⇒ Π b_r² ≈ 1e-48 < FLT_MIN), so the weights are formed from the
+// ratios τ / b_r with the single-instruction FP32 reciprocal, which costs one MUFU each.
+__device__ __forceinline__ double weno5z(double a, double b, double c, double d, double e) {
+    const double K = 13.0 / 3.0, EPSP = WENO_EPS / 0.75;
+    double s0 = fma(-2.0, d, c) + e, t0 = fma(3.0, c, fma(-4.0, d, e));
+    double s1 = fma(-2.0, c, b) + d, t1 = b - d;
+    double s2 = fma(-2.0, b, a) + c, t2 = fma(3.0, c, fma(-4.0, b, a));
+    double b0 = fma(s0 * K, s0, fma(t0, t0, EPSP));
+    double b1 = fma(s1 * K, s1, fma(t1, t1, EPSP));
+    double b2 = fma(s2 * K, s2, fma(t2, t2, EPSP));
+    double tau = b0 - b2;
+    double r0 = tau * fast_rcp(b0), r1 = tau * fast_rcp(b1), r2 = tau * fast_rcp(b2);
+    double a0 = 0.3 * fma(r0, r0, 1.0), a1 = 0.6 * fma(r1, r1, 1.0), a2 = 0.1 * fma(r2, r2, 1.0);
+    double rs = fast_rcp(a0 + a1 + a2);
+    double qc = fma(-1.0 / 6.0, b, fma(5.0 / 6.0, c, (1.0 / 3.0) * d));
+    return fma((a0 * rs) * (1.0 / 6.0), s1 - s0, fma((a2 * rs) * (1.0 / 3.0), s2 - s1, qc));
+}
+#else
 __device__ __forceinline__ double weno5z(double a, double b, double c, double d, double e) {
     const double K = 13.0 / 3.0, EPSP = WENO_EPS / 0.75;
     double s0 = fma(-2.0, d, c) + e, t0 = fma(3.0, c, fma(-4.0, d, e));   // stencil (c, d, e)
@@ -67,8 +100,19 @@ __device__ __forceinline__ double weno5z(double a, double b, double c, double d,
     double den = fma(3.0, w0, fma(6.0, w1, w2));
     return fma(num, fast_rcp(den), qc);
 }
+#endif
 
 // WENO3-Z: left-biased value at the face between b and c from a b | c.
+#ifdef BZ_F32
+__device__ __forceinline__ double weno3z(double a, double b, double c) {      // ratio form (range, as for weno5z)
+    double d0 = c - b, d1 = b - a;
+    double b0 = d0 * d0, b1 = d1 * d1;
+    double tau = fabs(b0 - b1);
+    double r0 = tau * fast_rcp(b0 + WENO_EPS), r1 = tau * fast_rcp(b1 + WENO_EPS);
+    double a0 = (2.0 / 3.0) * fma(r0, r0, 1.0), a1 = (1.0 / 3.0) * fma(r1, r1, 1.0);
+    return (a0 * (0.5 * (b + c)) + a1 * (1.5 * b - 0.5 * a)) * fast_rcp(a0 + a1);
+}
+#else
 __device__ __forceinline__ double weno3z(double a, double b, double c) {
     double d0 = c - b, d1 = b - a;
     double b0 = d0 * d0, b1 = d1 * d1;
@@ -82,6 +126,7 @@ __device__ __forceinline__ double weno3z(double a, double b, double c) {
     double p1 = 3.0 * b - a;
     return (w0 * p0 + w1 * p1) * fast_rcp(2.0 * (w0 + w1));
 }
+#endif
 
 // Six consecutive values v0..v5 = ψ[i-3..i+2] around the "face" between v2 and v3; R = buffer (3, 2 or 1).
 __device__ __forceinline__ double biased6(double v0, double v1, double v2, double v3, double v4, double v5, int R, bool left) {

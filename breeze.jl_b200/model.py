@@ -39,13 +39,16 @@ class B200:
     """The architecture: hand-written sm_100a kernels behind libbreeze_b200.so (one context per GPU)."""
 
     def __init__(self, device: int = 0, rank: int = 0, n_ranks: int = 1, nccl_unique_id: bytes | None = None,
-                 use_tma: int = 0, z_chunks: int = 0):
+                 use_tma: int = 0, z_chunks: int = 0, float_type: str = "Float64"):
+        if float_type not in ("Float64", "Float32"):
+            raise ValueError(f"float_type must be Float64 or Float32, got {float_type!r}")
         self.device, self.rank, self.n_ranks = device, rank, n_ranks
         self.nccl_unique_id = nccl_unique_id
         self.use_tma, self.z_chunks = use_tma, z_chunks
+        self.float_type = float_type                      # RectilinearGrid(GPU(), Float32; ...) of the reference (benchmarking/README.md:74)
 
     def library(self) -> abi.Library:
-        return abi.load_cuda_library()
+        return abi.load_cuda_library_f32() if self.float_type == "Float32" else abi.load_cuda_library()
 
 
 @dataclass

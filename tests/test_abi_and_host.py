@@ -172,3 +172,16 @@ def test_nan_checker_and_slices(oracle_arch):
     sim = bz.Simulation(model, Δt=0.1, stop_iteration=10)
     bz.run_(sim, nan_check_interval=1)
     assert model.clock["iteration"] == 3                              # the checker stopped the run before another step
+
+
+def test_float32_library_exports_the_same_entry_points():
+    """csrc/libbreeze_b200_f32.so (make_f32.py): every entry point of include/breeze_b200.h under the prefix bzf_; loading binds them all."""
+    from breeze_b200 import abi
+    lib = abi.load_cuda_library_f32()
+    assert lib.prefix == "bzf_" and lib.real is np.float32
+    for name in list(abi.abi_symbols()) + list(abi.cuda_only_symbols()):
+        assert hasattr(lib.dll, "bzf_" + name), name
+    assert lib.abi_version() == abi.BZ_ABI_VERSION
+    generated = os.path.join(ROOT, "breeze.jl_b200", "csrc", "f32", "stage_kernel.cuh")
+    code = [ln.split("//")[0] for ln in open(generated).read().split("\n")]
+    assert not any(re.search(r"\bdouble\b", ln) for ln in code)
