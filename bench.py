@@ -374,6 +374,58 @@ def bench_shipped_bubble(args):
     return out
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# Float32 build of the same path (libbreeze_b200_f32.so): the precision the reference benchmarks in by default (benchmarking/README.md:74)
+# ---------------------------------------------------------------------------------------------------------------------
+def bench_float32(args, N):
+    import torch
+    import breeze_b200 as bz
+    dev = int(os.environ.get("LOCAL_RANK", "0"))
+    grid = bz.RectilinearGrid(bz.B200(device=dev, float_type="Float32"), size=(N, N, N), x=(-10e3, 10e3), y=(-10e3, 10e3), z=(0, 10e3))
+    m = bz.AtmosphereModel(grid, dynamics=bz.AnelasticDynamics(bz.ReferenceState(grid, potential_temperature=300)), advection=bz.WENO(order=5))
+    m.set(θ=bubble)
+    ctx = m.context
+    ext_stream = torch.cuda.ExternalStream(ctx.stream())
+    for _ in range(3):
+        ctx.time_step(args.dt)
+    ctx.profile_enable(True)
+    for _ in range(10):
+        ctx.time_step(args.dt)
+    ctx.profile_read()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ctx.synchronize(); torch.cuda.synchronize()
+    e0.record(ext_stream)
+    for _ in range(10):
+        ctx.time_step(args.dt)
+    e1.record(ext_stream)
+    ctx.synchronize(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    fam_ms, fam_n = ctx.profile_read()
+    ctx.profile_enable(False)
+    peak, peak_src = measured_peak()
+    stage_ms = float(fam_ms[0]) / max(1, int(fam_n[0]))
+    bpc = STAGE_BYTES_PER_CELL / 2
+    achieved = bpc * N ** 3 / (stage_ms * 1e-3) / 1e9
+    # the same 64^3 bubble stepped by the Float64 CPU oracle: the declared Float32 tolerance of tests/test_gpu_float32.py, measured here
+    small = bubble_model(bz.B200(device=dev, float_type="Float32"), 64)
+    oracle_lib, _ = oracle_library()
+    ref = bubble_model(oracle_lib.CPUOracle(), 64)
+    for _ in range(5):
+        small.time_step(2.0); ref.time_step(2.0)
+    errs = {}
+    for n in ("ρθ", "ρu", "ρw"):
+        b = ref.field(n); a = small.field(n).astype(np.float64)
+        sc = max(float(np.abs(ref.field(k)).max()) for k in (("ρu", "ρv", "ρw") if n != "ρθ" else ("ρθ",)))
+        errs[n] = float(np.abs(a - b).max() / sc)
+    return {"value": N ** 3 / (ms * 1e-3) / 1e6, "unit": "Mcell-updates/s", "ms_per_step": ms, "steps": 10, "dtype": "f32",
+            "workload": f"3-D dry thermal bubble {N}^3, anelastic, WENO5, SSP-RK3, Float32, dt={args.dt}",
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "kernel": "stage_kernel (Float32 build: two CTAs per SM)", "kernel_ms": stage_ms, "bytes_per_cell": bpc, "peak_source": peak_src},
+            "breakdown_ms_per_step": {n: round(float(fam_ms[f]) / 10, 4) for f, n in enumerate(["stage_tendency_rk", "poisson_forward", "thomas", "poisson_inverse", "projection_halo"])},
+            "checks": {"finite": ctx.state_is_finite(), "max_abs_divergence": ctx.max_abs_divergence(),
+                       "vs_float64_oracle_64cubed_5_steps": {"max_rel": errs, "tol": 2e-5, "ok": bool(max(errs.values()) < 2e-5)}}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -710,6 +762,10 @@ def main():
                 out["config3_bomex"]["workload"] = c3["config"]["workload"]
             except Exception as e:
                 out["config3_bomex"] = {"error": str(e)}
+            try:
+                out["float32_mode"] = bench_float32(args, N)
+            except Exception as e:
+                out["float32_mode"] = {"error": str(e)}
             try:
                 out["shipped_scheme_weno9_static_energy"] = bench_shipped_bubble(args)
             except Exception as e:

@@ -371,7 +371,7 @@ _CUDA_LIB_F32 = None
 
 
 def cuda_library_path_f32() -> str:
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libbreeze_b200_f32.so")
+    return os.environ.get("BZ_F32_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libbreeze_b200_f32.so")   # BZ_F32_LIB: A/B of variant builds
 
 
 def load_cuda_library_f32() -> Library:

@@ -16,6 +16,23 @@
 #include <vector>
 
 #include "common.cuh"
+// launch bounds of the transforms (CTAs per SM): the register budget follows the word size of the library's real type.
+// Float32 sweep at 512^3 (profiles/r2s_f32_fft_launch_bounds.txt): (y, x) = (4, 3) 3.75 + 2.64, (5, 4) 3.54 + 2.65, (6, 5) 3.33 + 2.62,
+// (8, 6) 3.22 + 2.49 ms per step (forward + inverse).
+#ifdef BZ_F32
+#ifndef BZ_FFT_Y_MINB
+#define BZ_FFT_Y_MINB 8
+#endif
+#ifndef BZ_FFT_X_MINB
+#define BZ_FFT_X_MINB 6
+#endif
+#endif
+#ifndef BZ_FFT_Y_MINB
+#define BZ_FFT_Y_MINB 4
+#endif
+#ifndef BZ_FFT_X_MINB
+#define BZ_FFT_X_MINB 3
+#endif
 #include "stage_kernel.cuh"
 #include "stage_hi.cuh"
 #include "poisson.cuh"
@@ -303,8 +320,8 @@ static int setup_poisson(bz_ctx* c) {
         c->lines_y = lines;
         size_t sm = fft_smem_bytes(g.Ny, lines);
         FFT_DISPATCH(g.Ny, {
-            CUDA_TRY(c, cudaFuncSetAttribute(poisson_forward_y<FN, 256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-            CUDA_TRY(c, cudaFuncSetAttribute(poisson_inverse_y<FN, 256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            CUDA_TRY(c, cudaFuncSetAttribute(poisson_forward_y<FN, 256, BZ_FFT_Y_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            CUDA_TRY(c, cudaFuncSetAttribute(poisson_inverse_y<FN, 256, BZ_FFT_Y_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
         })
     }
     if (!L.flat_x) {
@@ -314,7 +331,7 @@ static int setup_poisson(bz_ctx* c) {
         while (lines & (lines - 1)) lines &= lines - 1;
         c->lines_x = lines;
         size_t sm = fft_smem_bytes(g.Nx, lines);
-        FFT_DISPATCH(g.Nx, { CUDA_TRY(c, cudaFuncSetAttribute(fft_x_kernel<FN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); })
+        FFT_DISPATCH(g.Nx, { CUDA_TRY(c, cudaFuncSetAttribute(fft_x_kernel<FN, 256, BZ_FFT_X_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); })
     }
     return setup_thomas(c);
 }
@@ -342,7 +359,7 @@ static int poisson_solve(bz_ctx* c, double dt) {
         if (!do_x || line1 <= line0) return;
         int lines = c->lines_x;
         size_t sm = fft_smem_bytes(G.Nx, lines);
-        FFT_DISPATCH(G.Nx, (fft_x_kernel<FN><<<(unsigned)((line1 - line0 + lines - 1) / lines), fft_threads(G.Nx, lines), sm, s>>>(G, c->W2, line1, c->tw_x, lines, inverse, peers, do_pull, (int)line0)));
+        FFT_DISPATCH(G.Nx, (fft_x_kernel<FN, 256, BZ_FFT_X_MINB><<<(unsigned)((line1 - line0 + lines - 1) / lines), fft_threads(G.Nx, lines), sm, s>>>(G, c->W2, line1, c->tw_x, lines, inverse, peers, do_pull, (int)line0)));
         c->launches++;
     };
     // ---- forward: source term + y transform (x-slab layout), transpose, x transform
@@ -353,7 +370,7 @@ static int poisson_solve(bz_ctx* c, double dt) {
                 int lines = c->lines_y;
                 dim3 grid((L.nx + 2 * lines - 1) / (2 * lines), L.Nz);
                 size_t sm = fft_smem_bytes(G.Ny, lines);
-                FFT_DISPATCH(G.Ny, (poisson_forward_y<FN, 256, 4><<<grid, fft_threads(G.Ny, lines), sm, c->stream>>>(L, G, U[0], U[1], U[2], dz_over_dt, c->W, c->tw_y, lines, 0)));
+                FFT_DISPATCH(G.Ny, (poisson_forward_y<FN, 256, BZ_FFT_Y_MINB><<<grid, fft_threads(G.Ny, lines), sm, c->stream>>>(L, G, U[0], U[1], U[2], dz_over_dt, c->W, c->tw_y, lines, 0)));
             } else {
                 dim3 grid((L.nx + 127) / 128, L.Nz);
                 poisson_pack_flat_y<<<grid, 128, 0, c->stream>>>(L, G, U[0], U[1], U[2], dz_over_dt, c->W);
@@ -374,7 +391,7 @@ static int poisson_solve(bz_ctx* c, double dt) {
             const int k0 = ch * kper, k1 = (k0 + kper < L.Nz) ? k0 + kper : L.Nz;
             if (k1 <= k0) break;
             dim3 grid((L.nx + 2 * lines - 1) / (2 * lines), k1 - k0);
-            FFT_DISPATCH(G.Ny, (poisson_forward_y<FN, 256, 4><<<grid, fft_threads(G.Ny, lines), sm, c->stream>>>(L, G, U[0], U[1], U[2], dz_over_dt, c->W, c->tw_y, lines, k0)));
+            FFT_DISPATCH(G.Ny, (poisson_forward_y<FN, 256, BZ_FFT_Y_MINB><<<grid, fft_threads(G.Ny, lines), sm, c->stream>>>(L, G, U[0], U[1], U[2], dz_over_dt, c->W, c->tw_y, lines, k0)));
             c->launches++;
             CUDA_TRY(c, cudaEventRecord(c->ev_chunk[ch], c->stream));
             CUDA_TRY(c, cudaStreamWaitEvent(c->s2, c->ev_chunk[ch], 0));
@@ -411,7 +428,7 @@ static int poisson_solve(bz_ctx* c, double dt) {
             int lines = c->lines_y;
             dim3 grid((L.nx + 2 * lines - 1) / (2 * lines), L.Nz);
             size_t sm = fft_smem_bytes(G.Ny, lines);
-            FFT_DISPATCH(G.Ny, (poisson_inverse_y<FN, 256, 4><<<grid, fft_threads(G.Ny, lines), sm, c->stream>>>(L, G, c->W, c->phi, c->tw_y, lines, scale, peers, pull ? 1 : 0, 0)));
+            FFT_DISPATCH(G.Ny, (poisson_inverse_y<FN, 256, BZ_FFT_Y_MINB><<<grid, fft_threads(G.Ny, lines), sm, c->stream>>>(L, G, c->W, c->phi, c->tw_y, lines, scale, peers, pull ? 1 : 0, 0)));
         } else {
             dim3 grid((L.nx + 127) / 128, L.Nz);
             poisson_unpack_flat_y<<<grid, 128, 0, c->stream>>>(L, G, c->W, c->phi, scale);
@@ -430,7 +447,7 @@ static int poisson_solve(bz_ctx* c, double dt) {
             int rc = comm_barrier(c->comm, c->s2, 1);                   // every rank has inverted its ky modes of chunk ch
             if (rc) { bz_set_error(c, "transpose: %s", c->comm.err); return rc; }
             dim3 grid((L.nx + 2 * lines - 1) / (2 * lines), k1 - k0);
-            FFT_DISPATCH(G.Ny, (poisson_inverse_y<FN, 256, 4><<<grid, fft_threads(G.Ny, lines), sm, c->s2>>>(L, G, c->W, c->phi, c->tw_y, lines, scale, peers, 1, k0)));
+            FFT_DISPATCH(G.Ny, (poisson_inverse_y<FN, 256, BZ_FFT_Y_MINB><<<grid, fft_threads(G.Ny, lines), sm, c->s2>>>(L, G, c->W, c->phi, c->tw_y, lines, scale, peers, 1, k0)));
             c->launches++;
         }
         CUDA_TRY(c, cudaEventRecord(c->ev_join, c->s2));
@@ -504,6 +521,7 @@ static int launch_stage_t(bz_ctx* c, const StageParams& P, int nz_chunks) {
     const int dev = c->cfg.device;
     if (dev < 0 || dev >= 64 || !configured[dev]) {
         CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SM)));
+        CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     dim3 grid((P.nx_u + TX - 1) / TX, (c->L.Ny + TY - 1) / TY, nz_chunks);
@@ -649,7 +667,7 @@ static int pressure_correct(bz_ctx* c, double dt) {
     if (!split) {
         {
             ProfScope ps(c, 4);
-            dim3 grid((L.nx + 127) / 128, L.Ny, L.Nz);
+            dim3 grid((L.nx + 128 * PROJ_ILP - 1) / (128 * PROJ_ILP), L.Ny, L.Nz);
             project_momentum<<<grid, 128, 0, c->stream>>>(L, c->col, U[0], U[1], U[2], c->phi, dt, wrap_x);
             c->launches++;
             CUDA_TRY(c, cudaGetLastError());

@@ -30,6 +30,17 @@
 #include <type_traits>
 
 #define RING 8
+#ifdef BZ_F32
+// Float32 build: the plane ring is half the size, so TWO CTAs fit an SM once role 1 stores ρq itself (no hand-over buffer: 114.6 KB per
+// CTA) and the kernel is compiled for 64 registers (no spills: a Float32 value is one register). Measured at 512^3
+// (profiles/r2r_f32_stage_variants.txt): 7.96 -> 7.20 ms per launch; the role-1 variant alone, at one CTA per SM, 8.26 ms.
+#ifndef BZ_STAGE_MINB
+#define BZ_STAGE_MINB 2
+#endif
+#ifndef BZ_ROLE1_STORES_Q
+#define BZ_ROLE1_STORES_Q 1
+#endif
+#endif
 #ifndef BZ_PLAIN_BARRIER
 #define BZ_SPLIT_BARRIER 1     // default: split level barrier (arrive after the x/y fluxes, wait before the tendency assembly)
 #endif
@@ -226,8 +237,11 @@ __device__ __forceinline__ double biased6c(double v0, double v1, double v2, doub
     return left ? v2 : v3;
 }
 
+#ifndef BZ_STAGE_MINB
+#define BZ_STAGE_MINB 1
+#endif
 template <int TX, int TY, bool HAS_Y, bool FLAT_X, int MICRO, bool FORCED>
-__global__ void __launch_bounds__(2 * TX * TY, 1) stage_kernel(const __grid_constant__ StageParams P) {
+__global__ void __launch_bounds__(2 * TX * TY, BZ_STAGE_MINB) stage_kernel(const __grid_constant__ StageParams P) {
     using SM = StageShared<TX, TY, HAS_Y>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     SM& S = *reinterpret_cast<SM*>(smem_raw);

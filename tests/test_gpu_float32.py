@@ -7,7 +7,7 @@ round-off, P-independent properties). Declared tolerances (relative to each fiel
   * set! + projection (pressure solve, velocities, θ, T)      : 2e-5   (the solve amplifies 6e-8 by the condition of the Poisson operator)
   * one tendency evaluation                                    : 5e-3   (θ ≈ 300 K: the WENO second differences of θ carry 300 · 6e-8 of noise)
   * five SSP-RK3 steps of the bubble, thermodynamic fields     : 1e-5
-  * five steps, momentum (relative to the largest component)   : 5e-3
+  * five steps, momentum (relative to the largest component)   : 2e-5
 """
 import numpy as np
 import pytest
@@ -17,7 +17,7 @@ from conftest import bubble_theta, make_bubble_model, rel_err, report
 pytestmark = pytest.mark.gpu
 
 PROGNOSTIC = ["ρu", "ρv", "ρw", "ρθ", "ρq"]
-TOL_HOOK, TOL_TENDENCY, TOL_THERMO, TOL_MOMENTUM = 2e-5, 5e-3, 1e-5, 5e-3
+TOL_HOOK, TOL_TENDENCY, TOL_THERMO, TOL_MOMENTUM = 2e-5, 5e-3, 1e-5, 2e-5      # measured 2e-6, 1.2e-3, 2e-6, 2e-6 (profiles/r2p_parity_errors_f32.txt)
 
 
 def _pair(oracle_arch, size, flat_y=False, seed=0, order=5, **kw):
