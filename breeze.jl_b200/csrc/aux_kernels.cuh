@@ -34,7 +34,13 @@ __global__ void halo_fill_periodic(Layout L, FieldSet F, int mode) {
 }
 
 // _pressure_correct_momentum! (src/AnelasticEquations/anelastic_time_stepping.jl:45-54), in place.
+// cells per thread of project_momentum: 4 in the Float32 build (3.51 -> 3.08 ms per step at 512^3), 1 in Float64 (4 measured 12 % slower:
+// 1.37 -> 1.53 ms per launch, profiles/r2t_launches_bench_512.txt against r2l)
+#ifdef BZ_F32
 #define PROJ_ILP 4
+#else
+#define PROJ_ILP 1
+#endif
 // wrap_x / the y wrap: the periodic images of φ are addressed directly, so φ needs no ghost fill on one GPU (across slabs, wrap_x = 0,
 // its first ghost column on the left is pulled from the neighbour).
 __global__ void project_momentum(Layout L, Columns col, double* __restrict__ ru, double* __restrict__ rv, double* __restrict__ rw,

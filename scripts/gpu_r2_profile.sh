@@ -8,7 +8,7 @@ if [[ "$2" == *tests* ]]; then
   (time timeout 900 python -m pytest tests -m gpu -q -p no:cacheprovider) > $OUT/${TAG}_pytest.log 2>&1; tail -n 6 $OUT/${TAG}_pytest.log
 fi
 (time timeout 600 python bench.py) > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo bench rc=$?; head -c 1500 $OUT/${TAG}_bench.json; echo
-timeout 360 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches_bench.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $OUT/${TAG}_ncu_bench.log 2>&1; echo launches rc=$?
+timeout 360 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches_bench.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-ensemble > $OUT/${TAG}_ncu_bench.log 2>&1; echo launches rc=$?
 reduce() {   # name: raw page always, SASS source page gzipped, report deleted
   ncu -i $OUT/$1.ncu-rep --page raw --csv > $OUT/$1_raw.csv 2>/dev/null
   ncu -i $OUT/$1.ncu-rep --page source --csv --print-source sass 2>/dev/null | gzip > $OUT/$1_source_sass.csv.gz
