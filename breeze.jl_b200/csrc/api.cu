@@ -83,6 +83,10 @@ struct bz_ctx {
     // on two copy streams (one per PCIe direction) so that a download and the upload that follows it run full duplex
     cudaStream_t s2 = nullptr;           // second compute stream: x-halo exchanges overlapped with the Poisson solve / the interior projection (slabs)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_chunk[8] = {};
+    int dma_transpose = 0;               // slabs: BZ_DMA_TRANSPOSE=1 runs the transposes as copy-engine transfers pipelined over z chunks; default: peer loads
+                                         // inside the transforms. Measured at 2 slabs of 512^3 (profiles/r2v_transpose_variants.txt): peer loads 29.86 ms per step;
+                                         // DMA with 1 / 2 / 4 / 8 chunks 31.57 / 30.45 / 30.00 / 30.52 — the copies do overlap the transforms, but they add a pass over
+                                         // W2 that the fused peer loads do not have
     int fft_z_chunks = 1;                // z chunks of the pipelined distributed transform (BZ_FFT_Z_CHUNKS). Measured at 2 slabs of 512^3
                                          // (profiles/r2j_fft_z_chunks.txt): 1 -> 29.73, 2 -> 29.77, 4 -> 30.25, 8 -> 30.79 ms per step — the pulls
                                          // already run at NVLink rate and do not overlap the next chunk's transform, so the default stays 1
@@ -337,11 +341,40 @@ static int setup_poisson(bz_ctx* c) {
 }
 
 // compute_pressure_correction! (anelastic_time_stepping.jl:26-39): momentum ghosts must be valid on entry.
-// Slabs with peer memory: the two transposes of the distributed transform are peer loads inside fft_x (forward) and inverse_y
-// (backward). With BZ_FFT_Z_CHUNKS > 1 both are pipelined over z chunks across the two streams: while the high-priority second stream
-// waits for every rank to have finished chunk c and pulls it over NVLink, the main stream already transforms chunk c + 1 (an experiment
-// that measured no gain, see bz_ctx::fft_z_chunks).
+// Slabs with peer memory: the two transposes of the distributed transform are peer LOADS inside the consuming transforms — fft_x
+// (forward) and inverse_y (backward) read the other ranks' spectra straight from their arenas, so a transpose costs no memory pass of
+// its own. Two alternatives are built in and measured slower (bz_ctx::dma_transpose, ::fft_z_chunks): pipelining those pulls over z
+// chunks across the two streams, and BZ_DMA_TRANSPOSE=1 — per chunk, the second stream waits for every rank (flag barrier), moves the
+// chunk with the copy engines (transpose_chunk_dma) and runs the consuming transform while the main stream transforms the next chunk.
 #define FFT_Z_CHUNKS_MAX 8
+
+// One z chunk [k0, k1) of a transpose of the distributed transform as copy-engine transfers between the peer-blocked layouts (poisson.cuh):
+//   forward : my W2 block p  <-  rank p's W  block `me` (my ky modes of p's columns)
+//   backward: my W  block p  <-  rank p's W2 block `me` (p's ky modes of my columns)
+// Every block's chunk is one contiguous run, so a transpose is n_ranks cudaMemcpyAsync calls; the DMA engines move them over NVLink while
+// the SMs transform the next chunk.
+static int transpose_chunk_dma(bz_ctx* c, bool forward, int k0, int k1, cudaStream_t s) {
+    const PoissonGeom& G = c->PG;
+    const int P = c->comm.n_ranks, me = c->comm.rank, nx = c->L.nx;
+    int st_me, cnt_me; ky_block(G.nky, P, me, &st_me, &cnt_me);
+    for (int q = 0; q < P; ++q) {
+        const int p = (me + q) % P;                                   // start with the local block, then spread the peers round-robin
+        int st_p, cnt_p; ky_block(G.nky, P, p, &st_p, &cnt_p);
+        const double2* src; double2* dst; size_t count;
+        if (forward) {
+            count = (size_t)(k1 - k0) * cnt_me * nx;
+            src = reinterpret_cast<const double2*>(c->comm.peer_base[p] + c->off_W) + (size_t)st_me * nx * G.Nz + (size_t)k0 * cnt_me * nx;
+            dst = c->W2 + (size_t)p * G.Nz * cnt_me * nx + (size_t)k0 * cnt_me * nx;
+        } else {
+            count = (size_t)(k1 - k0) * cnt_p * nx;
+            src = reinterpret_cast<const double2*>(c->comm.peer_base[p] + c->off_W2) + (size_t)me * G.Nz * cnt_p * nx + (size_t)k0 * cnt_p * nx;
+            dst = c->W + (size_t)st_p * nx * G.Nz + (size_t)k0 * cnt_p * nx;
+        }
+        if (count) CUDA_TRY(c, cudaMemcpyAsync(dst, src, count * sizeof(double2), cudaMemcpyDeviceToDevice, s));
+    }
+    return BZ_OK;
+}
+
 static int poisson_solve(bz_ctx* c, double dt) {
     const Layout& L = c->L;
     const PoissonGeom& G = c->PG;
@@ -354,6 +387,7 @@ static int poisson_solve(bz_ctx* c, double dt) {
     const bool do_x = !L.flat_x;
     int nch = 1;
     if (pull && c->overlap && do_x) { nch = c->fft_z_chunks; if (nch > L.Nz / 8) nch = L.Nz / 8; if (nch < 1) nch = 1; }
+    const bool chunked = nch > 1 || (pull && c->overlap && do_x && c->dma_transpose);
     const int kper = (L.Nz + nch - 1) / nch;
     auto launch_fft_x = [&](int inverse, int do_pull, long long line0, long long line1, cudaStream_t s) {
         if (!do_x || line1 <= line0) return;
@@ -363,7 +397,7 @@ static int poisson_solve(bz_ctx* c, double dt) {
         c->launches++;
     };
     // ---- forward: source term + y transform (x-slab layout), transpose, x transform
-    if (nch == 1) {
+    if (!chunked) {
         {
             ProfScope ps(c, 1);
             if (!L.flat_y) {
@@ -397,7 +431,8 @@ static int poisson_solve(bz_ctx* c, double dt) {
             CUDA_TRY(c, cudaStreamWaitEvent(c->s2, c->ev_chunk[ch], 0));
             int rc = comm_barrier(c->comm, c->s2, 1);                   // every rank has transformed chunk ch
             if (rc) { bz_set_error(c, "transpose: %s", c->comm.err); return rc; }
-            launch_fft_x(0, 1, (long long)k0 * G.nky_loc, (long long)k1 * G.nky_loc, c->s2);
+            if (c->dma_transpose && (rc = transpose_chunk_dma(c, true, k0, k1, c->s2))) return rc;
+            launch_fft_x(0, c->dma_transpose ? 0 : 1, (long long)k0 * G.nky_loc, (long long)k1 * G.nky_loc, c->s2);
         }
         CUDA_TRY(c, cudaEventRecord(c->ev_join, c->s2));
         CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
@@ -416,7 +451,7 @@ static int poisson_solve(bz_ctx* c, double dt) {
     }
     // ---- inverse: x transform, transpose back, y transform → φ
     const double scale = 1.0 / ((L.flat_x ? 1.0 : (double)G.Nx) * (L.flat_y ? 1.0 : (double)G.Ny));
-    if (nch == 1) {
+    if (!chunked) {
         if (n_lines > 0) { ProfScope ps(c, 3); launch_fft_x(1, 0, 0, n_lines, c->stream); }
         if (c->comm.n_ranks > 1) {
             ProfScope ps(c, 5);
@@ -446,8 +481,9 @@ static int poisson_solve(bz_ctx* c, double dt) {
             CUDA_TRY(c, cudaStreamWaitEvent(c->s2, c->ev_chunk[ch], 0));
             int rc = comm_barrier(c->comm, c->s2, 1);                   // every rank has inverted its ky modes of chunk ch
             if (rc) { bz_set_error(c, "transpose: %s", c->comm.err); return rc; }
+            if (c->dma_transpose && (rc = transpose_chunk_dma(c, false, k0, k1, c->s2))) return rc;
             dim3 grid((L.nx + 2 * lines - 1) / (2 * lines), k1 - k0);
-            FFT_DISPATCH(G.Ny, (poisson_inverse_y<FN, 256, BZ_FFT_Y_MINB><<<grid, fft_threads(G.Ny, lines), sm, c->s2>>>(L, G, c->W, c->phi, c->tw_y, lines, scale, peers, 1, k0)));
+            FFT_DISPATCH(G.Ny, (poisson_inverse_y<FN, 256, BZ_FFT_Y_MINB><<<grid, fft_threads(G.Ny, lines), sm, c->s2>>>(L, G, c->W, c->phi, c->tw_y, lines, scale, peers, c->dma_transpose ? 0 : 1, k0)));
             c->launches++;
         }
         CUDA_TRY(c, cudaEventRecord(c->ev_join, c->s2));
@@ -835,6 +871,8 @@ int bz_create(const bz_config* cfg, bz_ctx** out) {
         TRYCUDA(cudaStreamCreateWithPriority(&c->s2, cudaStreamNonBlocking, hi));
     }
     for (int e = 0; e < 8; ++e) TRYCUDA(cudaEventCreateWithFlags(&c->ev_chunk[e], cudaEventDisableTiming));
+    if (const char* e = getenv("BZ_DMA_TRANSPOSE")) c->dma_transpose = atoi(e) ? 1 : 0;
+    c->fft_z_chunks = c->dma_transpose ? 4 : 1;
     if (const char* e = getenv("BZ_FFT_Z_CHUNKS")) { int v = atoi(e); if (v >= 1 && v <= FFT_Z_CHUNKS_MAX) c->fft_z_chunks = v; }
     TRYCUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     TRYCUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));

@@ -29,9 +29,10 @@ if [[ $LEGS == *ab* ]]; then
   run packed_serial BZ_NO_OVERLAP=1
 fi
 if [[ $LEGS == *chunks* ]]; then
-  run zchunks1 BZ_FFT_Z_CHUNKS=1
-  run zchunks2 BZ_FFT_Z_CHUNKS=2
-  run zchunks8 BZ_FFT_Z_CHUNKS=8
+  run dma_chunks1 BZ_FFT_Z_CHUNKS=1
+  run dma_chunks2 BZ_FFT_Z_CHUNKS=2
+  run dma_chunks8 BZ_FFT_Z_CHUNKS=8
+  run pull_chunks1 BZ_DMA_TRANSPOSE=0
 fi
 if [[ $LEGS == *r1style* ]]; then
   run nccl_serial_direct BZ_NO_OVERLAP=1 BZ_NCCL_BARRIER=1 BZ_DIRECT_PULL=1
