@@ -182,6 +182,8 @@ def test_float32_library_exports_the_same_entry_points():
     for name in list(abi.abi_symbols()) + list(abi.cuda_only_symbols()):
         assert hasattr(lib.dll, "bzf_" + name), name
     assert lib.abi_version() == abi.BZ_ABI_VERSION
+    declared = _declared_symbols("breeze_b200_f32.h", "bzf_")           # include/breeze_b200_f32.h declares exactly what is exported
+    assert set(declared) == {"bzf_" + n for n in list(abi.abi_symbols()) + list(abi.cuda_only_symbols())}
     generated = os.path.join(ROOT, "breeze.jl_b200", "csrc", "f32", "stage_kernel.cuh")
     code = [ln.split("//")[0] for ln in open(generated).read().split("\n")]
     assert not any(re.search(r"\bdouble\b", ln) for ln in code)
