@@ -96,6 +96,100 @@ def test_slab_logic_world_size_2():
     assert all(msg == "ok" for _, msg in results), results
 
 
+def _flat_worker(rank, world, port, q):
+    """The peer-blocked flat layouts and the chunked transposes exactly as api.cu issues them (transpose_chunk_dma): every rank exposes its
+    flat W / W2 to the others (all_gather stands in for the mapped peer arenas) and PULLS the contiguous runs of the plan."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from breeze_b200 import slab
+        Nx, Ny, Nz, chunks = 24, 12, 7, 3                                # nky = 7: uneven ky blocks (4 + 3 over two ranks, 3 + 2 + 2 over three)
+        rng = np.random.default_rng(1)
+        full = rng.standard_normal((Nz, Ny, Nx))
+        i0, nx = slab.slab(Nx, world, rank)
+        Wy = np.fft.rfft(full[:, :, i0:i0 + nx], axis=1)                 # [k, ky, i_local]
+        nky = Wy.shape[1]
+        ky0, nky_loc = slab.split_range(nky, world, rank)
+        # my flat W in the peer-blocked layout
+        W = np.zeros(nx * nky * Nz, dtype=np.complex128)
+        for k in range(Nz):
+            for ky in range(nky):
+                o = slab.w_offset(nky, world, nx, Nz, k, ky, 0)
+                W[o:o + nx] = Wy[k, ky]
+        def gather(flat, n):
+            t = torch.zeros(n, dtype=torch.complex128); t[:flat.size] = torch.from_numpy(flat)
+            parts = [torch.zeros(n, dtype=torch.complex128) for _ in range(world)]
+            dist.all_gather(parts, t)
+            return [p_.numpy() for p_ in parts]
+        n_w2_max = Nx * max(slab.split_range(nky, world, r)[1] for r in range(world)) * Nz
+        peers_W = gather(W, W.size)
+        W2 = np.zeros(Nx * nky_loc * Nz, dtype=np.complex128)
+        kper = -(-Nz // chunks)
+        for ch in range(chunks):                                         # forward transpose, chunk by chunk
+            k0, k1 = ch * kper, min(Nz, (ch + 1) * kper)
+            for peer, src, dst, count in slab.transpose_chunk_plan(True, nky, world, rank, nx, Nz, k0, k1):
+                W2[dst:dst + count] = peers_W[peer][src:src + count]
+        ref = np.fft.rfft(full, axis=1)                                  # [k, ky, x_global]
+        for k in range(Nz):
+            for kyl in range(nky_loc):
+                for kx in range(Nx):
+                    assert W2[slab.w2_offset(nky_loc, nx, Nz, k, kyl, kx)] == ref[k, ky0 + kyl, kx]
+        # x transform in the transposed layout, then the backward transpose and the inverse y transform reproduce the slab
+        W2x = W2.copy()
+        for k in range(Nz):
+            for kyl in range(nky_loc):
+                idx = [slab.w2_offset(nky_loc, nx, Nz, k, kyl, kx) for kx in range(Nx)]
+                W2x[idx] = np.fft.ifft(np.fft.fft(W2[idx]))
+        peers_W2 = gather(W2x, n_w2_max)
+        Wb = np.zeros_like(W)
+        for ch in range(chunks):
+            k0, k1 = ch * kper, min(Nz, (ch + 1) * kper)
+            for peer, src, dst, count in slab.transpose_chunk_plan(False, nky, world, rank, nx, Nz, k0, k1):
+                Wb[dst:dst + count] = peers_W2[peer][src:src + count]
+        assert np.allclose(Wb, W, rtol=1e-13, atol=1e-13)
+        # packed x faces (comm.cuh pack_faces_both / unpack_faces_both): my right ghosts are the right neighbour's side 0
+        H, nf = 2, 3
+        fields = rng.standard_normal((nf, Nz, Ny, Nx))
+        mine = fields[:, :, :, i0:i0 + nx]
+        buf = np.zeros(2 * nf * H * Ny * Nz)
+        for side in (0, 1):
+            for f in range(nf):
+                for k in range(Nz):
+                    for j in range(Ny):
+                        for c in range(H):
+                            buf[slab.packed_face_index(nf, H, Ny, Nz, side, f, k, j, c)] = mine[f, k, j, (0 if side == 0 else nx - H) + c]
+        t = torch.from_numpy(buf); parts = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(parts, t)
+        right, left = parts[(rank + 1) % world].numpy(), parts[(rank - 1) % world].numpy()
+        for f in range(nf):
+            for k in (0, Nz - 1):
+                for j in (0, Ny - 1):
+                    for c in range(H):
+                        assert right[slab.packed_face_index(nf, H, Ny, Nz, 0, f, k, j, c)] == fields[f, k, j, (i0 + nx + c) % Nx]
+                        assert left[slab.packed_face_index(nf, H, Ny, Nz, 1, f, k, j, c)] == fields[f, k, j, (i0 - H + c) % Nx]
+        q.put((rank, "ok"))
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        q.put((rank, traceback.format_exc()[-600:]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_peer_blocked_layouts_and_chunked_transposes(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000 + world
+    procs = [ctx.Process(target=_flat_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(msg == "ok" for _, msg in results), results
+
+
 def test_split_range_partitions():
     sys.path.insert(0, ROOT)
     from breeze_b200 import slab
