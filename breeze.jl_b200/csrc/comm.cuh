@@ -61,8 +61,6 @@ struct Comm {
     char err[256] = {};
 };
 
-struct PeerPtrs { const char* base[8]; };
-
 #define NCCL_TRY(cm, call)                                                                                  \
     do {                                                                                                    \
         int r_ = (call);                                                                                    \
