@@ -24,6 +24,11 @@
 #else
 #define BZ_REAL_EPS 2.220446049250313e-16
 #endif
+// Float32 library: the stage kernel reconstructs its WENO5-Z fluxes two at a time in f32x2 registers (weno.cuh weno5z_x2; 7.19 -> 6.60 ms
+// per 512^3 launch, profiles/r2l_f32_packed.txt). -DBZ_F32_SCALAR rebuilds the one-at-a-time form.
+#if defined(BZ_F32) && !defined(BZ_F32_SCALAR) && !defined(BZ_F32_PACKED)
+#define BZ_F32_PACKED 1
+#endif
 #define NPROG 5
 #define NFAM 8
 

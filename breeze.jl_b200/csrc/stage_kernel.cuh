@@ -493,6 +493,52 @@ __global__ void __launch_bounds__(2 * TX * TY, BZ_STAGE_MINB) stage_kernel(const
                     return rho_ft * w_top * bz(ZS(kind, -2), ZS(kind, -1), ZS(kind, 0), ZS(kind, 1), ZS(kind, 2), ZS(kind, 3), Rf_top, positive(w_top));
                 }
             };
+#ifdef BZ_F32_PACKED
+            // Packed Float32 pairs (weno.cuh weno5z_x2): the x / y fluxes of a role are reconstructed two at a time. x_rec / y_rec gather what
+            // x_flux / y_flux feed into their reconstruction — the advecting factor and the five values selected by its sign.
+            struct Rec6 { float adv, a, b, c, d, e; };
+            auto mk = [](float adv, float v0, float v1, float v2, float v3, float v4, float v5, bool left) -> Rec6 {
+                return Rec6{adv, left ? v0 : v5, left ? v1 : v4, left ? v2 : v3, left ? v3 : v2, left ? v4 : v1};
+            };
+            auto x_rec = [&](auto kind_tag, const float* cell, int zoff) -> Rec6 {
+                constexpr int kind = decltype(kind_tag)::value;
+                const float u_i = XS(0, 0);
+                float ut;
+                if (kind == 0) ut = rho_k * sym4(XS(0, -2), XS(0, -1), u_i, XS(0, 1), 2);
+                else if (kind == 1) ut = HAS_Y ? rho_k * sym4(cell[-2 * SW], cell[-SW], u_i, cell[SW], 2) : rho_k * u_i;
+                else if (kind == 2) ut = (!FULL && k < 1) ? 0.0f : sz(r_m2 * Lp[0][zoff], r_m1 * Lp[1][zoff], rho_k * u_i, r_p1 * Lp[3][zoff], Rf_k2);
+                else ut = rho_k * u_i;
+                return mk(ut, XS(kind, -3), XS(kind, -2), XS(kind, -1), XS(kind, 0), XS(kind, 1), XS(kind, 2), positive(kind >= 3 ? u_i : ut));
+            };
+            auto y_rec = [&](auto kind_tag, const float* row, int zoff) -> Rec6 {
+                constexpr int kind = decltype(kind_tag)::value;
+                const float v_j = YS(1, 0);
+                float vt;
+                if (kind == 0) vt = FLAT_X ? rho_k * v_j : rho_k * sym4(row[PL - 2], row[PL - 1], v_j, row[PL + 1], 2);
+                else if (kind == 1) vt = rho_k * sym4(YS(1, -2), YS(1, -1), v_j, YS(1, 1), 2);
+                else if (kind == 2) vt = (!FULL && k < 1) ? 0.0f : sz(r_m2 * Lp[0][PL + zoff], r_m1 * Lp[1][PL + zoff], rho_k * v_j, r_p1 * Lp[3][PL + zoff], Rf_k2);
+                else vt = rho_k * v_j;
+                return mk(vt, YS(kind, -3), YS(kind, -2), YS(kind, -1), YS(kind, 0), YS(kind, 1), YS(kind, 2), positive(kind >= 3 ? v_j : vt));
+            };
+            // z pairs only in the interior-level instantiation (FULL): there every z reconstruction is the full-order one
+            auto z_rec = [&](auto kind_tag) -> Rec6 {
+                constexpr int kind = decltype(kind_tag)::value;
+                const float w_top = Lt[2 * PL];
+                float wt;
+                if (kind == 0) wt = rho_ft * sym4(Lt[2 * PL - 2], Lt[2 * PL - 1], w_top, Lt[2 * PL + 1], 2);
+                else if (kind == 1) wt = rho_ft * sym4(Lt[2 * PL - 2 * SW], Lt[2 * PL - SW], w_top, Lt[2 * PL + SW], 2);
+                else wt = rho_ft * w_top;
+                return mk(wt, ZS(kind, -2), ZS(kind, -1), ZS(kind, 0), ZS(kind, 1), ZS(kind, 2), ZS(kind, 3), positive(kind >= 3 ? w_top : wt));
+            };
+            auto pair_flux = [](const Rec6& A, const Rec6& B, float& fa, float& fb) {
+                float ra, rb;
+                upk2(weno5z_x2(pk2(A.a, B.a), pk2(A.b, B.b), pk2(A.c, B.c), pk2(A.d, B.d), pk2(A.e, B.e)), ra, rb);
+                fa = A.adv * ra; fb = B.adv * rb;
+            };
+            constexpr bool PACKED = HAS_Y && !FLAT_X;
+#else
+            constexpr bool PACKED = false;
+#endif
             using K0 = std::integral_constant<int, 0>; using K1 = std::integral_constant<int, 1>; using K2 = std::integral_constant<int, 2>;
             using K3 = std::integral_constant<int, 3>; using K4 = std::integral_constant<int, 4>;
             const double* const edge = Lk + (TY - ty) * SW;               // the row of y-faces just above the tile
@@ -523,8 +569,16 @@ __global__ void __launch_bounds__(2 * TX * TY, BZ_STAGE_MINB) stage_kernel(const
 #endif
             if (PHASE == 0) {
                 if (role == 0) {
+#ifdef BZ_F32_PACKED
+                    if (PACKED) {       // six reconstructions as three packed pairs
+                        float fa, fb;
+                        pair_flux(x_rec(K0{}, Lk, 0), x_rec(K1{}, Lk, 0), fa, fb); FX[0][ty][tx] = fa; FX[1][ty][tx] = fb;
+                        pair_flux(x_rec(K3{}, Lk, 0), y_rec(K0{}, Lk, 0), fa, fb); FX[3][ty][tx] = fa; FY[0][ty][tx] = fb;
+                        pair_flux(y_rec(K1{}, Lk, 0), y_rec(K3{}, Lk, 0), fa, fb); FY[1][ty][tx] = fa; FY[3][ty][tx] = fb;
+                    }
+#endif
                     if (!FLAT_X) {
-                        FX[0][ty][tx] = x_flux(K0{}, Lk, 0); FX[1][ty][tx] = x_flux(K1{}, Lk, 0); FX[3][ty][tx] = x_flux(K3{}, Lk, 0);
+                        if (!PACKED) { FX[0][ty][tx] = x_flux(K0{}, Lk, 0); FX[1][ty][tx] = x_flux(K1{}, Lk, 0); FX[3][ty][tx] = x_flux(K3{}, Lk, 0); }
                         if (!BALANCED && lane < TY) {
                             if (wrp == XE0) FX[0][lane][TX] = x_flux(K0{}, xedge, xoff);
                             else if (wrp == XE0 + 1) FX[1][lane][TX] = x_flux(K1{}, xedge, xoff);
@@ -532,7 +586,7 @@ __global__ void __launch_bounds__(2 * TX * TY, BZ_STAGE_MINB) stage_kernel(const
                         }
                     }
                     if (HAS_Y) {
-                        FY[0][ty][tx] = y_flux(K0{}, Lk, 0); FY[1][ty][tx] = y_flux(K1{}, Lk, 0); FY[3][ty][tx] = y_flux(K3{}, Lk, 0);
+                        if (!PACKED) { FY[0][ty][tx] = y_flux(K0{}, Lk, 0); FY[1][ty][tx] = y_flux(K1{}, Lk, 0); FY[3][ty][tx] = y_flux(K3{}, Lk, 0); }
                         // the extra row of y-faces above the tile: one flux kind per warp (rows 0..2 of this role)
                         if (!BALANCED) {
                             if (ty == 0) FY[0][TY][tx] = y_flux(K0{}, edge, ezoff);
@@ -544,8 +598,15 @@ __global__ void __launch_bounds__(2 * TX * TY, BZ_STAGE_MINB) stage_kernel(const
 #ifdef BZ_BALANCED_STORES
                     zt2 = z_flux(K4{}); S.fz[k & 1][ty][tx] = zt2 - zb2;      // ρq is stored by role 0
 #endif
+#ifdef BZ_F32_PACKED
+                    if (PACKED) {       // four reconstructions as two packed pairs
+                        float fa, fb;
+                        pair_flux(x_rec(K2{}, Lk, 0), x_rec(K4{}, Lk, 0), fa, fb); FX[2][ty][tx] = fa; FX[4][ty][tx] = fb;
+                        pair_flux(y_rec(K2{}, Lk, 0), y_rec(K4{}, Lk, 0), fa, fb); FY[2][ty][tx] = fa; FY[4][ty][tx] = fb;
+                    }
+#endif
                     if (!FLAT_X) {
-                        FX[2][ty][tx] = x_flux(K2{}, Lk, 0); FX[4][ty][tx] = x_flux(K4{}, Lk, 0);
+                        if (!PACKED) { FX[2][ty][tx] = x_flux(K2{}, Lk, 0); FX[4][ty][tx] = x_flux(K4{}, Lk, 0); }
                         if (BALANCED) {
                             // x-edge column: warp 0 takes kinds 0..3 (lane = kind * TY + row), warp 1 takes kind 4
                             if (wrp == 0 || (wrp == 1 && lane < TY)) {
@@ -559,7 +620,7 @@ __global__ void __launch_bounds__(2 * TX * TY, BZ_STAGE_MINB) stage_kernel(const
                         }
                     }
                     if (HAS_Y) {
-                        FY[2][ty][tx] = y_flux(K2{}, Lk, 0); FY[4][ty][tx] = y_flux(K4{}, Lk, 0);
+                        if (!PACKED) { FY[2][ty][tx] = y_flux(K2{}, Lk, 0); FY[4][ty][tx] = y_flux(K4{}, Lk, 0); }
                         if (BALANCED) {                      // y-edge row: one kind per warp, warps 2..6
                             if (ty == 2) FY[0][TY][tx] = y_flux(K0{}, edge, ezoff);
                             else if (ty == 3) FY[1][TY][tx] = y_flux(K1{}, edge, ezoff);
@@ -573,12 +634,25 @@ __global__ void __launch_bounds__(2 * TX * TY, BZ_STAGE_MINB) stage_kernel(const
                     }
                 }
             } else {
-                if (role == 0) { zt0 = z_flux(K0{}); zt1 = z_flux(K1{}); }
-                else {
+#ifdef BZ_F32_PACKED
+                constexpr bool PACKED_Z = PACKED && FULL;
+#else
+                constexpr bool PACKED_Z = false;
+#endif
+                if (role == 0) {
+#ifdef BZ_F32_PACKED
+                    if (PACKED_Z) pair_flux(z_rec(K0{}), z_rec(K1{}), zt0, zt1);
+#endif
+                    if (!PACKED_Z) { zt0 = z_flux(K0{}); zt1 = z_flux(K1{}); }
+                } else {
 #ifdef BZ_BALANCED_STORES
                     zt0 = z_flux(K2{}); zt1 = z_flux(K3{});
 #else
-                    zt0 = z_flux(K2{}); zt1 = z_flux(K3{}); zt2 = z_flux(K4{});
+                    zt0 = z_flux(K2{});
+#ifdef BZ_F32_PACKED
+                    if (PACKED_Z) pair_flux(z_rec(K3{}), z_rec(K4{}), zt1, zt2);
+#endif
+                    if (!PACKED_Z) { zt1 = z_flux(K3{}); zt2 = z_flux(K4{}); }
 #endif
                     if (MICRO == BZ_THERMO_STATIC_ENERGY) {
                         // the ρe tendency needs the buoyancy at k-1, k, k+1 (static_energy_tendency.jl:60-63): evaluate it one level ahead

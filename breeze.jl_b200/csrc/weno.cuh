@@ -102,6 +102,38 @@ __device__ __forceinline__ double weno5z(double a, double b, double c, double d,
 }
 #endif
 
+#ifdef BZ_F32_PACKED
+// Packed Float32 pair: TWO independent left-biased WENO5-Z reconstructions of one thread evaluated in f32x2 registers (Blackwell's
+// add / mul / fma.rn.f32x2: two results per lane and instruction at the issue cost of one — scripts/ubench/fp32_rate.cu measured 2.11 cycles
+// per FFMA2 warp instruction against 1.38 per FFMA). The Float32 stage kernel is issue-bound, so halving the arithmetic issue slots of a
+// pair is the lever; the reciprocals stay scalar (MUFU). Same ratio form as the scalar Float32 weno5z above.
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pk2(float x, float y) { f32x2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y)); return r; }
+__device__ __forceinline__ void upk2(f32x2_t v, float& x, float& y) { asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v)); }
+__device__ __forceinline__ f32x2_t fma2(f32x2_t a, f32x2_t b, f32x2_t c) { f32x2_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2_t mul2(f32x2_t a, f32x2_t b) { f32x2_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2_t add2(f32x2_t a, f32x2_t b) { f32x2_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2_t sub2(f32x2_t a, f32x2_t b) { f32x2_t d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2_t rcp2(f32x2_t a) { float x, y; upk2(a, x, y); return pk2(fast_rcp(x), fast_rcp(y)); }
+__device__ __forceinline__ f32x2_t cst2(float c) { return pk2(c, c); }
+// (a, b, c, d, e) of reconstruction A in the .x halves, of reconstruction B in the .y halves; returns (value A, value B)
+__device__ __forceinline__ f32x2_t weno5z_x2(f32x2_t a, f32x2_t b, f32x2_t c, f32x2_t d, f32x2_t e) {
+    const f32x2_t M2 = cst2(-2.0f), M4 = cst2(-4.0f), P3 = cst2(3.0f), K = cst2(13.0f / 3.0f), EPSP = cst2((float)(WENO_EPS / 0.75)), ONE = cst2(1.0f);
+    f32x2_t s0 = add2(fma2(M2, d, c), e), t0 = fma2(P3, c, fma2(M4, d, e));
+    f32x2_t s1 = add2(fma2(M2, c, b), d), t1 = sub2(b, d);
+    f32x2_t s2 = add2(fma2(M2, b, a), c), t2 = fma2(P3, c, fma2(M4, b, a));
+    f32x2_t b0 = fma2(mul2(s0, K), s0, fma2(t0, t0, EPSP));
+    f32x2_t b1 = fma2(mul2(s1, K), s1, fma2(t1, t1, EPSP));
+    f32x2_t b2 = fma2(mul2(s2, K), s2, fma2(t2, t2, EPSP));
+    f32x2_t tau = sub2(b0, b2);
+    f32x2_t r0 = mul2(tau, rcp2(b0)), r1 = mul2(tau, rcp2(b1)), r2 = mul2(tau, rcp2(b2));
+    f32x2_t a0 = mul2(cst2(0.3f), fma2(r0, r0, ONE)), a1 = mul2(cst2(0.6f), fma2(r1, r1, ONE)), a2 = mul2(cst2(0.1f), fma2(r2, r2, ONE));
+    f32x2_t rs = rcp2(add2(add2(a0, a1), a2));
+    f32x2_t qc = fma2(cst2(-1.0f / 6.0f), b, fma2(cst2(5.0f / 6.0f), c, mul2(cst2(1.0f / 3.0f), d)));
+    return fma2(mul2(mul2(a0, rs), cst2(1.0f / 6.0f)), sub2(s1, s0), fma2(mul2(mul2(a2, rs), cst2(1.0f / 3.0f)), sub2(s2, s1), qc));
+}
+#endif
+
 // WENO3-Z: left-biased value at the face between b and c from a b | c.
 #ifdef BZ_F32
 __device__ __forceinline__ double weno3z(double a, double b, double c) {      // ratio form (range, as for weno5z)
