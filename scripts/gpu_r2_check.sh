@@ -1,8 +1,8 @@
 #!/bin/bash
-# Round-2 GPU-box call: parity suite with the measured errors logged, library variants A/B, FFT launch-shape sweep, bench line.
-#   gpurun --timeout 1500 -- 'bash scripts/gpu_r2_check.sh TAG [legs]'      legs: any of  tests variants fft bench ncu  (default: all but ncu)
+# Round-2 GPU-box call: parity suite with the measured errors logged, library variants A/B, bench line + reference arm.
+#   gpurun --timeout 1500 -- 'bash scripts/gpu_r2_check.sh TAG [legs]'      legs: any of  tests variants bench ncu  (default: all but ncu)
 TAG=${1:-r2}
-LEGS=${2:-"tests variants fft bench"}
+LEGS=${2:-"tests variants bench"}
 OUT=gpurun_out
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/${TAG}_smi.txt 2>&1
@@ -15,10 +15,6 @@ fi
 if [[ $LEGS == *variants* ]] && ls breeze.jl_b200/csrc/variants/*.so >/dev/null 2>&1; then
   timeout 420 python scripts/variant_bench.py $(ls breeze.jl_b200/csrc/variants/*.so) --steps 5 > $OUT/${TAG}_variants.log 2>&1
   cat $OUT/${TAG}_variants.log | tail -n 8
-fi
-if [[ $LEGS == *fft* ]]; then
-  timeout 420 python scripts/fft_sweep.py --steps 5 > $OUT/${TAG}_fft_sweep.log 2>&1
-  cat $OUT/${TAG}_fft_sweep.log | tail -n 10
 fi
 if [[ $LEGS == *bench* ]]; then
   ( time timeout 600 python bench.py ) > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
