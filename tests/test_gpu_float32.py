@@ -8,6 +8,8 @@ round-off, P-independent properties). Declared tolerances (relative to each fiel
   * one tendency evaluation                                    : 5e-3   (θ ≈ 300 K: the WENO second differences of θ carry 300 · 6e-8 of noise)
   * five SSP-RK3 steps of the bubble, thermodynamic fields     : 1e-5
   * five steps, momentum (relative to the largest component)   : 2e-5
+  * BOMEX with cloud / StaticEnergy bubble, five steps         : thermodynamic fields 1e-5, momentum 2e-5 of the largest component,
+    cloud liquid 5e-3 of its maximum (measured 4e-7, 5e-7 / 4e-6, 2.4e-4: profiles/r2z_parity_errors_f32_forced_moist.txt)
 """
 import numpy as np
 import pytest
@@ -116,3 +118,49 @@ def test_float32_512_cubed_properties():
     assert abs(rt.sum() - s0) < 1e-6 * abs(s0)
     assert np.abs(m.field("w")).max() > 1e-3
     assert m.context.max_abs_divergence() < 1e-6
+
+
+def test_bomex_with_cloud_matches_oracle(oracle_arch):
+    """Forced + moist instantiation of the Float32 stage kernel (FPlane, subsidence, geostrophic, drying / cooling, flux BCs, saturation
+    adjustment with its secant branch active): five steps of the BOMEX case against the FP64 oracle."""
+    import breeze_b200 as bz
+    gpu = bz.cases.bomex_model(bz.B200(float_type="Float32"), size=(32, 16, 30), extent=3200.0, cloud=True)
+    cpu = bz.cases.bomex_model(oracle_arch, size=(32, 16, 30), extent=3200.0, cloud=True)
+    for _ in range(5):
+        gpu.time_step(1.0)
+        cpu.time_step(1.0)
+    for name in ("ρθ", "ρq", "θ", "T"):
+        assert rel_err(gpu.field(name).astype(np.float64), cpu.field(name)) < TOL_THERMO, name
+    mom = max(np.abs(cpu.field(n)).max() for n in ("ρu", "ρv", "ρw"))
+    for name in ("ρu", "ρv", "ρw"):
+        err = np.abs(gpu.field(name) - cpu.field(name)).max() / mom
+        report(err, name)
+        assert err < TOL_MOMENTUM, name
+    ql_c = cpu.field("qˡ")
+    assert ql_c.max() > 1e-4                                              # the secant branch ran
+    assert rel_err(gpu.field("qˡ").astype(np.float64), ql_c) < 5e-3
+    assert gpu.context.state_is_finite()
+
+
+def test_static_energy_bubble_matches_oracle(oracle_arch):
+    """StaticEnergy instantiation (ρe prognostic, buoyancy-flux term) of the Float32 stage kernel, WENO5 and WENO9."""
+    import breeze_b200 as bz
+    for order in (5, 9):
+        models = []
+        for arch in (bz.B200(float_type="Float32"), oracle_arch):
+            grid = bz.RectilinearGrid(arch, size=(32, 16, 24), x=(-10e3, 10e3), y=(-10e3, 10e3), z=(0, 10e3))
+            m = bz.AtmosphereModel(grid, dynamics=bz.AnelasticDynamics(bz.ReferenceState(grid, potential_temperature=300)),
+                                   advection=bz.WENO(order=order), formulation="StaticEnergy")
+            m.set(θ=bubble_theta(), u=2.0, v=-1.0)
+            models.append(m)
+        gpu, cpu = models
+        for _ in range(5):
+            gpu.time_step(2.0)
+            cpu.time_step(2.0)
+        for name in ("ρθ", "T"):
+            assert rel_err(gpu.field(name).astype(np.float64), cpu.field(name)) < TOL_THERMO, (order, name)
+        mom = max(np.abs(cpu.field(n)).max() for n in ("ρu", "ρv", "ρw"))
+        for name in ("ρu", "ρv", "ρw"):
+            err = np.abs(gpu.field(name) - cpu.field(name)).max() / mom
+            report(err, f"order {order} {name}")
+            assert err < TOL_MOMENTUM, (order, name)
