@@ -157,7 +157,11 @@ struct ProfScope {
 
 static int is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
 // line lengths of the in-house FFT: 2^m in [8, 2048] or 3 * 2^m in [24, 1536]
-static int fft_length_ok(int n) { return (is_pow2(n) && n >= 8 && n <= 2048) || (n % 3 == 0 && is_pow2(n / 3) && n >= 24 && n <= 1536); }
+static int fft_length_ok(int n) {
+    if (is_pow2(n)) return n >= 8 && n <= 2048;
+    for (int r = 3; r <= 7; r += 2) if (n % r == 0 && is_pow2(n / r)) return n / r >= 8 && n <= 2048;     // 3 · 2^m .. 1536, 5 · 2^m .. 1280, 7 · 2^m .. 1792
+    return 0;
+}
 static int fft_threads(int N, int lines) { return lines * N / fft_pt(N); }
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -821,8 +825,8 @@ int bz_create(const bz_config* cfg, bz_ctx** out) {
     const int fx = cfg->topology_x == BZ_FLAT, fy = cfg->topology_y == BZ_FLAT;
     if ((fx && cfg->Nx != 1) || (fy && cfg->Ny != 1)) FAIL(BZ_ERR_INVALID, "a Flat dimension must have size 1");
     if (fx && !fy) FAIL(BZ_ERR_UNSUPPORTED, "(Flat, Periodic, Bounded) is not supported; use (Periodic, Flat, Bounded)");
-    if (!fx && !fft_length_ok(cfg->Nx)) FAIL(BZ_ERR_UNSUPPORTED, "Nx must be 2^m in [8, 2048] or 3 * 2^m in [24, 1536] (in-house FFT), got %d", cfg->Nx);
-    if (!fy && !fft_length_ok(cfg->Ny)) FAIL(BZ_ERR_UNSUPPORTED, "Ny must be 2^m in [8, 2048] or 3 * 2^m in [24, 1536] (in-house FFT), got %d", cfg->Ny);
+    if (!fx && !fft_length_ok(cfg->Nx)) FAIL(BZ_ERR_UNSUPPORTED, "Nx must be 2^m, 3 * 2^m, 5 * 2^m or 7 * 2^m with m >= 3 and Nx <= 2048 (in-house FFT), got %d", cfg->Nx);
+    if (!fy && !fft_length_ok(cfg->Ny)) FAIL(BZ_ERR_UNSUPPORTED, "Ny must be 2^m, 3 * 2^m, 5 * 2^m or 7 * 2^m with m >= 3 and Ny <= 2048 (in-house FFT), got %d", cfg->Ny);
     const int P = cfg->n_ranks < 1 ? 1 : cfg->n_ranks;
     if (cfg->use_tma == 1 && cfg->advection_order != 5) FAIL(BZ_ERR_UNSUPPORTED, "TMA staging belongs to the WENO(order=5) stage kernel");
     if (P > 1 && (fx || cfg->Nx % P != 0 || (cfg->Nx / P) < 8)) FAIL(BZ_ERR_INVALID, "x-slabs: Nx must be divisible by n_ranks with at least 8 columns per rank");

@@ -74,6 +74,39 @@ __device__ __forceinline__ void dft3(cpx& x0, cpx& x1, cpx& x2) {          // fo
     cpx r = {sn * d.y, -sn * d.x};                                        // -i sin(2π/3) (x1 - x2)
     x0 = x0 + s; x1 = m + r; x2 = m - r;
 }
+// forward DFT of odd prime length R = 5 / 7 in the symmetric form: with S_k = x_k + x_{R-k}, D_k = x_k - x_{R-k},
+//   X_m = x_0 + Σ_k cos(2π m k / R) S_k - i Σ_k sin(2π m k / R) D_k,   X_{R-m} = the same with + i      (m, k = 1 .. (R-1)/2)
+template <int R>
+__device__ __forceinline__ void dft_odd(cpx* v) {
+    constexpr int H = (R - 1) / 2;
+    // cos / sin (2π j / R), j = 1 .. H
+    constexpr double C5[2] = {0.30901699437494742410, -0.80901699437494742410}, S5[2] = {0.95105651629515357212, 0.58778525229247312917};
+    constexpr double C7[3] = {0.62348980185873353053, -0.22252093395631440429, -0.90096886790241912624},
+                     S7[3] = {0.78183148246802980871, 0.97492791218182360702, 0.43388373911755812048};
+    cpx S[H], D[H];
+#pragma unroll
+    for (int k = 0; k < H; ++k) { S[k] = v[k + 1] + v[R - 1 - k]; D[k] = v[k + 1] - v[R - 1 - k]; }
+    const cpx x0 = v[0];
+    cpx sum = x0;
+#pragma unroll
+    for (int k = 0; k < H; ++k) sum = sum + S[k];
+    v[0] = sum;
+#pragma unroll
+    for (int m = 1; m <= H; ++m) {
+        cpx a = x0, b = {0.0, 0.0};
+#pragma unroll
+        for (int k = 1; k <= H; ++k) {
+            const int j = (m * k) % R;                       // cos(2π j / R) = cos(2π (R - j) / R), sin changes sign
+            const int jj = j <= H ? j : R - j;
+            const double c = (R == 5) ? C5[jj - 1] : C7[jj - 1];
+            const double sn = ((R == 5) ? S5[jj - 1] : S7[jj - 1]) * (j <= H ? 1.0 : -1.0);
+            a = {a.x + c * S[k - 1].x, a.y + c * S[k - 1].y};
+            b = {b.x + sn * D[k - 1].x, b.y + sn * D[k - 1].y};
+        }
+        const cpx r = {b.y, -b.x};                          // -i b
+        v[m] = a + r; v[R - m] = a - r;
+    }
+}
 __device__ __forceinline__ void dft8(cpx* v) {
     const double h = 0.70710678118654752440;
     cpx a0 = v[0] + v[4], a4 = v[0] - v[4];
@@ -99,9 +132,12 @@ __host__ __device__ __forceinline__ int line_pitch(int N) { return ((N + (N >> 4
 __host__ __device__ __forceinline__ int imag_offset(int N, int lines) { int o = lines * line_pitch(N); return o + ((2 - o) & 15); }
 __host__ __device__ __forceinline__ size_t fft_smem_bytes(int N, int lines) { return (size_t)(imag_offset(N, lines) + lines * line_pitch(N)) * sizeof(double); }
 
-// Line lengths: N = 2^m (8 .. 2048) or N = 3 · 2^m (24 .. 1536; the reference benchmarks 768 x 768 x 256, Benchmarks.yml:41).
+// Line lengths: N = 2^m (8 .. 2048), 3 · 2^m (24 .. 1536; the reference benchmarks 768 x 768 x 256, Benchmarks.yml:41), 5 · 2^m (40 .. 1280)
+// or 7 · 2^m (56 .. 1792; 896^3 is the largest Float32 case of the reference's memory table, benchmarking/README.md:225-233).
 // Points per thread: 8 for the powers of two (radix-8 / 4 / 2 passes), 12 for 3 · 2^m (radix-4 / 2 passes and one radix-3 pass last, so
-// that every earlier pass keeps a power-of-two Ns).
+// that every earlier pass keeps a power-of-two Ns). 5 · 2^m and 7 · 2^m also run 8 points per thread through radix-8 / 4 / 2 passes; their
+// last pass (radix 5 / 7) has N / R butterflies for N / 8 threads of a line, so its second round is partly idle (guarded).
+__host__ __device__ constexpr int fft_odd_radix(int N) { return (N % 3 == 0) ? 3 : (N % 5 == 0) ? 5 : (N % 7 == 0) ? 7 : 1; }
 __host__ __device__ constexpr int fft_pt(int N) { return (N % 3 == 0) ? 12 : 8; }
 
 // One Stockham pass of radix R over lines of compile-time length N held as re[l*LP + pidx(n)], im[l*LP + pidx(n)].
@@ -123,8 +159,9 @@ struct NoLineIO {
 template <int N, int R, int Ns, bool IN = false, bool OUT = false, typename LD = NoLineIO, typename ST = NoLineIO>
 __device__ __forceinline__ void stockham_pass(double* __restrict__ re, double* __restrict__ im, const double2* __restrict__ tw,
                                               const LD& ld = LD(), const ST& st = ST()) {
-    constexpr int PT = fft_pt(N), ITEMS = PT / R, PER_LINE = N / PT, NR = N / R, LP = ((N + (N >> 4) + 15) & ~15) + 4, STEP = N / (Ns * R);
-    static_assert(PT % R == 0 && N % (Ns * R) == 0 && (Ns & (Ns - 1)) == 0, "pass shape");
+    constexpr int PT = fft_pt(N), PER_LINE = N / PT, NR = N / R, ITEMS = (NR + PER_LINE - 1) / PER_LINE, LP = ((N + (N >> 4) + 15) & ~15) + 4, STEP = N / (Ns * R);
+    constexpr bool GUARD = (NR % PER_LINE) != 0;       // radix 5 / 7 with 8 points per thread: the last round of butterflies is partial
+    static_assert(N % (Ns * R) == 0 && (Ns & (Ns - 1)) == 0, "pass shape");
     const int l = threadIdx.x / PER_LINE, t = threadIdx.x % PER_LINE;
     double* lre = re + l * LP;
     double* lim = im + l * LP;
@@ -132,6 +169,7 @@ __device__ __forceinline__ void stockham_pass(double* __restrict__ re, double* _
 #pragma unroll
     for (int it = 0; it < ITEMS; ++it) {
         const int j = t + it * PER_LINE;            // butterfly index in [0, N/R)
+        if (GUARD && j >= NR) continue;
         const int pj = pidx(j);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -146,6 +184,7 @@ __device__ __forceinline__ void stockham_pass(double* __restrict__ re, double* _
 #pragma unroll
     for (int it = 0; it < ITEMS; ++it) {
         const int j = t + it * PER_LINE;
+        if (GUARD && j >= NR) continue;
         const int k = j & (Ns - 1);
         if (Ns > 1) {
 #pragma unroll
@@ -157,6 +196,7 @@ __device__ __forceinline__ void stockham_pass(double* __restrict__ re, double* _
         if constexpr (R == 8) dft8(v[it]);
         else if constexpr (R == 4) dft4(v[it][0], v[it][1], v[it][2], v[it][3]);
         else if constexpr (R == 3) dft3(v[it][0], v[it][1], v[it][2]);
+        else if constexpr (R == 5 || R == 7) dft_odd<R>(v[it]);
         else dft2(v[it][0], v[it][1]);
         const int j0 = (j - k) * R + k;
         const int pj0 = pidx(j0);
@@ -183,7 +223,18 @@ __device__ __forceinline__ void pow2_passes_r4(double* __restrict__ re, double* 
 template <int N, bool IO = false, typename LD = NoLineIO, typename ST = NoLineIO>
 __device__ __forceinline__ void fft_lines_smem(double* __restrict__ re, double* __restrict__ im, const double2* __restrict__ tw,
                                                const LD& ld = LD(), const ST& st = ST()) {
-    if constexpr (N % 3 == 0) {
+    if constexpr (N % 5 == 0 || N % 7 == 0) {
+        constexpr int R = fft_odd_radix(N), M = N / R;
+        constexpr int m = (M == 8) ? 3 : (M == 16) ? 4 : (M == 32) ? 5 : (M == 64) ? 6 : (M == 128) ? 7 : 8;
+        static_assert((1 << m) == M, "N must be 5 * 2^m (40 .. 1280) or 7 * 2^m (56 .. 1792)");
+        constexpr int n8 = m / 3, rem = m % 3;      // radix-8 passes over the power-of-two factor, one radix-4 / 2 pass, the odd radix last
+        stockham_pass<N, 8, 1, IO, false, LD>(re, im, tw, ld);
+        if constexpr (n8 >= 2) stockham_pass<N, 8, 8>(re, im, tw);
+        constexpr int Ns = 1 << (n8 * 3);
+        if constexpr (rem == 2) stockham_pass<N, 4, Ns>(re, im, tw);
+        else if constexpr (rem == 1) stockham_pass<N, 2, Ns>(re, im, tw);
+        stockham_pass<N, R, M, false, IO, LD, ST>(re, im, tw, ld, st);
+    } else if constexpr (N % 3 == 0) {
         constexpr int M = N / 3;
         static_assert((M & (M - 1)) == 0 && M >= 8 && M <= 512, "N must be 3 * 2^m, 24 <= N <= 1536");
         pow2_passes_r4<N, 1, M, IO, LD>(re, im, tw, ld);
@@ -221,7 +272,7 @@ __device__ __forceinline__ double source_term(const Layout& L, const double* __r
 // MAXT / MINB: launch bounds. The default (256, 3) is the tuned configuration; (512, 2) exists for the wide-tile experiment
 // (8 lines per CTA = 128-byte rows of the momentum fields; BZ_FFT_LINES_Y).
 template <int N, int MAXT = 256, int MINB = 3>
-__global__ void __launch_bounds__(MAXT, (N % 3 == 0 && MINB > 2) ? 2 : MINB) poisson_forward_y(Layout L, PoissonGeom G, const double* __restrict__ ru, const double* __restrict__ rv,
+__global__ void __launch_bounds__(MAXT, (fft_odd_radix(N) > 1 && MINB > 2) ? 2 : MINB) poisson_forward_y(Layout L, PoissonGeom G, const double* __restrict__ ru, const double* __restrict__ rv,
                                   const double* __restrict__ rw, double dz_over_dt, double2* __restrict__ W,
                                   const double2* __restrict__ tw_y, int lines, int k_base) {
     extern __shared__ double sm[];
@@ -275,7 +326,7 @@ __global__ void poisson_pack_flat_y(Layout L, PoissonGeom G, const double* __res
 
 // ---- pass 5: complex-to-real inverse FFT along y → φ (padded field interior) -------------------------------------
 template <int N, int MAXT = 256, int MINB = 3>
-__global__ void __launch_bounds__(MAXT, (N % 3 == 0 && MINB > 2) ? 2 : MINB) poisson_inverse_y(Layout L, PoissonGeom G, const double2* __restrict__ W, double* __restrict__ phi,
+__global__ void __launch_bounds__(MAXT, (fft_odd_radix(N) > 1 && MINB > 2) ? 2 : MINB) poisson_inverse_y(Layout L, PoissonGeom G, const double2* __restrict__ W, double* __restrict__ phi,
                                   const double2* __restrict__ tw_y, int lines, double scale, PeerBases peers, int pull, int k_base) {
     extern __shared__ double sm[];
     constexpr int LP = ((N + (N >> 4) + 15) & ~15) + 4;
@@ -344,7 +395,7 @@ __global__ void poisson_unpack_flat_y(Layout L, PoissonGeom G, const double2* __
 // ---- passes 2 / 4: complex FFT along x, in place; one line = Nx contiguous complex numbers ----------------------
 // grid ceil(n_lines / lines); block lines*Nx/8 <= 256 threads; smem 2*lines*line_pitch(Nx) doubles.
 template <int N, int MAXT = 256, int MINB = 3>
-__global__ void __launch_bounds__(MAXT, (N % 3 == 0 && MINB > 2) ? 2 : MINB) fft_x_kernel(PoissonGeom G, double2* __restrict__ W, long long n_lines, const double2* __restrict__ tw_x, int lines, int inverse,
+__global__ void __launch_bounds__(MAXT, (fft_odd_radix(N) > 1 && MINB > 2) ? 2 : MINB) fft_x_kernel(PoissonGeom G, double2* __restrict__ W, long long n_lines, const double2* __restrict__ tw_x, int lines, int inverse,
                                                        PeerBases peers, int pull, int line_base) {
     extern __shared__ double sm[];
     double* re = sm;
@@ -479,7 +530,7 @@ __global__ void remove_mean_mode(PoissonGeom G, double2* __restrict__ W) {
     for (int k = threadIdx.x; k < G.Nz; k += blockDim.x) { double2 v = W[k * stride]; W[k * stride] = make_double2(v.x - mr, v.y - mi); }
 }
 
-// Host-side dispatch on the line length (2^m or 3 · 2^m).
+// Host-side dispatch on the line length (2^m, 3 · 2^m, 5 · 2^m, 7 · 2^m).
 #define FFT_DISPATCH(n, CALL)                                                                                    \
     switch (n) {                                                                                                  \
         case 8: { constexpr int FN = 8; CALL; break; }       case 16: { constexpr int FN = 16; CALL; break; }     \
@@ -490,5 +541,12 @@ __global__ void remove_mean_mode(PoissonGeom G, double2* __restrict__ W) {
         case 24: { constexpr int FN = 24; CALL; break; }     case 48: { constexpr int FN = 48; CALL; break; }     \
         case 96: { constexpr int FN = 96; CALL; break; }     case 192: { constexpr int FN = 192; CALL; break; }   \
         case 384: { constexpr int FN = 384; CALL; break; }   case 768: { constexpr int FN = 768; CALL; break; }   \
-        case 1536: { constexpr int FN = 1536; CALL; break; } default: break;                                      \
+        case 1536: { constexpr int FN = 1536; CALL; break; }                                                      \
+        case 40: { constexpr int FN = 40; CALL; break; }     case 80: { constexpr int FN = 80; CALL; break; }     \
+        case 160: { constexpr int FN = 160; CALL; break; }   case 320: { constexpr int FN = 320; CALL; break; }   \
+        case 640: { constexpr int FN = 640; CALL; break; }   case 1280: { constexpr int FN = 1280; CALL; break; } \
+        case 56: { constexpr int FN = 56; CALL; break; }     case 112: { constexpr int FN = 112; CALL; break; }   \
+        case 224: { constexpr int FN = 224; CALL; break; }   case 448: { constexpr int FN = 448; CALL; break; }   \
+        case 896: { constexpr int FN = 896; CALL; break; }   case 1792: { constexpr int FN = 1792; CALL; break; } \
+        default: break;                                                                                           \
     }

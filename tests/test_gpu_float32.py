@@ -57,7 +57,7 @@ def test_float32_library_is_float32(oracle_arch):
         bz.AtmosphereModel(grid, dynamics=bz.CompressibleDynamics(bz.SplitExplicitTimeDiscretization(substeps=6)))
 
 
-@pytest.mark.parametrize("size,flat_y", [((32, 16, 24), False), ((64, 40), True), ((48, 24, 16), False)])
+@pytest.mark.parametrize("size,flat_y", [((32, 16, 24), False), ((64, 40), True), ((48, 24, 16), False), ((40, 56, 12), False)])
 @pytest.mark.parametrize("use_tma", [1, 2])
 def test_set_state_projection_matches_oracle(oracle_arch, size, flat_y, use_tma):
     gpu, cpu = _pair(oracle_arch, size, flat_y, use_tma=use_tma)

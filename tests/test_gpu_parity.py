@@ -305,10 +305,14 @@ def test_cell_advection_timescale_and_finite_check_match_oracle(oracle_arch):
     assert not gpu.context.state_is_finite()
 
 
-@pytest.mark.parametrize("size,flat_y", [((24, 48, 16), False), ((96, 24, 12), False), ((192, 20), True), ((48, 64, 10), False)])
+@pytest.mark.parametrize("size,flat_y", [((24, 48, 16), False), ((96, 24, 12), False), ((192, 20), True), ((48, 64, 10), False),
+                                         ((40, 56, 12), False), ((80, 112, 10), False), ((160, 24, 8), False), ((224, 20), True),
+                                         ((320, 16), True), ((448, 40, 6), False), ((640, 8, 6), False), ((16, 896, 6), False),
+                                         ((1280, 12), True), ((8, 1792, 4), False)])
 def test_mixed_radix_grids_match_oracle(oracle_arch, size, flat_y):
-    """Horizontal sizes 3 · 2^m (the reference benchmarks 768 x 768 x 256, .github/workflows/Benchmarks.yml:41): the in-house FFT's
-    radix-3 pass, the projection and three full steps against the oracle (whose DFT is an independent mixed-radix implementation)."""
+    """Horizontal sizes 3 · 2^m (the reference benchmarks 768 x 768 x 256, .github/workflows/Benchmarks.yml:41), 5 · 2^m and 7 · 2^m
+    (896^3: benchmarking/README.md:225-233): the in-house FFT's radix-3 / 5 / 7 passes, the projection and three full steps against the
+    oracle (whose DFT is an independent mixed-radix implementation)."""
     gpu, cpu = _pair(oracle_arch, size, flat_y, seed=5, moist=True)
     for name in PROGNOSTIC + ["φ"]:
         assert rel_err(gpu.field(name), cpu.field(name)) < TOL_HOOK, name
