@@ -754,6 +754,24 @@ def main():
                 c4 = bench_compressible(args, 10, 3, with_cpu=False, with_e2e=False)
                 out["config4_compressible"] = {k: c4[k] for k in ("value", "unit", "ms_per_step", "roofline", "breakdown_ms_per_step", "gpu_launches")}
                 out["config4_compressible"]["workload"] = c4["config"]["workload"]
+                try:    # the precision examples/splitting_supercell.jl:86 sets: same case through the Float32 library (bzcf_*), device time of 10 steps
+                    m32 = supercell_model(bz.B200(device=local_rank, float_type="Float32"), (256, 256, 64), 6)
+                    for _ in range(3):
+                        m32.time_step(6.0)
+                    m32.context.synchronize()
+                    st32 = torch.cuda.ExternalStream(m32.context.stream())
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(st32)
+                    for _ in range(10):
+                        m32.time_step(6.0)
+                    e1.record(st32)
+                    m32.context.synchronize(); torch.cuda.synchronize()
+                    ms32 = e0.elapsed_time(e1) / 10
+                    out["config4_compressible"]["float32_mode"] = {"value": 256 * 256 * 64 / (ms32 * 1e-3) / 1e6, "unit": "Mcell-updates/s", "ms_per_step": ms32,
+                                                                   "dtype": "f32", "finite": bool(np.isfinite(m32.field("w")).all())}
+                    del m32
+                except Exception as e:
+                    out["config4_compressible"]["float32_mode"] = {"error": str(e)}
             except Exception as e:                       # never lose the headline line
                 out["config4_compressible"] = {"error": str(e)}
             try:

@@ -47,32 +47,43 @@ class bzc_config(C.Structure):
 
 _dp, _vp = C.POINTER(C.c_double), C.c_void_p
 
-# name -> (restype, argtypes); every symbol include/breeze_b200_compressible.h declares for both libraries
-ABI_SYMBOLS = {
-    "default_config": (None, [C.POINTER(bzc_config)]),
-    "create": (C.c_int, [C.POINTER(bzc_config), C.POINTER(_vp)]),
-    "destroy": (None, [_vp]),
-    "last_error": (C.c_char_p, [_vp]),
-    "set_reference_potential_temperature": (C.c_int, [_vp, _dp]),
-    "get_reference_state": (C.c_int, [_vp, _dp, _dp, _dp]),
-    "set_state": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _dp, _dp]),
-    "time_step": (C.c_int, [_vp, C.c_double]),
-    "time_steps": (C.c_int, [_vp, C.c_double, C.c_int]),
-    "compute_slow_tendencies": (C.c_int, [_vp]),
-    "stage_substep_count_and_size": (C.c_int, [_vp, C.c_double, C.c_double, C.POINTER(C.c_int32), _dp]),
-    "acoustic_substep_loop": (C.c_int, [_vp, C.c_double, C.c_double]),
-    "get_field": (C.c_int, [_vp, C.c_int, _dp]),
-    "get_state": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _dp, _dp]),
-    "get_clock": (C.c_int, [_vp, _dp, C.POINTER(C.c_int64)]),
-    "synchronize": (C.c_int, [_vp]),
-}
-CUDA_ONLY_SYMBOLS = {
-    "profile_enable": (C.c_int, [_vp, C.c_int]),
-    "profile_read": (C.c_int, [_vp, _dp, C.POINTER(C.c_int64)]),
-    "kernel_launch_count": (C.c_int64, [_vp]),
-    "stream": (_vp, [_vp]),
-    "device_bytes": (C.c_int64, [_vp]),
-}
+def abi_symbols(real=C.c_double):
+    """name -> (restype, argtypes) of every symbol include/breeze_b200_compressible.h declares. `real` is the library's field type: c_double
+    for bzc_ (libbreeze_b200.so) and orcc_ (the oracle), c_float for bzcf_ (libbreeze_b200_f32.so), whose entry points are the same with every
+    `double` array / scalar argument a `float` (bzc_config and the clock of get_clock stay double)."""
+    rp = C.POINTER(real)
+    return {
+        "default_config": (None, [C.POINTER(bzc_config)]),
+        "create": (C.c_int, [C.POINTER(bzc_config), C.POINTER(_vp)]),
+        "destroy": (None, [_vp]),
+        "last_error": (C.c_char_p, [_vp]),
+        "set_reference_potential_temperature": (C.c_int, [_vp, rp]),
+        "get_reference_state": (C.c_int, [_vp, rp, rp, rp]),
+        "set_state": (C.c_int, [_vp, rp, rp, rp, rp, rp, rp]),
+        "time_step": (C.c_int, [_vp, real]),
+        "time_steps": (C.c_int, [_vp, real, C.c_int]),
+        "compute_slow_tendencies": (C.c_int, [_vp]),
+        "stage_substep_count_and_size": (C.c_int, [_vp, real, real, C.POINTER(C.c_int32), rp]),
+        "acoustic_substep_loop": (C.c_int, [_vp, real, real]),
+        "get_field": (C.c_int, [_vp, C.c_int, rp]),
+        "get_state": (C.c_int, [_vp, rp, rp, rp, rp, rp, rp]),
+        "get_clock": (C.c_int, [_vp, _dp, C.POINTER(C.c_int64)]),
+        "synchronize": (C.c_int, [_vp]),
+    }
+
+
+def cuda_only_symbols(real=C.c_double):
+    return {
+        "profile_enable": (C.c_int, [_vp, C.c_int]),
+        "profile_read": (C.c_int, [_vp, C.POINTER(real), C.POINTER(C.c_int64)]),
+        "kernel_launch_count": (C.c_int64, [_vp]),
+        "stream": (_vp, [_vp]),
+        "device_bytes": (C.c_int64, [_vp]),
+    }
+
+
+ABI_SYMBOLS = abi_symbols()
+CUDA_ONLY_SYMBOLS = cuda_only_symbols()
 
 
 class CompressibleLibrary:
@@ -80,10 +91,12 @@ class CompressibleLibrary:
 
     def __init__(self, lib: abi.Library):
         self.base, self.dll, self.cuda = lib, lib.dll, lib.cuda
-        self.prefix = lib.prefix[:-1] + "c_"
-        table = dict(ABI_SYMBOLS)
+        self.prefix = {"bz_": "bzc_", "bzf_": "bzcf_", "orc_": "orcc_"}.get(lib.prefix, lib.prefix[:-1] + "c_")
+        self.real = getattr(lib, "creal", C.c_double)           # ctypes type of the library's reals
+        self.dtype = getattr(lib, "real", np.float64)           # numpy type of its field arrays
+        table = dict(abi_symbols(self.real))
         if lib.cuda:
-            table.update(CUDA_ONLY_SYMBOLS)
+            table.update(cuda_only_symbols(self.real))
         for name, (res, args) in table.items():
             fn = getattr(self.dll, self.prefix + name)       # AttributeError if the symbol is not exported
             fn.restype, fn.argtypes = res, args
@@ -100,10 +113,11 @@ def compressible_library(lib: abi.Library) -> CompressibleLibrary:
 
 
 def _as_dp(a):
+    """pointer to a C-contiguous float64 or float32 array (ctypes checks it against the bound library's argument type)"""
     if a is None:
         return None
-    assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
-    return a.ctypes.data_as(_dp)
+    assert a.dtype in (np.float64, np.float32) and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.POINTER(C.c_double if a.dtype == np.float64 else C.c_float))
 
 
 class CompressibleContext:
@@ -111,6 +125,7 @@ class CompressibleContext:
 
     def __init__(self, lib: CompressibleLibrary, cfg: bzc_config):
         self.lib, self.cfg, self.handle = lib, cfg, _vp()
+        self.real = lib.dtype                                    # numpy dtype of every field array of this library
         rc = lib.create(C.byref(cfg), C.byref(self.handle))
         if rc != 0:
             msg = lib.last_error(None)
@@ -140,13 +155,13 @@ class CompressibleContext:
         return (self.Nz + 1 if fid in Z_FACE_FIELDS else self.Nz, self.Ny, self.Nx)
 
     def set_reference_potential_temperature(self, theta_r):
-        a = np.ascontiguousarray(theta_r, dtype=np.float64)
+        a = np.ascontiguousarray(theta_r, dtype=self.real)
         if a.shape != (self.Nz,):
             raise BreezeError(f"θᵣ profile: expected {self.Nz} values, got {a.shape}")
         self._check(self.lib.set_reference_potential_temperature(self.handle, _as_dp(a)), "set_reference_potential_temperature")
 
     def reference_state(self):
-        p, rho, pi = (np.empty(self.Nz) for _ in range(3))
+        p, rho, pi = (np.empty(self.Nz, dtype=self.real) for _ in range(3))
         self._check(self.lib.get_reference_state(self.handle, _as_dp(p), _as_dp(rho), _as_dp(pi)), "get_reference_state")
         return p, rho, pi
 
@@ -157,7 +172,7 @@ class CompressibleContext:
             if a is None:
                 arrs.append(None)
                 continue
-            a = np.ascontiguousarray(a, dtype=np.float64)
+            a = np.ascontiguousarray(a, dtype=self.real)
             if a.shape != self.shape(fid if fid < 5 else 0):
                 raise BreezeError(f"field {PROGNOSTIC[fid]}: expected shape {self.shape(fid if fid < 5 else 0)}, got {a.shape}")
             arrs.append(a)
@@ -173,7 +188,7 @@ class CompressibleContext:
         self._check(self.lib.compute_slow_tendencies(self.handle), "compute_slow_tendencies")
 
     def stage_substep_count_and_size(self, dt, beta):
-        n, d = C.c_int32(), C.c_double()
+        n, d = C.c_int32(), self.lib.real()
         self._check(self.lib.stage_substep_count_and_size(self.handle, float(dt), float(beta), C.byref(n), C.byref(d)),
                     "stage_substep_count_and_size")
         return n.value, d.value
@@ -183,14 +198,14 @@ class CompressibleContext:
 
     def get_field(self, name_or_id):
         fid = FIELD_IDS[name_or_id] if isinstance(name_or_id, str) else int(name_or_id)
-        out = np.empty(self.shape(fid))
+        out = np.empty(self.shape(fid), dtype=self.real)
         self._check(self.lib.get_field(self.handle, fid, _as_dp(out)), "get_field")
         return out
 
     def get_state(self, out=None):
         """The prognostics (ρᵈ, ρu, ρv, ρw, ρθ[, ρqᵛ]) in one call, into `out` (e.g. pinned buffers) when given."""
         if out is None:
-            out = [np.empty(self.shape(f)) for f in range(5)]
+            out = [np.empty(self.shape(f), dtype=self.real) for f in range(5)]
         ptrs = [_as_dp(a) for a in out] + [None] * (6 - len(out))
         self._check(self.lib.get_state(self.handle, *ptrs), "get_state")
         return out
@@ -208,7 +223,7 @@ class CompressibleContext:
         self._check(self.lib.profile_enable(self.handle, int(on)), "profile_enable")
 
     def profile_read(self):
-        ms, n = np.zeros(8), np.zeros(8, dtype=np.int64)
+        ms, n = np.zeros(8, dtype=self.real), np.zeros(8, dtype=np.int64)
         self._check(self.lib.profile_read(self.handle, _as_dp(ms), n.ctypes.data_as(C.POINTER(C.c_int64))), "profile_read")
         return ms, n
 
@@ -328,8 +343,6 @@ class CompressibleAtmosphereModel:
         from .model import Flat, ThermodynamicConstants, WENO
         if microphysics is not None:
             raise NotImplementedError("the compressible path carries vapour only (microphysics = nothing)")
-        if getattr(grid.architecture, "float_type", "Float64") != "Float64":
-            raise NotImplementedError("the Float32 library carries the anelastic path only; the compressible path is Float64")
         self._moist = False
         self.grid, self.architecture, self.dynamics = grid, grid.architecture, dynamics
         self.thermodynamic_constants = thermodynamic_constants or ThermodynamicConstants()

@@ -1415,7 +1415,5 @@ int64_t bz_device_bytes(const bz_ctx* c) { return c ? c->bytes : 0; }
 
 }  // extern "C"
 
-// second hot-path family: compressible WS-RK3 with acoustic substepping (include/breeze_b200_compressible.h); FP64 library only
-#ifndef BZ_F32
+// second hot-path family: compressible WS-RK3 with acoustic substepping (include/breeze_b200_compressible.h; bzc_ / bzcf_ entry points)
 #include "compressible_api.cuh"
-#endif

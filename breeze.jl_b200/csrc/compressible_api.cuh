@@ -28,7 +28,7 @@ struct bzc_ctx {
     double *rqv = nullptr, *rqv0 = nullptr, *Grqv = nullptr, *qv = nullptr, *rho_tot = nullptr;
     double* dense = nullptr;
     cudaStream_t stream = nullptr;
-    double time = 0.0;
+    double time = 0.0;                   // BZ_KEEP_F64 (the clock stays double in the Float32 build)
     int64_t iteration = 0, launches = 0, bytes = 0;
     int prof_on = 0;
     std::vector<cudaEvent_t> prof_ev;
@@ -505,7 +505,7 @@ int bzc_time_step(bzc_ctx* c, double dt) {
     }
     if (g && g->seen) {
         const long long l0 = c->launches;
-        const double t0 = c->time; const int64_t it0 = c->iteration;
+        const double t0 = c->time; const int64_t it0 = c->iteration;   // BZ_KEEP_F64
         cudaGraph_t graph = nullptr;
         CC_TRY(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
         int rc = c_time_step(c, dt);
@@ -640,7 +640,7 @@ int bzc_get_state(bzc_ctx* c, double* rho, double* ru, double* rv, double* rw, d
     return BZ_OK;
 }
 
-int bzc_get_clock(bzc_ctx* c, double* time, int64_t* iteration) {
+int bzc_get_clock(bzc_ctx* c, double* time, int64_t* iteration) {   // BZ_KEEP_F64
     if (!c) return BZ_ERR_INVALID;
     if (time) *time = c->time;
     if (iteration) *iteration = c->iteration;

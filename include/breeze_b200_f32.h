@@ -6,7 +6,7 @@
  * bzf_, every `double` array or scalar argument a `float` — host arrays are Julia `Array{Float32,3}` interiors, x fastest — except the
  * clock of bzf_get_clock, which stays double. The configuration and forcing structs (bz_config, bz_forcing) are shared with
  * breeze_b200.h and keep their double fields; bz_ctx is opaque in both. The library is compiled from a mechanically retyped copy of the
- * FP64 sources (breeze.jl_b200/make_f32.py); the compressible path (breeze_b200_compressible.h) is FP64 only.
+ * FP64 sources (breeze.jl_b200/make_f32.py); the compressible path's Float32 entry points (bzcf_*) are in breeze_b200_compressible_f32.h.
  * Each entry point stands behind the same reference method as its bz_ namesake (see breeze_b200.h for the file:line citations).
  */
 #ifndef BREEZE_B200_F32_H

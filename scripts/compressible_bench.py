@@ -1,5 +1,5 @@
 """Device timing of the compressible split-explicit path at the BASELINE config-4 shape (256 x 256 x 64, WS-RK3, acoustic
-substepping): python scripts/compressible_bench.py [Nx Ny Nz] [--steps K] [--substeps N]
+substepping): python scripts/compressible_bench.py [Nx Ny Nz] [--steps K] [--substeps N] [--float32]
 
 Prints ms per step, Mcell-updates/s, per-kernel-family device time, and the achieved HBM bandwidth of the two substep kernels
 against their algorithmic bytes. Development / profiling tool (also the command profiled with ncu)."""
@@ -29,7 +29,9 @@ def main():
         from breeze_b200 import abi
         abi._CUDA_LIB = abi.Library(os.path.abspath(sys.argv[sys.argv.index("--lib") + 1]), "bz_", cuda=True)
         print("library:", sys.argv[sys.argv.index("--lib") + 1])
-    grid = bz.RectilinearGrid(bz.B200(), size=size, x=(0, 168e3), y=(0, 168e3), z=(0, 20e3))
+    ftype = "Float32" if "--float32" in sys.argv else "Float64"
+    print("precision:", ftype)
+    grid = bz.RectilinearGrid(bz.B200(float_type=ftype), size=size, x=(0, 168e3), y=(0, 168e3), z=(0, 20e3))
     dyn = bz.CompressibleDynamics(bz.SplitExplicitTimeDiscretization(substeps=nsub), reference_potential_temperature=300.0)
     m = bz.AtmosphereModel(grid, dynamics=dyn)
     _, rho, _ = m.reference_profiles()

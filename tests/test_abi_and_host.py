@@ -187,3 +187,19 @@ def test_float32_library_exports_the_same_entry_points():
     generated = os.path.join(ROOT, "breeze.jl_b200", "csrc", "f32", "stage_kernel.cuh")
     code = [ln.split("//")[0] for ln in open(generated).read().split("\n")]
     assert not any(re.search(r"\bdouble\b", ln) for ln in code)
+
+
+def test_float32_library_exports_the_compressible_entry_points():
+    """The compressible path of the Float32 library (prefix bzcf_, include/breeze_b200_compressible_f32.h — the precision
+    examples/splitting_supercell.jl:86 runs in): every declared symbol is exported, and the header is what make_f32.py --headers generates."""
+    from breeze_b200 import abi, compressible
+    lib = compressible.compressible_library(abi.load_cuda_library_f32())
+    assert lib.prefix == "bzcf_" and lib.dtype is np.float32
+    names = list(compressible.abi_symbols()) + list(compressible.cuda_only_symbols())
+    for name in names:
+        assert hasattr(lib.dll, "bzcf_" + name), name
+    assert set(_declared_symbols("breeze_b200_compressible_f32.h", "bzcf_")) == {"bzcf_" + n for n in names}
+    assert set(_declared_symbols("breeze_b200_compressible.h", "bzc_")) == {"bzc_" + n for n in names}
+    generated = os.path.join(ROOT, "breeze.jl_b200", "csrc", "f32", "compressible.cuh")
+    code = [ln.split("//")[0] for ln in open(generated).read().split("\n")]
+    assert not any(re.search(r"\bdouble\b", ln) for ln in code)
