@@ -194,4 +194,9 @@ function time_step!(model::B200AcousticModel, Δt; callbacks = [])
     return nothing
 end
 
+# Float32 models (`Oceananigans.defaults.FloatType = Float32`, examples/splitting_supercell.jl:86) bind the same entry points of
+# libbreeze_b200_f32 under the prefix bzcf_ (include/breeze_b200_compressible_f32.h): Ptr{Float32} arrays, Cfloat scalars, the same BzcConfig.
+#   ccall((:bzcf_set_state, lib32), Cint, (Ptr{Cvoid}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}), …)
+#   ccall((:bzcf_time_step, lib32), Cint, (Ptr{Cvoid}, Cfloat), ctx.handle, Δt)
+
 end # module
